@@ -1,0 +1,194 @@
+/*
+ * snoutrx.h -- C ABI of libsnoutrx.so, the B200-native IQ -> packet receive engine
+ * that replaces Snout's two receive engines behind their own boundaries.
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Every entry point
+ * returns 0 on success or a negative SNRX_E* code (snrx_strerror() explains it).
+ * There is no CPU fallback anywhere behind this interface: if no CUDA device
+ * is usable snrx_create() fails with SNRX_ENODEV.
+ *
+ * Which reference interface each entry point replaces (paths relative to the
+ * nislab/snout tree):
+ *
+ *   snrx_create / snrx_destroy
+ *       BLE   : process start of `btle_rx -c <ch> -g 6 -a 8e89bed6 -k 555555`
+ *               (snout/util/btle.py:53-69; option table
+ *               vendor/BTLE/host/btle-tools/src/btle_rx.c:1209-1294; board
+ *               set-up config_run_board() btle_rx.c:623; crc_init_reorder()
+ *               btle_rx.c:1801-1825 applied once at start, btle_rx.c:2335).
+ *       Zigbee: construction of the flowgraph `top_block(channel=...)`
+ *               (snout/modulations/Zigbee/hackrf/Zigbee_rx/top_block.py:29-89).
+ *   snrx_process
+ *       BLE   : rx_callback() filling the ring (btle_rx.c:489-498) + the
+ *               half-buffer loop calling receiver() (btle_rx.c:2341-2393,
+ *               receiver() 2020-2155, search_unique_bits() 1369-1421,
+ *               demod_byte() 1348-1367, scramble_byte() 1158-1163,
+ *               crc_check() 1826-1848).
+ *       Zigbee: the stream edges source -> quadrature_demod_cf -> (x - iir(x))
+ *               -> clock_recovery_mm_ff -> packet_sink (top_block.py:52-73,
+ *               80-89) and the sink's general_work()
+ *               (scapy-radio/gnuradio/gr-zigbee/lib/packet_sink_scapy_impl.cc:158-374).
+ *       Wideband modes additionally run the 96 Msps polyphase channelizer,
+ *       which has no counterpart in the reference (it retunes one channel at
+ *       a time: snout/util/btle.py:62, snout/core/radio.py:415).
+ *   snrx_poll
+ *       BLE   : the printf()/fflush() of one line per frame (btle_rx.c:2137-2145,
+ *               2383) that snout/core/pcontroller.py:115-131 reads back.
+ *       Zigbee: message_port_pub() of the PSDU blob
+ *               (packet_sink_scapy_impl.cc:333-349) -> UDP 127.0.0.1:52002
+ *               (top_block.py:71) -> GnuradioSocket.recv
+ *               (scapy-radio/scapy/scapy/modules/gnuradio.py:67-73).
+ *   snrx_set_channel
+ *       Zigbee: top_block.set_channel() via XMLRPC (top_block.py:94-96).
+ *   snrx_debug_stage
+ *       no reference counterpart: exposes intermediate streams (quantised
+ *       channel streams, discriminator output, soft chips) for parity tests.
+ */
+#ifndef SNOUTRX_H
+#define SNOUTRX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNRX_ABI_VERSION 1
+
+/* protocol ids = scapy-radio GnuradioPacket.proto values
+ * (scapy-radio/scapy/scapy/layers/gnuradio.py:19-25) */
+#define SNRX_PROTO_ZIGBEE 2
+#define SNRX_PROTO_BLE    3
+
+/* error codes */
+#define SNRX_OK        0
+#define SNRX_EINVAL   -1   /* bad argument / configuration            */
+#define SNRX_ENODEV   -2   /* no usable CUDA device                   */
+#define SNRX_ENOMEM   -3   /* host or device allocation failed        */
+#define SNRX_ECUDA    -4   /* CUDA runtime error (see snrx_last_error) */
+#define SNRX_ERANGE   -5   /* input larger than the configured capacity */
+#define SNRX_EOVERFLOW -6  /* more candidates / frames than capacity  */
+#define SNRX_ESTATE   -7   /* call out of sequence                    */
+
+/* receive modes */
+#define SNRX_MODE_BLE_NB     0  /* one BLE channel, 4 Msps cf32 in          (BASELINE config 1) */
+#define SNRX_MODE_ZB_NB      1  /* one 802.15.4 channel, 4 Msps cf32 in     (config 2)          */
+#define SNRX_MODE_ZB_WB16    2  /* 96 Msps in -> 16 Zigbee receivers        (config 3)          */
+#define SNRX_MODE_BLE_WB40   3  /* 96 Msps in -> 40 BLE receivers           (config 4)          */
+#define SNRX_MODE_MIXED_WB56 4  /* 96 Msps in -> 40 BLE + 16 Zigbee         (config 5)          */
+
+/* geometry constants of the wideband channelizer (DESIGN.md "Channelizer") */
+#define SNRX_WB_RATE      96000000
+#define SNRX_WB_CENTER    2440000000ull
+#define SNRX_WB_DECIM     24        /* 96 Msps -> 4 Msps per channel          */
+#define SNRX_NB_RATE      4000000
+#define SNRX_BLE_WINDOW   8192      /* btle_rx half buffer in IQ samples (btle_rx.c:180-182) */
+
+/* One decoded frame.  Fixed 160 bytes so it can be all-gathered as-is. */
+typedef struct snrx_frame {
+    int64_t  sample_index;  /* channel-rate (4 Msps) IQ index, capture relative:
+                               BLE: sample carrying access-address bit 0 (may be
+                               -4..-1 at a window origin, btle_rx.c:1409);
+                               Zigbee: input position of the chip completing the SFD */
+    uint32_t capture_id;    /* index of the capture inside the processed batch */
+    uint32_t window;        /* BLE: 8192-IQ window that reported it; Zigbee: segment */
+    uint16_t channel;       /* BLE 0..39 / 802.15.4 11..26                    */
+    uint8_t  proto;         /* SNRX_PROTO_*                                   */
+    uint8_t  crc_ok;        /* BLE: CRC-24 matches (btle_rx prints CRC0); Zigbee: FCS-16 matches */
+    uint8_t  lqi;           /* Zigbee: min(255,(sum/8)<<3) (packet_sink_scapy_impl.cc:334-335) */
+    uint8_t  phase;         /* BLE: sample phase 0..3 of the hit                */
+    uint16_t len;           /* valid bytes in bytes[]: BLE 2+payload+3, Zigbee PSDU length */
+    uint32_t access_addr;   /* BLE                                            */
+    uint8_t  bytes[132];    /* BLE: header|payload|crc (de-whitened); Zigbee: PSDU incl. FCS */
+} snrx_frame_t;
+
+typedef struct snrx_config {
+    uint32_t abi_version;    /* must be SNRX_ABI_VERSION                                   */
+    int32_t  device;         /* CUDA device ordinal                                        */
+    int32_t  mode;           /* SNRX_MODE_*                                                */
+    int32_t  channel;        /* NB modes: BLE 0..39 / Zigbee 11..26 ; ignored in WB modes  */
+    uint32_t access_addr;    /* BLE `-a`  (default 0x8E89BED6, btle_rx.c:188)              */
+    uint32_t crc_init;       /* BLE `-k`  as typed (0x555555, btle_rx.c:189)               */
+    int32_t  zb_threshold;   /* packet sink threshold (10, top_block.py:67)                */
+    float    quant_scale;    /* BLE: q = clamp(rint(x*quant_scale), -128, 127)             */
+    uint64_t max_samples;    /* capacity: input samples per capture                        */
+    uint32_t max_captures;   /* capacity: captures per snrx_process batch                  */
+    uint32_t max_frames;     /* capacity: frames per snrx_process batch                    */
+    uint32_t zb_segment;     /* Zigbee: chain segment body, channel-rate samples (0 = default 131072) */
+    uint32_t zb_prehalo;     /* Zigbee: chain warm-up, channel-rate samples (0 = default 4096)    */
+    uint32_t pfb_taps;       /* WB: prototype length, 384 or 768 (0 = default 384)         */
+    uint32_t flags;          /* SNRX_F_*                                                   */
+} snrx_config_t;
+
+#define SNRX_F_KEEP_STREAMS 1u  /* also store channel streams so snrx_debug_stage can return them */
+
+typedef struct snrx_stats {
+    uint64_t samples_in;      /* input-rate samples consumed by the last snrx_process */
+    uint64_t channel_samples; /* channel-rate samples produced (all channels)         */
+    uint32_t candidates;      /* BLE access-address hits / Zigbee chains run          */
+    uint32_t frames;          /* frames emitted                                       */
+    uint32_t frames_crc_ok;
+    uint32_t kernel_launches; /* kernels launched by the last snrx_process            */
+    float    gpu_ms;          /* device time of the last snrx_process (CUDA events)   */
+    float    gpu_ms_frontend; /* of which: channelizer / slicer kernel                */
+} snrx_stats_t;
+
+/* debug stages for snrx_debug_stage() */
+#define SNRX_STAGE_BLE_Q8      1  /* int8 I,Q quantised channel streams [cap][ch][n][2]      */
+#define SNRX_STAGE_BLE_BITS    2  /* uint32 sliced bit words [cap][ch][phase][words]         */
+#define SNRX_STAGE_CHAN_CF32   3  /* cf32 channel streams [cap][ch][n] (WB modes)             */
+#define SNRX_STAGE_ZB_DISC     4  /* f32 discriminator minus DC [cap][ch][n]                  */
+#define SNRX_STAGE_ZB_CHIPS    5  /* f32 soft chips of every chain, see DESIGN.md             */
+
+typedef struct snrx snrx_t;
+
+int  snrx_abi_version(void);
+const char* snrx_strerror(int code);
+const char* snrx_last_error(snrx_t* h);          /* detail text of the last failure (may be "") */
+
+int  snrx_device_count(int* n);
+int  snrx_create(snrx_t** h, const snrx_config_t* cfg);
+void snrx_destroy(snrx_t* h);
+
+/* Run the receive path over a batch of `n_captures` captures, each `n_samples`
+ * interleaved cf32 IQ samples long and `stride_samples` apart (input rate).
+ * `iq` is a host pointer (pageable or pinned; copied in chunks overlapped with
+ * compute) or, if is_device_ptr != 0, a device pointer on cfg.device.
+ * `first_window` is the index of the first BLE window / Zigbee segment of the
+ * buffer inside its capture (time-sharded captures; 0 otherwise), and
+ * `n_body` the number of samples whose frames belong to this call (frames
+ * anchored in [n_body, n_samples) -- the post halo -- are dropped; 0 = all).
+ * Asynchronous with respect to the host when the input is a device pointer. */
+int  snrx_process(snrx_t* h, const float* iq, uint32_t n_captures,
+                  uint64_t n_samples, uint64_t stride_samples,
+                  uint64_t n_body, uint32_t first_window, uint32_t first_capture_id,
+                  int is_device_ptr);
+
+/* Wait for the batch and copy up to `cap` frames out, in reference order:
+ * (capture, channel, window, sample_index).  *n_out = frames available. */
+int  snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out);
+
+/* Device-side view of the frame list of the last batch (for NCCL all-gather
+ * from the host runtime): pointers stay valid until the next snrx_process. */
+int  snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev);
+
+int  snrx_set_channel(snrx_t* h, int channel);           /* NB modes */
+int  snrx_set_stream(snrx_t* h, void* cuda_stream);       /* run on a caller stream */
+int  snrx_sync(snrx_t* h);
+int  snrx_stats(snrx_t* h, snrx_stats_t* s);
+int  snrx_debug_stage(snrx_t* h, int stage, void* out, uint64_t cap_bytes, uint64_t* n_bytes);
+
+/* pinned host staging for callers that want full PCIe rate */
+int  snrx_host_alloc(void** p, uint64_t bytes);
+int  snrx_host_free(void* p);
+
+/* channel plan helpers (btle_rx.c:932-948; top_block.py:56,94-96) */
+int  snrx_ble_channel_mhz(int channel);          /* 37->2402 ... ; <0 on error */
+int  snrx_zigbee_channel_mhz(int channel);       /* 11->2405 ... 26->2480      */
+int  snrx_ble_channel_bin(int channel);          /* PFB bin (0..95) of a BLE channel  */
+int  snrx_zigbee_channel_bin(int channel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNOUTRX_H */
