@@ -1,0 +1,287 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the receive path (contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one synthetic capture per GPU.  Default workload is
+BASELINE.json configs[3], the configuration the metric is quoted on: a 96 Msps wideband capture
+channelized into all 40 BLE channels and decoded (access-address search, de-whitening, CRC-24) on
+one B200.  Rank 0 prints ONE JSON line.
+
+  value      input-rate Msamples/s, whole job, capture resident in HBM, timed with CUDA events
+  e2e        same metric through RxEngine.run() on a pinned HOST buffer (H2D + frame D2H inside)
+  roofline   channelizer kernel: algorithmic 8 B/sample / its measured launch time vs MEASURED_PEAKS
+  cpu_baseline  the CPU statement of the same path (oracle) timed on this box's host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (engine mode, BASELINE config, description)
+    "ble_wb40": ("ble_wb40", "configs[3]", "BLE all 40 channels: 96 Msps wideband capture PFB-channelized into 40 GFSK receivers"),
+    "ble_nb": ("ble_nb", "configs[0]", "BLE advertising channel 37: 4 Msps cf32, 1e7 samples"),
+    "zb_nb": ("zb_nb", "configs[1]", "Zigbee 802.15.4 channel 11: 4 Msps O-QPSK capture, 1e7 samples"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_capture(workload, seconds_base, seed):
+    from snout_b200 import synth
+    if workload == "ble_wb40":
+        base = synth.wideband_capture(seconds=seconds_base, kind="ble", seed=seed, esn0_db=25.0)
+        return base.iq, len(base.truth)
+    if workload == "ble_nb":
+        c = synth.ble_capture(n=10_000_000, channel=37, seed=1001, esn0_db=30.0)
+        return c.iq, len(c.truth)
+    c = synth.zigbee_capture(n=10_000_000, channel=11, seed=2001, esn0_db=30.0)
+    return c.iq, len(c.truth)
+
+
+def cpu_path(workload, sample, repeat=1):
+    """CPU statement of the path on `sample` using every host core; returns (seconds, frames, cores, kind)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from snout_b200 import _abi, chanplan
+    oracle.build(native=True)
+    cores = os.cpu_count() or 1
+    kind = "port"
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(repeat):
+        if workload == "ble_wb40":
+            impl = "reference" if oracle.have_ref("btle_ref") else "port"
+            kind = "reference" if impl == "reference" else "port"
+            h = _abi.pfb_prototype(_abi.MODE_BLE_WB40, 384) if os.path.exists(_abi.LIB_PATH) else None
+            y = oracle.pfb(sample, h, [chanplan.ble_channel_bin(c) for c in range(40)], fast=True)   # OpenMP, all cores
+            def one(c):
+                return len(oracle.ble_decode(oracle.ble_quantize(y[c], 100.0), c, impl="port" if impl == "port" else "port"))
+            with ThreadPoolExecutor(cores) as ex:
+                frames = sum(ex.map(one, range(40)))
+            kind = "port"      # channelizer has no reference counterpart; per-channel decode = port of btle_rx.c
+        elif workload == "ble_nb":
+            impl = "reference" if oracle.have_ref("btle_ref") else "port"
+            kind = impl
+            q = oracle.ble_quantize(sample, 128.0)
+            frames = len(oracle.ble_decode(q, 37, impl=impl))
+            cores = 1
+        else:
+            frames = len(oracle.zb_receive(sample, 11))
+            cores = 1
+    return time.perf_counter() - t0, frames, cores, kind
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ble_wb40", choices=sorted(WORKLOADS))
+    ap.add_argument("--base-seconds", type=float, default=0.1, help="length of the generated capture that is tiled")
+    ap.add_argument("--tiles", type=int, default=10, help="copies of the generated capture per step (wideband)")
+    ap.add_argument("--taps", type=int, default=384)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    mode, cfg_name, desc = WORKLOADS[args.workload]
+    unit = "Msamples/s"
+    metric = "input IQ Msamples/s channelized+decoded (whole job)"
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        base, n_truth = make_capture(args.workload, min(args.base_seconds, 0.05), 4000)
+        times = []
+        for i in range(args.warmup + args.steps):
+            dt, frames, cores, kind = cpu_path(args.workload, base)
+            if i >= args.warmup:
+                times.append(dt)
+        t = float(np.mean(times))
+        v = len(base) / t / 1e6
+        line = {
+            "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "sample_samples": int(len(base)),
+                       "note": "CPU statement of the same path on the host cores; the reference itself has no channelizer "
+                               "(it retunes one 4 Msps channel at a time)"},
+            "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": kind,
+                             "sample": f"{len(base)} samples of the workload per step, {frames} frames"},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    from snout_b200 import _abi, dist as sdist
+    from snout_b200.engine import RxEngine
+    rank, world, local = sdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    base, n_truth = make_capture(args.workload, args.base_seconds, 4000 + 37 * rank)
+    tiles = args.tiles if args.workload == "ble_wb40" else 1
+    n = len(base) * tiles
+    pinned = _abi.PinnedBuffer(n, np.complex64)
+    for i in range(tiles):
+        pinned.array[i * len(base):(i + 1) * len(base)] = base
+    x_dev = torch.from_numpy(pinned.array).to(dev)                   # resident input, larger than L2 for the wideband run
+    eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps if mode == "ble_wb40" else 0, device=local,
+                   channel=None, max_frames=1 << 18)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as d
+            d.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        fr = eng.process(x_dev).poll()
+        if world > 1:
+            fr = sdist.allgather_frames(fr, dev)
+        return fr
+
+    for _ in range(args.warmup):
+        fr = step_resident()
+    frames_per_step = len(fr)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    front_ms, launches = [], 0
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+        st = eng.stats()
+        front_ms.append(st["gpu_ms_frontend"])
+        launches += st["kernel_launches"]
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        import torch.distributed as d
+        t = torch.tensor([ms], device=dev)
+        d.all_reduce(t, op=d.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * n * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- end to end: pinned host buffer in, frames out, every step
+    for _ in range(2):
+        eng.run(pinned)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        fr = eng.run(pinned)
+        d2h += fr.nbytes + 32
+        if world > 1:
+            sdist.allgather_frames(fr, dev)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as d
+        t = torch.tensor([e2e_s], device=dev)
+        d.all_reduce(t, op=d.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * n * args.steps / e2e_s / 1e6
+
+    if rank != 0:
+        return 0
+    peak, peak_src = peaks()
+    fms = float(np.mean(front_ms))
+    achieved = n * 8 / (fms * 1e-3) / 1e9
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": f"synthetic: {args.base_seconds}s seeded GFSK capture with AWGN, tiled x{tiles}; random frames on every channel",
+        "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "samples_per_step_per_gpu": int(n),
+                   "input_bytes_per_step_per_gpu": int(n * 8), "pfb_taps": args.taps if mode == "ble_wb40" else None,
+                   "l2": "input (%.0f MB) larger than L2; no flush needed" % (n * 8 / 1e6),
+                   "frames_per_step": int(frames_per_step), "timed": "process()+poll() incl. frame D2H, CUDA events on the engine stream"},
+        "frames_per_s": frames_per_step * args.steps / (ms * 1e-3),
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(d2h / args.steps),
+                "note": "RxEngine.run(pinned host buffer): chunked H2D overlapped with the channelizer, frames read back"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "k_pfb_ble (channelizer+slicer)" if mode == "ble_wb40" else "front-end kernel",
+                     "algorithmic_bytes_per_launch": int(n * 8), "kernel_ms": fms,
+                     "note": "8 B per input sample (one cf32 read); the fused channelizer is FP32-pipe limited, see DESIGN.md"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sample = base[: min(len(base), 4_800_000)] if args.workload == "ble_wb40" else base
+        dt, frames, cores, kind = cpu_path(args.workload, sample)
+        line["cpu_baseline"] = {"value": len(sample) / dt / 1e6, "unit": unit, "cores": cores, "kind": kind,
+                                "sample": f"{len(sample)} samples of the same capture, {frames} frames, {dt:.2f} s"}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -114,7 +114,7 @@ typedef struct snrx_config {
     uint64_t max_samples;    /* capacity: input samples per capture                        */
     uint32_t max_captures;   /* capacity: captures per snrx_process batch                  */
     uint32_t max_frames;     /* capacity: frames per snrx_process batch                    */
-    uint32_t zb_segment;     /* Zigbee: chain segment body, channel-rate samples (0 = default 131072) */
+    uint32_t zb_segment;     /* Zigbee: chain segment body, channel-rate samples (0 = default 65536) */
     uint32_t zb_prehalo;     /* Zigbee: chain warm-up, channel-rate samples (0 = default 4096)    */
     uint32_t pfb_taps;       /* WB: prototype length, 384 or 768 (0 = default 384)         */
     uint32_t flags;          /* SNRX_F_*                                                   */
@@ -137,10 +137,12 @@ typedef struct snrx_stats {
 #define SNRX_STAGE_BLE_Q8      1  /* int8 I,Q quantised channel streams [cap][ch][n][2]      */
 #define SNRX_STAGE_BLE_BITS    2  /* uint32 sliced bit words [cap][ch][phase][words]         */
 #define SNRX_STAGE_CHAN_CF32   3  /* cf32 channel streams [cap][ch][n] (WB modes)             */
-#define SNRX_STAGE_ZB_DISC     4  /* f32 discriminator minus DC [cap][ch][n]                  */
-#define SNRX_STAGE_ZB_CHIPS    5  /* f32 soft chips of every chain, see DESIGN.md             */
+#define SNRX_STAGE_ZB_DISC     4  /* f32 discriminator minus DC [cap][ch][stride] (stride = bytes/(4*cap*ch)) */
+#define SNRX_STAGE_ZB_CHIPS    5  /* f32 soft chips [chain][chips_cap], chain = (cap, ch, segment)  */
+#define SNRX_STAGE_ZB_F        6  /* f32 discriminator output before DC removal [cap][ch][stride] */
+#define SNRX_STAGE_ZB_NCHIPS   7  /* int64 number of chips each chain produced [chain]            */
 
-typedef struct snrx snrx_t;
+typedef struct snrx_handle snrx_t;
 
 int  snrx_abi_version(void);
 const char* snrx_strerror(int code);
@@ -150,19 +152,27 @@ int  snrx_device_count(int* n);
 int  snrx_create(snrx_t** h, const snrx_config_t* cfg);
 void snrx_destroy(snrx_t* h);
 
+/* Time shard of a longer capture (multi-GPU / streaming): the buffer handed to snrx_process
+ * starts `pre_samples` before the shard body (read-only halo: channelizer history, Zigbee
+ * warm-up) and may extend past it (post halo, so frames that start in the body can be
+ * decoded completely).  Only frames anchored inside the body are reported. */
+typedef struct snrx_shard {
+    uint64_t pre_samples;      /* input-rate samples of pre halo; multiple of 128 channel samples */
+    uint64_t body_samples;     /* input-rate samples of the body (0 = rest of the buffer)         */
+    uint32_t first_window;     /* index inside the capture of the body's first BLE window /
+                                  Zigbee segment (the body starts on that grid)                   */
+    uint32_t first_capture_id; /* capture_id reported for capture 0 of the batch                  */
+} snrx_shard_t;
+
 /* Run the receive path over a batch of `n_captures` captures, each `n_samples`
- * interleaved cf32 IQ samples long and `stride_samples` apart (input rate).
+ * interleaved cf32 IQ samples long and `stride_samples` apart (input rate; 0 = n_samples).
  * `iq` is a host pointer (pageable or pinned; copied in chunks overlapped with
- * compute) or, if is_device_ptr != 0, a device pointer on cfg.device.
- * `first_window` is the index of the first BLE window / Zigbee segment of the
- * buffer inside its capture (time-sharded captures; 0 otherwise), and
- * `n_body` the number of samples whose frames belong to this call (frames
- * anchored in [n_body, n_samples) -- the post halo -- are dropped; 0 = all).
- * Asynchronous with respect to the host when the input is a device pointer. */
+ * compute) or, if is_device_ptr != 0, a device pointer on cfg.device; 16-byte aligned.
+ * `shard` is NULL for whole captures.  Asynchronous with respect to the host when
+ * the input is a device pointer; results are collected with snrx_poll. */
 int  snrx_process(snrx_t* h, const float* iq, uint32_t n_captures,
                   uint64_t n_samples, uint64_t stride_samples,
-                  uint64_t n_body, uint32_t first_window, uint32_t first_capture_id,
-                  int is_device_ptr);
+                  const snrx_shard_t* shard, int is_device_ptr);
 
 /* Wait for the batch and copy up to `cap` frames out, in reference order:
  * (capture, channel, window, sample_index).  *n_out = frames available. */
@@ -177,6 +187,9 @@ int  snrx_set_stream(snrx_t* h, void* cuda_stream);       /* run on a caller str
 int  snrx_sync(snrx_t* h);
 int  snrx_stats(snrx_t* h, snrx_stats_t* s);
 int  snrx_debug_stage(snrx_t* h, int stage, void* out, uint64_t cap_bytes, uint64_t* n_bytes);
+
+/* prototype low-pass of the wideband channelizer (taps = 384 or 768 doubles) */
+int  snrx_pfb_prototype(int mode, uint32_t taps, double* out);
 
 /* pinned host staging for callers that want full PCIe rate */
 int  snrx_host_alloc(void** p, uint64_t bytes);

@@ -1,0 +1,299 @@
+// ble_back.cuh -- BLE back end on sliced bit streams: access-address sliding correlation,
+// per-candidate de-whitening + CRC-24, and the per-window resolver that replays the
+// order-dependent acceptance rules of the reference receiver.
+//
+// Reference behaviour reproduced (vendor/BTLE/host/btle-tools/src/btle_rx.c):
+//   search_unique_bits()  1369-1421   sliding 32-bit compare over 4 sample phases, history
+//                                     zeroed at every call (1377)
+//   demod_byte()          1348-1367   LSB-first packing of symbol-spaced bit decisions
+//   scramble_byte()       1158-1163   XOR with scramble_table[channel]
+//   crc_update/crc_check  1137-1156, 1826-1848
+//   parse_*_header_byte   1771-1795   length fields, ADV gate 6..37 in receiver() 2096-2104
+//   receiver()            2020-2155   search -> header -> payload -> resume after the frame
+//   main loop             2341-2393   one receiver() call per 8192-IQ half buffer
+//
+// The kernels work on bits only: the slicer decision b[n] = (I[n]Q[n+1] - I[n+1]Q[n]) > 0 is all
+// that search_unique_bits() and demod_byte() ever look at, so the front ends (narrow-band slicer,
+// wideband channelizer) hand over one bit per channel-rate sample, phase-deinterleaved:
+// word w of phase j holds samples n = 4*(32*(w-1) + i) + j in bit i.
+#pragma once
+#include "common.cuh"
+
+namespace snrx {
+
+SNRX_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
+SNRX_HD int hi_bit_plus1(uint32_t d) {   // 0 for d == 0, else index of highest set bit + 1
+#ifdef __CUDA_ARCH__
+    return 32 - __clz(d);
+#else
+    int n = 0; while (d) { n++; d >>= 1; } return n;
+#endif
+}
+
+// number of low access-address positions that a zeroed history satisfies "for free"
+// (btle_rx.c:1377,1395-1401): positions p with aa[p] == 0 or mask[p] == 0, counted from p = 0
+SNRX_HD int aa_virtual_bits(uint32_t aa, uint32_t mask) {
+    uint32_t v = aa & mask;
+    int z = 0;
+    while (z < 31 && !((v >> z) & 1u)) z++;
+    return z;
+}
+
+// Sliding correlation over one 32-slot word of one phase stream: bit i of `hits` is set when the
+// 32 symbol-spaced decisions starting at slot (32*(w-1) + i) match the access address in every
+// masked position >= z.  (full matches and "virtual" matches usable only at a search origin)
+SNRX_HD uint32_t aa_word_hits(uint32_t lo, uint32_t hi, uint32_t aa, uint32_t mask_hi /* mask & ~((1<<z)-1) */) {
+    uint32_t hits = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        uint32_t r = funnel_r(lo, hi, i);
+        if (((r ^ aa) & mask_hi) == 0) hits |= (1u << i);
+    }
+    return hits;
+}
+
+// 32 consecutive symbol decisions of one phase stream starting at slot t (t >= -32)
+SNRX_HD uint32_t slots32(const uint32_t* phase_words, int t) {
+    int w = (t + 32) >> 5, sh = (t + 32) & 31;
+    return funnel_r(phase_words[w], phase_words[w + 1], sh);
+}
+
+// Finish the decode of a candidate from its de-whitened 4-byte chunks (chunk c = bytes 4c..4c+3
+// counted from the PDU header).  Mirrors receiver() btle_rx.c:2066-2125.
+SNRX_HD void ble_finish(const uint32_t* chunk /*[11]*/, bool adv_channel, uint32_t crc_init_internal,
+                        const uint32_t* crc_tab, Dec& d) {
+    uint8_t* b = d.bytes;
+#pragma unroll
+    for (int c = 0; c < 11; c++) {
+        uint32_t v = chunk[c];
+        b[4 * c] = (uint8_t)v; b[4 * c + 1] = (uint8_t)(v >> 8);
+        b[4 * c + 2] = (uint8_t)(v >> 16); b[4 * c + 3] = (uint8_t)(v >> 24);
+    }
+    int len = adv_channel ? (b[1] & 0x3F) : (b[1] & 0x1F);     // btle_rx.c:1794 / 1776
+    d.len = (uint8_t)len;
+    d.emit = (uint8_t)(adv_channel ? (len >= 6 && len <= 37) : 1);   // btle_rx.c:2096
+    uint32_t crc = crc_init_internal;
+    uint32_t recv = 0;
+    d.crc_ok = 0;
+    if (d.emit) {
+        for (int i = 0; i < len + 2; i++) crc = (crc_tab[(crc ^ b[i]) & 0xFF] ^ (crc >> 8)) & 0xFFFFFFu;
+        recv = (uint32_t)b[len + 2] | ((uint32_t)b[len + 3] << 8) | ((uint32_t)b[len + 4] << 16);
+        d.crc_ok = (uint8_t)(crc == recv);
+    }
+}
+
+// Replay of receiver() for one 8192-IQ window starting at local sample W.
+//   cands[c0, c1) : hits of this (capture, channel), ascending in s
+//   EMIT(idx)     : called for every accepted, printed frame with the candidate index
+// Returns the number of frames.
+template <class EMIT>
+SNRX_HD int ble_resolve_window(const Cand* cands, const Dec* decs, int c0, int c1, int W, int z, EMIT emit) {
+    int n = 0;
+    int eaten = 0;                                   // int8 units past W, as the reference counts
+    for (;;) {
+        int slots = (kSpanInt8 - eaten) / (kSps * 2);    // num_symbol_left, btle_rx.c:2032,2075,2123
+        if (slots <= 0) break;
+        const int P = W + eaten / 2;                 // search origin (local sample index)
+        // first candidate with s >= P - 4z
+        int lo = c0, hi = c1;
+        const int s_min = P - 4 * z;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (cands[mid].s < s_min) lo = mid + 1; else hi = mid; }
+        int found = -1;
+        for (int k = lo; k < c1; k++) {
+            const int s = cands[k].s;
+            const int vneed = cands[k].vneed;        // number of low AA bits that do NOT match (0 = full)
+            if (s >= P) {
+                int t = 31 + (s - P) / kSps;
+                if (t >= slots) break;               // beyond this call's search span
+                if (vneed == 0) { found = k; break; }
+            } else {
+                int v = (P - s + kSps - 1) / kSps;   // history slots still zero when this position is tested
+                int t = 31 - v;
+                if (v <= z && vneed <= v && t < slots) { found = k; break; }
+            }
+        }
+        if (found < 0) break;
+        const int s = cands[found].s;
+        eaten = 2 * (s - W) + 32 * kSps * 2 + 16 * kSps * 2;     // AA + 2 header bytes, btle_rx.c:2058,2066
+        if (eaten > kDemodLimitInt8) break;          // btle_rx.c:2067
+        const Dec& d = decs[found];
+        if (!d.emit) continue;                       // ADV length gate: resume after the header
+        eaten += 8 * ((int)d.len + 3) * kSps * 2;    // btle_rx.c:2113
+        if (eaten > kDemodLimitInt8) break;          // btle_rx.c:2115
+        emit(found);
+        n++;
+    }
+    return n;
+}
+
+SNRX_HD void ble_fill_frame(snrx_frame_t& f, const Cand& c, const Dec& d, const BleParams& p, int window_local,
+                            int channel_number) {
+    f.sample_index = (int64_t)(c.s - p.m_origin) + (int64_t)kWindow * p.first_window;
+    f.capture_id = p.first_capture + c.cap;
+    f.window = p.first_window + (uint32_t)window_local;
+    f.channel = (uint16_t)channel_number;
+    f.proto = SNRX_PROTO_BLE;
+    f.crc_ok = d.crc_ok;
+    f.lqi = 0;
+    f.phase = (uint8_t)(((c.s % 4) + 4) % 4);
+    f.len = (uint16_t)(d.len + 5);
+    f.access_addr = p.aa;
+    const int nb = d.len + 5;
+#pragma unroll 4
+    for (int i = 0; i < 132; i++) f.bytes[i] = (i < nb && i < 44) ? d.bytes[i] : 0;
+}
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------ kernels
+
+// Sliding access-address correlation.  One warp per (capture, channel, chunk of 32 words); each
+// lane owns one word of each phase stream and obtains the following word from its neighbour by
+// warp shuffle.  COUNT pass writes hits per chunk, FILL pass writes the candidates at the
+// scanned offsets, ascending in s.
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ bits, BitsLayout lay, BleParams p,
+                                                   uint32_t n_chunks, uint32_t* __restrict__ counts,
+                                                   const uint32_t* __restrict__ offsets, Cand* __restrict__ cands,
+                                                   uint32_t cand_cap) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t n_items = p.n_captures * p.n_channels * n_chunks;
+    const int z = aa_virtual_bits(p.aa, p.aa_mask);
+    const uint32_t mask_hi = p.aa_mask & ~((1u << z) - 1u);
+    for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
+         item += gridDim.x * warps_per_block) {
+        const uint32_t chunk = item % n_chunks;
+        const uint32_t ch = (item / n_chunks) % p.n_channels;
+        const uint32_t cap = item / (n_chunks * p.n_channels);
+        const uint32_t w = chunk * 32 + lane;                       // word owned by this lane
+        const bool valid = (w + 1) < lay.words_per_phase;
+        uint32_t hits[4];
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t* pw = bits + lay.index(cap, ch, j, 0);
+            uint32_t lo = valid ? __ldg(pw + w) : 0u;
+            uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
+            if (lane == 31) hi = (w + 1 < lay.words_per_phase) ? __ldg(pw + w + 1) : 0u;
+            uint32_t hj = valid ? aa_word_hits(lo, hi, p.aa, mask_hi) : 0u;
+            // positions whose first sample lies beyond the capture carry no data
+            const int nvalid = ((p.n_out - 1 - j) >> 2) - 32 * ((int)w - 1) + 1;
+            if (nvalid <= 0) hj = 0u; else if (nvalid < 32) hj &= (1u << nvalid) - 1u;
+            hits[j] = hj;
+            cnt += __popc(hj);
+        }
+        const uint32_t any = __ballot_sync(0xffffffffu, cnt != 0);
+        if (!FILL) {
+            int tot = cnt;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (lane == 0) counts[item] = (uint32_t)tot;
+        } else if (any) {
+            // exclusive prefix over lanes
+            int pre = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+            pre -= cnt;
+            uint32_t dst = offsets[item] + (uint32_t)pre;
+            if (cnt) {
+                for (int i = 0; i < 32; i++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if ((hits[j] >> i) & 1u) {
+                            const int t = 32 * ((int)w - 1) + i;
+                            const uint32_t* pw = bits + lay.index(cap, ch, j, 0);
+                            uint32_t r = slots32(pw, t);
+                            uint32_t d = (r ^ p.aa) & p.aa_mask;
+                            if (dst < cand_cap) {
+                                Cand c;
+                                c.s = 4 * t + j; c.ch_idx = (uint16_t)ch; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = cap;
+                                cands[dst] = c;
+                            }
+                            dst++;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One warp per candidate: lanes 0..10 each pull 32 symbol decisions (4 bytes) of the frame out of
+// the candidate's phase stream and de-whiten them; lane 0 gathers them by shuffle, applies the
+// header rules and runs the CRC-24.
+__global__ void __launch_bounds__(128) k_ble_decode(const uint32_t* __restrict__ bits, BitsLayout lay, BleParams p,
+                                                    const uint32_t* __restrict__ n_cands_dev, uint32_t cand_cap,
+                                                    const Cand* __restrict__ cands, Dec* __restrict__ decs,
+                                                    const uint32_t* __restrict__ crc_tab,
+                                                    const uint32_t* __restrict__ whiten /*[40][11]*/,
+                                                    const int32_t* __restrict__ channel_numbers) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    uint32_t n = *n_cands_dev;
+    if (n > cand_cap) n = cand_cap;
+    for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < n; k += gridDim.x * warps_per_block) {
+        const Cand c = cands[k];
+        const int j = ((c.s % 4) + 4) % 4;
+        const int t0 = (c.s - j) / 4;                                 // slot of AA bit 0 (may be -1)
+        const int chn = channel_numbers[c.ch_idx];
+        const uint32_t* pw = bits + lay.index(c.cap, c.ch_idx, j, 0);
+        uint32_t mine = 0;
+        if (lane < 11) mine = slots32(pw, t0 + 32 + 32 * lane) ^ whiten[chn * 11 + lane];
+        uint32_t chunk[11];
+#pragma unroll
+        for (int q = 0; q < 11; q++) chunk[q] = __shfl_sync(0xffffffffu, mine, q);
+        if (lane == 0) {
+            Dec d;
+            d.s = c.s; d.resume = 0; d.vneed = c.vneed;
+            ble_finish(chunk, chn >= 37 && chn <= 39, p.crc_init_internal, crc_tab, d);
+            decs[k] = d;
+        }
+    }
+}
+
+// One thread per (capture, channel, window): replay of receiver().  COUNT pass stores the
+// number of frames of the window, FILL pass writes the frame records at the scanned offsets.
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_ble_resolve(const Cand* __restrict__ cands, const Dec* __restrict__ decs,
+                                                     const uint32_t* __restrict__ cand_offsets, uint32_t n_chunks,
+                                                     BleParams p, uint32_t* __restrict__ counts,
+                                                     const uint32_t* __restrict__ frame_offsets,
+                                                     snrx_frame_t* __restrict__ frames, uint32_t frame_cap,
+                                                     const int32_t* __restrict__ channel_numbers, uint32_t cand_cap) {
+    const uint32_t n_items = p.n_captures * p.n_channels * (uint32_t)p.n_windows;
+    const int z = aa_virtual_bits(p.aa, p.aa_mask);
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+        const uint32_t w = item % (uint32_t)p.n_windows;
+        const uint32_t ch = (item / (uint32_t)p.n_windows) % p.n_channels;
+        const uint32_t cap = item / ((uint32_t)p.n_windows * p.n_channels);
+        const uint32_t base = (cap * p.n_channels + ch) * n_chunks;
+        uint32_t c0 = cand_offsets[base], c1 = cand_offsets[base + n_chunks];
+        if (c0 > cand_cap) c0 = cand_cap;
+        if (c1 > cand_cap) c1 = cand_cap;
+        int nf = 0;
+        if (c1 > c0) {
+            const int W = p.m_origin + kWindow * (int)w;
+            if (!FILL) {
+                nf = ble_resolve_window(cands, decs, (int)c0, (int)c1, W, z, [](int) {});
+            } else {
+                uint32_t dst = frame_offsets[item];
+                const int chn = channel_numbers[ch];
+                nf = ble_resolve_window(cands, decs, (int)c0, (int)c1, W, z, [&](int k) {
+                    if (dst < frame_cap) ble_fill_frame(frames[dst], cands[k], decs[k], p, (int)w, chn);
+                    dst++;
+                });
+            }
+        }
+        if (!FILL) counts[item] = (uint32_t)nf;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace snrx

@@ -1,0 +1,128 @@
+// common.cuh -- shared definitions of the libsnoutrx kernels.
+//
+// Every arithmetic core is written as a __host__ __device__ function so that
+// tests/emu (an nvcc-built HOST harness, test infrastructure only) can step the
+// same per-thread code on the CPU and compare it with the oracle before any GPU
+// time is spent.  libsnoutrx.so itself contains no host execution path for
+// them: the ABI launches kernels or fails.
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include "../../include/snoutrx.h"
+
+#if defined(__CUDACC__)
+#define SNRX_HD __host__ __device__ __forceinline__
+#define SNRX_D __device__ __forceinline__
+#else
+#define SNRX_HD inline
+#define SNRX_D inline
+#endif
+
+namespace snrx {
+
+// ---- explicitly rounded float ops: never contracted / re-associated, identical on host and device
+SNRX_HD float f_fma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+SNRX_HD float f_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+SNRX_HD float f_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+SNRX_HD float f_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b; return r;
+#endif
+}
+SNRX_HD float f_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b; return r;
+#endif
+}
+SNRX_HD double d_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+SNRX_HD double d_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+
+// ---- BLE constants (vendor/BTLE/host/btle-tools/src/btle_rx.c) -------------------------------
+constexpr int kSps = 4;                    // SAMPLE_PER_SYMBOL, btle_rx.c:176
+constexpr int kWindow = SNRX_BLE_WINDOW;   // 8192 IQ per receiver() call, btle_rx.c:180-182, 2382
+constexpr int kSpanInt8 = 31 * 8 + 16384;  // receiver() buf_len, btle_rx.c:2382
+constexpr int kDemodLimitInt8 = 19392;     // demod_buf_len, btle_rx.c:2025
+constexpr int kBleMaxBytes = 42;           // 2 header + 37 payload + 3 crc, btle_rx.c:1344
+constexpr int kBitsLeadWords = 1;          // slots -32..-1 (only slot -1 is ever read)
+constexpr int kBitsTailWords = 16;         // zero words after the last tile: a frame at the very end reads
+                                           // 32+16+8*40 = 368 slots = 11.5 words past its start
+
+// Bit layout: for capture c, channel k, phase j: word w holds slots t = 32*(w-1) .. 32*(w-1)+31,
+// bit i of the word is the slicer decision of channel-rate sample n = 4*t + j.
+struct BitsLayout {
+    uint32_t words_per_phase;   // kBitsLeadWords + tiles + kBitsTailWords
+    uint32_t n_channels;
+    SNRX_HD size_t index(uint32_t cap, uint32_t ch, uint32_t phase, uint32_t w) const {
+        return (((size_t)cap * n_channels + ch) * 4 + phase) * (size_t)words_per_phase + w;
+    }
+};
+
+// An access-address hit found by the sliding correlation.
+struct Cand {
+    int32_t s;          // channel-rate sample index of AA bit 0 (local to the processed buffer)
+    uint16_t ch_idx;    // channel slot (index into the engine's channel list)
+    uint8_t vneed;      // low AA positions that do NOT match: 0 = full 32-bit match, v>0 = usable only at a
+                        // search origin whose zeroed history covers the first v positions (btle_rx.c:1377)
+    uint8_t pad;
+    uint32_t cap;       // capture index inside the batch
+};
+
+// Speculative decode of a candidate (one warp per candidate).
+struct Dec {
+    int32_t s;
+    int32_t resume;     // sample where the reference resumes searching after this hit
+    uint8_t len;        // payload length field
+    uint8_t emit;       // 1: a frame is printed (length gate passed / data channel)
+    uint8_t crc_ok;
+    uint8_t vneed;
+    uint8_t bytes[44];  // de-whitened header | payload | crc
+};
+
+struct BleParams {
+    uint32_t aa;
+    uint32_t aa_mask;
+    uint32_t crc_init_internal;   // crc_init_reorder(-k), btle_rx.c:1801-1825
+    int32_t n_out;                // channel-rate samples per capture in this buffer
+    int32_t m_origin;             // local sample index where window `first_window` starts (multiple of 128)
+    int32_t n_windows;            // windows whose frames belong to this call
+    uint32_t first_window;
+    uint32_t first_capture;
+    uint32_t n_captures;
+    uint32_t n_channels;
+};
+
+}  // namespace snrx

@@ -1,0 +1,276 @@
+// pfb.cuh -- wideband polyphase-filterbank channelizer fused with the BLE slicer.
+//
+// No reference counterpart: Snout retunes one 4 Msps channel at a time
+// (snout/util/btle.py:62, snout/core/radio.py:415).  Definition (DESIGN.md "Channelizer",
+// restated on the CPU in oracle/pfb_oracle.c):
+//
+//   y_k[m] = (-j)^(k m) * sum_{n<L} h[n] exp(+j 2 pi k n / 96) x[24 m - n]      M = 96 bins, D = 24
+//
+// BLE mode needs the 40 even bins only, so the bank is evaluated as a 48-branch bank:
+//   v_r[m]   = sum_{p<L/48} h[r + 48 p] x[24 m - r - 48 p]            r = 0..47   (FIR, FP32 FMA)
+//   y_2q[m]  = (-1)^(q m) * sum_r v_r[m] exp(+j 2 pi q r / 48)                     (48-point inverse DFT)
+// followed, per channel, by the int8-grid quantiser and the reference's one-sample
+// cross-product slicer (btle_rx.c:1357-1361); only ONE BIT per channel sample leaves the SM.
+//
+// One CTA (192 threads) produces 128 channel-rate samples x 40 channels (+1 extra time step so
+// the last slicer decision of the tile has its successor) from 3072 + L input samples:
+//   phase 0  cp.async stages the input tile into shared memory (coalesced 16-byte copies); the
+//            tile is laid out flat with a 64-byte skew every 384 samples so that phase 1 is
+//            bank-conflict free;
+//   phase 1  FIR: thread (rho, chunk) owns decimated sequence X_rho[c] = x[24 c - rho] and 16
+//            consecutive output times; taps of that rho live in registers, each loaded sample
+//            feeds up to 16 FMAs (register sliding window);
+//   phase 2  one thread per output time runs the fully unrolled 48-point inverse DFT in
+//            registers (fft.cuh), applies the bin rotation, quantises;
+//   phase 3  neighbour samples by warp shuffle, cross product, __ballot_sync -> bit masks,
+//            de-interleaved into the 4 sample phases and written as 160 words.
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+
+namespace snrx {
+
+constexpr int kPfbD = 24;
+constexpr int kTileT = 128;                    // channel-rate samples per tile
+constexpr int kChunkT = 16;                    // output times per FIR thread
+constexpr int kFirThreads = 24 * (kTileT / kChunkT);   // 192
+constexpr int kVStride = 193;                  // float2 per V row: 128 + 8*8 skew columns + 1
+constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x)
+
+// BLE bank: even bin 2q (q = 0..47) -> BLE channel number, or -1 (bins +-41..+-47 MHz carry no channel)
+SNRX_HD constexpr int ble_channel_of_q(int q) {
+    int mhz = (q <= 23) ? 2440 + 2 * q : 2440 + 2 * (q - 48);
+    if (mhz < 2402 || mhz > 2480) return -1;
+    int k = (mhz - 2402) / 2;                  // RF channel index 0..39
+    return k == 0 ? 37 : k <= 11 ? k - 1 : k == 12 ? 38 : k <= 38 ? k - 2 : 39;   // btle_rx.c:932-948 inverted
+}
+
+// position (in float2 units) of tile sample i' inside the skewed shared-memory tile
+SNRX_HD constexpr int xs_pos(int ip) { return ip + 8 * ((ip + 12) / 384); }
+
+template <int NT> struct PfbGeom {
+    static constexpr int kHist = 24 * NT;                              // L: 384 or 768
+    static constexpr int kTileIn = kHist + kPfbD * kTileT + 2;         // samples i' = 0 .. kTileIn-1 (even count)
+    static constexpr int kXsLen = xs_pos(kTileIn) + 8;                 // float2
+    static constexpr int kSmemBytes = (kXsLen + 48 * kVStride) * 8 + 40 * 4 * 4 + 5 * 48 * 8;
+};
+
+// FIR of one thread.  xb = &xs[xs_pos-base of this thread], see fir_base().  acc[a][e] accumulates
+// branch rho + 24 a at output time 16 q + e.
+template <int NT, int A>
+SNRX_HD void pfb_fir_thread(const float2* xb, int s0 /* 8 if rho <= 12 else 0 */, const float* g /*[NT]*/,
+                            float2 (&acc)[A][kChunkT]) {
+#pragma unroll
+    for (int a = 0; a < A; a++)
+#pragma unroll
+        for (int e = 0; e < kChunkT; e++) acc[a][e] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = -(NT - 1); u <= kChunkT - 1; u++) {
+        // skew of row u for rho >= 13 (floor((24u - 13 + 12)/384)), boundary rows add s0
+        const int fl = (24 * u - 1 >= 0) ? (24 * u - 1) / 384 : -((-(24 * u - 1) + 383) / 384);
+        const int off = 24 * u + 8 * fl + ((u % 16 == 0) ? s0 : 0);
+        const float2 x = xb[off];
+#pragma unroll
+        for (int e = 0; e < kChunkT; e++) {
+            const int d = e - u;
+            if (d >= 0 && d < NT) {
+                acc[d % A][e].x = f_fma(g[d], x.x, acc[d % A][e].x);
+                acc[d % A][e].y = f_fma(g[d], x.y, acc[d % A][e].y);
+            }
+        }
+    }
+}
+
+// base pointer of FIR thread (rho, q): element u of pfb_fir_thread is tile sample
+// i' = kHist + 384 q + 24 u - rho, stored at xs_pos(i')
+template <int NT>
+SNRX_HD int fir_base(int rho, int q) { return PfbGeom<NT>::kHist + 384 * q - rho + 8 * (PfbGeom<NT>::kHist / 384 + q); }
+
+SNRX_HD constexpr int v_col(int m) { return m + 8 * (m / 16); }
+
+SNRX_HD float quant_fused(float y, float scale_signed) {
+    float t = f_fma(y, scale_signed, kMagic);
+    t = fminf(fmaxf(t, kMagic - 128.0f), kMagic + 127.0f);
+    return f_sub(t, kMagic);
+}
+
+// 48-point inverse DFT of one output time + rotation + quantisation, in place:
+// on return y[q] holds the quantised (I, Q) of even bin 2q as integer-valued floats.
+// s_even / s_odd: quantiser scale with the sign of (-1)^(q m) folded in (0 beyond the capture end).
+SNRX_HD void pfb_dft48_quant(const float2* vcol /* &V[0][v_col(m)] */, cf (&y)[48], float s_even, float s_odd,
+                             cf (&raw)[48], bool keep_raw) {
+    cf v[48];
+#pragma unroll
+    for (int r = 0; r < 48; r++) { float2 t = vcol[r * kVStride]; v[r].r = t.x; v[r].i = t.y; }
+    Idft3xQ<48>::run(v, y);
+#pragma unroll
+    for (int q = 0; q < 48; q++) {
+        const float s = (q & 1) ? s_odd : s_even;
+        if (keep_raw) raw[q] = y[q];
+        y[q].r = quant_fused(y[q].r, s);
+        y[q].i = quant_fused(y[q].i, s);
+    }
+}
+
+// every 4th bit of x starting at bit 0 -> low 8 bits
+SNRX_HD uint32_t compress4(uint32_t x) {
+    x &= 0x11111111u;
+    x = (x | (x >> 3)) & 0x03030303u;
+    x = (x | (x >> 6)) & 0x000F000Fu;
+    x = (x | (x >> 12)) & 0x000000FFu;
+    return x;
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+struct PfbBleArgs {
+    const float2* x;          // [n_captures][stride] cf32
+    uint64_t stride;          // samples between captures
+    int64_t n_in;             // samples per capture
+    int32_t n_out;            // channel-rate samples per capture (n_in / 24)
+    int32_t n_tiles;          // tiles of this launch
+    int32_t tile0;            // first tile of this launch
+    const float* taps_rho;    // [24][NT]: taps_rho[rho*NT + d] = h[rho + 24 d]
+    const float* taps_flat;   // [L] h[n] (for the extra time step)
+    float scale;              // quantiser scale
+    uint32_t* bits;
+    BitsLayout lay;
+    int8_t* dbg_q8;           // [cap][40][n_out][2] or null
+    float2* dbg_cf;           // [cap][40][n_out] or null
+};
+
+template <int NT, bool DEBUG>
+__global__ void __launch_bounds__(kFirThreads, 2) k_pfb_ble(PfbBleArgs a) {
+    using G = PfbGeom<NT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* xs = reinterpret_cast<float2*>(smem_raw);
+    float2* V = xs + G::kXsLen;                                   // [48][kVStride]
+    uint32_t* wordbuf = reinterpret_cast<uint32_t*>(V + 48 * kVStride);   // [40][4]
+    float2* edge = reinterpret_cast<float2*>(wordbuf + 160);      // [5][48] first lane of each warp
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tile = a.tile0 + (int)(blockIdx.x % a.n_tiles);
+    const int cap = blockIdx.x / a.n_tiles;
+    const float2* xcap = a.x + (size_t)cap * a.stride;
+
+    // ---- phase 0: stage input tile.  tile sample i' <-> capture sample i = x0 + i'
+    const int64_t x0 = (int64_t)kPfbD * kTileT * tile - G::kHist;
+    for (int v = tid; v < G::kTileIn / 2; v += kFirThreads) {
+        const int ip = 2 * v;
+        const int64_t i = x0 + ip;
+        const bool ok = (i >= 0) && (i + 1 < a.n_in);
+        cp_async16(xs + xs_pos(ip), xcap + (ok ? i : 0), ok);
+    }
+    // FIR taps of this thread's rho while the copies fly
+    const int rho_lo = lane & 7, cq = lane >> 3;
+    const int rho = 8 * (wid % 3) + rho_lo;
+    const int q = 4 * (wid / 3) + cq;
+    float g[NT];
+#pragma unroll
+    for (int d = 0; d < NT; d++) g[d] = __ldg(a.taps_rho + rho * NT + d);
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    // ---- phase 1: FIR -> V[r][v_col(m)]
+    {
+        float2 acc[2][kChunkT];
+        pfb_fir_thread<NT, 2>(xs + fir_base<NT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+#pragma unroll
+        for (int e = 0; e < kChunkT; e++) {
+            V[rho * kVStride + 24 * q + e] = acc[0][e];
+            V[(rho + 24) * kVStride + 24 * q + e] = acc[1][e];
+        }
+        if (tid < 48) {                       // extra time step m = 128, branch r = tid
+            float2 s = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int p = 0; p < NT / 2; p++) {
+                const int n = tid + 48 * p;
+                const float2 xv = xs[xs_pos(G::kHist + kPfbD * kTileT - n)];
+                const float c = __ldg(a.taps_flat + n);
+                s.x = f_fma(c, xv.x, s.x);
+                s.y = f_fma(c, xv.y, s.y);
+            }
+            V[tid * kVStride + v_col(kTileT)] = s;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: 48-point inverse DFT + rotation + quantiser, one thread per output time
+    cf y[48];
+    const int m = tid;                                   // 0..128 active
+    const int mg = kTileT * tile + m;                    // channel-rate sample index in the capture
+    if (m <= kTileT) {
+        const float s = (mg < a.n_out) ? a.scale : 0.0f;
+        cf raw[48];
+        pfb_dft48_quant(V + v_col(m), y, s, (mg & 1) ? -s : s, raw, DEBUG);
+        if (DEBUG && m < kTileT && mg < a.n_out) {
+#pragma unroll
+            for (int qq = 0; qq < 48; qq++) {
+                constexpr int dummy = 0; (void)dummy;
+                const int ch = ble_channel_of_q(qq);
+                if (ch >= 0) {
+                    const size_t o = ((size_t)cap * 40 + ch) * (size_t)a.n_out + mg;
+                    if (a.dbg_q8) { a.dbg_q8[2 * o] = (int8_t)y[qq].r; a.dbg_q8[2 * o + 1] = (int8_t)y[qq].i; }
+                    if (a.dbg_cf) {
+                        const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
+                        a.dbg_cf[o] = make_float2(raw[qq].r * sg, raw[qq].i * sg);
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int qq = 0; qq < 48; qq++) edge[wid * 48 + qq] = make_float2(y[qq].r, y[qq].i);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: slicer bits.  b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0   (btle_rx.c:1357-1361)
+    if (wid < 4) {
+        uint32_t mine0 = 0, mine1 = 0;        // masks of the channels this lane will de-interleave
+#pragma unroll
+        for (int qq = 0; qq < 48; qq++) {
+            if (ble_channel_of_q(qq) < 0) continue;
+            float i1 = __shfl_down_sync(0xffffffffu, y[qq].r, 1);
+            float q1 = __shfl_down_sync(0xffffffffu, y[qq].i, 1);
+            if (lane == 31) { const float2 n = edge[(wid + 1) * 48 + qq]; i1 = n.x; q1 = n.y; }
+            const float cross = f_fma(y[qq].r, q1, -f_mul(i1, y[qq].i));
+            const uint32_t mask = __ballot_sync(0xffffffffu, cross > 0.0f);
+            if (qq < 32) { if (lane == qq) mine0 = mask; } else { if (lane == qq - 32) mine1 = mask; }
+        }
+        // lane L de-interleaves bin q = L (and q = L + 32): warp `wid` supplies byte `wid` of each phase word
+        unsigned char* wb = reinterpret_cast<unsigned char*>(wordbuf);
+        {
+            const int ch = ble_channel_of_q(lane);
+            if (ch >= 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wb[(ch * 4 + j) * 4 + wid] = (unsigned char)compress4(mine0 >> j);
+            }
+        }
+        if (lane < 16) {
+            const int ch = ble_channel_of_q(lane + 32);
+            if (ch >= 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) wb[(ch * 4 + j) * 4 + wid] = (unsigned char)compress4(mine1 >> j);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 160) {
+        const int ch = tid >> 2, j = tid & 3;
+        a.bits[a.lay.index(cap, ch, j, kBitsLeadWords + tile)] = wordbuf[tid];
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace snrx

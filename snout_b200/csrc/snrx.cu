@@ -1,0 +1,658 @@
+// snrx.cu -- C ABI of libsnoutrx.so (include/snoutrx.h) and the host-side orchestration of the
+// receive pipelines.  All signal processing happens in the CUDA kernels of this directory; there
+// is no CPU implementation behind this interface (no device -> SNRX_ENODEV).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "ble_back.cuh"
+#include "ble_front.cuh"
+#include "common.cuh"
+#include "pfb.cuh"
+#include "pfb_taps.h"
+#include "scan.cuh"
+#include "zb.cuh"
+
+using namespace snrx;
+
+namespace snrx {
+// wideband Zigbee front end: pfb_zb.cuh (next milestone)
+int zb_wideband_front(ZbState&, const snrx_config_t&, const float2*, uint32_t, uint64_t, uint64_t, uint32_t, cudaStream_t, int&,
+                      std::string& err) {
+    err = "wideband Zigbee front end not built in this version";
+    return SNRX_EINVAL;
+}
+}  // namespace snrx
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct snrx_handle {
+    snrx_config_t cfg{};
+    int device = 0;
+    cudaStream_t stream = nullptr;       // compute stream (own or caller supplied)
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D staging
+    cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_stop = nullptr;
+    std::vector<cudaEvent_t> ev_chunks;
+    int sm_count = 148;
+    std::string err;
+
+    // geometry
+    bool wideband = false, has_ble = false, has_zb = false;
+    int decim = 1;
+    uint32_t n_ble_ch = 0, n_zb_ch = 0;
+    uint64_t max_in = 0;                 // input samples per capture
+    uint32_t max_caps = 1;
+    uint32_t max_out = 0;                // channel-rate samples per capture
+    uint32_t wpp = 0;                    // bit words per phase stream
+    uint32_t n_chunks = 0;               // aa-search chunks per phase stream
+    uint32_t max_windows = 0;
+    uint32_t cand_cap = 0, frame_cap = 0;
+    int pfb_nt = 16;
+
+    // device memory
+    float2* d_x = nullptr; size_t d_x_bytes = 0;          // staging of host input
+    uint32_t* d_bits = nullptr; size_t d_bits_bytes = 0;
+    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
+    uint32_t *d_wcounts = nullptr, *d_woffsets = nullptr;
+    Cand* d_cands = nullptr;
+    Dec* d_decs = nullptr;
+    snrx_frame_t* d_frames = nullptr;
+    uint32_t* d_totals = nullptr;        // [0] frames, [1] candidates, [2] zigbee frames (gathered at poll)
+    uint32_t *d_crc_tab = nullptr, *d_whiten = nullptr;
+    int32_t* d_ble_channels = nullptr;
+    float *d_taps_rho = nullptr, *d_taps_flat = nullptr;
+    int8_t* d_q8 = nullptr; size_t d_q8_bytes = 0;
+    float2* d_cf = nullptr; size_t d_cf_bytes = 0;
+    ZbState zb;
+
+    // last batch
+    bool batch_valid = false;
+    uint32_t b_caps = 0; uint64_t b_n_in = 0; uint32_t b_n_out = 0; uint32_t b_windows = 0;
+    uint32_t b_aa_items = 0, b_w_items = 0;
+    uint32_t n_frames_ready = 0;
+    bool polled = false;
+    snrx_frame_t* h_frames = nullptr;    // pinned
+    snrx_stats_t stats{};
+    int launches = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            char b__[512];                                                                         \
+            snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            if (h) h->err = b__; else g_err = b__;                                                 \
+            return e__ == cudaErrorMemoryAllocation ? SNRX_ENOMEM : SNRX_ECUDA;                    \
+        }                                                                                          \
+    } while (0)
+
+int fail(snrx_handle* h, int code, const char* msg) {
+    if (h) h->err = msg; else g_err = msg;
+    return code;
+}
+
+// ---- BLE tables, built from their definitions --------------------------------------------------
+// CRC-24 (x^24+x^10+x^9+x^6+x^4+x^3+x+1) processed LSB first: reflected polynomial 0xDA6000.
+// Equals crc_table[] of btle_rx.c:897-930 (tests/test_oracle_ble.py compares via the oracle).
+void make_crc_table(uint32_t* t) {
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t r = i;
+        for (int k = 0; k < 8; k++) r = (r & 1u) ? (r >> 1) ^ 0xDA6000u : (r >> 1);
+        t[i] = r;
+    }
+}
+// Whitening LFSR x^7+x^4+1, register = 1 | channel MSB first (Core spec Vol 6 Part B 3.2);
+// 42 bytes per channel packed little-endian into 11 words.  Equals scramble_table.h.
+void make_whiten_table(uint32_t* w /*[40][11]*/) {
+    for (int ch = 0; ch < 40; ch++) {
+        uint8_t bytes[44] = {0};
+        unsigned reg = 0;                       // bit p = register position p
+        reg |= 1u;
+        for (int k = 0; k < 6; k++) reg |= ((unsigned)(ch >> (5 - k)) & 1u) << (1 + k);
+        for (int i = 0; i < 42; i++) {
+            uint8_t v = 0;
+            for (int b = 0; b < 8; b++) {
+                unsigned out = (reg >> 6) & 1u;
+                v |= (uint8_t)(out << b);
+                reg = ((reg << 1) & 0x7Fu) | out;
+                reg ^= out << 4;
+            }
+            bytes[i] = v;
+        }
+        for (int c = 0; c < 11; c++)
+            w[ch * 11 + c] = (uint32_t)bytes[4 * c] | ((uint32_t)bytes[4 * c + 1] << 8) |
+                             ((uint32_t)bytes[4 * c + 2] << 16) | ((uint32_t)bytes[4 * c + 3] << 24);
+    }
+}
+// crc_init_reorder(), btle_rx.c:1801-1825: byte swap then 24-bit bit reversal
+uint32_t crc_init_internal(uint32_t k) {
+    uint32_t sw = ((k & 0xFFu) << 16) | (k & 0xFF00u) | ((k >> 16) & 0xFFu);
+    uint32_t r = 0;
+    for (int i = 0; i < 24; i++) r |= ((sw >> i) & 1u) << (23 - i);
+    return r;
+}
+
+int ble_mhz(int ch) {                           // get_freq_by_channel_number, btle_rx.c:932-948
+    if (ch == 37) return 2402;
+    if (ch == 38) return 2426;
+    if (ch == 39) return 2480;
+    if (ch >= 0 && ch <= 10) return 2404 + 2 * ch;
+    if (ch >= 11 && ch <= 36) return 2428 + 2 * (ch - 11);
+    return -1;
+}
+int zb_mhz(int ch) { return (ch >= 11 && ch <= 26) ? 2400 + 5 * (ch - 10) : -1; }   // top_block.py:56
+
+template <class T>
+int dev_alloc(snrx_handle* h, T** p, size_t count) {
+    CK(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return SNRX_OK;
+}
+
+uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+int grid_for(snrx_handle* h, uint64_t items, int per_block, int blocks_per_sm) {
+    uint64_t need = (items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t)h->sm_count * blocks_per_sm;
+    return (int)std::max<uint64_t>(1, std::min(need, cap));
+}
+
+}  // namespace
+
+extern "C" {
+
+int snrx_abi_version(void) { return SNRX_ABI_VERSION; }
+
+const char* snrx_strerror(int code) {
+    switch (code) {
+        case SNRX_OK: return "ok";
+        case SNRX_EINVAL: return "invalid argument or configuration";
+        case SNRX_ENODEV: return "no usable CUDA device (libsnoutrx has no CPU fallback)";
+        case SNRX_ENOMEM: return "out of host or device memory";
+        case SNRX_ECUDA: return "CUDA runtime error";
+        case SNRX_ERANGE: return "input exceeds the configured capacity";
+        case SNRX_EOVERFLOW: return "more candidates or frames than the configured capacity";
+        case SNRX_ESTATE: return "call out of sequence";
+        default: return "unknown error";
+    }
+}
+
+const char* snrx_last_error(snrx_t* h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int snrx_device_count(int* n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (n) *n = (e == cudaSuccess) ? c : 0;
+    return (e == cudaSuccess && c > 0) ? SNRX_OK : SNRX_ENODEV;
+}
+
+int snrx_ble_channel_mhz(int ch) { return ble_mhz(ch); }
+int snrx_zigbee_channel_mhz(int ch) { return zb_mhz(ch); }
+int snrx_ble_channel_bin(int ch) { int m = ble_mhz(ch); return m < 0 ? -1 : ((m - 2440) % 96 + 96) % 96; }
+int snrx_zigbee_channel_bin(int ch) { int m = zb_mhz(ch); return m < 0 ? -1 : ((m - 2440) % 96 + 96) % 96; }
+
+int snrx_pfb_prototype(int mode, uint32_t taps, double* out) {
+    const bool zb = (mode == SNRX_MODE_ZB_WB16);
+    const double* src = nullptr;
+    if (taps == 384) src = zb ? SNRX_PFB_ZB_384 : SNRX_PFB_BLE_384;
+    else if (taps == 768) src = zb ? SNRX_PFB_ZB_768 : SNRX_PFB_BLE_768;
+    else return SNRX_EINVAL;
+    memcpy(out, src, sizeof(double) * taps);
+    return SNRX_OK;
+}
+
+void snrx_destroy(snrx_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* bufs[] = {h->d_x, h->d_bits, h->d_counts, h->d_offsets, h->d_scratch, h->d_wcounts, h->d_woffsets,
+                    h->d_cands, h->d_decs, h->d_frames, h->d_totals, h->d_crc_tab, h->d_whiten, h->d_ble_channels,
+                    h->d_taps_rho, h->d_taps_flat, h->d_q8, h->d_cf};
+    for (void* b : bufs) if (b) cudaFree(b);
+    zb_free(h->zb);
+    if (h->h_frames) cudaFreeHost(h->h_frames);
+    for (cudaEvent_t e : h->ev_chunks) cudaEventDestroy(e);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_front0) cudaEventDestroy(h->ev_front0);
+    if (h->ev_front) cudaEventDestroy(h->ev_front);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+}
+
+int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
+    snrx_handle* h = nullptr;
+    if (!out || !cfg) return fail(nullptr, SNRX_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SNRX_ABI_VERSION) return fail(nullptr, SNRX_EINVAL, "abi_version mismatch");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(nullptr, SNRX_ENODEV, "no CUDA device: libsnoutrx has no CPU path");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SNRX_ENODEV, "device ordinal out of range");
+    h = new (std::nothrow) snrx_handle();
+    if (!h) return fail(nullptr, SNRX_ENOMEM, "host allocation failed");
+    h->cfg = *cfg;
+    h->device = cfg->device;
+#define CKD(call) do { int r__ = (call); if (r__ != SNRX_OK) { g_err = h->err; snrx_destroy(h); return r__; } } while (0)
+    auto body = [&]() -> int {
+        CK(cudaSetDevice(h->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, h->device));
+        h->sm_count = prop.multiProcessorCount;
+        if (prop.major < 10) return fail(h, SNRX_ENODEV, "libsnoutrx is built for sm_100a (B200) only");
+        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        CK(cudaEventCreate(&h->ev_start));
+        CK(cudaEventCreate(&h->ev_front0));
+        CK(cudaEventCreate(&h->ev_front));
+        CK(cudaEventCreate(&h->ev_stop));
+
+        snrx_config_t& c = h->cfg;
+        switch (c.mode) {
+            case SNRX_MODE_BLE_NB: h->has_ble = true; h->n_ble_ch = 1; h->decim = 1; break;
+            case SNRX_MODE_ZB_NB: h->has_zb = true; h->n_zb_ch = 1; h->decim = 1; break;
+            case SNRX_MODE_BLE_WB40: h->has_ble = true; h->wideband = true; h->n_ble_ch = 40; h->decim = kPfbD; break;
+            case SNRX_MODE_ZB_WB16: h->has_zb = true; h->wideband = true; h->n_zb_ch = 16; h->decim = kPfbD; break;
+            case SNRX_MODE_MIXED_WB56:
+                h->has_ble = h->has_zb = true; h->wideband = true; h->n_ble_ch = 40; h->n_zb_ch = 16; h->decim = kPfbD; break;
+            default: return fail(h, SNRX_EINVAL, "unknown mode");
+        }
+        if (c.access_addr == 0 && c.crc_init == 0) { c.access_addr = 0x8E89BED6u; c.crc_init = 0x555555u; }
+        if (c.zb_threshold <= 0) c.zb_threshold = 10;
+        if (c.quant_scale <= 0.0f) c.quant_scale = h->wideband ? 100.0f : 128.0f;
+        if (c.max_captures == 0) c.max_captures = 1;
+        if (c.max_samples == 0) c.max_samples = h->wideband ? 96000000ull : 10000000ull;
+        if (c.max_frames == 0) c.max_frames = 1u << 17;
+        if (c.zb_segment == 0) c.zb_segment = 65536;
+        if (c.zb_prehalo == 0) c.zb_prehalo = 4096;
+        if (c.pfb_taps == 0) c.pfb_taps = 384;
+        if (c.pfb_taps != 384 && c.pfb_taps != 768) return fail(h, SNRX_EINVAL, "pfb_taps must be 384 or 768");
+        h->pfb_nt = (int)c.pfb_taps / 24;
+        if (h->has_ble && !h->wideband && (c.channel < 0 || c.channel > 39)) return fail(h, SNRX_EINVAL, "BLE channel 0..39");
+        if (h->has_zb && !h->wideband && (c.channel < 11 || c.channel > 26)) return fail(h, SNRX_EINVAL, "802.15.4 channel 11..26");
+        if (h->wideband && (c.max_samples % (uint64_t)(kPfbD * 2)) != 0) c.max_samples += (kPfbD * 2) - c.max_samples % (kPfbD * 2);
+        h->max_in = c.max_samples;
+        h->max_caps = c.max_captures;
+        h->max_out = (uint32_t)(h->max_in / h->decim);
+        h->frame_cap = c.max_frames;
+        h->cand_cap = std::max<uint32_t>(1u << 16, 4 * c.max_frames);
+
+        CKD(dev_alloc(h, &h->d_totals, 8));
+        CKD(dev_alloc(h, &h->d_frames, h->frame_cap));
+        CK(cudaHostAlloc((void**)&h->h_frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap, cudaHostAllocDefault));
+
+        if (h->has_ble) {
+            const uint32_t tiles = div_up(h->max_out, kTileT);
+            h->wpp = kBitsLeadWords + tiles + kBitsTailWords;
+            h->n_chunks = div_up(h->wpp - 1, 32);
+            h->max_windows = div_up(h->max_out, kWindow);
+            h->d_bits_bytes = (size_t)h->max_caps * h->n_ble_ch * 4 * h->wpp * sizeof(uint32_t);
+            CK(cudaMalloc((void**)&h->d_bits, h->d_bits_bytes));
+            const size_t aa_items = (size_t)h->max_caps * h->n_ble_ch * h->n_chunks;
+            const size_t w_items = (size_t)h->max_caps * h->n_ble_ch * h->max_windows;
+            CKD(dev_alloc(h, &h->d_counts, aa_items + 1));
+            CKD(dev_alloc(h, &h->d_offsets, aa_items + 1));
+            CKD(dev_alloc(h, &h->d_wcounts, w_items + 1));
+            CKD(dev_alloc(h, &h->d_woffsets, w_items + 1));
+            CKD(dev_alloc(h, &h->d_scratch, scan_scratch_items(std::max(aa_items, w_items))));
+            CKD(dev_alloc(h, &h->d_cands, h->cand_cap));
+            CKD(dev_alloc(h, &h->d_decs, h->cand_cap));
+            uint32_t crc[256], wh[40 * 11];
+            make_crc_table(crc);
+            make_whiten_table(wh);
+            CKD(dev_alloc(h, &h->d_crc_tab, 256));
+            CKD(dev_alloc(h, &h->d_whiten, 40 * 11));
+            CK(cudaMemcpy(h->d_crc_tab, crc, sizeof crc, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(h->d_whiten, wh, sizeof wh, cudaMemcpyHostToDevice));
+            int32_t chans[40];
+            for (int i = 0; i < 40; i++) chans[i] = h->wideband ? i : c.channel;
+            CKD(dev_alloc(h, &h->d_ble_channels, 40));
+            CK(cudaMemcpy(h->d_ble_channels, chans, sizeof chans, cudaMemcpyHostToDevice));
+            if (h->wideband) {
+                const int L = (int)c.pfb_taps, NT = h->pfb_nt;
+                const double* proto = (L == 384) ? SNRX_PFB_BLE_384 : SNRX_PFB_BLE_768;
+                std::vector<float> flat(L), rho(L);
+                for (int n = 0; n < L; n++) flat[n] = (float)proto[n];
+                for (int r = 0; r < 24; r++) for (int d = 0; d < NT; d++) rho[r * NT + d] = flat[r + 24 * d];
+                CKD(dev_alloc(h, &h->d_taps_rho, L));
+                CKD(dev_alloc(h, &h->d_taps_flat, L));
+                CK(cudaMemcpy(h->d_taps_rho, rho.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
+                CK(cudaMemcpy(h->d_taps_flat, flat.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
+                CK(cudaFuncSetAttribute(k_pfb_ble<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<16>::kSmemBytes));
+                CK(cudaFuncSetAttribute(k_pfb_ble<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<16>::kSmemBytes));
+                CK(cudaFuncSetAttribute(k_pfb_ble<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<32>::kSmemBytes));
+                CK(cudaFuncSetAttribute(k_pfb_ble<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<32>::kSmemBytes));
+            }
+            if (c.flags & SNRX_F_KEEP_STREAMS) {
+                h->d_q8_bytes = (size_t)h->max_caps * h->n_ble_ch * h->max_out * 2;
+                CK(cudaMalloc((void**)&h->d_q8, h->d_q8_bytes));
+                if (h->wideband) {
+                    h->d_cf_bytes = (size_t)h->max_caps * h->n_ble_ch * h->max_out * sizeof(float2);
+                    CK(cudaMalloc((void**)&h->d_cf, h->d_cf_bytes));
+                }
+            }
+        }
+        if (h->has_zb) {
+            int r = zb_create(h->zb, h->cfg, h->wideband, h->n_zb_ch, h->max_caps, h->max_out, h->sm_count, h->err);
+            if (r != SNRX_OK) return r;
+        }
+        CK(cudaMemset(h->d_totals, 0, 8 * sizeof(uint32_t)));
+        return SNRX_OK;
+    };
+    int r = body();
+    if (r != SNRX_OK) { g_err = h->err; snrx_destroy(h); return r; }
+    *out = h;
+    return SNRX_OK;
+#undef CKD
+}
+
+int snrx_set_stream(snrx_t* h, void* cuda_stream) {
+    if (!h) return SNRX_EINVAL;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return SNRX_OK;
+}
+
+int snrx_set_channel(snrx_t* h, int channel) {
+    if (!h) return SNRX_EINVAL;
+    if (h->wideband) return fail(h, SNRX_EINVAL, "set_channel applies to the narrow-band modes");
+    if (h->has_ble) {
+        if (channel < 0 || channel > 39) return fail(h, SNRX_EINVAL, "BLE channel 0..39");
+        CK(cudaSetDevice(h->device));
+        int32_t chans[40];
+        for (int i = 0; i < 40; i++) chans[i] = channel;
+        CK(cudaMemcpyAsync(h->d_ble_channels, chans, sizeof chans, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        if (channel < 11 || channel > 26) return fail(h, SNRX_EINVAL, "802.15.4 channel 11..26");
+    }
+    h->cfg.channel = channel;
+    return SNRX_OK;
+}
+
+int snrx_sync(snrx_t* h) {
+    if (!h) return SNRX_EINVAL;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return SNRX_OK;
+}
+
+// ------------------------------------------------------------------------------------ process
+static int launch_ble_front(snrx_handle* h, const float2* x, uint32_t caps, uint64_t n_in, uint64_t stride,
+                            uint32_t n_out, int tile_begin, int tile_end, BitsLayout lay) {
+    const bool dbg = (h->cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
+    if (h->wideband) {
+        PfbBleArgs a;
+        a.x = x; a.stride = stride; a.n_in = (int64_t)n_in; a.n_out = (int32_t)n_out;
+        a.n_tiles = tile_end - tile_begin;
+        a.taps_rho = h->d_taps_rho; a.taps_flat = h->d_taps_flat; a.scale = h->cfg.quant_scale;
+        a.bits = h->d_bits; a.lay = lay; a.dbg_q8 = h->d_q8; a.dbg_cf = h->d_cf;
+        a.tile0 = tile_begin;
+        const dim3 grid((unsigned)(a.n_tiles) * caps);
+        if (h->pfb_nt == 16) {
+            if (dbg) k_pfb_ble<16, true><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, h->stream>>>(a);
+            else k_pfb_ble<16, false><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, h->stream>>>(a);
+        } else {
+            if (dbg) k_pfb_ble<32, true><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, h->stream>>>(a);
+            else k_pfb_ble<32, false><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, h->stream>>>(a);
+        }
+    } else {
+        NbArgs a;
+        a.x = reinterpret_cast<const float4*>(x); a.stride = stride; a.n = (int64_t)n_in;
+        a.n_groups = (int32_t)div_up(n_in, 128); a.n_captures = caps; a.scale = h->cfg.quant_scale;
+        a.bits = h->d_bits; a.lay = lay; a.dbg_q8 = h->d_q8;
+        const uint64_t items = (uint64_t)caps * a.n_groups;
+        const int grid = grid_for(h, items, 8, 8);
+        if (dbg) k_ble_slice_nb<true><<<grid, 256, 0, h->stream>>>(a);
+        else k_ble_slice_nb<false><<<grid, 256, 0, h->stream>>>(a);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return SNRX_OK;
+}
+
+int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_samples, uint64_t stride_samples,
+                 const snrx_shard_t* shard, int is_device_ptr) {
+    if (!h || !iq) return SNRX_EINVAL;
+    if (n_captures == 0 || n_samples == 0) return fail(h, SNRX_EINVAL, "empty batch");
+    if (n_captures > h->max_caps || n_samples > h->max_in) return fail(h, SNRX_ERANGE, "batch exceeds max_captures/max_samples");
+    if (stride_samples == 0) stride_samples = n_samples;
+    if (stride_samples < n_samples) return fail(h, SNRX_EINVAL, "stride smaller than the capture");
+    if ((((uintptr_t)iq) & 15) || (n_captures > 1 && (stride_samples & 1))) return fail(h, SNRX_EINVAL, "captures must be 16-byte aligned (even stride)");
+    if (h->wideband && (n_samples % kPfbD) != 0) return fail(h, SNRX_EINVAL, "wideband captures must hold a multiple of 24 samples");
+    CK(cudaSetDevice(h->device));
+    h->batch_valid = false;
+    h->polled = false;
+    h->launches = 0;
+
+    const uint32_t n_out = (uint32_t)(n_samples / h->decim);
+    uint32_t pre_out = 0, body_out = n_out, first_window = 0, first_capture = 0;
+    if (shard) {
+        if (shard->pre_samples % (uint64_t)(h->decim * kTileT)) return fail(h, SNRX_EINVAL, "pre_samples must be a multiple of 128 channel samples");
+        pre_out = (uint32_t)(shard->pre_samples / h->decim);
+        body_out = shard->body_samples ? (uint32_t)(shard->body_samples / h->decim) : n_out - pre_out;
+        first_window = shard->first_window;
+        first_capture = shard->first_capture_id;
+        if ((uint64_t)pre_out + body_out > n_out) return fail(h, SNRX_EINVAL, "shard body exceeds the buffer");
+    }
+
+    CK(cudaEventRecord(h->ev_start, h->stream));
+    CK(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(uint32_t), h->stream));
+
+    // ---- input: device pointer as is, host pointer staged in chunks overlapped with the front end
+    const float2* x = reinterpret_cast<const float2*>(iq);
+    uint64_t x_stride = stride_samples;
+    const bool staged = !is_device_ptr;
+    const uint64_t chunk_samples = 4ull << 20;                      // 32 MiB per copy
+    if (staged) {
+        const size_t need = (size_t)n_captures * n_samples * sizeof(float2);
+        if (need > h->d_x_bytes) {
+            if (h->d_x) { cudaFree(h->d_x); h->d_x = nullptr; h->d_x_bytes = 0; }
+            CK(cudaMalloc((void**)&h->d_x, need));
+            h->d_x_bytes = need;
+        }
+        x = h->d_x;
+        x_stride = n_samples;
+    }
+
+    BitsLayout lay{};
+    if (h->has_ble) {
+        const uint32_t tiles = div_up(n_out, kTileT);
+        lay.words_per_phase = kBitsLeadWords + tiles + kBitsTailWords;
+        lay.n_channels = h->n_ble_ch;
+        CK(cudaMemsetAsync(h->d_bits, 0, (size_t)n_captures * h->n_ble_ch * 4 * lay.words_per_phase * sizeof(uint32_t), h->stream));
+    }
+
+    if (staged) {
+        CK(cudaEventRecord(h->ev_front0, h->stream));
+        // copy stream must not start overwriting the staging buffer before earlier work on the compute stream finished
+        CK(cudaEventRecord(h->ev_front, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_front, 0));
+        size_t ev_i = 0;
+        for (uint32_t c = 0; c < n_captures; c++) {
+            const float2* src = reinterpret_cast<const float2*>(iq) + (size_t)c * stride_samples;
+            float2* dst = h->d_x + (size_t)c * n_samples;
+            int tile_done = 0;
+            for (uint64_t off = 0; off < n_samples; off += chunk_samples) {
+                const uint64_t len = std::min<uint64_t>(chunk_samples, n_samples - off);
+                CK(cudaMemcpyAsync(dst + off, src + off, len * sizeof(float2), cudaMemcpyHostToDevice, h->copy_stream));
+                if (ev_i >= h->ev_chunks.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunks.push_back(e); }
+                CK(cudaEventRecord(h->ev_chunks[ev_i], h->copy_stream));
+                CK(cudaStreamWaitEvent(h->stream, h->ev_chunks[ev_i], 0));
+                ev_i++;
+                if (h->has_ble && h->wideband && !h->has_zb && n_captures == 1) {
+                    // launch the channelizer on the tiles whose input has fully arrived
+                    const uint64_t have = off + len;
+                    const bool last = (have == n_samples);
+                    int tile_end = last ? (int)div_up(n_out, kTileT) : (int)((have / kPfbD) / kTileT) - 1;
+                    if (tile_end > tile_done) {
+                        int r = launch_ble_front(h, x, 1, n_samples, x_stride, n_out, tile_done, tile_end, lay);
+                        if (r != SNRX_OK) return r;
+                        tile_done = tile_end;
+                    }
+                }
+            }
+        }
+    }
+
+    if (h->has_ble) {
+        const bool pipelined = staged && h->wideband && !h->has_zb && n_captures == 1;
+        if (!pipelined) {
+            CK(cudaEventRecord(h->ev_front0, h->stream));
+            int r = launch_ble_front(h, x, n_captures, n_samples, x_stride, n_out, 0, (int)div_up(n_out, kTileT), lay);
+            if (r != SNRX_OK) return r;
+        }
+        CK(cudaEventRecord(h->ev_front, h->stream));
+
+        BleParams p{};
+        p.aa = h->cfg.access_addr;
+        p.aa_mask = 0xFFFFFFFFu;
+        p.crc_init_internal = crc_init_internal(h->cfg.crc_init);
+        p.n_out = (int32_t)n_out;
+        p.m_origin = (int32_t)pre_out;
+        p.n_windows = (int32_t)div_up(body_out, kWindow);
+        p.first_window = first_window;
+        p.first_capture = first_capture;
+        p.n_captures = n_captures;
+        p.n_channels = h->n_ble_ch;
+        const uint32_t n_chunks = div_up(lay.words_per_phase - 1, 32);
+        const uint32_t aa_items = n_captures * h->n_ble_ch * n_chunks;
+        const uint32_t w_items = n_captures * h->n_ble_ch * (uint32_t)p.n_windows;
+
+        const int g_aa = grid_for(h, aa_items, 8, 8);
+        k_aa_search<false><<<g_aa, 256, 0, h->stream>>>(h->d_bits, lay, p, n_chunks, h->d_counts, nullptr, nullptr, 0);
+        h->launches += 1 + exclusive_scan(h->d_counts, aa_items, h->d_offsets, h->d_scratch, h->stream);
+        k_aa_search<true><<<g_aa, 256, 0, h->stream>>>(h->d_bits, lay, p, n_chunks, nullptr, h->d_offsets, h->d_cands, h->cand_cap);
+        k_ble_decode<<<h->sm_count * 4, 128, 0, h->stream>>>(h->d_bits, lay, p, h->d_offsets + aa_items, h->cand_cap, h->d_cands,
+                                                          h->d_decs, h->d_crc_tab, h->d_whiten, h->d_ble_channels);
+        const int g_w = grid_for(h, w_items, 256, 8);
+        k_ble_resolve<false><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, h->d_wcounts, nullptr,
+                                                        nullptr, 0, h->d_ble_channels, h->cand_cap);
+        h->launches += 3 + exclusive_scan(h->d_wcounts, w_items, h->d_woffsets, h->d_scratch, h->stream);
+        k_ble_resolve<true><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, nullptr, h->d_woffsets,
+                                                       h->d_frames, h->frame_cap, h->d_ble_channels, h->cand_cap);
+        h->launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->d_totals + 0, h->d_woffsets + w_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_totals + 1, h->d_offsets + aa_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+        h->b_aa_items = aa_items;
+        h->b_w_items = w_items;
+    }
+    if (h->has_zb) {
+        int r = zb_process(h->zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_window,
+                           first_capture, h->d_frames, h->frame_cap, h->d_totals, h->has_ble, h->stream, h->sm_count,
+                           h->launches, h->err);
+        if (r != SNRX_OK) return r;
+        if (!h->has_ble) { CK(cudaEventRecord(h->ev_front0, h->stream)); CK(cudaEventRecord(h->ev_front, h->stream)); }
+    }
+    CK(cudaEventRecord(h->ev_stop, h->stream));
+    h->b_caps = n_captures; h->b_n_in = n_samples; h->b_n_out = n_out;
+    h->batch_valid = true;
+    return SNRX_OK;
+}
+
+int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h) return SNRX_EINVAL;
+    if (!h->batch_valid) return fail(h, SNRX_ESTATE, "snrx_poll without a processed batch");
+    CK(cudaSetDevice(h->device));
+    if (!h->polled) {
+        uint32_t totals[8];
+        CK(cudaMemcpyAsync(totals, h->d_totals, sizeof totals, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        const uint32_t n_ble = totals[0], n_cand = totals[1], n_zb = totals[2];
+        h->stats.candidates = n_cand;
+        if (n_cand > h->cand_cap) return fail(h, SNRX_EOVERFLOW, "access-address candidates exceed capacity (raise max_frames)");
+        if ((uint64_t)n_ble + n_zb > h->frame_cap) return fail(h, SNRX_EOVERFLOW, "frames exceed max_frames");
+        h->n_frames_ready = n_ble + n_zb;
+        if (h->n_frames_ready)
+            CK(cudaMemcpyAsync(h->h_frames, h->d_frames, sizeof(snrx_frame_t) * (size_t)h->n_frames_ready,
+                               cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f, msf = 0.f;
+        cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
+        cudaEventElapsedTime(&msf, h->ev_front0, h->ev_front);
+        uint32_t ok = 0;
+        for (uint32_t i = 0; i < h->n_frames_ready; i++) ok += h->h_frames[i].crc_ok;
+        h->stats.samples_in = (uint64_t)h->b_caps * h->b_n_in;
+        h->stats.channel_samples = (uint64_t)h->b_caps * h->b_n_out * (h->n_ble_ch + h->n_zb_ch);
+        h->stats.frames = h->n_frames_ready;
+        h->stats.frames_crc_ok = ok;
+        h->stats.kernel_launches = (uint32_t)h->launches;
+        h->stats.gpu_ms = ms;
+        h->stats.gpu_ms_frontend = msf;
+        h->polled = true;
+    }
+    if (n_out) *n_out = h->n_frames_ready;
+    if (out && cap) memcpy(out, h->h_frames, sizeof(snrx_frame_t) * (size_t)std::min(cap, h->n_frames_ready));
+    return SNRX_OK;
+}
+
+int snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev) {
+    if (!h || !h->batch_valid) return SNRX_ESTATE;
+    if (frames_dev) *frames_dev = h->d_frames;
+    if (count_dev) *count_dev = h->d_totals;
+    return SNRX_OK;
+}
+
+int snrx_stats(snrx_t* h, snrx_stats_t* s) {
+    if (!h || !s) return SNRX_EINVAL;
+    *s = h->stats;
+    return SNRX_OK;
+}
+
+int snrx_debug_stage(snrx_t* h, int stage, void* out, uint64_t cap_bytes, uint64_t* n_bytes) {
+    if (!h || !h->batch_valid) return SNRX_ESTATE;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    const void* src = nullptr;
+    uint64_t bytes = 0;
+    switch (stage) {
+        case SNRX_STAGE_BLE_Q8:
+            if (!h->d_q8) return fail(h, SNRX_ESTATE, "create the engine with SNRX_F_KEEP_STREAMS");
+            src = h->d_q8; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 2; break;
+        case SNRX_STAGE_CHAN_CF32:
+            if (!h->d_cf) return fail(h, SNRX_ESTATE, "create a wideband engine with SNRX_F_KEEP_STREAMS");
+            src = h->d_cf; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 8; break;
+        case SNRX_STAGE_BLE_BITS: {
+            if (!h->d_bits) return SNRX_ESTATE;
+            const uint32_t wpp = kBitsLeadWords + div_up(h->b_n_out, kTileT) + kBitsTailWords;
+            src = h->d_bits; bytes = (uint64_t)h->b_caps * h->n_ble_ch * 4 * wpp * 4; break;
+        }
+        default: {
+            int r = zb_debug_stage(h->zb, stage, h->b_caps, h->b_n_out, &src, &bytes);
+            if (r != SNRX_OK) return fail(h, r, "stage not available in this mode");
+        }
+    }
+    if (n_bytes) *n_bytes = bytes;
+    if (out) {
+        if (cap_bytes < bytes) return fail(h, SNRX_ERANGE, "debug buffer too small");
+        CK(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    }
+    return SNRX_OK;
+}
+
+int snrx_host_alloc(void** p, uint64_t bytes) {
+    if (!p) return SNRX_EINVAL;
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? SNRX_OK : SNRX_ENOMEM;
+}
+int snrx_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? SNRX_OK : SNRX_ECUDA; }
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+"""RxEngine -- Python host of the receive engine (thin layer over the C ABI).
+
+Mirrors the two receiver interfaces of Snout on the hot path:
+
+* BLE: what `btle_rx -c <ch> -a <aa> -k <crcinit>` does per channel
+  (vendor/BTLE/host/btle-tools/src/btle_rx.c:2288-2393), here for one channel (narrow band) or all
+  40 at once (wideband);
+* Zigbee: what the flowgraph `top_block(channel=...)` does
+  (snout/modulations/Zigbee/hackrf/Zigbee_rx/top_block.py:29-103), one channel or all 16.
+
+All DSP runs in libsnoutrx.so on the GPU.  This module only moves pointers and records.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+from . import _abi, chanplan
+from ._abi import (FRAME_DTYPE, MODE_BLE_NB, MODE_BLE_WB40, MODE_MIXED_WB56, MODE_ZB_NB, MODE_ZB_WB16, Config, Shard,
+                   SnrxError, Stats)
+
+MODES = {
+    "ble_nb": MODE_BLE_NB, "zb_nb": MODE_ZB_NB, "zb_wb16": MODE_ZB_WB16, "ble_wb40": MODE_BLE_WB40,
+    "mixed_wb56": MODE_MIXED_WB56,
+}
+
+
+def _is_torch_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+class RxEngine:
+    """One engine = one GPU + one receive mode.  Not thread safe; engines are independent."""
+
+    def __init__(self, mode: str | int = "ble_nb", channel: int | None = None, device: int = 0,
+                 max_samples: int = 0, max_captures: int = 1, max_frames: int = 0,
+                 access_addr: int = chanplan.BLE_ADV_AA, crc_init: int = chanplan.BLE_ADV_CRC_INIT,
+                 zb_threshold: int = 10, quant_scale: float = 0.0, zb_segment: int = 0, zb_prehalo: int = 0,
+                 pfb_taps: int = 0, keep_streams: bool = False):
+        self.lib = _abi.load()
+        self.mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        if channel is None:
+            channel = 11 if self.mode == MODE_ZB_NB else 37
+        cfg = Config()
+        cfg.abi_version = _abi.ABI_VERSION
+        cfg.device = device
+        cfg.mode = self.mode
+        cfg.channel = channel
+        cfg.access_addr = access_addr
+        cfg.crc_init = crc_init
+        cfg.zb_threshold = zb_threshold
+        cfg.quant_scale = quant_scale
+        cfg.max_samples = max_samples
+        cfg.max_captures = max_captures
+        cfg.max_frames = max_frames
+        cfg.zb_segment = zb_segment
+        cfg.zb_prehalo = zb_prehalo
+        cfg.pfb_taps = pfb_taps
+        cfg.flags = _abi.F_KEEP_STREAMS if keep_streams else 0
+        self.cfg = cfg
+        self.handle = c_void_p()
+        rc = self.lib.snrx_create(byref(self.handle), byref(cfg))
+        if rc != 0:
+            what = self.lib.snrx_strerror(rc).decode()
+            detail = self.lib.snrx_last_error(None).decode()
+            self.handle = c_void_p()
+            raise SnrxError(rc, what, detail)
+        self.wideband = self.mode in (MODE_ZB_WB16, MODE_BLE_WB40, MODE_MIXED_WB56)
+        self.decim = chanplan.WB_DECIM if self.wideband else 1
+        self.n_ble = {MODE_BLE_NB: 1, MODE_BLE_WB40: 40, MODE_MIXED_WB56: 40}.get(self.mode, 0)
+        self.n_zb = {MODE_ZB_NB: 1, MODE_ZB_WB16: 16, MODE_MIXED_WB56: 16}.get(self.mode, 0)
+        self._keepalive = None
+        self._last = None
+
+    # ------------------------------------------------------------------ life cycle
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.snrx_destroy(self.handle)
+            self.handle = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SnrxError(rc, self.lib.snrx_strerror(rc).decode(), self.lib.snrx_last_error(self.handle).decode())
+
+    # ------------------------------------------------------------------ control
+    def set_channel(self, channel: int):
+        """Narrow-band modes: retune (top_block.set_channel, top_block.py:94-96 / btle_rx -c)."""
+        self._check(self.lib.snrx_set_channel(self.handle, int(channel)))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.snrx_set_stream(self.handle, c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        self._check(self.lib.snrx_sync(self.handle))
+
+    # ------------------------------------------------------------------ data path
+    def process(self, iq, shard: dict | None = None, n_samples: int | None = None, stride: int = 0):
+        """Queue one batch.  `iq`: complex64 numpy array [n] or [captures, n] (host memory), a
+        _abi.PinnedBuffer, or a torch CUDA tensor of complex64 [n] / [captures, n]."""
+        sh = None
+        if shard:
+            sh = Shard(int(shard.get("pre_samples", 0)), int(shard.get("body_samples", 0)),
+                       int(shard.get("first_window", 0)), int(shard.get("first_capture_id", 0)))
+        if isinstance(iq, _abi.PinnedBuffer):
+            iq = iq.array
+        if _is_torch_tensor(iq):
+            import torch
+            if not iq.is_cuda:
+                iq = iq.numpy()
+            else:
+                assert iq.dtype == torch.complex64 and iq.is_contiguous()
+                caps = 1 if iq.dim() == 1 else iq.shape[0]
+                n = iq.shape[-1] if n_samples is None else n_samples
+                st = stride or iq.shape[-1]
+                self.set_stream(torch.cuda.current_stream(iq.device).cuda_stream)
+                self._keepalive = iq
+                self._check(self.lib.snrx_process(self.handle, c_void_p(iq.data_ptr()), caps, n, st,
+                                                  byref(sh) if sh else None, 1))
+                self._last = (caps, n)
+                return self
+        a = np.asarray(iq)
+        if a.dtype != np.complex64 or not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a, dtype=np.complex64)
+        caps = 1 if a.ndim == 1 else a.shape[0]
+        n = a.shape[-1] if n_samples is None else n_samples
+        st = stride or a.shape[-1]
+        self._keepalive = a
+        self._check(self.lib.snrx_process(self.handle, a.ctypes.data_as(c_void_p), caps, n, st,
+                                          byref(sh) if sh else None, 0))
+        self._last = (caps, n)
+        return self
+
+    def process_device_ptr(self, ptr: int, n_captures: int, n_samples: int, stride: int = 0, shard: Shard | None = None):
+        self._check(self.lib.snrx_process(self.handle, c_void_p(ptr), n_captures, n_samples, stride,
+                                          byref(shard) if shard else None, 1))
+        self._last = (n_captures, n_samples)
+        return self
+
+    def poll(self) -> np.ndarray:
+        """Wait for the queued batch; frames in reference order (capture, channel, window, index)."""
+        n = c_uint32(0)
+        self._check(self.lib.snrx_poll(self.handle, None, 0, byref(n)))
+        out = np.zeros(n.value, dtype=FRAME_DTYPE)
+        if n.value:
+            self._check(self.lib.snrx_poll(self.handle, out.ctypes.data_as(c_void_p), n.value, byref(n)))
+        return out
+
+    def run(self, iq, **kw) -> np.ndarray:
+        return self.process(iq, **kw).poll()
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.snrx_stats(self.handle, byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def frames_device(self) -> tuple[int, int]:
+        f, c = c_void_p(), c_void_p()
+        self._check(self.lib.snrx_frames_device(self.handle, byref(f), byref(c)))
+        return f.value, c.value
+
+    # ------------------------------------------------------------------ debug / parity
+    def debug_stage(self, stage: int) -> np.ndarray:
+        nb = c_uint64(0)
+        self._check(self.lib.snrx_debug_stage(self.handle, stage, None, 0, byref(nb)))
+        raw = np.zeros(nb.value, dtype=np.uint8)
+        self._check(self.lib.snrx_debug_stage(self.handle, stage, raw.ctypes.data_as(c_void_p), nb.value, byref(nb)))
+        caps, n_in = self._last
+        n_out = n_in // self.decim
+        if stage == _abi.STAGE_BLE_Q8:
+            return raw.view(np.int8).reshape(caps, self.n_ble, n_out, 2)
+        if stage == _abi.STAGE_CHAN_CF32:
+            return raw.view(np.complex64).reshape(caps, self.n_ble, n_out)
+        if stage == _abi.STAGE_BLE_BITS:
+            return raw.view(np.uint32).reshape(caps, self.n_ble, 4, -1)
+        if stage in (_abi.STAGE_ZB_DISC, _abi.STAGE_ZB_F):
+            return raw.view(np.float32).reshape(caps, self.n_zb, -1)[:, :, :n_out]
+        if stage == _abi.STAGE_ZB_NCHIPS:
+            return raw.view(np.int64)
+        if stage == _abi.STAGE_ZB_CHIPS:
+            n_chains = len(self.debug_stage(_abi.STAGE_ZB_NCHIPS))
+            return raw.view(np.float32).reshape(n_chains, -1)
+        return raw

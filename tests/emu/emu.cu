@@ -1,0 +1,235 @@
+// TEST INFRASTRUCTURE ONLY.  Host-side stepping of the kernels' __host__ __device__ cores, built
+// by nvcc into tests/emu/libemu.so and run on the CPU (no GPU needed).  It lets the CPU test
+// suite check the kernels' index math and arithmetic against the oracle before GPU time is
+// spent.  The glue between cores (shuffles, ballots, shared-memory hand-over) is restated here
+// with plain loops; the cores themselves are the very functions the kernels call.
+// Never part of libsnoutrx.so.
+#include <cstring>
+#include <vector>
+#include "../../snout_b200/csrc/ble_back.cuh"
+#include "../../snout_b200/csrc/ble_front.cuh"
+#include "../../snout_b200/csrc/fft.cuh"
+#include "../../snout_b200/csrc/pfb.cuh"
+#include "../../snout_b200/csrc/zb.cuh"
+
+using namespace snrx;
+
+extern "C" {
+
+void emu_idft48(const float* in, float* out) {
+    cf a[48], b[48];
+    for (int i = 0; i < 48; i++) { a[i].r = in[2 * i]; a[i].i = in[2 * i + 1]; }
+    Idft3xQ<48>::run(a, b);
+    for (int i = 0; i < 48; i++) { out[2 * i] = b[i].r; out[2 * i + 1] = b[i].i; }
+}
+void emu_idft96(const float* in, float* out) {
+    cf a[96], b[96];
+    for (int i = 0; i < 96; i++) { a[i].r = in[2 * i]; a[i].i = in[2 * i + 1]; }
+    Idft3xQ<96>::run(a, b);
+    for (int i = 0; i < 96; i++) { out[2 * i] = b[i].r; out[2 * i + 1] = b[i].i; }
+}
+
+int emu_ble_channel_of_q(int q) { return ble_channel_of_q(q); }
+
+}  // extern "C"
+
+// ---- one tile of k_pfb_ble<NT, *>, phases 0..3 ------------------------------------------------
+// x: capture cf32 (n_in samples).  Outputs: words[40][4], q8[40][128][2] (int8), raw[40][128] cf32.
+template <int NT>
+static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho, const float* taps_flat,
+                     float scale, uint32_t* words, int8_t* q8, float* raw_out) {
+    using G = PfbGeom<NT>;
+    std::vector<float2> xs(G::kXsLen, make_float2(0.f, 0.f));
+    std::vector<float2> V(48 * kVStride, make_float2(0.f, 0.f));
+    const int64_t x0 = (int64_t)kPfbD * kTileT * tile - G::kHist;
+    for (int v = 0; v < G::kTileIn / 2; v++) {
+        const int ip = 2 * v;
+        const int64_t i = x0 + ip;
+        const bool ok = (i >= 0) && (i + 1 < n_in);
+        for (int k = 0; k < 2; k++)
+            xs[xs_pos(ip) + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
+    }
+    for (int tid = 0; tid < kFirThreads; tid++) {
+        const int lane = tid & 31, wid = tid >> 5;
+        const int rho = 8 * (wid % 3) + (lane & 7), q = 4 * (wid / 3) + (lane >> 3);
+        float g[NT];
+        for (int d = 0; d < NT; d++) g[d] = taps_rho[rho * NT + d];
+        float2 acc[2][kChunkT];
+        pfb_fir_thread<NT, 2>(xs.data() + fir_base<NT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+        for (int e = 0; e < kChunkT; e++) {
+            V[rho * kVStride + 24 * q + e] = acc[0][e];
+            V[(rho + 24) * kVStride + 24 * q + e] = acc[1][e];
+        }
+        if (tid < 48) {
+            float2 s = make_float2(0.f, 0.f);
+            for (int p = 0; p < NT / 2; p++) {
+                const int n = tid + 48 * p;
+                const float2 xv = xs[xs_pos(G::kHist + kPfbD * kTileT - n)];
+                s.x = f_fma(taps_flat[n], xv.x, s.x);
+                s.y = f_fma(taps_flat[n], xv.y, s.y);
+            }
+            V[tid * kVStride + v_col(kTileT)] = s;
+        }
+    }
+    std::vector<cf> Y((kTileT + 1) * 48);
+    for (int m = 0; m <= kTileT; m++) {
+        const int mg = kTileT * tile + m;
+        const float s = (mg < n_out) ? scale : 0.0f;
+        cf y[48], raw[48];
+        pfb_dft48_quant(V.data() + v_col(m), y, s, (mg & 1) ? -s : s, raw, true);
+        for (int qq = 0; qq < 48; qq++) {
+            Y[m * 48 + qq] = y[qq];
+            const int ch = ble_channel_of_q(qq);
+            if (ch >= 0 && m < kTileT) {
+                q8[(ch * kTileT + m) * 2] = (int8_t)y[qq].r;
+                q8[(ch * kTileT + m) * 2 + 1] = (int8_t)y[qq].i;
+                const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
+                raw_out[(ch * kTileT + m) * 2] = raw[qq].r * sg;
+                raw_out[(ch * kTileT + m) * 2 + 1] = raw[qq].i * sg;
+            }
+        }
+    }
+    memset(words, 0, sizeof(uint32_t) * 160);
+    for (int wid = 0; wid < 4; wid++) {
+        for (int qq = 0; qq < 48; qq++) {
+            const int ch = ble_channel_of_q(qq);
+            if (ch < 0) continue;
+            uint32_t mask = 0;
+            for (int lane = 0; lane < 32; lane++) {
+                const int m = 32 * wid + lane;
+                const cf a = Y[m * 48 + qq], b = Y[(m + 1) * 48 + qq];
+                if (f_fma(a.r, b.i, -f_mul(b.r, a.i)) > 0.0f) mask |= 1u << lane;
+            }
+            for (int j = 0; j < 4; j++) words[ch * 4 + j] |= compress4(mask >> j) << (8 * wid);
+        }
+    }
+}
+
+extern "C" {
+
+void emu_pfb_ble_tile(int nt, const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
+                      const float* taps_flat, float scale, uint32_t* words, int8_t* q8, float* raw) {
+    if (nt == 16) pfb_tile<16>(x, n_in, n_out, tile, taps_rho, taps_flat, scale, words, q8, raw);
+    else pfb_tile<32>(x, n_in, n_out, tile, taps_rho, taps_flat, scale, words, q8, raw);
+}
+
+// ---- narrow-band slicer: whole capture -> phase words (layout of BitsLayout, 1 channel) --------
+void emu_ble_slice_nb(const float* x, int64_t n, float scale, uint32_t* bits, uint32_t wpp, int8_t* q8) {
+    memset(bits, 0, sizeof(uint32_t) * 4 * wpp);
+    auto qv = [&](int64_t k, int c) -> float { return k < n ? quant_exact(x[2 * k + c], scale) : quant_exact(0.f, scale); };
+    for (int64_t k = 0; k < n; k++) {
+        if (q8) { q8[2 * k] = (int8_t)qv(k, 0); q8[2 * k + 1] = (int8_t)qv(k, 1); }
+        if (slicer_bit(qv(k, 0), qv(k, 1), qv(k + 1, 0), qv(k + 1, 1))) {
+            const int64_t t = k / 4; const int j = (int)(k % 4);
+            bits[(size_t)j * wpp + (size_t)((t + 32) >> 5)] |= 1u << ((t + 32) & 31);
+        }
+    }
+}
+
+// ---- BLE back end over one (capture, channel) bit stream: aa search, decode, resolve -----------
+int emu_ble_back(const uint32_t* bits, uint32_t wpp, int n_out, int m_origin, int n_windows, uint32_t first_window,
+                 int channel, uint32_t aa, uint32_t aa_mask, uint32_t crc_init_internal, const uint32_t* crc_tab,
+                 const uint32_t* whiten /*[40][11]*/, snrx_frame_t* out, int cap, int* n_cands_out) {
+    BitsLayout lay; lay.words_per_phase = wpp; lay.n_channels = 1;
+    BleParams p{};
+    p.aa = aa; p.aa_mask = aa_mask; p.crc_init_internal = crc_init_internal; p.n_out = n_out; p.m_origin = m_origin;
+    p.n_windows = n_windows; p.first_window = first_window; p.first_capture = 0; p.n_captures = 1; p.n_channels = 1;
+    const int z = aa_virtual_bits(aa, aa_mask);
+    const uint32_t mask_hi = aa_mask & ~((1u << z) - 1u);
+    std::vector<Cand> cands;
+    for (uint32_t w = 0; w + 1 < wpp; w++) {
+        uint32_t hits[4];
+        for (int j = 0; j < 4; j++) {
+            const uint32_t* pw = bits + lay.index(0, 0, j, 0);
+            uint32_t hj = aa_word_hits(pw[w], pw[w + 1], aa, mask_hi);
+            const int nvalid = ((n_out - 1 - j) >> 2) - 32 * ((int)w - 1) + 1;
+            if (nvalid <= 0) hj = 0u; else if (nvalid < 32) hj &= (1u << nvalid) - 1u;
+            hits[j] = hj;
+        }
+        for (int i = 0; i < 32; i++)
+            for (int j = 0; j < 4; j++)
+                if ((hits[j] >> i) & 1u) {
+                    const int t = 32 * ((int)w - 1) + i;
+                    const uint32_t* pw = bits + lay.index(0, 0, j, 0);
+                    uint32_t d = (slots32(pw, t) ^ aa) & aa_mask;
+                    Cand c; c.s = 4 * t + j; c.ch_idx = 0; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = 0;
+                    cands.push_back(c);
+                }
+    }
+    std::vector<Dec> decs(cands.size());
+    for (size_t k = 0; k < cands.size(); k++) {
+        const Cand c = cands[k];
+        const int j = ((c.s % 4) + 4) % 4;
+        const int t0 = (c.s - j) / 4;
+        const uint32_t* pw = bits + lay.index(0, 0, j, 0);
+        uint32_t chunk[11];
+        for (int q = 0; q < 11; q++) chunk[q] = slots32(pw, t0 + 32 + 32 * q) ^ whiten[channel * 11 + q];
+        Dec d; d.s = c.s; d.resume = 0; d.vneed = c.vneed;
+        ble_finish(chunk, channel >= 37 && channel <= 39, crc_init_internal, crc_tab, d);
+        decs[k] = d;
+    }
+    int n = 0;
+    for (int w = 0; w < n_windows; w++) {
+        const int W = m_origin + kWindow * w;
+        ble_resolve_window(cands.data(), decs.data(), 0, (int)cands.size(), W, z, [&](int k) {
+            if (n < cap) ble_fill_frame(out[n], cands[k], decs[k], p, w, channel);
+            n++;
+        });
+    }
+    if (n_cands_out) *n_cands_out = (int)cands.size();
+    return n;
+}
+
+// ---- Zigbee cores -----------------------------------------------------------------------------
+void emu_zb_quad(const float* x, int64_t n, float* f) {
+    for (int64_t k = 0; k < n; k++) {
+        const float pr = k ? x[2 * (k - 1)] : 0.f, pi = k ? x[2 * (k - 1) + 1] : 0.f;
+        f[k] = quad_demod(x[2 * k], x[2 * k + 1], pr, pi, SNRX_ATAN_TAB);
+    }
+}
+void emu_zb_dc(const float* f, int64_t n, float* z) {
+    std::vector<double> pw(SNRX_IIR_BLOCK);
+    { volatile double p = 1.0; const double b = SNRX_IIR_BETA; for (int i = 0; i < SNRX_IIR_BLOCK; i++) { p = p * b; pw[i] = p; } }
+    const int nb = (int)((n + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK);
+    std::vector<double> block_end(nb), carry_in(nb);
+    for (int b = 0; b < nb; b++) {                      // k_zb_iir_sum
+        const int len = (int)std::min<int64_t>(SNRX_IIR_BLOCK, n - (int64_t)b * SNRX_IIR_BLOCK);
+        double l = 0.0;
+        for (int i = 0; i < len; i++) l = d_add(d_mul(SNRX_IIR_ALPHA, (double)f[(size_t)b * SNRX_IIR_BLOCK + i]), d_mul(SNRX_IIR_BETA, l));
+        block_end[b] = l;
+    }
+    double carry = 0.0;                                 // k_zb_iir_carry
+    for (int b = 0; b < nb; b++) {
+        carry_in[b] = carry;
+        const int len = (int)std::min<int64_t>(SNRX_IIR_BLOCK, n - (int64_t)b * SNRX_IIR_BLOCK);
+        carry = d_add(block_end[b], d_mul(pw[len - 1], carry));
+    }
+    for (int b = 0; b < nb; b++) {                      // k_zb_dc
+        const int len = (int)std::min<int64_t>(SNRX_IIR_BLOCK, n - (int64_t)b * SNRX_IIR_BLOCK);
+        double l = 0.0;
+        for (int i = 0; i < len; i++) {
+            const float fv = f[(size_t)b * SNRX_IIR_BLOCK + i];
+            l = d_add(d_mul(SNRX_IIR_ALPHA, (double)fv), d_mul(SNRX_IIR_BETA, l));
+            const double y = d_add(l, d_mul(pw[i], carry_in[b]));
+            z[(size_t)b * SNRX_IIR_BLOCK + i] = f_sub(fv, (float)y);
+        }
+    }
+}
+int emu_zb_chains(const float* z, int n_out, int origin, int body, int segment, int prehalo, uint32_t first_segment,
+                  int threshold, int channel, snrx_frame_t* out, int cap) {
+    ZbChainParams p{};
+    p.n_out = n_out; p.origin = origin; p.body = body; p.segment = segment; p.prehalo = prehalo;
+    p.n_segments = (body + segment - 1) / segment; p.first_segment = first_segment; p.first_capture = 0;
+    p.n_captures = 1; p.n_channels = 1; p.threshold = threshold; p.slots_per_chain = segment / kZbMinFrameSamples + 2;
+    p.z_stride = 0;
+    ChipMap map = make_chip_map();
+    std::vector<snrx_frame_t> slots(p.slots_per_chain);
+    int n = 0;
+    for (int seg = 0; seg < p.n_segments; seg++) {
+        uint32_t nf = zb_run_chain(z, p, seg, &SNRX_MMSE_TAPS[0][0], map.w, channel, 0, slots.data(), nullptr, 0, nullptr);
+        for (uint32_t k = 0; k < nf && k < p.slots_per_chain; k++) { if (n < cap) out[n] = slots[k]; n++; }
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+"""CPU stepping of the CUDA kernels' __host__ __device__ cores (tests/emu) against the oracle.
+
+Not a product path: tests/emu/libemu.so is a test harness built from the same headers the kernels
+use.  It proves index math and arithmetic before GPU time is spent; the real parity tests are the
+`-m gpu` ones, which call the kernels through the C ABI."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import assert_frames_equal
+from snout_b200 import chanplan, synth
+
+P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _whiten_words(oracle_mod):
+    wh, crc, ci = oracle_mod.ble_tables("port")
+    w = np.zeros((40, 44), dtype=np.uint8)
+    w[:, :42] = wh
+    return w.view("<u4").reshape(40, 11).copy(), crc, ci
+
+
+def _back(emu, oracle_mod, bits, wpp, n_out, ch, m_origin=0, n_windows=None, first_window=0):
+    wh11, crc, ci = _whiten_words(oracle_mod)
+    if n_windows is None:
+        n_windows = (n_out - m_origin + 8191) // 8192
+    out = np.zeros(8192, dtype=oracle_mod.FRAME_DTYPE)
+    nc = ctypes.c_int(0)
+    n = emu.emu_ble_back(P(bits), ctypes.c_uint32(wpp), n_out, m_origin, n_windows, ctypes.c_uint32(first_window), ch,
+                         ctypes.c_uint32(0x8E89BED6), ctypes.c_uint32(0xFFFFFFFF), ctypes.c_uint32(ci), P(crc), P(wh11),
+                         P(out), 8192, ctypes.byref(nc))
+    return out[:n].copy()
+
+
+def _slice_nb(emu, q_or_x, scale):
+    x = np.ascontiguousarray(q_or_x, dtype=np.float32).reshape(-1)
+    n = len(x) // 2
+    wpp = 1 + (n + 127) // 128 + 16
+    bits = np.zeros(4 * wpp, dtype=np.uint32)
+    q8 = np.zeros((n, 2), dtype=np.int8)
+    emu.emu_ble_slice_nb(P(x), ctypes.c_int64(n), ctypes.c_float(scale), P(bits), ctypes.c_uint32(wpp), P(q8))
+    return bits, wpp, q8
+
+
+def test_fft_codelets(emu):
+    rng = np.random.default_rng(0)
+    for n, fn in ((48, emu.emu_idft48), (96, emu.emu_idft96)):
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        y = np.zeros(n, dtype=np.complex64)
+        fn(P(x), P(y))
+        ref = np.fft.ifft(x.astype(np.complex128)) * n
+        assert np.abs(y - ref).max() / np.abs(ref).max() < 1e-6
+
+
+def test_bin_to_channel_map(emu):
+    seen = {}
+    for q in range(48):
+        ch = emu.emu_ble_channel_of_q(q)
+        if ch >= 0:
+            assert chanplan.ble_channel_bin(ch) == 2 * q
+            seen[ch] = q
+    assert sorted(seen) == list(range(40))
+
+
+def test_nb_slicer_and_back_end_golden(emu, oracle_mod, golden):
+    g = golden("btle_sample_iq_4msps.npz")
+    bits, wpp, q8 = _slice_nb(emu, g["iq"].astype(np.float32) / 128.0, 128.0)
+    assert np.array_equal(q8, g["iq"])
+    assert_frames_equal(_back(emu, oracle_mod, bits, wpp, len(q8), 37), g["frames"], what="golden capture")
+
+
+def test_back_end_window_boundary(emu, oracle_mod, golden):
+    g = golden("btle_sample_iq_4msps.npz")["iq"]
+    b = golden("btle_boundary_ref.npz")
+    for d in range(403, 414):
+        gd = np.concatenate([np.zeros((d, 2), np.int8), g[:200_000]])
+        bits, wpp, _ = _slice_nb(emu, gd.astype(np.float32) / 128.0, 128.0)
+        assert_frames_equal(_back(emu, oracle_mod, bits, wpp, len(gd), 37), b[f"frames_{d}"], what=f"delay {d}")
+
+
+@pytest.mark.parametrize("seed,ch,esn0", [(1001, 37, 30.0), (1002, 38, 24.0), (1004, 5, 26.0)])
+def test_back_end_synthetic(emu, oracle_mod, golden, seed, ch, esn0):
+    cap = synth.ble_capture(n=600_000, channel=ch, seed=seed, esn0_db=esn0)
+    bits, wpp, q8 = _slice_nb(emu, np.ascontiguousarray(cap.iq).view(np.float32), 128.0)
+    assert np.array_equal(q8, oracle_mod.ble_quantize(cap.iq, 128.0))
+    assert_frames_equal(_back(emu, oracle_mod, bits, wpp, len(q8), ch), golden("btle_synth_ref.npz")[f"frames_{seed}"],
+                        what=f"seed {seed}")
+
+
+def test_back_end_shard_origin(emu, oracle_mod):
+    """A shard that starts 128 samples before window 3 must report exactly the frames of windows 3..5."""
+    cap = synth.ble_capture(n=8192 * 8, channel=37, seed=9, esn0_db=30, gap=(100, 1500))
+    q = oracle_mod.ble_quantize(cap.iq, 128.0)
+    want = oracle_mod.ble_decode(q, 37, first_window=3, n_windows=3)
+    lo = 3 * 8192 - 128
+    part = q[lo:]
+    bits, wpp, _ = _slice_nb(emu, part.astype(np.float32) / 128.0, 128.0)
+    got = _back(emu, oracle_mod, bits, wpp, len(part), 37, m_origin=128, n_windows=3, first_window=3)
+    assert len(want) > 3
+    assert_frames_equal(got, want, what="shard")
+
+
+@pytest.mark.parametrize("nt,name", [(16, "BLE_384"), (32, "BLE_768")])
+def test_pfb_tile_kernel(emu, oracle_mod, nt, name):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from gen_tables import PFB_DESIGNS, kaiser_lowpass
+    h = kaiser_lowpass(*PFB_DESIGNS[name])
+    L = len(h)
+    hf = h.astype(np.float32)
+    rho = np.array([hf[r + 24 * d] for r in range(24) for d in range(nt)], dtype=np.float32)
+    cap = synth.wideband_capture(seconds=0.0025, kind="ble", seed=4000, gap=(200, 2000))
+    x = np.ascontiguousarray(cap.iq)[: 24 * 8192 - 24 * 40]          # ragged: n_out = 8152, last tile partial
+    n_in = len(x)
+    n_out = n_in // 24
+    tiles = (n_out + 127) // 128
+    wpp = 1 + tiles + 16
+    bits = np.zeros((40, 4, wpp), dtype=np.uint32)
+    q8 = np.zeros((40, tiles * 128, 2), dtype=np.int8)
+    raw = np.zeros((40, tiles * 128), dtype=np.complex64)
+    xf = x.view(np.float32)
+    for t in range(tiles):
+        w = np.zeros(160, dtype=np.uint32)
+        q = np.zeros((40, 128, 2), dtype=np.int8)
+        r = np.zeros((40, 128), dtype=np.complex64)
+        emu.emu_pfb_ble_tile(nt, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), P(hf), ctypes.c_float(100.0), P(w), P(q), P(r))
+        bits[:, :, 1 + t] = w.reshape(40, 4)
+        q8[:, t * 128:(t + 1) * 128] = q
+        raw[:, t * 128:(t + 1) * 128] = r
+    assert not q8[:, n_out:].any()                                   # beyond the capture: zeros
+    q8, raw = q8[:, :n_out], raw[:, :n_out]
+    yd = oracle_mod.pfb(x, h, [chanplan.ble_channel_bin(c) for c in range(40)])
+    rms = np.sqrt(np.mean(np.abs(yd) ** 2))
+    assert np.abs(raw - yd).max() / rms < 1e-4                       # stated channelizer tolerance
+    qo = np.clip(np.rint(np.stack([yd.real, yd.imag], -1) * 100.0), -128, 127)
+    assert np.abs(q8.astype(int) - qo).max() <= 1
+    n_frames = 0
+    for c in range(40):
+        b2, _, _ = _slice_nb(emu, q8[c].astype(np.float32) / 128.0, 128.0)
+        assert np.array_equal(b2.reshape(4, wpp), bits[c]), f"slicer words of channel {c}"
+        got = _back(emu, oracle_mod, np.ascontiguousarray(bits[c]).reshape(-1), wpp, n_out, c)
+        assert_frames_equal(got, oracle_mod.ble_decode(q8[c], c), what=f"channel {c}")
+        n_frames += len(got)
+    assert n_frames > 100
+
+
+def test_zigbee_cores(emu, oracle_mod):
+    cap = synth.zigbee_capture(n=400_000, channel=11, seed=2001, esn0_db=15.0)
+    x = np.ascontiguousarray(cap.iq).view(np.float32)
+    n = len(cap.iq)
+    f = np.zeros(n, dtype=np.float32)
+    z = np.zeros(n, dtype=np.float32)
+    emu.emu_zb_quad(P(x), ctypes.c_int64(n), P(f))
+    assert np.array_equal(f, oracle_mod.zb_quad_demod(cap.iq))       # bit exact
+    emu.emu_zb_dc(P(f), ctypes.c_int64(n), P(z))
+    assert np.array_equal(z, oracle_mod.zb_dc_remove(f))
+    out = np.zeros(1024, dtype=oracle_mod.FRAME_DTYPE)
+    k = emu.emu_zb_chains(P(z), n, 0, n, 65536, 4096, ctypes.c_uint32(0), 10, 11, P(out), 1024)
+    want = oracle_mod.zb_receive(cap.iq, 11, segment=65536, prehalo=4096)
+    assert len(want) > 5
+    assert_frames_equal(out[:k], want, what="zigbee chains")
