@@ -198,31 +198,44 @@ def main():
             d.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        fr = eng.process(x_dev).poll()
-        if world > 1:
-            fr = sdist.allgather_frames(fr, dev)
-        return fr
+    def run_resident(k, min_seconds=0.0):
+        """k steps, software pipelined two deep: batch i+1 is queued before batch i is collected, so
+        the GPU never waits for the host.  Returns (frames of last step, front-end ms list, launches)."""
+        front, launches, nfr, done = [], 0, 0, 0
+        t0 = time.perf_counter()
+        eng.process(x_dev)
+        while True:
+            more = (done + 1 < k) or (time.perf_counter() - t0 < min_seconds)
+            if more:
+                eng.process(x_dev)
+            fr = eng.poll(copy=False)
+            if world > 1:
+                fr = sdist.allgather_frames(fr, dev)
+            st = eng.stats()
+            front.append(st["gpu_ms_frontend"])
+            launches += st["kernel_launches"]
+            nfr = len(fr)
+            done += 1
+            if not more:
+                break
+        return nfr, front, launches, done
 
-    for _ in range(args.warmup):
-        fr = step_resident()
-    frames_per_step = len(fr)
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
         sampler.start()
+    # warm-up: at least W steps and at least ~1.5 s under load so that nvidia-smi (100 ms period) sees the clocks
+    frames_per_step, _, _, _ = run_resident(args.warmup, min_seconds=1.5)
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    front_ms, launches = [], 0
     ev0.record()
-    for _ in range(args.steps):
-        step_resident()
-        st = eng.stats()
-        front_ms.append(st["gpu_ms_frontend"])
-        launches += st["kernel_launches"]
+    frames_per_step, front_ms, launches, done = run_resident(args.steps)
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    assert done == args.steps
     ms = ev0.elapsed_time(ev1)
+    # keep the load on for the clock sampler a little longer, then stop it
+    run_resident(3, min_seconds=0.5)
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as d
         t = torch.tensor([ms], device=dev)
@@ -262,7 +275,7 @@ def main():
         "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "samples_per_step_per_gpu": int(n),
                    "input_bytes_per_step_per_gpu": int(n * 8), "pfb_taps": args.taps if mode == "ble_wb40" else None,
                    "l2": "input (%.0f MB) larger than L2; no flush needed" % (n * 8 / 1e6),
-                   "frames_per_step": int(frames_per_step), "timed": "process()+poll() incl. frame D2H, CUDA events on the engine stream"},
+                   "frames_per_step": int(frames_per_step), "timed": "K x (process + poll), two batches in flight, frames land in pinned host memory; CUDA events on the engine stream"},
         "frames_per_s": frames_per_step * args.steps / (ms * 1e-3),
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -174,12 +174,18 @@ int  snrx_process(snrx_t* h, const float* iq, uint32_t n_captures,
                   uint64_t n_samples, uint64_t stride_samples,
                   const snrx_shard_t* shard, int is_device_ptr);
 
-/* Wait for the batch and copy up to `cap` frames out, in reference order:
- * (capture, channel, window, sample_index).  *n_out = frames available. */
+/* Up to two batches may be queued (snrx_process, snrx_process, snrx_poll, ...): results are
+ * collected oldest first.  snrx_poll waits for the oldest queued batch; *n_out = its number of
+ * frames, in reference order (capture, channel, window, sample_index).  With out == NULL it only
+ * reports the count; with out != NULL it copies up to `cap` frames and retires the batch.
+ * snrx_poll_view retires the batch and returns a pointer to the engine's pinned host copy of the
+ * frames (written by the kernels directly, no extra copy), valid until the second-next
+ * snrx_process. */
 int  snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out);
+int  snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out);
 
-/* Device-side view of the frame list of the last batch (for NCCL all-gather
- * from the host runtime): pointers stay valid until the next snrx_process. */
+/* Device-visible pointers of the frame list / totals of the most recent snrx_process (the frame
+ * list lives in host-mapped pinned memory). */
 int  snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev);
 
 int  snrx_set_channel(snrx_t* h, int channel);           /* NB modes */

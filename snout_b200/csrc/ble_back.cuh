@@ -46,17 +46,25 @@ SNRX_HD int aa_virtual_bits(uint32_t aa, uint32_t mask) {
     return z;
 }
 
-// Sliding correlation over one 32-slot word of one phase stream: bit i of `hits` is set when the
-// 32 symbol-spaced decisions starting at slot (32*(w-1) + i) match the access address in every
-// masked position >= z.  (full matches and "virtual" matches usable only at a search origin)
-SNRX_HD uint32_t aa_word_hits(uint32_t lo, uint32_t hi, uint32_t aa, uint32_t mask_hi /* mask & ~((1<<z)-1) */) {
-    uint32_t hits = 0;
+// Sliding correlation over one 32-slot word of one phase stream, bit-parallel over the 32 start
+// positions ("shift-and"): bit i of the result is set when the 32 symbol-spaced decisions starting
+// at slot (32*(w-1) + i) equal the access address in every masked position >= z (full matches and
+// the "virtual" matches that are usable only at a search origin).  After access-address bit p has
+// been applied, a random position survives with probability 2^-(p+1); `keep_going` lets a warp
+// stop as soon as none of its lanes has a survivor.
+template <class KEEP>
+SNRX_HD uint32_t aa_word_hits(uint32_t lo, uint32_t hi, uint32_t aa, uint32_t mask_hi /* mask & ~((1<<z)-1) */,
+                              KEEP keep_going) {
+    uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-        uint32_t r = funnel_r(lo, hi, i);
-        if (((r ^ aa) & mask_hi) == 0) hits |= (1u << i);
+    for (int p = 0; p < 32; p++) {
+        const uint32_t s = funnel_r(lo, hi, p);                       // bit i = decision of slot i + p
+        const uint32_t want0 = ((aa >> p) & 1u) - 1u;                 // all ones when AA bit p is 0
+        const uint32_t dont_care = ((mask_hi >> p) & 1u) - 1u;        // all ones when position p is not compared
+        m &= (s ^ want0) | dont_care;
+        if ((p & 3) == 3 && p >= 11 && p < 31) { if (!keep_going(m)) return 0u; }
     }
-    return hits;
+    return m;
 }
 
 // 32 consecutive symbol decisions of one phase stream starting at slot t (t >= -32)
@@ -133,21 +141,31 @@ SNRX_HD int ble_resolve_window(const Cand* cands, const Dec* decs, int c0, int c
     return n;
 }
 
+// Build the 160-byte frame record in registers and store it as ten 16-byte words.
 SNRX_HD void ble_fill_frame(snrx_frame_t& f, const Cand& c, const Dec& d, const BleParams& p, int window_local,
                             int channel_number) {
-    f.sample_index = (int64_t)(c.s - p.m_origin) + (int64_t)kWindow * p.first_window;
-    f.capture_id = p.first_capture + c.cap;
-    f.window = p.first_window + (uint32_t)window_local;
-    f.channel = (uint16_t)channel_number;
-    f.proto = SNRX_PROTO_BLE;
-    f.crc_ok = d.crc_ok;
-    f.lqi = 0;
-    f.phase = (uint8_t)(((c.s % 4) + 4) % 4);
-    f.len = (uint16_t)(d.len + 5);
-    f.access_addr = p.aa;
-    const int nb = d.len + 5;
-#pragma unroll 4
-    for (int i = 0; i < 132; i++) f.bytes[i] = (i < nb && i < 44) ? d.bytes[i] : 0;
+    uint32_t w[40];
+    const int64_t si = (int64_t)(c.s - p.m_origin) + (int64_t)kWindow * p.first_window;
+    w[0] = (uint32_t)(uint64_t)si;
+    w[1] = (uint32_t)((uint64_t)si >> 32);
+    w[2] = p.first_capture + c.cap;
+    w[3] = p.first_window + (uint32_t)window_local;
+    w[4] = (uint32_t)(channel_number & 0xFFFF) | ((uint32_t)SNRX_PROTO_BLE << 16) | ((uint32_t)d.crc_ok << 24);
+    const uint32_t nb = (uint32_t)d.len + 5u;
+    w[5] = ((uint32_t)(((c.s % 4) + 4) % 4) << 8) | (nb << 16);          // lqi = 0 | phase | len
+    w[6] = p.aa;
+    const uint32_t* db = reinterpret_cast<const uint32_t*>(d.bytes);     // Dec::bytes is 4-byte aligned
+#pragma unroll
+    for (int j = 0; j < 11; j++) {
+        const int left = (int)nb - 4 * j;
+        const uint32_t keep = left >= 4 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << (8 * left)) - 1u);
+        w[7 + j] = db[j] & keep;
+    }
+#pragma unroll
+    for (int j = 18; j < 40; j++) w[j] = 0u;
+    uint4* dst = reinterpret_cast<uint4*>(&f);
+#pragma unroll
+    for (int j = 0; j < 10; j++) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
 }
 
 #if defined(__CUDACC__)
@@ -159,7 +177,7 @@ SNRX_HD void ble_fill_frame(snrx_frame_t& f, const Cand& c, const Dec& d, const 
 // scanned offsets, ascending in s.
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ bits, BitsLayout lay, BleParams p,
-                                                   uint32_t n_chunks, uint32_t* __restrict__ counts,
+                                                   uint32_t n_chunks, uint32_t* counts,
                                                    const uint32_t* __restrict__ offsets, Cand* __restrict__ cands,
                                                    uint32_t cand_cap) {
     const int lane = threadIdx.x & 31;
@@ -169,6 +187,7 @@ __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ 
     const uint32_t mask_hi = p.aa_mask & ~((1u << z) - 1u);
     for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
          item += gridDim.x * warps_per_block) {
+        if (FILL && counts[item] == 0u) continue;                   // nothing found here by the count pass
         const uint32_t chunk = item % n_chunks;
         const uint32_t ch = (item / n_chunks) % p.n_channels;
         const uint32_t cap = item / (n_chunks * p.n_channels);
@@ -182,7 +201,9 @@ __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ 
             uint32_t lo = valid ? __ldg(pw + w) : 0u;
             uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
             if (lane == 31) hi = (w + 1 < lay.words_per_phase) ? __ldg(pw + w + 1) : 0u;
-            uint32_t hj = valid ? aa_word_hits(lo, hi, p.aa, mask_hi) : 0u;
+            uint32_t hj = aa_word_hits(valid ? lo : 0u, valid ? hi : 0u, p.aa, mask_hi,
+                                       [](uint32_t m) { return __any_sync(0xffffffffu, m != 0u) != 0; });
+            if (!valid) hj = 0u;
             // positions whose first sample lies beyond the capture carry no data
             const int nvalid = ((p.n_out - 1 - j) >> 2) - 32 * ((int)w - 1) + 1;
             if (nvalid <= 0) hj = 0u; else if (nvalid < 32) hj &= (1u << nvalid) - 1u;
@@ -234,6 +255,9 @@ __global__ void __launch_bounds__(128) k_ble_decode(const uint32_t* __restrict__
                                                     const uint32_t* __restrict__ crc_tab,
                                                     const uint32_t* __restrict__ whiten /*[40][11]*/,
                                                     const int32_t* __restrict__ channel_numbers) {
+    __shared__ uint32_t crc_s[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) crc_s[i] = crc_tab[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warps_per_block = blockDim.x >> 5;
     uint32_t n = *n_cands_dev;
@@ -252,7 +276,7 @@ __global__ void __launch_bounds__(128) k_ble_decode(const uint32_t* __restrict__
         if (lane == 0) {
             Dec d;
             d.s = c.s; d.resume = 0; d.vneed = c.vneed;
-            ble_finish(chunk, chn >= 37 && chn <= 39, p.crc_init_internal, crc_tab, d);
+            ble_finish(chunk, chn >= 37 && chn <= 39, p.crc_init_internal, crc_s, d);
             decs[k] = d;
         }
     }
@@ -263,13 +287,14 @@ __global__ void __launch_bounds__(128) k_ble_decode(const uint32_t* __restrict__
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_ble_resolve(const Cand* __restrict__ cands, const Dec* __restrict__ decs,
                                                      const uint32_t* __restrict__ cand_offsets, uint32_t n_chunks,
-                                                     BleParams p, uint32_t* __restrict__ counts,
+                                                     BleParams p, uint32_t* counts,
                                                      const uint32_t* __restrict__ frame_offsets,
                                                      snrx_frame_t* __restrict__ frames, uint32_t frame_cap,
                                                      const int32_t* __restrict__ channel_numbers, uint32_t cand_cap) {
     const uint32_t n_items = p.n_captures * p.n_channels * (uint32_t)p.n_windows;
     const int z = aa_virtual_bits(p.aa, p.aa_mask);
     for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+        if (FILL && counts[item] == 0u) continue;
         const uint32_t w = item % (uint32_t)p.n_windows;
         const uint32_t ch = (item / (uint32_t)p.n_windows) % p.n_channels;
         const uint32_t cap = item / ((uint32_t)p.n_windows * p.n_channels);

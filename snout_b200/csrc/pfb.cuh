@@ -12,18 +12,20 @@
 // followed, per channel, by the int8-grid quantiser and the reference's one-sample
 // cross-product slicer (btle_rx.c:1357-1361); only ONE BIT per channel sample leaves the SM.
 //
-// One CTA (192 threads) produces 128 channel-rate samples x 40 channels (+1 extra time step so
-// the last slicer decision of the tile has its successor) from 3072 + L input samples:
-//   phase 0  cp.async stages the input tile into shared memory (coalesced 16-byte copies); the
-//            tile is laid out flat with a 64-byte skew every 384 samples so that phase 1 is
-//            bank-conflict free;
+// One CTA (192 threads) computes 128 channel-rate samples x 40 channels from 3048 + L input
+// samples and emits the 127 slicer decisions that have their successor inside the tile (tiles
+// advance by 127 samples, so tiles are independent: no carry, no stitch pass):
+//   phase 0  cp.async stages the input tile into shared memory in 3 KiB pieces (coalesced 16-byte
+//            copies, one per thread and piece); the tile is laid out flat with a 64-byte skew
+//            every 384 samples so that phase 1 is bank-conflict free;
 //   phase 1  FIR: thread (rho, chunk) owns decimated sequence X_rho[c] = x[24 c - rho] and 16
 //            consecutive output times; taps of that rho live in registers, each loaded sample
 //            feeds up to 16 FMAs (register sliding window);
 //   phase 2  one thread per output time runs the fully unrolled 48-point inverse DFT in
 //            registers (fft.cuh), applies the bin rotation, quantises;
 //   phase 3  neighbour samples by warp shuffle, cross product, __ballot_sync -> bit masks,
-//            de-interleaved into the 4 sample phases and written as 160 words.
+//            de-interleaved into the 4 sample phases, assembled into words in shared memory and
+//            OR-ed into the global bit streams.
 #pragma once
 #include "common.cuh"
 #include "fft.cuh"
@@ -31,7 +33,8 @@
 namespace snrx {
 
 constexpr int kPfbD = 24;
-constexpr int kTileT = 128;                    // channel-rate samples per tile
+constexpr int kTileT = 128;                    // channel-rate samples computed per tile
+constexpr int kTileStride = 127;               // samples whose slicer bit the tile emits (needs y[m+1])
 constexpr int kChunkT = 16;                    // output times per FIR thread
 constexpr int kFirThreads = 24 * (kTileT / kChunkT);   // 192
 constexpr int kVStride = 193;                  // float2 per V row: 128 + 8*8 skew columns + 1
@@ -45,33 +48,37 @@ SNRX_HD constexpr int ble_channel_of_q(int q) {
     return k == 0 ? 37 : k <= 11 ? k - 1 : k == 12 ? 38 : k <= 38 ? k - 2 : 39;   // btle_rx.c:932-948 inverted
 }
 
-// position (in float2 units) of tile sample i' inside the skewed shared-memory tile
-SNRX_HD constexpr int xs_pos(int ip) { return ip + 8 * ((ip + 12) / 384); }
+// position (in float2 units) of tile sample i' inside the skewed shared-memory tile: a 64-byte
+// skew every 24*TT samples (TT = output times per FIR thread) keeps the FIR loads conflict free
+template <int TT>
+SNRX_HD constexpr int xs_pos(int ip) { return ip + 8 * ((ip + 12) / (24 * TT)); }
 
-template <int NT> struct PfbGeom {
+template <int NT, int TT = 16> struct PfbGeom {
     static constexpr int kHist = 24 * NT;                              // L: 384 or 768
-    static constexpr int kTileIn = kHist + kPfbD * kTileT + 2;         // samples i' = 0 .. kTileIn-1 (even count)
-    static constexpr int kXsLen = xs_pos(kTileIn) + 8;                 // float2
-    static constexpr int kSmemBytes = (kXsLen + 48 * kVStride) * 8 + 40 * 4 * 4 + 5 * 48 * 8;
+    static constexpr int kTileIn = kHist + kPfbD * (kTileT - 1) + 2;   // samples i' = 0 .. kTileIn-1 (even count)
+    static constexpr int kPieces = (kTileIn + 12 + 24 * TT - 1) / (24 * TT);   // skew periods touched
+    static constexpr int kXsLen = xs_pos<TT>(kTileIn) + 8;             // float2
+    static constexpr int kSmemBytes = (kXsLen + 48 * kVStride) * 8 + 40 * 4 * 2 * 4 + 4 * 48 * 8;   // BLE kernel
 };
 
 // FIR of one thread.  xb = &xs[xs_pos-base of this thread], see fir_base().  acc[a][e] accumulates
 // branch rho + 24 a at output time 16 q + e.
-template <int NT, int A>
+template <int NT, int A, int TT>
 SNRX_HD void pfb_fir_thread(const float2* xb, int s0 /* 8 if rho <= 12 else 0 */, const float* g /*[NT]*/,
-                            float2 (&acc)[A][kChunkT]) {
+                            float2 (&acc)[A][TT]) {
+    constexpr int kPer = 24 * TT;                     // skew period in samples
 #pragma unroll
     for (int a = 0; a < A; a++)
 #pragma unroll
-        for (int e = 0; e < kChunkT; e++) acc[a][e] = make_float2(0.f, 0.f);
+        for (int e = 0; e < TT; e++) acc[a][e] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int u = -(NT - 1); u <= kChunkT - 1; u++) {
-        // skew of row u for rho >= 13 (floor((24u - 13 + 12)/384)), boundary rows add s0
-        const int fl = (24 * u - 1 >= 0) ? (24 * u - 1) / 384 : -((-(24 * u - 1) + 383) / 384);
-        const int off = 24 * u + 8 * fl + ((u % 16 == 0) ? s0 : 0);
+    for (int u = -(NT - 1); u <= TT - 1; u++) {
+        // skew of row u for rho >= 13 (floor((24u - 13 + 12)/kPer)), boundary rows add s0
+        const int fl = (24 * u - 1 >= 0) ? (24 * u - 1) / kPer : -((-(24 * u - 1) + kPer - 1) / kPer);
+        const int off = 24 * u + 8 * fl + ((u % TT == 0) ? s0 : 0);
         const float2 x = xb[off];
 #pragma unroll
-        for (int e = 0; e < kChunkT; e++) {
+        for (int e = 0; e < TT; e++) {
             const int d = e - u;
             if (d >= 0 && d < NT) {
                 acc[d % A][e].x = f_fma(g[d], x.x, acc[d % A][e].x);
@@ -82,9 +89,11 @@ SNRX_HD void pfb_fir_thread(const float2* xb, int s0 /* 8 if rho <= 12 else 0 */
 }
 
 // base pointer of FIR thread (rho, q): element u of pfb_fir_thread is tile sample
-// i' = kHist + 384 q + 24 u - rho, stored at xs_pos(i')
-template <int NT>
-SNRX_HD int fir_base(int rho, int q) { return PfbGeom<NT>::kHist + 384 * q - rho + 8 * (PfbGeom<NT>::kHist / 384 + q); }
+// i' = kHist + 24 TT q + 24 u - rho, stored at xs_pos<TT>(i')
+template <int NT, int TT>
+SNRX_HD int fir_base(int rho, int q) {
+    return PfbGeom<NT, TT>::kHist + 24 * TT * q - rho + 8 * (PfbGeom<NT, TT>::kHist / (24 * TT) + q);
+}
 
 SNRX_HD constexpr int v_col(int m) { return m + 8 * (m / 16); }
 
@@ -112,6 +121,21 @@ SNRX_HD void pfb_dft48_quant(const float2* vcol /* &V[0][v_col(m)] */, cf (&y)[4
     }
 }
 
+// Where the slicer bits of one warp go.  A tile starts at channel sample g_first = 127*tile; warp
+// w holds decisions of samples g0 = g_first + 32 w + lane.  For sample phase j the 8 lanes
+// sh + 4 i (sh = (j - g0) & 3) are consecutive symbol slots t0 .. t0+7 of phase stream j.
+struct BitPlace { int sh; int word; int off; };
+SNRX_HD BitPlace bit_place(int g_first, int w, int j) {
+    const int g0 = g_first + 32 * w;
+    BitPlace b;
+    b.sh = (j - g0) & 3;
+    const int t0 = (g0 + b.sh) >> 2;
+    const int wbase = ((g_first >> 2) + 32) >> 5;
+    b.word = ((t0 + 32) >> 5) - wbase;          // 0 or 1 (+1 when the 8 bits straddle a word)
+    b.off = t0 & 31;
+    return b;
+}
+
 // every 4th bit of x starting at bit 0 -> low 8 bits
 SNRX_HD uint32_t compress4(uint32_t x) {
     x &= 0x11111111u;
@@ -133,6 +157,26 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
+// Stage tile samples i' = 0 .. kTileIn-1 (capture samples x0 + i') into the skewed tile: piece p holds
+// i' in [24 TT p - 12, 24 TT (p+1) - 12) at position i' + 8 p; each thread copies one 16-byte pair per piece.
+template <int NT, int TT, int THREADS>
+__device__ __forceinline__ void pfb_stage_tile(float2* xs, const float2* xcap, int64_t x0, int64_t n_in, int tid) {
+    using G = PfbGeom<NT, TT>;
+    constexpr int kPer = 24 * TT;
+    static_assert(kPer / 2 <= THREADS, "one pair per thread and piece");
+    if (tid < kPer / 2) {
+#pragma unroll
+        for (int p = 0; p < G::kPieces; p++) {
+            const int ip = kPer * p - 12 + 2 * tid;
+            if (ip >= 0 && ip < G::kTileIn) {
+                const int64_t i = x0 + ip;
+                const bool ok = (i >= 0) && (i + 1 < n_in);
+                cp_async16(xs + ip + 8 * p, xcap + (ok ? i : 0), ok);
+            }
+        }
+    }
+}
+
 struct PfbBleArgs {
     const float2* x;          // [n_captures][stride] cf32
     uint64_t stride;          // samples between captures
@@ -141,9 +185,8 @@ struct PfbBleArgs {
     int32_t n_tiles;          // tiles of this launch
     int32_t tile0;            // first tile of this launch
     const float* taps_rho;    // [24][NT]: taps_rho[rho*NT + d] = h[rho + 24 d]
-    const float* taps_flat;   // [L] h[n] (for the extra time step)
     float scale;              // quantiser scale
-    uint32_t* bits;
+    uint32_t* bits;           // zero-initialised; tiles OR their words in
     BitsLayout lay;
     int8_t* dbg_q8;           // [cap][40][n_out][2] or null
     float2* dbg_cf;           // [cap][40][n_out] or null
@@ -154,121 +197,109 @@ __global__ void __launch_bounds__(kFirThreads, 2) k_pfb_ble(PfbBleArgs a) {
     using G = PfbGeom<NT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);
-    float2* V = xs + G::kXsLen;                                   // [48][kVStride]
-    uint32_t* wordbuf = reinterpret_cast<uint32_t*>(V + 48 * kVStride);   // [40][4]
-    float2* edge = reinterpret_cast<float2*>(wordbuf + 160);      // [5][48] first lane of each warp
+    float2* V = xs + G::kXsLen;                                            // [48][kVStride]
+    uint32_t* wordbuf = reinterpret_cast<uint32_t*>(V + 48 * kVStride);    // [40][4][2]
+    float2* edge = reinterpret_cast<float2*>(wordbuf + 320);               // [4][48] first lane of each warp
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = a.tile0 + (int)(blockIdx.x % a.n_tiles);
     const int cap = blockIdx.x / a.n_tiles;
     const float2* xcap = a.x + (size_t)cap * a.stride;
+    const int g_first = kTileStride * tile;                                // first channel sample of the tile
 
-    // ---- phase 0: stage input tile.  tile sample i' <-> capture sample i = x0 + i'
-    const int64_t x0 = (int64_t)kPfbD * kTileT * tile - G::kHist;
-    for (int v = tid; v < G::kTileIn / 2; v += kFirThreads) {
-        const int ip = 2 * v;
-        const int64_t i = x0 + ip;
-        const bool ok = (i >= 0) && (i + 1 < a.n_in);
-        cp_async16(xs + xs_pos(ip), xcap + (ok ? i : 0), ok);
-    }
-    // FIR taps of this thread's rho while the copies fly
-    const int rho_lo = lane & 7, cq = lane >> 3;
-    const int rho = 8 * (wid % 3) + rho_lo;
-    const int q = 4 * (wid / 3) + cq;
+    // ---- phase 0: stage the input tile
+    pfb_stage_tile<NT, kChunkT, kFirThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, tid);
+    const int rho = 8 * (wid % 3) + (lane & 7);
+    const int q = 4 * (wid / 3) + (lane >> 3);
     float g[NT];
 #pragma unroll
-    for (int d = 0; d < NT; d++) g[d] = __ldg(a.taps_rho + rho * NT + d);
+    for (int d = 0; d < NT; d++) g[d] = __ldg(a.taps_rho + rho * NT + d);   // taps of this thread's rho
+    for (int i = tid; i < 320; i += kFirThreads) wordbuf[i] = 0u;
     cp_async_commit_wait_all();
     __syncthreads();
 
     // ---- phase 1: FIR -> V[r][v_col(m)]
     {
         float2 acc[2][kChunkT];
-        pfb_fir_thread<NT, 2>(xs + fir_base<NT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+        pfb_fir_thread<NT, 2, kChunkT>(xs + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
 #pragma unroll
         for (int e = 0; e < kChunkT; e++) {
             V[rho * kVStride + 24 * q + e] = acc[0][e];
             V[(rho + 24) * kVStride + 24 * q + e] = acc[1][e];
         }
-        if (tid < 48) {                       // extra time step m = 128, branch r = tid
-            float2 s = make_float2(0.f, 0.f);
-#pragma unroll 4
-            for (int p = 0; p < NT / 2; p++) {
-                const int n = tid + 48 * p;
-                const float2 xv = xs[xs_pos(G::kHist + kPfbD * kTileT - n)];
-                const float c = __ldg(a.taps_flat + n);
-                s.x = f_fma(c, xv.x, s.x);
-                s.y = f_fma(c, xv.y, s.y);
-            }
-            V[tid * kVStride + v_col(kTileT)] = s;
-        }
     }
     __syncthreads();
 
     // ---- phase 2: 48-point inverse DFT + rotation + quantiser, one thread per output time
-    cf y[48];
-    const int m = tid;                                   // 0..128 active
-    const int mg = kTileT * tile + m;                    // channel-rate sample index in the capture
-    if (m <= kTileT) {
-        const float s = (mg < a.n_out) ? a.scale : 0.0f;
-        cf raw[48];
-        pfb_dft48_quant(V + v_col(m), y, s, (mg & 1) ? -s : s, raw, DEBUG);
-        if (DEBUG && m < kTileT && mg < a.n_out) {
+    if (wid < 4) {
+        cf y[48];
+        const int m = tid;                                   // 0..127
+        const int mg = g_first + m;                          // channel-rate sample index in the capture
+        {
+            const float s = (mg < a.n_out) ? a.scale : 0.0f;
+            cf raw[48];
+            pfb_dft48_quant(V + v_col(m), y, s, (mg & 1) ? -s : s, raw, DEBUG);
+            if (DEBUG && m < kTileStride && mg < a.n_out) {
 #pragma unroll
-            for (int qq = 0; qq < 48; qq++) {
-                constexpr int dummy = 0; (void)dummy;
-                const int ch = ble_channel_of_q(qq);
-                if (ch >= 0) {
-                    const size_t o = ((size_t)cap * 40 + ch) * (size_t)a.n_out + mg;
-                    if (a.dbg_q8) { a.dbg_q8[2 * o] = (int8_t)y[qq].r; a.dbg_q8[2 * o + 1] = (int8_t)y[qq].i; }
-                    if (a.dbg_cf) {
-                        const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
-                        a.dbg_cf[o] = make_float2(raw[qq].r * sg, raw[qq].i * sg);
+                for (int qq = 0; qq < 48; qq++) {
+                    const int ch = ble_channel_of_q(qq);
+                    if (ch >= 0) {
+                        const size_t o = ((size_t)cap * 40 + ch) * (size_t)a.n_out + mg;
+                        if (a.dbg_q8) { a.dbg_q8[2 * o] = (int8_t)y[qq].r; a.dbg_q8[2 * o + 1] = (int8_t)y[qq].i; }
+                        if (a.dbg_cf) {
+                            const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
+                            a.dbg_cf[o] = make_float2(raw[qq].r * sg, raw[qq].i * sg);
+                        }
                     }
                 }
             }
-        }
-        if (lane == 0) {
+            if (lane == 0) {
 #pragma unroll
-            for (int qq = 0; qq < 48; qq++) edge[wid * 48 + qq] = make_float2(y[qq].r, y[qq].i);
+                for (int qq = 0; qq < 48; qq++) edge[wid * 48 + qq] = make_float2(y[qq].r, y[qq].i);
+            }
         }
-    }
-    __syncthreads();
+        asm volatile("bar.sync 1, 128;\n" ::);                // only the 4 DFT warps exchange edges
 
-    // ---- phase 3: slicer bits.  b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0   (btle_rx.c:1357-1361)
-    if (wid < 4) {
+        // ---- phase 3: slicer bits.  b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0   (btle_rx.c:1357-1361)
         uint32_t mine0 = 0, mine1 = 0;        // masks of the channels this lane will de-interleave
+        const float2* nextw = edge + ((wid + 1) & 3) * 48;
 #pragma unroll
         for (int qq = 0; qq < 48; qq++) {
             if (ble_channel_of_q(qq) < 0) continue;
             float i1 = __shfl_down_sync(0xffffffffu, y[qq].r, 1);
             float q1 = __shfl_down_sync(0xffffffffu, y[qq].i, 1);
-            if (lane == 31) { const float2 n = edge[(wid + 1) * 48 + qq]; i1 = n.x; q1 = n.y; }
+            if (lane == 31) { const float2 n = nextw[qq]; i1 = n.x; q1 = n.y; }
             const float cross = f_fma(y[qq].r, q1, -f_mul(i1, y[qq].i));
-            const uint32_t mask = __ballot_sync(0xffffffffu, cross > 0.0f);
+            uint32_t mask = __ballot_sync(0xffffffffu, cross > 0.0f);
             if (qq < 32) { if (lane == qq) mine0 = mask; } else { if (lane == qq - 32) mine1 = mask; }
         }
-        // lane L de-interleaves bin q = L (and q = L + 32): warp `wid` supplies byte `wid` of each phase word
-        unsigned char* wb = reinterpret_cast<unsigned char*>(wordbuf);
-        {
-            const int ch = ble_channel_of_q(lane);
-            if (ch >= 0) {
+        if (wid == 3) { mine0 &= 0x7FFFFFFFu; mine1 &= 0x7FFFFFFFu; }     // sample 127 has no successor in this tile
+        // lane L de-interleaves bin q = L (and q = L + 32) into the tile's two-word windows
 #pragma unroll
-                for (int j = 0; j < 4; j++) wb[(ch * 4 + j) * 4 + wid] = (unsigned char)compress4(mine0 >> j);
-            }
-        }
-        if (lane < 16) {
-            const int ch = ble_channel_of_q(lane + 32);
-            if (ch >= 0) {
+        for (int half = 0; half < 2; half++) {
+            const int ch = ble_channel_of_q(lane + 32 * half);
+            const uint32_t mk = half ? mine1 : mine0;
+            if (ch >= 0 && (half == 0 || lane < 16)) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) wb[(ch * 4 + j) * 4 + wid] = (unsigned char)compress4(mine1 >> j);
+                for (int j = 0; j < 4; j++) {
+                    const BitPlace bp = bit_place(g_first, wid, j);
+                    const uint32_t B = compress4(mk >> bp.sh);
+                    if (B) {
+                        uint32_t* w2 = wordbuf + (ch * 4 + j) * 2;
+                        atomicOr(w2 + bp.word, B << bp.off);
+                        if (bp.off > 24) atomicOr(w2 + bp.word + 1, B >> (32 - bp.off));
+                    }
+                }
             }
         }
     }
     __syncthreads();
-    if (tid < 160) {
-        const int ch = tid >> 2, j = tid & 3;
-        a.bits[a.lay.index(cap, ch, j, kBitsLeadWords + tile)] = wordbuf[tid];
+    {
+        const uint32_t wbase = (uint32_t)(((g_first >> 2) + 32) >> 5);
+        for (int i = tid; i < 320; i += kFirThreads) {
+            const uint32_t v = wordbuf[i];
+            if (v) atomicOr(a.bits + a.lay.index(cap, i >> 3, (i >> 1) & 3, wbase + (i & 1)), v);
+        }
     }
 }
 #endif  // __CUDACC__

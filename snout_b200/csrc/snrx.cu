@@ -17,17 +17,9 @@
 #include "pfb_taps.h"
 #include "scan.cuh"
 #include "zb.cuh"
+#include "pfb_zb.cuh"
 
 using namespace snrx;
-
-namespace snrx {
-// wideband Zigbee front end: pfb_zb.cuh (next milestone)
-int zb_wideband_front(ZbState&, const snrx_config_t&, const float2*, uint32_t, uint64_t, uint64_t, uint32_t, cudaStream_t, int&,
-                      std::string& err) {
-    err = "wideband Zigbee front end not built in this version";
-    return SNRX_EINVAL;
-}
-}  // namespace snrx
 
 namespace {
 
@@ -44,7 +36,16 @@ struct snrx_handle {
     cudaStream_t stream = nullptr;       // compute stream (own or caller supplied)
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D staging
-    cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_stop = nullptr;
+    // Output ring: snrx_process(i+1) may be queued before snrx_poll(i), so the GPU never idles between
+    // batches.  Frames are stored by the kernels straight into host-mapped pinned memory (zero copy).
+    struct OutSlot {
+        snrx_frame_t* frames = nullptr;     // pinned + mapped, frame_cap records
+        uint32_t* totals = nullptr;         // pinned: [0] BLE frames [1] candidates [2] Zigbee frames
+        cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_done = nullptr;
+        bool pending = false, done = false;
+        uint32_t caps = 0, n_out = 0, n_frames = 0; uint64_t n_in = 0; int launches = 0;
+    } slot[2];
+    uint64_t seq_process = 0, seq_poll = 0;
     std::vector<cudaEvent_t> ev_chunks;
     int sm_count = 148;
     std::string err;
@@ -69,7 +70,6 @@ struct snrx_handle {
     uint32_t *d_wcounts = nullptr, *d_woffsets = nullptr;
     Cand* d_cands = nullptr;
     Dec* d_decs = nullptr;
-    snrx_frame_t* d_frames = nullptr;
     uint32_t* d_totals = nullptr;        // [0] frames, [1] candidates, [2] zigbee frames (gathered at poll)
     uint32_t *d_crc_tab = nullptr, *d_whiten = nullptr;
     int32_t* d_ble_channels = nullptr;
@@ -82,9 +82,6 @@ struct snrx_handle {
     bool batch_valid = false;
     uint32_t b_caps = 0; uint64_t b_n_in = 0; uint32_t b_n_out = 0; uint32_t b_windows = 0;
     uint32_t b_aa_items = 0, b_w_items = 0;
-    uint32_t n_frames_ready = 0;
-    bool polled = false;
-    snrx_frame_t* h_frames = nullptr;    // pinned
     snrx_stats_t stats{};
     int launches = 0;
 };
@@ -223,16 +220,16 @@ void snrx_destroy(snrx_t* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     void* bufs[] = {h->d_x, h->d_bits, h->d_counts, h->d_offsets, h->d_scratch, h->d_wcounts, h->d_woffsets,
-                    h->d_cands, h->d_decs, h->d_frames, h->d_totals, h->d_crc_tab, h->d_whiten, h->d_ble_channels,
+                    h->d_cands, h->d_decs, h->d_totals, h->d_crc_tab, h->d_whiten, h->d_ble_channels,
                     h->d_taps_rho, h->d_taps_flat, h->d_q8, h->d_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     zb_free(h->zb);
-    if (h->h_frames) cudaFreeHost(h->h_frames);
+    for (auto& sl : h->slot) {
+        if (sl.frames) cudaFreeHost(sl.frames);
+        if (sl.totals) cudaFreeHost(sl.totals);
+        for (cudaEvent_t e : {sl.ev_start, sl.ev_front0, sl.ev_front, sl.ev_done}) if (e) cudaEventDestroy(e);
+    }
     for (cudaEvent_t e : h->ev_chunks) cudaEventDestroy(e);
-    if (h->ev_start) cudaEventDestroy(h->ev_start);
-    if (h->ev_front0) cudaEventDestroy(h->ev_front0);
-    if (h->ev_front) cudaEventDestroy(h->ev_front);
-    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -261,10 +258,6 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
-        CK(cudaEventCreate(&h->ev_start));
-        CK(cudaEventCreate(&h->ev_front0));
-        CK(cudaEventCreate(&h->ev_front));
-        CK(cudaEventCreate(&h->ev_stop));
 
         snrx_config_t& c = h->cfg;
         switch (c.mode) {
@@ -297,8 +290,14 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         h->cand_cap = std::max<uint32_t>(1u << 16, 4 * c.max_frames);
 
         CKD(dev_alloc(h, &h->d_totals, 8));
-        CKD(dev_alloc(h, &h->d_frames, h->frame_cap));
-        CK(cudaHostAlloc((void**)&h->h_frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap, cudaHostAllocDefault));
+        for (auto& sl : h->slot) {
+            CK(cudaHostAlloc((void**)&sl.frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap, cudaHostAllocMapped));
+            CK(cudaHostAlloc((void**)&sl.totals, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+            CK(cudaEventCreate(&sl.ev_start));
+            CK(cudaEventCreate(&sl.ev_front0));
+            CK(cudaEventCreate(&sl.ev_front));
+            CK(cudaEventCreate(&sl.ev_done));
+        }
 
         if (h->has_ble) {
             const uint32_t tiles = div_up(h->max_out, kTileT);
@@ -354,6 +353,11 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         if (h->has_zb) {
             int r = zb_create(h->zb, h->cfg, h->wideband, h->n_zb_ch, h->max_caps, h->max_out, h->sm_count, h->err);
             if (r != SNRX_OK) return r;
+            if (h->wideband) {
+                const double* proto = (c.pfb_taps == 384) ? SNRX_PFB_ZB_384 : SNRX_PFB_ZB_768;
+                r = zb_wideband_init(h->zb, h->cfg, proto, h->max_caps, h->max_out, h->err);
+                if (r != SNRX_OK) return r;
+            }
         }
         CK(cudaMemset(h->d_totals, 0, 8 * sizeof(uint32_t)));
         return SNRX_OK;
@@ -383,6 +387,11 @@ int snrx_set_channel(snrx_t* h, int channel) {
         CK(cudaStreamSynchronize(h->stream));
     } else {
         if (channel < 11 || channel > 26) return fail(h, SNRX_EINVAL, "802.15.4 channel 11..26");
+        CK(cudaSetDevice(h->device));
+        int32_t chans[16];
+        for (int i = 0; i < 16; i++) chans[i] = channel;
+        CK(cudaMemcpyAsync(h->zb.d_channels, chans, sizeof chans, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
     }
     h->cfg.channel = channel;
     return SNRX_OK;
@@ -403,7 +412,7 @@ static int launch_ble_front(snrx_handle* h, const float2* x, uint32_t caps, uint
         PfbBleArgs a;
         a.x = x; a.stride = stride; a.n_in = (int64_t)n_in; a.n_out = (int32_t)n_out;
         a.n_tiles = tile_end - tile_begin;
-        a.taps_rho = h->d_taps_rho; a.taps_flat = h->d_taps_flat; a.scale = h->cfg.quant_scale;
+        a.taps_rho = h->d_taps_rho; a.scale = h->cfg.quant_scale;
         a.bits = h->d_bits; a.lay = lay; a.dbg_q8 = h->d_q8; a.dbg_cf = h->d_cf;
         a.tile0 = tile_begin;
         const dim3 grid((unsigned)(a.n_tiles) * caps);
@@ -439,8 +448,8 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     if ((((uintptr_t)iq) & 15) || (n_captures > 1 && (stride_samples & 1))) return fail(h, SNRX_EINVAL, "captures must be 16-byte aligned (even stride)");
     if (h->wideband && (n_samples % kPfbD) != 0) return fail(h, SNRX_EINVAL, "wideband captures must hold a multiple of 24 samples");
     CK(cudaSetDevice(h->device));
-    h->batch_valid = false;
-    h->polled = false;
+    snrx_handle::OutSlot& sl = h->slot[h->seq_process & 1];
+    if (sl.pending) return fail(h, SNRX_ESTATE, "two batches already queued: snrx_poll the oldest first");
     h->launches = 0;
 
     const uint32_t n_out = (uint32_t)(n_samples / h->decim);
@@ -454,7 +463,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         if ((uint64_t)pre_out + body_out > n_out) return fail(h, SNRX_EINVAL, "shard body exceeds the buffer");
     }
 
-    CK(cudaEventRecord(h->ev_start, h->stream));
+    CK(cudaEventRecord(sl.ev_start, h->stream));
     CK(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(uint32_t), h->stream));
 
     // ---- input: device pointer as is, host pointer staged in chunks overlapped with the front end
@@ -482,10 +491,10 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     }
 
     if (staged) {
-        CK(cudaEventRecord(h->ev_front0, h->stream));
+        CK(cudaEventRecord(sl.ev_front0, h->stream));
         // copy stream must not start overwriting the staging buffer before earlier work on the compute stream finished
-        CK(cudaEventRecord(h->ev_front, h->stream));
-        CK(cudaStreamWaitEvent(h->copy_stream, h->ev_front, 0));
+        CK(cudaEventRecord(sl.ev_front, h->stream));
+        CK(cudaStreamWaitEvent(h->copy_stream, sl.ev_front, 0));
         size_t ev_i = 0;
         for (uint32_t c = 0; c < n_captures; c++) {
             const float2* src = reinterpret_cast<const float2*>(iq) + (size_t)c * stride_samples;
@@ -502,7 +511,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
                     // launch the channelizer on the tiles whose input has fully arrived
                     const uint64_t have = off + len;
                     const bool last = (have == n_samples);
-                    int tile_end = last ? (int)div_up(n_out, kTileT) : (int)((have / kPfbD) / kTileT) - 1;
+                    int tile_end = last ? (int)div_up(n_out, kTileStride) : (int)(((int64_t)(have / kPfbD) - kTileT) / kTileStride);
                     if (tile_end > tile_done) {
                         int r = launch_ble_front(h, x, 1, n_samples, x_stride, n_out, tile_done, tile_end, lay);
                         if (r != SNRX_OK) return r;
@@ -516,11 +525,11 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     if (h->has_ble) {
         const bool pipelined = staged && h->wideband && !h->has_zb && n_captures == 1;
         if (!pipelined) {
-            CK(cudaEventRecord(h->ev_front0, h->stream));
-            int r = launch_ble_front(h, x, n_captures, n_samples, x_stride, n_out, 0, (int)div_up(n_out, kTileT), lay);
+            CK(cudaEventRecord(sl.ev_front0, h->stream));
+            int r = launch_ble_front(h, x, n_captures, n_samples, x_stride, n_out, 0, (int)div_up(n_out, h->wideband ? kTileStride : kTileT), lay);
             if (r != SNRX_OK) return r;
         }
-        CK(cudaEventRecord(h->ev_front, h->stream));
+        CK(cudaEventRecord(sl.ev_front, h->stream));
 
         BleParams p{};
         p.aa = h->cfg.access_addr;
@@ -540,15 +549,15 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         const int g_aa = grid_for(h, aa_items, 8, 8);
         k_aa_search<false><<<g_aa, 256, 0, h->stream>>>(h->d_bits, lay, p, n_chunks, h->d_counts, nullptr, nullptr, 0);
         h->launches += 1 + exclusive_scan(h->d_counts, aa_items, h->d_offsets, h->d_scratch, h->stream);
-        k_aa_search<true><<<g_aa, 256, 0, h->stream>>>(h->d_bits, lay, p, n_chunks, nullptr, h->d_offsets, h->d_cands, h->cand_cap);
-        k_ble_decode<<<h->sm_count * 4, 128, 0, h->stream>>>(h->d_bits, lay, p, h->d_offsets + aa_items, h->cand_cap, h->d_cands,
+        k_aa_search<true><<<g_aa, 256, 0, h->stream>>>(h->d_bits, lay, p, n_chunks, h->d_counts, h->d_offsets, h->d_cands, h->cand_cap);
+        k_ble_decode<<<h->sm_count * 16, 128, 0, h->stream>>>(h->d_bits, lay, p, h->d_offsets + aa_items, h->cand_cap, h->d_cands,
                                                           h->d_decs, h->d_crc_tab, h->d_whiten, h->d_ble_channels);
         const int g_w = grid_for(h, w_items, 256, 8);
         k_ble_resolve<false><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, h->d_wcounts, nullptr,
                                                         nullptr, 0, h->d_ble_channels, h->cand_cap);
         h->launches += 3 + exclusive_scan(h->d_wcounts, w_items, h->d_woffsets, h->d_scratch, h->stream);
-        k_ble_resolve<true><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, nullptr, h->d_woffsets,
-                                                       h->d_frames, h->frame_cap, h->d_ble_channels, h->cand_cap);
+        k_ble_resolve<true><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, h->d_wcounts, h->d_woffsets,
+                                                       sl.frames, h->frame_cap, h->d_ble_channels, h->cand_cap);
         h->launches += 1;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h->d_totals + 0, h->d_woffsets + w_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
@@ -558,56 +567,84 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     }
     if (h->has_zb) {
         int r = zb_process(h->zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_window,
-                           first_capture, h->d_frames, h->frame_cap, h->d_totals, h->has_ble, h->stream, h->sm_count,
+                           first_capture, sl.frames, h->frame_cap, h->d_totals, h->has_ble, h->stream, h->sm_count,
                            h->launches, h->err);
         if (r != SNRX_OK) return r;
-        if (!h->has_ble) { CK(cudaEventRecord(h->ev_front0, h->stream)); CK(cudaEventRecord(h->ev_front, h->stream)); }
+        if (!h->has_ble) { CK(cudaEventRecord(sl.ev_front0, h->stream)); CK(cudaEventRecord(sl.ev_front, h->stream)); }
     }
-    CK(cudaEventRecord(h->ev_stop, h->stream));
+    CK(cudaMemcpyAsync(sl.totals, h->d_totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaEventRecord(sl.ev_done, h->stream));
+    sl.pending = true; sl.done = false;
+    sl.caps = n_captures; sl.n_in = n_samples; sl.n_out = n_out; sl.launches = h->launches;
+    h->seq_process++;
     h->b_caps = n_captures; h->b_n_in = n_samples; h->b_n_out = n_out;
     h->batch_valid = true;
     return SNRX_OK;
 }
 
-int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
-    if (!h) return SNRX_EINVAL;
-    if (!h->batch_valid) return fail(h, SNRX_ESTATE, "snrx_poll without a processed batch");
-    CK(cudaSetDevice(h->device));
-    if (!h->polled) {
-        uint32_t totals[8];
-        CK(cudaMemcpyAsync(totals, h->d_totals, sizeof totals, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        const uint32_t n_ble = totals[0], n_cand = totals[1], n_zb = totals[2];
+// wait for the oldest queued batch, fill its stats; does not consume it
+static int finish_oldest(snrx_handle* h, snrx_handle::OutSlot** out_slot) {
+    snrx_handle::OutSlot& sl = h->slot[h->seq_poll & 1];
+    if (!sl.pending) return fail(h, SNRX_ESTATE, "snrx_poll without a queued batch");
+    if (!sl.done) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaEventSynchronize(sl.ev_done));
+        const uint32_t n_ble = sl.totals[0], n_cand = sl.totals[1], n_zb = sl.totals[2];
         h->stats.candidates = n_cand;
-        if (n_cand > h->cand_cap) return fail(h, SNRX_EOVERFLOW, "access-address candidates exceed capacity (raise max_frames)");
-        if ((uint64_t)n_ble + n_zb > h->frame_cap) return fail(h, SNRX_EOVERFLOW, "frames exceed max_frames");
-        h->n_frames_ready = n_ble + n_zb;
-        if (h->n_frames_ready)
-            CK(cudaMemcpyAsync(h->h_frames, h->d_frames, sizeof(snrx_frame_t) * (size_t)h->n_frames_ready,
-                               cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        sl.done = true;
+        sl.n_frames = 0;
+        if (n_cand > h->cand_cap) { sl.pending = false; h->seq_poll++; return fail(h, SNRX_EOVERFLOW, "access-address candidates exceed capacity (raise max_frames)"); }
+        if ((uint64_t)n_ble + n_zb > h->frame_cap) { sl.pending = false; h->seq_poll++; return fail(h, SNRX_EOVERFLOW, "frames exceed max_frames"); }
+        sl.n_frames = n_ble + n_zb;
         float ms = 0.f, msf = 0.f;
-        cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
-        cudaEventElapsedTime(&msf, h->ev_front0, h->ev_front);
+        cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_done);
+        cudaEventElapsedTime(&msf, sl.ev_front0, sl.ev_front);
         uint32_t ok = 0;
-        for (uint32_t i = 0; i < h->n_frames_ready; i++) ok += h->h_frames[i].crc_ok;
-        h->stats.samples_in = (uint64_t)h->b_caps * h->b_n_in;
-        h->stats.channel_samples = (uint64_t)h->b_caps * h->b_n_out * (h->n_ble_ch + h->n_zb_ch);
-        h->stats.frames = h->n_frames_ready;
+        for (uint32_t i = 0; i < sl.n_frames; i++) ok += sl.frames[i].crc_ok;
+        h->stats.samples_in = (uint64_t)sl.caps * sl.n_in;
+        h->stats.channel_samples = (uint64_t)sl.caps * sl.n_out * (h->n_ble_ch + h->n_zb_ch);
+        h->stats.frames = sl.n_frames;
         h->stats.frames_crc_ok = ok;
-        h->stats.kernel_launches = (uint32_t)h->launches;
+        h->stats.kernel_launches = (uint32_t)sl.launches;
         h->stats.gpu_ms = ms;
         h->stats.gpu_ms_frontend = msf;
-        h->polled = true;
     }
-    if (n_out) *n_out = h->n_frames_ready;
-    if (out && cap) memcpy(out, h->h_frames, sizeof(snrx_frame_t) * (size_t)std::min(cap, h->n_frames_ready));
+    *out_slot = &sl;
+    return SNRX_OK;
+}
+
+int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h) return SNRX_EINVAL;
+    snrx_handle::OutSlot* sl = nullptr;
+    int r = finish_oldest(h, &sl);
+    if (r != SNRX_OK) return r;
+    if (n_out) *n_out = sl->n_frames;
+    if (out) {                                   // copying the frames out consumes the batch
+        memcpy(out, sl->frames, sizeof(snrx_frame_t) * (size_t)std::min(cap, sl->n_frames));
+        sl->pending = false;
+        h->seq_poll++;
+    }
+    return SNRX_OK;
+}
+
+int snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out) {
+    if (!h) return SNRX_EINVAL;
+    snrx_handle::OutSlot* sl = nullptr;
+    int r = finish_oldest(h, &sl);
+    if (r != SNRX_OK) return r;
+    if (frames) *frames = sl->frames;
+    if (n_out) *n_out = sl->n_frames;
+    sl->pending = false;
+    h->seq_poll++;
     return SNRX_OK;
 }
 
 int snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev) {
     if (!h || !h->batch_valid) return SNRX_ESTATE;
-    if (frames_dev) *frames_dev = h->d_frames;
+    snrx_handle::OutSlot& sl = h->slot[(h->seq_process + 1) & 1];      // slot of the most recent snrx_process
+    void* dp = nullptr;
+    CK(cudaHostGetDevicePointer(&dp, sl.frames, 0));
+    if (frames_dev) *frames_dev = dp;
     if (count_dev) *count_dev = h->d_totals;
     return SNRX_OK;
 }
@@ -629,6 +666,11 @@ int snrx_debug_stage(snrx_t* h, int stage, void* out, uint64_t cap_bytes, uint64
             if (!h->d_q8) return fail(h, SNRX_ESTATE, "create the engine with SNRX_F_KEEP_STREAMS");
             src = h->d_q8; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 2; break;
         case SNRX_STAGE_CHAN_CF32:
+            if (h->cfg.mode == SNRX_MODE_ZB_WB16) {
+                int r = zb_debug_stage(h->zb, stage, h->b_caps, h->b_n_out, &src, &bytes);
+                if (r != SNRX_OK) return fail(h, r, "create the engine with SNRX_F_KEEP_STREAMS");
+                break;
+            }
             if (!h->d_cf) return fail(h, SNRX_ESTATE, "create a wideband engine with SNRX_F_KEEP_STREAMS");
             src = h->d_cf; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 8; break;
         case SNRX_STAGE_BLE_BITS: {

@@ -407,13 +407,14 @@ struct ZbState {
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
     uint32_t max_chains = 0, slots_per_chain = 0;
     float* d_chips = nullptr; int64_t* d_nchips = nullptr; int64_t chips_cap = 0;
+    float *d_wb_taps_rho = nullptr, *d_wb_taps_flat = nullptr; float2* d_wb_cf = nullptr; int wb_nt = 16;   // wideband front end
     ChipMap map;
     uint32_t last_chains = 0;
 };
 
 inline void zb_free(ZbState& s) {
     void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_pw, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
-                    s.d_counts, s.d_offsets, s.d_scratch, s.d_chips, s.d_nchips};
+                    s.d_counts, s.d_offsets, s.d_scratch, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     s = ZbState();
 }
@@ -470,8 +471,8 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     return SNRX_OK;
 }
 
-// declared in pfb_zb.cuh (wideband front end); defined there
-int zb_wideband_front(ZbState& s, const snrx_config_t& cfg, const float2* x, uint32_t n_captures, uint64_t n_samples,
+// wideband front end (channelizer + discriminator): defined in pfb_zb.cuh
+inline int zb_wideband_front(ZbState& s, const snrx_config_t& cfg, const float2* x, uint32_t n_captures, uint64_t n_samples,
                       uint64_t stride, uint32_t n_out, cudaStream_t st, int& launches, std::string& err);
 
 inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uint32_t n_captures, uint64_t n_samples,
@@ -535,6 +536,10 @@ inline int zb_debug_stage(ZbState& s, int stage, uint32_t caps, uint32_t n_out, 
         *src = s.d_nchips; *bytes = (uint64_t)s.last_chains * sizeof(int64_t); return SNRX_OK;
     }
     if (stage == SNRX_STAGE_ZB_F) { *src = s.d_f; *bytes = (uint64_t)caps * s.n_ch * s.stride * sizeof(float); return SNRX_OK; }
+    if (stage == SNRX_STAGE_CHAN_CF32) {
+        if (!s.d_wb_cf) return SNRX_ESTATE;
+        *src = s.d_wb_cf; *bytes = (uint64_t)caps * s.n_ch * n_out * sizeof(float2); return SNRX_OK;
+    }
     return SNRX_EINVAL;
 }
 #endif  // __CUDACC__

@@ -150,14 +150,18 @@ class RxEngine:
         self._last = (n_captures, n_samples)
         return self
 
-    def poll(self) -> np.ndarray:
-        """Wait for the queued batch; frames in reference order (capture, channel, window, index)."""
+    def poll(self, copy: bool = True) -> np.ndarray:
+        """Wait for the oldest queued batch (up to two may be queued) and return its frames in
+        reference order (capture, channel, window, index).  copy=False returns a view of the engine's
+        pinned result buffer, valid until the second-next process()."""
         n = c_uint32(0)
-        self._check(self.lib.snrx_poll(self.handle, None, 0, byref(n)))
-        out = np.zeros(n.value, dtype=FRAME_DTYPE)
-        if n.value:
-            self._check(self.lib.snrx_poll(self.handle, out.ctypes.data_as(c_void_p), n.value, byref(n)))
-        return out
+        ptr = c_void_p()
+        self._check(self.lib.snrx_poll_view(self.handle, byref(ptr), byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=FRAME_DTYPE)
+        buf = (ctypes.c_char * (n.value * FRAME_DTYPE.itemsize)).from_address(ptr.value)
+        view = np.frombuffer(buf, dtype=FRAME_DTYPE)
+        return view.copy() if copy else view
 
     def run(self, iq, **kw) -> np.ndarray:
         return self.process(iq, **kw).poll()
@@ -183,7 +187,7 @@ class RxEngine:
         if stage == _abi.STAGE_BLE_Q8:
             return raw.view(np.int8).reshape(caps, self.n_ble, n_out, 2)
         if stage == _abi.STAGE_CHAN_CF32:
-            return raw.view(np.complex64).reshape(caps, self.n_ble, n_out)
+            return raw.view(np.complex64).reshape(caps, self.n_zb if self.mode == MODE_ZB_WB16 else self.n_ble, n_out)
         if stage == _abi.STAGE_BLE_BITS:
             return raw.view(np.uint32).reshape(caps, self.n_ble, 4, -1)
         if stage in (_abi.STAGE_ZB_DISC, _abi.STAGE_ZB_F):

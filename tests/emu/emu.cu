@@ -11,8 +11,15 @@
 #include "../../snout_b200/csrc/fft.cuh"
 #include "../../snout_b200/csrc/pfb.cuh"
 #include "../../snout_b200/csrc/zb.cuh"
+#include "../../snout_b200/csrc/pfb_zb.cuh"
 
 using namespace snrx;
+
+template <int C>
+static void zb_disc_tile_row(const cf* cur, const cf* nxt, float* f_out, int m) {
+    f_out[C * kTileStride + m] = zb_disc<C>(cur[C], nxt[C], SNRX_ATAN_TAB);
+    if constexpr (C + 1 < 16) zb_disc_tile_row<C + 1>(cur, nxt, f_out, m);
+}
 
 extern "C" {
 
@@ -34,53 +41,49 @@ int emu_ble_channel_of_q(int q) { return ble_channel_of_q(q); }
 }  // extern "C"
 
 // ---- one tile of k_pfb_ble<NT, *>, phases 0..3 ------------------------------------------------
-// x: capture cf32 (n_in samples).  Outputs: words[40][4], q8[40][128][2] (int8), raw[40][128] cf32.
+// x: capture cf32 (n_in samples).  Outputs: words[40][4][2] (to be OR-ed at word index wbase + half),
+// q8[40][128][2] (int8), raw[40][128] cf32 for samples g_first .. g_first+127.
 template <int NT>
-static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho, const float* taps_flat,
-                     float scale, uint32_t* words, int8_t* q8, float* raw_out) {
+static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
+                     float scale, uint32_t* words, int* wbase_out, int8_t* q8, float* raw_out) {
     using G = PfbGeom<NT>;
     std::vector<float2> xs(G::kXsLen, make_float2(0.f, 0.f));
     std::vector<float2> V(48 * kVStride, make_float2(0.f, 0.f));
-    const int64_t x0 = (int64_t)kPfbD * kTileT * tile - G::kHist;
-    for (int v = 0; v < G::kTileIn / 2; v++) {
-        const int ip = 2 * v;
-        const int64_t i = x0 + ip;
-        const bool ok = (i >= 0) && (i + 1 < n_in);
-        for (int k = 0; k < 2; k++)
-            xs[xs_pos(ip) + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
-    }
+    const int g_first = kTileStride * tile;
+    const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
+    constexpr int kPer = 24 * kChunkT;
+    for (int tid = 0; tid < kPer / 2; tid++)
+        for (int p = 0; p < G::kPieces; p++) {
+            const int ip = kPer * p - 12 + 2 * tid;
+            if (ip >= 0 && ip < G::kTileIn) {
+                const int64_t i = x0 + ip;
+                const bool ok = (i >= 0) && (i + 1 < n_in);
+                for (int k = 0; k < 2; k++)
+                    xs[ip + 8 * p + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
+            }
+        }
     for (int tid = 0; tid < kFirThreads; tid++) {
         const int lane = tid & 31, wid = tid >> 5;
         const int rho = 8 * (wid % 3) + (lane & 7), q = 4 * (wid / 3) + (lane >> 3);
         float g[NT];
         for (int d = 0; d < NT; d++) g[d] = taps_rho[rho * NT + d];
         float2 acc[2][kChunkT];
-        pfb_fir_thread<NT, 2>(xs.data() + fir_base<NT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+        pfb_fir_thread<NT, 2, kChunkT>(xs.data() + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
         for (int e = 0; e < kChunkT; e++) {
             V[rho * kVStride + 24 * q + e] = acc[0][e];
             V[(rho + 24) * kVStride + 24 * q + e] = acc[1][e];
         }
-        if (tid < 48) {
-            float2 s = make_float2(0.f, 0.f);
-            for (int p = 0; p < NT / 2; p++) {
-                const int n = tid + 48 * p;
-                const float2 xv = xs[xs_pos(G::kHist + kPfbD * kTileT - n)];
-                s.x = f_fma(taps_flat[n], xv.x, s.x);
-                s.y = f_fma(taps_flat[n], xv.y, s.y);
-            }
-            V[tid * kVStride + v_col(kTileT)] = s;
-        }
     }
-    std::vector<cf> Y((kTileT + 1) * 48);
-    for (int m = 0; m <= kTileT; m++) {
-        const int mg = kTileT * tile + m;
+    std::vector<cf> Y(kTileT * 48);
+    for (int m = 0; m < kTileT; m++) {
+        const int mg = g_first + m;
         const float s = (mg < n_out) ? scale : 0.0f;
         cf y[48], raw[48];
         pfb_dft48_quant(V.data() + v_col(m), y, s, (mg & 1) ? -s : s, raw, true);
         for (int qq = 0; qq < 48; qq++) {
             Y[m * 48 + qq] = y[qq];
             const int ch = ble_channel_of_q(qq);
-            if (ch >= 0 && m < kTileT) {
+            if (ch >= 0) {
                 q8[(ch * kTileT + m) * 2] = (int8_t)y[qq].r;
                 q8[(ch * kTileT + m) * 2 + 1] = (int8_t)y[qq].i;
                 const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
@@ -89,7 +92,8 @@ static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const fl
             }
         }
     }
-    memset(words, 0, sizeof(uint32_t) * 160);
+    memset(words, 0, sizeof(uint32_t) * 320);
+    *wbase_out = ((g_first >> 2) + 32) >> 5;
     for (int wid = 0; wid < 4; wid++) {
         for (int qq = 0; qq < 48; qq++) {
             const int ch = ble_channel_of_q(qq);
@@ -97,20 +101,81 @@ static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const fl
             uint32_t mask = 0;
             for (int lane = 0; lane < 32; lane++) {
                 const int m = 32 * wid + lane;
+                if (m + 1 >= kTileT) continue;                       // sample 127 has no successor in the tile
                 const cf a = Y[m * 48 + qq], b = Y[(m + 1) * 48 + qq];
                 if (f_fma(a.r, b.i, -f_mul(b.r, a.i)) > 0.0f) mask |= 1u << lane;
             }
-            for (int j = 0; j < 4; j++) words[ch * 4 + j] |= compress4(mask >> j) << (8 * wid);
+            for (int j = 0; j < 4; j++) {
+                const BitPlace bp = bit_place(g_first, wid, j);
+                const uint32_t B = compress4(mask >> bp.sh);
+                uint32_t* w2 = words + (ch * 4 + j) * 2;
+                w2[bp.word] |= B << bp.off;
+                if (bp.off > 24) w2[bp.word + 1] |= B >> (32 - bp.off);
+            }
         }
     }
 }
 
+// ---- one tile of k_pfb_zb<NT, *>: f[g_first+1 .. g_first+127] for 16 channels, rotated streams for debug
+template <int NT>
+static void pfb_zb_tile(const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
+                        float* f_out /*[16][127]*/, float* y_out /*[16][128] cf32 rotated*/) {
+    using G = PfbGeom<NT, kZbChunkT>;
+    std::vector<float2> xs(G::kXsLen, make_float2(0.f, 0.f));
+    std::vector<float2> V(96 * kZbVStride, make_float2(0.f, 0.f));
+    const int g_first = kTileStride * tile;
+    const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
+    constexpr int kPer = 24 * kZbChunkT;
+    for (int tid = 0; tid < kPer / 2; tid++)
+        for (int p = 0; p < G::kPieces; p++) {
+            const int ip = kPer * p - 12 + 2 * tid;
+            if (ip >= 0 && ip < G::kTileIn) {
+                const int64_t i = x0 + ip;
+                const bool ok = (i >= 0) && (i + 1 < n_in);
+                for (int k = 0; k < 2; k++)
+                    xs[ip + 8 * p + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
+            }
+        }
+    for (int tid = 0; tid < kZbFirThreads; tid++) {
+        const int lane = tid & 31, wid = tid >> 5;
+        const int rho = 8 * (wid % 3) + (lane & 7), q = 4 * (wid / 3) + (lane >> 3);
+        float g[NT];
+        for (int d = 0; d < NT; d++) g[d] = taps_rho[rho * NT + d];
+        float2 acc[4][kZbChunkT];
+        pfb_fir_thread<NT, 4, kZbChunkT>(xs.data() + fir_base<NT, kZbChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+        for (int br = 0; br < 4; br++)
+            for (int e = 0; e < kZbChunkT; e++) V[(rho + 24 * br) * kZbVStride + kZbChunkT * q + e] = acc[br][e];
+    }
+    std::vector<cf> Y(kTileT * 16);
+    for (int m = 0; m < kTileT; m++) {
+        cf y[16];
+        pfb_dft96_zb(V.data() + m, y);
+        const int mg = g_first + m;
+        for (int c = 0; c < 16; c++) {
+            Y[m * 16 + c] = y[c];
+            const int rot = (zb_bin_of_slot(c) * (mg & 3)) & 3;
+            const float rr = rot == 0 ? y[c].r : rot == 1 ? y[c].i : rot == 2 ? -y[c].r : -y[c].i;
+            const float ii = rot == 0 ? y[c].i : rot == 1 ? -y[c].r : rot == 2 ? -y[c].i : y[c].r;
+            y_out[(c * kTileT + m) * 2] = rr; y_out[(c * kTileT + m) * 2 + 1] = ii;
+        }
+    }
+    for (int m = 0; m < kTileStride; m++) zb_disc_tile_row<0>(&Y[m * 16], &Y[(m + 1) * 16], f_out, m);
+}
+
 extern "C" {
 
+void emu_pfb_zb_tile(int nt, const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho, float* f_out, float* y_out) {
+    if (nt == 16) pfb_zb_tile<16>(x, n_in, n_out, tile, taps_rho, f_out, y_out);
+    else pfb_zb_tile<32>(x, n_in, n_out, tile, taps_rho, f_out, y_out);
+}
+int emu_zb_bin_of_slot(int c) { return zb_bin_of_slot(c); }
+
+int emu_pfb_tile_stride(void) { return kTileStride; }
+
 void emu_pfb_ble_tile(int nt, const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
-                      const float* taps_flat, float scale, uint32_t* words, int8_t* q8, float* raw) {
-    if (nt == 16) pfb_tile<16>(x, n_in, n_out, tile, taps_rho, taps_flat, scale, words, q8, raw);
-    else pfb_tile<32>(x, n_in, n_out, tile, taps_rho, taps_flat, scale, words, q8, raw);
+                      float scale, uint32_t* words, int* wbase, int8_t* q8, float* raw) {
+    if (nt == 16) pfb_tile<16>(x, n_in, n_out, tile, taps_rho, scale, words, wbase, q8, raw);
+    else pfb_tile<32>(x, n_in, n_out, tile, taps_rho, scale, words, wbase, q8, raw);
 }
 
 // ---- narrow-band slicer: whole capture -> phase words (layout of BitsLayout, 1 channel) --------
@@ -141,7 +206,7 @@ int emu_ble_back(const uint32_t* bits, uint32_t wpp, int n_out, int m_origin, in
         uint32_t hits[4];
         for (int j = 0; j < 4; j++) {
             const uint32_t* pw = bits + lay.index(0, 0, j, 0);
-            uint32_t hj = aa_word_hits(pw[w], pw[w + 1], aa, mask_hi);
+            uint32_t hj = aa_word_hits(pw[w], pw[w + 1], aa, mask_hi, [](uint32_t m) { return m != 0u; });
             const int nvalid = ((n_out - 1 - j) >> 2) - 32 * ((int)w - 1) + 1;
             if (nvalid <= 0) hj = 0u; else if (nvalid < 32) hj &= (1u << nvalid) - 1u;
             hits[j] = hj;

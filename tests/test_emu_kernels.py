@@ -115,20 +115,26 @@ def test_pfb_tile_kernel(emu, oracle_mod, nt, name):
     x = np.ascontiguousarray(cap.iq)[: 24 * 8192 - 24 * 40]          # ragged: n_out = 8152, last tile partial
     n_in = len(x)
     n_out = n_in // 24
-    tiles = (n_out + 127) // 128
-    wpp = 1 + tiles + 16
+    stride = emu.emu_pfb_tile_stride()
+    tiles = (n_out + stride - 1) // stride
+    wpp = 1 + (n_out + 127) // 128 + 16
     bits = np.zeros((40, 4, wpp), dtype=np.uint32)
-    q8 = np.zeros((40, tiles * 128, 2), dtype=np.int8)
-    raw = np.zeros((40, tiles * 128), dtype=np.complex64)
+    q8 = np.zeros((40, tiles * stride + 1, 2), dtype=np.int8)
+    raw = np.zeros((40, tiles * stride + 1), dtype=np.complex64)
     xf = x.view(np.float32)
     for t in range(tiles):
-        w = np.zeros(160, dtype=np.uint32)
+        w = np.zeros(320, dtype=np.uint32)
         q = np.zeros((40, 128, 2), dtype=np.int8)
         r = np.zeros((40, 128), dtype=np.complex64)
-        emu.emu_pfb_ble_tile(nt, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), P(hf), ctypes.c_float(100.0), P(w), P(q), P(r))
-        bits[:, :, 1 + t] = w.reshape(40, 4)
-        q8[:, t * 128:(t + 1) * 128] = q
-        raw[:, t * 128:(t + 1) * 128] = r
+        wb = ctypes.c_int(0)
+        emu.emu_pfb_ble_tile(nt, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), ctypes.c_float(100.0), P(w), ctypes.byref(wb), P(q), P(r))
+        w = w.reshape(40, 4, 2)
+        bits[:, :, wb.value] |= w[:, :, 0]
+        bits[:, :, wb.value + 1] |= w[:, :, 1]
+        if t:                                                        # sample 127 of a tile == sample 0 of the next
+            assert np.array_equal(q8[:, t * stride], q[:, 0])
+        q8[:, t * stride:t * stride + 128] = q
+        raw[:, t * stride:t * stride + 128] = r
     assert not q8[:, n_out:].any()                                   # beyond the capture: zeros
     q8, raw = q8[:, :n_out], raw[:, :n_out]
     yd = oracle_mod.pfb(x, h, [chanplan.ble_channel_bin(c) for c in range(40)])
@@ -161,3 +167,41 @@ def test_zigbee_cores(emu, oracle_mod):
     want = oracle_mod.zb_receive(cap.iq, 11, segment=65536, prehalo=4096)
     assert len(want) > 5
     assert_frames_equal(out[:k], want, what="zigbee chains")
+
+
+@pytest.mark.parametrize("nt,name", [(16, "ZB_384"), (32, "ZB_768")])
+def test_pfb_zb_tile_kernel(emu, oracle_mod, nt, name):
+    """Wideband Zigbee front end: channel streams within tolerance of the CPU channelizer statement;
+    discriminator bit-identical to the oracle's quadrature demod of the kernel's own (rotated) streams."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from gen_tables import PFB_DESIGNS, kaiser_lowpass
+    h = kaiser_lowpass(*PFB_DESIGNS[name])
+    hf = h.astype(np.float32)
+    rho = np.array([hf[r + 24 * d] for r in range(24) for d in range(nt)], dtype=np.float32)
+    cap = synth.wideband_capture(seconds=0.0041, kind="zigbee", seed=3000, esn0_db=20.0, gap=(300, 2500))
+    x = np.ascontiguousarray(cap.iq)[: 24 * 16000]
+    n_in, n_out = len(x), len(x) // 24
+    stride = emu.emu_pfb_tile_stride()
+    tiles = max(1, (n_out - 1 + stride - 1) // stride)
+    f = np.zeros((16, tiles * stride + 1), dtype=np.float32)
+    y = np.zeros((16, tiles * stride + 1), dtype=np.complex64)
+    xf = x.view(np.float32)
+    for t in range(tiles):
+        fo = np.zeros((16, stride), dtype=np.float32)
+        yo = np.zeros((16, 128), dtype=np.complex64)
+        emu.emu_pfb_zb_tile(nt, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), P(fo), P(yo))
+        f[:, t * stride + 1:(t + 1) * stride + 1] = fo
+        y[:, t * stride:t * stride + 128] = yo
+    f, y = f[:, :n_out], y[:, :n_out]
+    bins = [emu.emu_zb_bin_of_slot(c) for c in range(16)]
+    assert bins == [chanplan.zigbee_channel_bin(11 + c) for c in range(16)]
+    yd = oracle_mod.pfb(x, h, bins)
+    assert np.abs(y - yd).max() / np.sqrt(np.mean(np.abs(yd) ** 2)) < 1e-4
+    ok = tot = 0
+    for c in range(16):
+        assert np.array_equal(f[c], oracle_mod.zb_quad_demod(y[c])), f"discriminator of slot {c}"
+        fr = oracle_mod.zb_receive_z(oracle_mod.zb_dc_remove(f[c]), 11 + c)
+        truth = {bytes(t.data) for t in cap.truth if t.channel == 11 + c and t.start + 4300 < n_out}
+        ok += len(truth & {bytes(q["bytes"][:q["len"]]) for q in fr if q["crc_ok"]})
+        tot += len(truth)
+    assert tot >= 8 and ok >= 0.9 * tot, (ok, tot)

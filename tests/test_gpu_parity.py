@@ -245,3 +245,80 @@ def test_zb_nb_full_size_config2(Engine, oracle_mod):
     assert_frames_equal(got, want, what="config 2")
     assert [bytes(f["bytes"][:f["len"]]) for f in got] == [bytes(t.data) for t in cap.truth]
     assert got["crc_ok"].all()
+
+
+# ------------------------------------------------------------------------------------ Zigbee wideband / mixed
+@pytest.mark.parametrize("taps", [384, 768])
+def test_zb_wb16_stagewise_parity(Engine, oracle_mod, taps):
+    cap = synth.wideband_capture(seconds=0.0125, kind="zigbee", seed=3000, esn0_db=20.0, gap=(400, 5000))
+    x = cap.iq[: len(cap.iq) - 24 * 33]
+    h = _abi.pfb_prototype(_abi.MODE_ZB_WB16, taps)
+    with Engine("zb_wb16", max_samples=len(x), pfb_taps=taps, keep_streams=True, zb_segment=16384, zb_prehalo=2048) as e:
+        got = e.run(x)
+        y = e.debug_stage(_abi.STAGE_CHAN_CF32)[0]
+        f = e.debug_stage(_abi.STAGE_ZB_F)[0]
+        z = e.debug_stage(_abi.STAGE_ZB_DISC)[0]
+    yd = oracle_mod.pfb(x, h, [chanplan.zigbee_channel_bin(c) for c in range(11, 27)])
+    assert np.abs(y - yd).max() / np.sqrt(np.mean(np.abs(yd) ** 2)) < CHAN_TOL
+    want = []
+    for c in range(16):
+        fo = oracle_mod.zb_quad_demod(y[c])
+        assert np.array_equal(f[c], fo), f"discriminator, channel {11 + c}"
+        zo = oracle_mod.zb_dc_remove(fo)
+        assert np.array_equal(z[c], zo), f"DC removal, channel {11 + c}"
+        want.append(oracle_mod.zb_receive_z(zo, 11 + c, segment=16384, prehalo=2048))
+    want = np.concatenate(want)
+    assert len(want) > 30
+    assert_frames_equal(got, want, what=f"zigbee wideband {taps} taps")
+    truth = {(t.channel, bytes(t.data)) for t in cap.truth if t.start + 4400 < len(x) // 24}
+    dec = {(int(q["channel"]), bytes(q["bytes"][:q["len"]])) for q in got if q["crc_ok"]}
+    assert len(truth & dec) >= 0.95 * len(truth)
+    with Engine("zb_wb16", max_samples=len(x), pfb_taps=taps, zb_segment=16384, zb_prehalo=2048) as e:
+        assert_frames_equal(e.run(x), want, what="production kernel")
+
+
+def test_mixed_wb56_equals_separate_engines(Engine):
+    cap = synth.wideband_capture(seconds=0.0125, kind="mixed", seed=5000, esn0_db=25.0, gap=(400, 5000))
+    x = cap.iq
+    with Engine("ble_wb40", max_samples=len(x)) as e:
+        a = e.run(x)
+    with Engine("zb_wb16", max_samples=len(x)) as e:
+        b = e.run(x)
+    with Engine("mixed_wb56", max_samples=len(x)) as e:
+        m = e.run(x)
+    assert len(a) > 50 and len(b) > 10
+    assert_frames_equal(m, np.concatenate([a, b]), what="mixed = BLE frames then Zigbee frames")
+
+
+def test_two_batches_in_flight(Engine):
+    caps = [synth.ble_capture(n=200_000, channel=37, seed=700 + i, esn0_db=30, gap=(100, 2000)).iq for i in range(3)]
+    with Engine("ble_nb", channel=37, max_samples=200_000) as e:
+        ref = [e.run(c) for c in caps]
+        e.process(caps[0])
+        e.process(caps[1])
+        with pytest.raises(_abi.SnrxError):
+            e.process(caps[2])                       # a third queued batch is refused, loudly
+        r0 = e.poll()
+        e.process(caps[2])
+        r1 = e.poll()
+        r2 = e.poll()
+        with pytest.raises(_abi.SnrxError):
+            e.poll()                                 # nothing queued
+    for got, want in zip((r0, r1, r2), ref):
+        assert len(want) > 5
+        assert_frames_equal(got, want, what="pipelined batches")
+
+
+def test_ble_wb40_batch_of_captures(Engine):
+    caps = [synth.wideband_capture(seconds=0.0045, kind="ble", seed=4300 + 50 * i, gap=(200, 2500)).iq for i in range(3)]
+    with Engine("ble_wb40", max_samples=len(caps[0]), max_captures=3) as e:
+        single = []
+        for i, c in enumerate(caps):
+            f = e.run(c)
+            f["capture_id"] = i
+            single.append(f)
+        got = e.run(np.stack(caps))
+    want = np.concatenate(single)
+    assert len(want) > 300
+    assert_frames_equal(got, want, what="batch of wideband captures")
+    assert np.array_equal(got["capture_id"], want["capture_id"])
