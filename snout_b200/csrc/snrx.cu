@@ -36,10 +36,13 @@ struct snrx_handle {
     cudaStream_t stream = nullptr;       // compute stream (own or caller supplied)
     cudaStream_t own_stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D staging
+    cudaStream_t export_stream = nullptr; // frames device -> pinned host, overlapped with the next batch
     // Output ring: snrx_process(i+1) may be queued before snrx_poll(i), so the GPU never idles between
     // batches.  Frames are stored by the kernels straight into host-mapped pinned memory (zero copy).
     struct OutSlot {
-        snrx_frame_t* frames = nullptr;     // pinned + mapped, frame_cap records
+        snrx_frame_t* frames = nullptr;     // pinned + mapped host copy, frame_cap records
+        snrx_frame_t* d_frames = nullptr;   // device copy the kernels write
+        cudaEvent_t ev_compute = nullptr, ev_exported = nullptr;
         uint32_t* totals = nullptr;         // pinned: [0] BLE frames [1] candidates [2] Zigbee frames
         cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_done = nullptr;
         bool pending = false, done = false;
@@ -173,6 +176,19 @@ int grid_for(snrx_handle* h, uint64_t items, int per_block, int blocks_per_sm) {
 
 }  // namespace
 
+// device frame list -> host-mapped pinned memory, fully coalesced 16-byte stores; also publishes the totals
+__global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __restrict__ src, const uint32_t* __restrict__ totals_dev,
+                                                       snrx_frame_t* __restrict__ dst_host, uint32_t* __restrict__ totals_host,
+                                                       uint32_t frame_cap) {
+    uint32_t n = totals_dev[0] + totals_dev[2];
+    if (n > frame_cap) n = frame_cap;
+    const size_t n16 = (size_t)n * (sizeof(snrx_frame_t) / 16);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst_host);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+    if (blockIdx.x == 0 && threadIdx.x < 8) totals_host[threadIdx.x] = totals_dev[threadIdx.x];
+}
+
 extern "C" {
 
 int snrx_abi_version(void) { return SNRX_ABI_VERSION; }
@@ -226,12 +242,15 @@ void snrx_destroy(snrx_t* h) {
     zb_free(h->zb);
     for (auto& sl : h->slot) {
         if (sl.frames) cudaFreeHost(sl.frames);
+        if (sl.d_frames) cudaFree(sl.d_frames);
+        for (cudaEvent_t e : {sl.ev_compute, sl.ev_exported}) if (e) cudaEventDestroy(e);
         if (sl.totals) cudaFreeHost(sl.totals);
         for (cudaEvent_t e : {sl.ev_start, sl.ev_front0, sl.ev_front, sl.ev_done}) if (e) cudaEventDestroy(e);
     }
     for (cudaEvent_t e : h->ev_chunks) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->export_stream) cudaStreamDestroy(h->export_stream);
     delete h;
 }
 
@@ -257,6 +276,7 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         if (prop.major < 10) return fail(h, SNRX_ENODEV, "libsnoutrx is built for sm_100a (B200) only");
         CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->export_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
 
         snrx_config_t& c = h->cfg;
@@ -289,14 +309,17 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         h->frame_cap = c.max_frames;
         h->cand_cap = std::max<uint32_t>(1u << 16, 4 * c.max_frames);
 
-        CKD(dev_alloc(h, &h->d_totals, 8));
+        CKD(dev_alloc(h, &h->d_totals, 24));
         for (auto& sl : h->slot) {
             CK(cudaHostAlloc((void**)&sl.frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap, cudaHostAllocMapped));
-            CK(cudaHostAlloc((void**)&sl.totals, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+            CK(cudaHostAlloc((void**)&sl.totals, 8 * sizeof(uint32_t), cudaHostAllocMapped));
             CK(cudaEventCreate(&sl.ev_start));
             CK(cudaEventCreate(&sl.ev_front0));
             CK(cudaEventCreate(&sl.ev_front));
             CK(cudaEventCreate(&sl.ev_done));
+            CK(cudaEventCreateWithFlags(&sl.ev_compute, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.ev_exported, cudaEventDisableTiming));
+            CK(cudaMalloc((void**)&sl.d_frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap));
         }
 
         if (h->has_ble) {
@@ -359,7 +382,7 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
                 if (r != SNRX_OK) return r;
             }
         }
-        CK(cudaMemset(h->d_totals, 0, 8 * sizeof(uint32_t)));
+        CK(cudaMemset(h->d_totals, 0, 24 * sizeof(uint32_t)));
         return SNRX_OK;
     };
     int r = body();
@@ -451,6 +474,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     snrx_handle::OutSlot& sl = h->slot[h->seq_process & 1];
     if (sl.pending) return fail(h, SNRX_ESTATE, "two batches already queued: snrx_poll the oldest first");
     h->launches = 0;
+    // this slot's previous export (two batches ago) has been polled, hence finished: its buffers are free
 
     const uint32_t n_out = (uint32_t)(n_samples / h->decim);
     uint32_t pre_out = 0, body_out = n_out, first_window = 0, first_capture = 0;
@@ -557,7 +581,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
                                                         nullptr, 0, h->d_ble_channels, h->cand_cap);
         h->launches += 3 + exclusive_scan(h->d_wcounts, w_items, h->d_woffsets, h->d_scratch, h->stream);
         k_ble_resolve<true><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, h->d_wcounts, h->d_woffsets,
-                                                       sl.frames, h->frame_cap, h->d_ble_channels, h->cand_cap);
+                                                       sl.d_frames, h->frame_cap, h->d_ble_channels, h->cand_cap);
         h->launches += 1;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h->d_totals + 0, h->d_woffsets + w_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
@@ -567,13 +591,21 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     }
     if (h->has_zb) {
         int r = zb_process(h->zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_window,
-                           first_capture, sl.frames, h->frame_cap, h->d_totals, h->has_ble, h->stream, h->sm_count,
+                           first_capture, sl.d_frames, h->frame_cap, h->d_totals, h->has_ble, h->stream, h->sm_count,
                            h->launches, h->err);
         if (r != SNRX_OK) return r;
         if (!h->has_ble) { CK(cudaEventRecord(sl.ev_front0, h->stream)); CK(cudaEventRecord(sl.ev_front, h->stream)); }
     }
-    CK(cudaMemcpyAsync(sl.totals, h->d_totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaEventRecord(sl.ev_done, h->stream));
+    // totals of this batch are snapshotted so that the next batch may reset d_totals while the export runs
+    CK(cudaMemcpyAsync(h->d_totals + 8 + 8 * (h->seq_process & 1), h->d_totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaEventRecord(sl.ev_compute, h->stream));
+    // export: device frame list -> pinned host memory on a side stream (overlaps the next batch's front end)
+    CK(cudaStreamWaitEvent(h->export_stream, sl.ev_compute, 0));
+    k_export_frames<<<h->sm_count * 2, 256, 0, h->export_stream>>>(sl.d_frames, h->d_totals + 8 + 8 * (h->seq_process & 1), sl.frames,
+                                                                 sl.totals, h->frame_cap);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(sl.ev_done, h->export_stream));
     sl.pending = true; sl.done = false;
     sl.caps = n_captures; sl.n_in = n_samples; sl.n_out = n_out; sl.launches = h->launches;
     h->seq_process++;
@@ -643,7 +675,7 @@ int snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev) {
     if (!h || !h->batch_valid) return SNRX_ESTATE;
     snrx_handle::OutSlot& sl = h->slot[(h->seq_process + 1) & 1];      // slot of the most recent snrx_process
     void* dp = nullptr;
-    CK(cudaHostGetDevicePointer(&dp, sl.frames, 0));
+    dp = sl.d_frames;
     if (frames_dev) *frames_dev = dp;
     if (count_dev) *count_dev = h->d_totals;
     return SNRX_OK;

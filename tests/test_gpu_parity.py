@@ -286,7 +286,7 @@ def test_mixed_wb56_equals_separate_engines(Engine):
         b = e.run(x)
     with Engine("mixed_wb56", max_samples=len(x)) as e:
         m = e.run(x)
-    assert len(a) > 50 and len(b) > 10
+    assert len(a) > 50 and len(b) > 4
     assert_frames_equal(m, np.concatenate([a, b]), what="mixed = BLE frames then Zigbee frames")
 
 
