@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define SNRX_ABI_VERSION 1
+#define SNRX_ABI_VERSION 2
 
 /* protocol ids = scapy-radio GnuradioPacket.proto values
  * (scapy-radio/scapy/scapy/layers/gnuradio.py:19-25) */
@@ -118,6 +118,9 @@ typedef struct snrx_config {
     uint32_t zb_prehalo;     /* Zigbee: chain warm-up, channel-rate samples (0 = default 4096)    */
     uint32_t pfb_taps;       /* WB: prototype length, 384 or 768 (0 = default 384)         */
     uint32_t flags;          /* SNRX_F_*                                                   */
+    uint32_t access_mask;    /* BLE `-m`: access-address bits that take part in the match
+                                (0 = default 0xFFFFFFFF, btle_rx.c:1203,2301)                */
+    uint32_t reserved;       /* must be 0                                                  */
 } snrx_config_t;
 
 #define SNRX_F_KEEP_STREAMS 1u  /* also store channel streams so snrx_debug_stage can return them */
@@ -155,13 +158,21 @@ void snrx_destroy(snrx_t* h);
 /* Time shard of a longer capture (multi-GPU / streaming): the buffer handed to snrx_process
  * starts `pre_samples` before the shard body (read-only halo: channelizer history, Zigbee
  * warm-up) and may extend past it (post halo, so frames that start in the body can be
- * decoded completely).  Only frames anchored inside the body are reported. */
+ * decoded completely).  Only frames anchored inside the body are reported, with the
+ * sample_index / window they have in the whole capture, so the union over shards equals
+ * the result of one call on the whole capture, bit for bit.  Requirements (channel rate):
+ *   BLE    pre halo multiple of 128 (>= 128 unless the shard starts the capture), post halo
+ *          >= 2048, body on the 8192-sample window grid;
+ *   Zigbee pre halo multiple of 4096 and >= 36864 + zb_prehalo unless the shard starts the
+ *          capture (the DC tracker remembers 8 blocks of 4096 and the first block of a buffer
+ *          starts without discriminator / channelizer history), post halo >= 16448, body on
+ *          the zb_segment grid, zb_segment a multiple of 8192. */
 typedef struct snrx_shard {
-    uint64_t pre_samples;      /* input-rate samples of pre halo; multiple of 128 channel samples */
-    uint64_t body_samples;     /* input-rate samples of the body (0 = rest of the buffer)         */
-    uint32_t first_window;     /* index inside the capture of the body's first BLE window /
-                                  Zigbee segment (the body starts on that grid)                   */
-    uint32_t first_capture_id; /* capture_id reported for capture 0 of the batch                  */
+    uint64_t pre_samples;      /* input-rate samples of pre halo                                   */
+    uint64_t body_samples;     /* input-rate samples of the body (0 = rest of the buffer)          */
+    uint32_t first_window;     /* index inside the capture of the body's first 8192-sample window
+                                  (channel rate); Zigbee segment = first_window * 8192 / zb_segment */
+    uint32_t first_capture_id; /* capture_id reported for capture 0 of the batch                   */
 } snrx_shard_t;
 
 /* Run the receive path over a batch of `n_captures` captures, each `n_samples`

@@ -115,6 +115,7 @@ def ble_decode(iq_int8, channel: int, aa: int = 0x8E89BED6, crc_init: int = 0x55
                                          c_int64(n_windows), _ptr(out), c_int(cap))
     elif impl == "reference":
         lib = _lib("btle_ref")
+        lib.btle_ref_set_mask(c_uint32(aa_mask))
         n = lib.btle_ref_windows(_ptr(q), c_int64(q.shape[0]), c_int(channel), c_uint32(aa),
                                  c_uint32(crc_init), _ptr(out), c_int(cap))
     else:

@@ -33,6 +33,10 @@ static IQ_TYPE* padded_copy(const int8_t* iq, int64_t n_iq, int64_t n_windows) {
     return buf;
 }
 
+/* access-address mask of the next calls (-m option, btle_rx.c:2301); default all ones */
+static uint32_t ref_mask = 0xFFFFFFFFu;
+void btle_ref_set_mask(uint32_t m) { ref_mask = m; }
+
 int64_t btle_ref_num_windows(int64_t n_iq) {
     return (n_iq + SNRX_BLE_WINDOW - 1) / SNRX_BLE_WINDOW;
 }
@@ -106,7 +110,7 @@ int btle_ref_windows(const int8_t* iq, int64_t n_iq, int channel, uint32_t aa,
     int64_t nw = btle_ref_num_windows(n_iq);
     IQ_TYPE* buf = padded_copy(iq, n_iq, nw);
     if (!buf) return -1;
-    uint32_to_bit_array(0xFFFFFFFFu, access_bit_mask);               /* btle_rx.c:2301, default mask */
+    uint32_to_bit_array(ref_mask, access_bit_mask);                  /* btle_rx.c:2301 */
     uint32_t crc_int = crc_init_reorder(crc_init_cmdline);           /* btle_rx.c:2335 */
     int n = 0;
     for (int64_t w = 0; w < nw; w++)
@@ -121,7 +125,7 @@ int btle_ref_receiver_print(const int8_t* iq, int64_t n_iq, int channel, uint32_
     int64_t nw = btle_ref_num_windows(n_iq);
     IQ_TYPE* buf = padded_copy(iq, n_iq, nw);
     if (!buf) return -1;
-    uint32_to_bit_array(0xFFFFFFFFu, access_bit_mask);
+    uint32_to_bit_array(ref_mask, access_bit_mask);
     uint32_t crc_int = crc_init_reorder(crc_init_cmdline);
     for (int64_t w = 0; w < nw; w++) {
         receiver(buf + REF_LEAD + w * (int64_t)REF_HALF, REF_SPAN, channel, aa, crc_int, 0, 0);
@@ -138,7 +142,7 @@ double btle_ref_time(const int8_t* iq, int64_t n_iq, int channel, uint32_t aa,
     int64_t nw = btle_ref_num_windows(n_iq);
     IQ_TYPE* buf = padded_copy(iq, n_iq, nw);
     if (!buf) return -1.0;
-    uint32_to_bit_array(0xFFFFFFFFu, access_bit_mask);
+    uint32_to_bit_array(ref_mask, access_bit_mask);
     uint32_t crc_int = crc_init_reorder(crc_init_cmdline);
     static snrx_frame_t scratch[4];
     struct timespec t0, t1;

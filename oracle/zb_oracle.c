@@ -25,8 +25,10 @@
  * Two deliberate restatement choices, part of the parity contract:
  *  - the single-pole DC tracker y[n] = a f[n] + (1-a) y[n-1] (double state) is
  *    evaluated in blocks of SNRX_IIR_BLOCK samples: inside a block from a zero
- *    state, plus (1-a)^(i+1) times the carried state of the previous block.
- *    Algebraically the same recurrence; it lets the GPU run blocks in parallel.
+ *    state, plus (1-a)^(i+1) times a carried state folded from the 8 preceding
+ *    blocks (memory truncated after 32768..36864 samples = 5.2 time constants,
+ *    residual weight e^-5.2 = 0.5 %).  Blocks run in parallel on the GPU, and the
+ *    output no longer depends on where a time shard of a long capture starts.
  *  - the 8-tap interpolator dot product is summed as a balanced tree.
  */
 #include <math.h>
@@ -79,15 +81,24 @@ void zb_oracle_quad_demod(const float* iq, int64_t n, float* f) {
     }
 }
 
-/* z[n] = f[n] - (float) y[n], y the blocked single-pole tracker described above. */
+/* z[n] = f[n] - (float) y[n], y the blocked single-pole tracker described above.
+ * The state carried into block b is folded from the SNRX_IIR_MEMORY_BLOCKS preceding blocks only,
+ * so z[n] depends on f[4096*(b-8) .. n] and nothing older: any buffer that starts on the
+ * absolute 4096-sample grid reproduces it exactly once 8 blocks have gone by. */
 void zb_oracle_dc_remove(const float* f, int64_t n, float* z) {
     const double a = SNRX_IIR_ALPHA, b = SNRX_IIR_BETA;
     static double pw[SNRX_IIR_BLOCK];
     double p = 1.0;
     for (int i = 0; i < SNRX_IIR_BLOCK; i++) { p = p * b; pw[i] = p; }
-    double carry = 0.0;
+    double ends[SNRX_IIR_MEMORY_BLOCKS];      /* block-local end values of the preceding blocks, oldest first */
+    int n_ends = 0;
     for (int64_t n0 = 0; n0 < n; n0 += SNRX_IIR_BLOCK) {
         int64_t len = (n - n0 < SNRX_IIR_BLOCK) ? n - n0 : SNRX_IIR_BLOCK;
+        double carry = 0.0;
+        for (int j = 0; j < n_ends; j++) {
+            double t = pw[SNRX_IIR_BLOCK - 1] * carry;
+            carry = ends[j] + t;
+        }
         double l = 0.0;
         for (int64_t i = 0; i < len; i++) {
             double t1 = a * (double)f[n0 + i];
@@ -96,7 +107,11 @@ void zb_oracle_dc_remove(const float* f, int64_t n, float* z) {
             double y = l + pw[i] * carry;
             z[n0 + i] = f[n0 + i] - (float)y;
         }
-        carry = l + pw[len - 1] * carry;
+        if (n_ends == SNRX_IIR_MEMORY_BLOCKS) {
+            for (int j = 1; j < n_ends; j++) ends[j - 1] = ends[j];
+            n_ends--;
+        }
+        ends[n_ends++] = l;
     }
 }
 

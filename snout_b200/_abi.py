@@ -14,7 +14,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsnoutrx.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MODE_BLE_NB, MODE_ZB_NB, MODE_ZB_WB16, MODE_BLE_WB40, MODE_MIXED_WB56 = 0, 1, 2, 3, 4
 F_KEEP_STREAMS = 1
@@ -35,6 +35,7 @@ class Config(Structure):
         ("access_addr", c_uint32), ("crc_init", c_uint32), ("zb_threshold", c_int32), ("quant_scale", c_float),
         ("max_samples", c_uint64), ("max_captures", c_uint32), ("max_frames", c_uint32),
         ("zb_segment", c_uint32), ("zb_prehalo", c_uint32), ("pfb_taps", c_uint32), ("flags", c_uint32),
+        ("access_mask", c_uint32), ("reserved", c_uint32),
     ]
 
 

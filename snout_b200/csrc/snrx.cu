@@ -485,6 +485,17 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         first_window = shard->first_window;
         first_capture = shard->first_capture_id;
         if ((uint64_t)pre_out + body_out > n_out) return fail(h, SNRX_EINVAL, "shard body exceeds the buffer");
+        if (h->has_zb) {
+            // the DC tracker is defined on the absolute 4096-sample grid with a memory of 8 blocks, the chains on
+            // the absolute segment grid: a shard reproduces the whole-capture result only from there on
+            const uint32_t seg = h->cfg.zb_segment;
+            if (seg % kWindow) return fail(h, SNRX_EINVAL, "Zigbee shards need zb_segment to be a multiple of 8192");
+            if (pre_out % SNRX_IIR_BLOCK) return fail(h, SNRX_EINVAL, "Zigbee shards: pre_samples must be a multiple of 4096 channel samples");
+            if (((uint64_t)first_window * kWindow) % seg) return fail(h, SNRX_EINVAL, "Zigbee shards: the body must start on the segment grid");
+            const uint32_t need = (SNRX_IIR_MEMORY_BLOCKS + 1) * SNRX_IIR_BLOCK + h->cfg.zb_prehalo;   // +1: the first block of a
+            // buffer holds a discriminator sample without history (and the channelizer start-up), so its end value is off
+            if (first_window != 0 && pre_out < need) return fail(h, SNRX_EINVAL, "Zigbee shards: pre halo shorter than 36864 + zb_prehalo channel samples");
+        }
     }
 
     CK(cudaEventRecord(sl.ev_start, h->stream));
@@ -557,7 +568,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
 
         BleParams p{};
         p.aa = h->cfg.access_addr;
-        p.aa_mask = 0xFFFFFFFFu;
+        p.aa_mask = h->cfg.access_mask ? h->cfg.access_mask : 0xFFFFFFFFu;
         p.crc_init_internal = crc_init_internal(h->cfg.crc_init);
         p.n_out = (int32_t)n_out;
         p.m_origin = (int32_t)pre_out;
@@ -590,7 +601,8 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         h->b_w_items = w_items;
     }
     if (h->has_zb) {
-        int r = zb_process(h->zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_window,
+        const uint32_t first_segment = (uint32_t)(((uint64_t)first_window * kWindow) / h->cfg.zb_segment);
+        int r = zb_process(h->zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_segment,
                            first_capture, sl.d_frames, h->frame_cap, h->d_totals, h->has_ble, h->stream, h->sm_count,
                            h->launches, h->err);
         if (r != SNRX_OK) return r;

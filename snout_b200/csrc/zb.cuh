@@ -13,7 +13,8 @@
 // Parallel decomposition (DESIGN.md "Zigbee"):
 //   k_zb_quad      one thread per sample: table atan2 of x[n] conj(x[n-1])
 //   k_zb_iir_*     the single-pole DC tracker evaluated in blocks of 4096 samples (block-local
-//                  recurrence + carried state), so blocks run in parallel
+//                  recurrence + a carried state folded from the 8 preceding blocks), so blocks run
+//                  in parallel and the result does not depend on where a time shard starts
 //   k_zb_chain     one thread per (capture, channel, segment): Mueller-Mueller clock recovery feeding
 //                  the packet-sink state machine; segments overlap by a warm-up pre-halo and a
 //                  longest-frame post-halo, a frame belongs to the segment holding its SFD position
@@ -182,6 +183,14 @@ SNRX_HD uint16_t zb_fcs16(const uint8_t* d, int n) {              // Dot15d4FCS.
     return (uint16_t)crc;
 }
 
+// state carried into block b of the DC tracker: fold of the (at most) SNRX_IIR_MEMORY_BLOCKS preceding
+// block-local end values, oldest first; decay = (1-alpha)^4096
+SNRX_HD double zb_iir_fold(const double* ends, int b, double decay) {
+    double carry = 0.0;
+    for (int j = (b > SNRX_IIR_MEMORY_BLOCKS ? b - SNRX_IIR_MEMORY_BLOCKS : 0); j < b; j++) carry = d_add(ends[j], d_mul(decay, carry));
+    return carry;
+}
+
 struct ZbMm { float mu, omega, last; int64_t ii; };
 
 SNRX_HD float zb_mm_step(ZbMm& st, const float* z, const float* taps /*[129][8]*/) {
@@ -317,14 +326,15 @@ __global__ void __launch_bounds__(128) k_zb_iir_sum(ZbIirArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(64) k_zb_iir_carry(ZbIirArgs a) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= a.n_streams) return;
-    double carry = 0.0;
-    for (int b = 0; b < a.n_blocks; b++) {
-        a.carry_in[(size_t)s * a.n_blocks + b] = carry;
-        const int len = min(SNRX_IIR_BLOCK, a.n - b * SNRX_IIR_BLOCK);
-        carry = d_add(a.block_end[(size_t)s * a.n_blocks + b], d_mul(a.pw[len - 1], carry));
+// carried state entering block b: folded from the SNRX_IIR_MEMORY_BLOCKS preceding blocks (all full
+// length), oldest first -- one thread per (stream, block), no serial pass over the stream
+__global__ void __launch_bounds__(128) k_zb_iir_carry(ZbIirArgs a) {
+    const uint32_t total = a.n_streams * (uint32_t)a.n_blocks;
+    const double decay = a.pw[SNRX_IIR_BLOCK - 1];
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const uint32_t s = idx / (uint32_t)a.n_blocks;
+        const int b = (int)(idx % (uint32_t)a.n_blocks);
+        a.carry_in[idx] = zb_iir_fold(a.block_end + (size_t)s * a.n_blocks, b, decay);
     }
 }
 
@@ -499,7 +509,7 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     ia.block_end = s.d_block_end; ia.carry_in = s.d_carry; ia.pw = s.d_pw;
     const uint32_t nb_total = streams * (uint32_t)ia.n_blocks;
     k_zb_iir_sum<<<(nb_total + 127) / 128, 128, 0, st>>>(ia);
-    k_zb_iir_carry<<<(streams + 63) / 64, 64, 0, st>>>(ia);
+    k_zb_iir_carry<<<(nb_total + 127) / 128, 128, 0, st>>>(ia);
     k_zb_dc<<<(nb_total + 127) / 128, 128, 0, st>>>(ia);
     launches += 3;
 

@@ -38,7 +38,7 @@ class RxEngine:
                  max_samples: int = 0, max_captures: int = 1, max_frames: int = 0,
                  access_addr: int = chanplan.BLE_ADV_AA, crc_init: int = chanplan.BLE_ADV_CRC_INIT,
                  zb_threshold: int = 10, quant_scale: float = 0.0, zb_segment: int = 0, zb_prehalo: int = 0,
-                 pfb_taps: int = 0, keep_streams: bool = False):
+                 pfb_taps: int = 0, keep_streams: bool = False, access_mask: int = 0):
         self.lib = _abi.load()
         self.mode = MODES[mode] if isinstance(mode, str) else int(mode)
         if channel is None:
@@ -59,6 +59,7 @@ class RxEngine:
         cfg.zb_prehalo = zb_prehalo
         cfg.pfb_taps = pfb_taps
         cfg.flags = _abi.F_KEEP_STREAMS if keep_streams else 0
+        cfg.access_mask = access_mask & 0xFFFFFFFF
         self.cfg = cfg
         self.handle = c_void_p()
         rc = self.lib.snrx_create(byref(self.handle), byref(cfg))
@@ -165,6 +166,10 @@ class RxEngine:
 
     def run(self, iq, **kw) -> np.ndarray:
         return self.process(iq, **kw).poll()
+
+    def alloc_host(self, n_samples: int) -> _abi.PinnedBuffer:
+        """Page-locked complex64 staging buffer (snrx_host_alloc) for full-rate host->device copies."""
+        return _abi.PinnedBuffer(int(n_samples), np.complex64)
 
     def stats(self) -> dict:
         s = Stats()

@@ -263,12 +263,7 @@ void emu_zb_dc(const float* f, int64_t n, float* z) {
         for (int i = 0; i < len; i++) l = d_add(d_mul(SNRX_IIR_ALPHA, (double)f[(size_t)b * SNRX_IIR_BLOCK + i]), d_mul(SNRX_IIR_BETA, l));
         block_end[b] = l;
     }
-    double carry = 0.0;                                 // k_zb_iir_carry
-    for (int b = 0; b < nb; b++) {
-        carry_in[b] = carry;
-        const int len = (int)std::min<int64_t>(SNRX_IIR_BLOCK, n - (int64_t)b * SNRX_IIR_BLOCK);
-        carry = d_add(block_end[b], d_mul(pw[len - 1], carry));
-    }
+    for (int b = 0; b < nb; b++) carry_in[b] = zb_iir_fold(block_end.data(), b, pw[SNRX_IIR_BLOCK - 1]);   // k_zb_iir_carry
     for (int b = 0; b < nb; b++) {                      // k_zb_dc
         const int len = (int)std::min<int64_t>(SNRX_IIR_BLOCK, n - (int64_t)b * SNRX_IIR_BLOCK);
         double l = 0.0;

@@ -15,6 +15,7 @@ the CUDA path on machines where /root/reference does not exist (the GPU box).
   btle_synth_ref.npz        reference frames + receiver() stdout on seeded synthetic captures
   btle_boundary_ref.npz     reference frames for the golden capture delayed by 403..413 samples
                             (window-boundary duplicate rule)
+  btle_mask_ref.npz         reference frames under partial access-address masks (-m)
   btle_tables_ref.npz       scramble_table[40][42], crc_table[256], crc_init_reorder(0x555555)
   zb_sink_ref.npz           CHIP_MAPPING[16] and, for seeded synthetic captures, the frames the
                             reference packet sink publishes when fed the oracle's soft chips
@@ -43,6 +44,29 @@ def frames_to_dict(fr):
 
 def main():
     oracle.build(ref=True)
+    only = sys.argv[1] if len(sys.argv) > 1 else "all"      # all | ble | zb   (ble fixtures embed wall-clock text)
+    if only in ("all", "ble"):
+        make_ble()
+    if only in ("all", "zb"):
+        make_zb_and_kats()
+    if only in ("all", "mask"):
+        make_mask()
+    print("golden fixtures written to", HERE)
+    for f in sorted(os.listdir(HERE)):
+        print(f"  {f:32s} {os.path.getsize(os.path.join(HERE, f)):9d} bytes")
+
+
+def make_mask():
+    """btle_mask_ref.npz: reference frames with a partial access-address mask (-m, btle_rx.c:1395-1401, 2301)."""
+    cap = synth.ble_capture(n=400_000, channel=37, seed=12, esn0_db=18, gap=(100, 1500))
+    q = oracle.ble_quantize(cap.iq, 128.0)
+    out = {"params": np.array([12, 18.0, 37, 400_000])}
+    for mask in (0xFFFFFF00, 0x00FFFFFF, 0xFFFF0000, 0xFFFFFFFE):
+        out[f"frames_{mask:08x}"] = oracle.ble_decode(q, 37, impl="reference", aa_mask=mask)
+    np.savez_compressed(f"{HERE}/btle_mask_ref.npz", **out)
+
+
+def make_ble():
     # ---- BLE golden capture
     txt = open(f"{REF}/vendor/BTLE/matlab/sample_iq_4msps.txt").read().replace(",", " ").split()
     g = np.array(txt, dtype=np.int64).astype(np.int8).reshape(-1, 2)
@@ -77,6 +101,9 @@ def main():
     wt, ct, ci = oracle.ble_tables("reference")
     np.savez_compressed(f"{HERE}/btle_tables_ref.npz", scramble_table=wt, crc_table=ct, crc_init_internal=np.uint32(ci))
 
+
+
+def make_zb_and_kats():
     # ---- Zigbee: reference sink on the oracle's soft chips
     out = {"chip_mapping": oracle.zb_chip_words("reference")}
     for seed, esn0 in ((2001, 30.0), (2002, 12.0), (2003, 9.0)):
@@ -108,9 +135,6 @@ def main():
     json.dump(kats, open(f"{HERE}/kats.json", "w"), indent=1)
     shutil.copyfile(f"{REF}/scapy-radio/scapy/test/rftap.pcap", f"{HERE}/rftap.pcap")
     os.chmod(f"{HERE}/rftap.pcap", 0o644)
-    print("golden fixtures written to", HERE)
-    for f in sorted(os.listdir(HERE)):
-        print(f"  {f:32s} {os.path.getsize(os.path.join(HERE, f)):9d} bytes")
 
 
 if __name__ == "__main__":

@@ -23,12 +23,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/snoutrx.h but not exported"
     assert sorted(n for n, _, _ in _abi.SYMBOLS) == declared
-    assert lib.snrx_abi_version() == 1
+    assert lib.snrx_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
     assert _abi.FRAME_DTYPE.itemsize == 160
-    assert ctypes.sizeof(_abi.Config) == 64 and ctypes.sizeof(_abi.Shard) == 24 and ctypes.sizeof(_abi.Stats) == 40
+    assert ctypes.sizeof(_abi.Config) == 72 and ctypes.sizeof(_abi.Shard) == 24 and ctypes.sizeof(_abi.Stats) == 40
 
 
 def test_channel_plan_helpers():

@@ -236,6 +236,48 @@ def test_zb_nb_batch_and_set_channel(Engine, oracle_mod):
     assert np.array_equal(got["capture_id"], want["capture_id"])
 
 
+def _zb_shards(n_ch, segment, cuts, pre=40960, post=16448 + 64):
+    """[(lo, hi, shard dict)] in channel-rate samples for bodies [cuts[i], cuts[i+1]) segments."""
+    out = []
+    for s0, s1 in zip(cuts[:-1], cuts[1:]):
+        b0, b1 = s0 * segment, min(n_ch, s1 * segment)
+        lo = max(0, b0 - pre)
+        hi = min(n_ch, b1 + post)
+        out.append((lo, hi, dict(pre_samples=b0 - lo, body_samples=b1 - b0, first_window=b0 // 8192)))
+    return out
+
+
+def test_zb_nb_shards_equal_whole(Engine, oracle_mod):
+    """Time shards (multi-GPU / streaming unit) reproduce the whole-capture result bit for bit: the DC
+    tracker and the chains are defined on absolute grids (oracle/zb_oracle.c)."""
+    cap = synth.zigbee_capture(n=1_200_000, channel=17, seed=77, esn0_db=14.0, gap=(500, 9000))
+    x = cap.iq
+    with Engine("zb_nb", channel=17, max_samples=len(x)) as e:
+        whole = e.run(x)
+        parts = [e.run(x[lo:hi].copy(), shard=sh) for lo, hi, sh in _zb_shards(len(x), 65536, [0, 5, 12, 19])]
+        with pytest.raises(_abi.SnrxError):          # pre halo too short for the tracker memory: refused
+            e.run(x[65536 - 4096:].copy(), shard=dict(pre_samples=4096, body_samples=0, first_window=8))
+    assert len(whole) > 40
+    assert_frames_equal(np.concatenate(parts), whole, what="zigbee: 3 time shards vs whole")
+    assert_frames_equal(whole, oracle_mod.zb_receive(x, 17), what="whole vs oracle")
+
+
+def test_zb_wb16_shards_equal_whole(Engine):
+    cap = synth.wideband_capture(seconds=0.05, kind="zigbee", seed=3100, esn0_db=20.0, gap=(400, 5000))
+    x = cap.iq
+    n_ch = len(x) // 24
+    with Engine("zb_wb16", max_samples=len(x), zb_segment=16384, zb_prehalo=4096) as e:
+        whole = e.run(x)
+        parts = []
+        for lo, hi, sh in _zb_shards(n_ch, 16384, [0, 4, 9, 13]):
+            sh = {k: (v * 24 if k != "first_window" else v) for k, v in sh.items()}
+            parts.append(e.run(x[lo * 24: hi * 24].copy(), shard=sh))
+    got = np.concatenate(parts)
+    order = np.lexsort((got["sample_index"], got["window"], got["channel"]))
+    assert len(whole) > 60
+    assert_frames_equal(got[order], whole, what="zigbee wideband: 3 time shards vs whole")
+
+
 def test_zb_nb_full_size_config2(Engine, oracle_mod):
     """BASELINE config 2: 1e7 samples of channel 11."""
     cap = synth.zigbee_capture(n=10_000_000, channel=11, seed=2001, esn0_db=30.0)

@@ -121,3 +121,17 @@ def test_restated_loop_equals_real_receiver_stdout(oracle_mod, golden):
             pdu = bytes(f["bytes"][:f["len"]])
             assert line.endswith(f"CRC{0 if f['crc_ok'] else 1}")
             assert f" Ch{f['channel']} " in line and f"PloadL{pdu[1] & 0x3F} " in line
+
+
+def test_access_mask_port_matches_reference_fixture(oracle_mod, golden):
+    """-m / access_bit_mask (btle_rx.c:1395-1401, 2301): masked-out bits do not take part in the match."""
+    g = golden("btle_mask_ref.npz")
+    s, esn0, ch, n = g["params"]
+    cap = synth.ble_capture(n=int(n), channel=int(ch), seed=int(s), esn0_db=float(esn0), gap=(100, 1500))
+    q = oracle_mod.ble_quantize(cap.iq, 128.0)
+    sizes = []
+    for mask in (0xFFFFFF00, 0x00FFFFFF, 0xFFFF0000, 0xFFFFFFFE):
+        fr = oracle_mod.ble_decode(q, int(ch), aa_mask=mask)
+        assert_frames_equal(fr, g[f"frames_{mask:08x}"], what=f"mask {mask:08x}")
+        sizes.append(len(fr))
+    assert min(sizes) > 10
