@@ -95,37 +95,57 @@ def make_capture(workload, seconds_base, seed):
     return c.iq, len(c.truth)
 
 
-def cpu_path(workload, sample, repeat=1):
-    """CPU statement of the path on `sample` using every host core; returns (seconds, frames, cores, kind)."""
+def cpu_path(workload, sample, min_seconds=0.0):
+    """CPU statement of the path on `sample` using every host core, repeated until at least `min_seconds`
+    of CPU work have been timed; returns (seconds, samples processed, frames of one pass, cores, kind)."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
     from snout_b200 import _abi, chanplan
     oracle.build(native=True)
     cores = os.cpu_count() or 1
     kind = "port"
+    h = _abi.pfb_prototype(_abi.MODE_BLE_WB40, 384) if workload == "ble_wb40" else None
+    bins = [chanplan.ble_channel_bin(c) for c in range(40)]
     t0 = time.perf_counter()
-    frames = 0
-    for _ in range(repeat):
+    frames, done = 0, 0
+    while True:
         if workload == "ble_wb40":
-            impl = "reference" if oracle.have_ref("btle_ref") else "port"
-            kind = "reference" if impl == "reference" else "port"
-            h = _abi.pfb_prototype(_abi.MODE_BLE_WB40, 384) if os.path.exists(_abi.LIB_PATH) else None
-            y = oracle.pfb(sample, h, [chanplan.ble_channel_bin(c) for c in range(40)], fast=True)   # OpenMP, all cores
+            # channelizer: no reference counterpart (the reference retunes one 4 Msps channel at a time), CPU
+            # statement = oracle/pfb_oracle.c with OpenMP over all cores; per-channel decode = the port of
+            # btle_rx.c's receiver(), one channel per thread
+            y = oracle.pfb(sample, h, bins, fast=True)
             def one(c):
-                return len(oracle.ble_decode(oracle.ble_quantize(y[c], 100.0), c, impl="port" if impl == "port" else "port"))
+                return len(oracle.ble_decode(oracle.ble_quantize(y[c], 100.0), c, impl="port"))
             with ThreadPoolExecutor(cores) as ex:
                 frames = sum(ex.map(one, range(40)))
-            kind = "port"      # channelizer has no reference counterpart; per-channel decode = port of btle_rx.c
         elif workload == "ble_nb":
-            impl = "reference" if oracle.have_ref("btle_ref") else "port"
-            kind = impl
+            kind = "reference" if oracle.have_ref("btle_ref") else "port"
             q = oracle.ble_quantize(sample, 128.0)
-            frames = len(oracle.ble_decode(q, 37, impl=impl))
+            frames = len(oracle.ble_decode(q, 37, impl=kind))
             cores = 1
         else:
             frames = len(oracle.zb_receive(sample, 11))
             cores = 1
-    return time.perf_counter() - t0, frames, cores, kind
+        done += len(sample)
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    return time.perf_counter() - t0, done, frames, cores, kind
+
+
+def ncu_traffic(n_samples):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_pfb_ble launch from the committed ncu --set full
+    summary (profiles/), valid when it was captured on this same workload size; else None."""
+    best = None
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+        if name.startswith("r") and "_pfb_ncu" in name and name.endswith(".json"):
+            try:
+                j = json.load(open(os.path.join(ROOT, "profiles", name)))
+                for l in j["launches"]:
+                    if "k_pfb_ble" in l["kernel"] and abs(l["dram_read_bytes"] / (n_samples * 8) - 1) < 0.2:
+                        best = (l["traffic_bytes"], name)
+            except Exception:
+                pass
+    return best
 
 
 def main():
@@ -139,6 +159,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=10, help="copies of the generated capture per step (wideband)")
     ap.add_argument("--taps", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work timed for cpu_baseline (bounded sample)")
+    ap.add_argument("--ref-step-seconds", type=float, default=1.5, help="--impl reference: CPU work per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -153,22 +175,22 @@ def main():
         if rank != 0:
             return 0
         base, n_truth = make_capture(args.workload, min(args.base_seconds, 0.05), 4000)
-        times = []
+        times, per_step = [], 0
         for i in range(args.warmup + args.steps):
-            dt, frames, cores, kind = cpu_path(args.workload, base)
+            dt, per_step, frames, cores, kind = cpu_path(args.workload, base, min_seconds=args.ref_step_seconds)
             if i >= args.warmup:
                 times.append(dt)
         t = float(np.mean(times))
-        v = len(base) / t / 1e6
+        v = per_step / t / 1e6
         line = {
             "impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "sample_samples": int(len(base)),
+            "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "sample_samples": int(per_step),
                        "note": "CPU statement of the same path on the host cores; the reference itself has no channelizer "
                                "(it retunes one 4 Msps channel at a time)"},
             "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": kind,
-                             "sample": f"{len(base)} samples of the workload per step, {frames} frames"},
+                             "sample": f"{per_step} samples per step = a {len(base)}-sample slice of the workload repeated for >= {args.ref_step_seconds} s, {frames} frames per pass"},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
@@ -287,11 +309,16 @@ def main():
                      "algorithmic_bytes_per_launch": int(n * 8), "kernel_ms": fms,
                      "note": "8 B per input sample (one cf32 read); the fused channelizer is FP32-pipe limited, see DESIGN.md"},
     }
+    tr = ncu_traffic(n) if mode == "ble_wb40" else None
+    if tr:
+        line["roofline"]["traffic"] = tr[0]
+        line["roofline"]["traffic_source"] = f"profiles/{tr[1]} (ncu --set full, dram read+write of one launch)"
     if world == 1 and not args.no_cpu_baseline:
         sample = base[: min(len(base), 4_800_000)] if args.workload == "ble_wb40" else base
-        dt, frames, cores, kind = cpu_path(args.workload, sample)
-        line["cpu_baseline"] = {"value": len(sample) / dt / 1e6, "unit": unit, "cores": cores, "kind": kind,
-                                "sample": f"{len(sample)} samples of the same capture, {frames} frames, {dt:.2f} s"}
+        dt, done, frames, cores, kind = cpu_path(args.workload, sample, min_seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": done / dt / 1e6, "unit": unit, "cores": cores, "kind": kind,
+                                "sample": f"{done} samples = a {len(sample)}-sample slice of the same capture repeated for "
+                                          f"{dt:.1f} s of CPU work, {frames} frames per pass"}
     print(json.dumps(line))
     return 0
 

@@ -57,7 +57,8 @@ USAGE = """Usage:
     -s --filename
       Store packets to this pcap file (LINKTYPE_BLUETOOTH_LE_LL_WITH_PHDR)
     --iq FILE|-
-      IQ source: interleaved samples from FILE or stdin
+      IQ source: interleaved samples from FILE or stdin (default: environment SNOUT_B200_IQ;
+      SNOUT_B200_IQ_FORMAT and SNOUT_B200_WIDEBAND likewise preset --format / --wideband)
     --format cf32|sc8
       Sample format of the source (default cf32; sc8 = HackRF int8)
     --scale S
@@ -113,6 +114,10 @@ def parse_commandline(argv: list[str], out=sys.stdout) -> Options | None:
     """Mirror of parse_commandline(), btle_rx.c:1165-1315.  Returns None after printing the usage
     (the reference then exits with -1)."""
     o = Options()
+    # Snout builds the argv itself (snout/util/btle.py:53), so the IQ source may also come from the environment
+    o.iq = os.environ.get("SNOUT_B200_IQ")
+    o.fmt = os.environ.get("SNOUT_B200_IQ_FORMAT", "cf32")
+    o.wideband = bool(os.environ.get("SNOUT_B200_WIDEBAND"))
     out.write(formats.BTLE_RX_BANNER)
     try:
         opts, rest = getopt.getopt(argv, "hc:g:a:k:vrf:m:os:",

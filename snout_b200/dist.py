@@ -31,26 +31,61 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
-def plan_time_shards(n_samples: int, decim: int, windows_per_shard: int, post_channel_samples: int = 2048,
-                     pre_channel_samples: int = 128):
-    """Cut one capture of n_samples input samples into time shards aligned to the 8192-sample BLE
-    window grid (= Zigbee segment grid when zb_segment divides 8192*k).  Returns a list of dicts
-    {lo, hi, pre_samples, body_samples, first_window} in input-rate samples."""
-    n_ch = n_samples // decim
-    n_win = (n_ch + chanplan.BLE_WINDOW - 1) // chanplan.BLE_WINDOW
-    shards = []
-    for w0 in range(0, n_win, windows_per_shard):
-        w1 = min(n_win, w0 + windows_per_shard)
-        lo_ch = max(0, w0 * chanplan.BLE_WINDOW - pre_channel_samples)
-        hi_ch = min(n_ch, w1 * chanplan.BLE_WINDOW + post_channel_samples)
-        body_ch = min(n_ch, w1 * chanplan.BLE_WINDOW) - w0 * chanplan.BLE_WINDOW
-        shards.append(dict(lo=lo_ch * decim, hi=hi_ch * decim, pre_samples=(w0 * chanplan.BLE_WINDOW - lo_ch) * decim,
-                           body_samples=body_ch * decim, first_window=w0))
-    return shards
+def plan_job(n_captures: int, n_samples: int, engine=None, units_per_shard: int = 0, geometry=None, decim: int | None = None):
+    """Work units of a batch job (BASELINE config 5: many long captures, sharded by time segment
+    with halo): one unit = (capture_id, time shard).  Returns a list of dicts
+    {capture, lo, hi, pre_samples, body_samples, first_window} in input-rate samples, ordered by
+    (capture, time).  The cut depends only on the engine geometry, never on the number of ranks,
+    so the union of the results is the same for any world size."""
+    from . import stream
+    if geometry is None:
+        geometry = stream.shard_geometry(engine.n_ble, engine.n_zb, engine.cfg.zb_segment or 65536, engine.cfg.zb_prehalo or 4096)
+    if decim is None:
+        decim = engine.decim
+    unit, pre, post = geometry
+    if not units_per_shard:
+        cap_in = int(engine.cfg.max_samples) or (96_000_000 if engine.wideband else 10_000_000)
+        units_per_shard = max(1, (cap_in // decim - pre - post) // unit)
+    units = []
+    for c in range(n_captures):
+        for sh in stream.plan_shards(n_samples, decim, unit, pre, post, units_per_shard):
+            units.append(dict(capture=c, **sh))
+    return units
 
 
 def assign_round_robin(n_units: int, rank: int, world: int):
+    """Unit u belongs to rank u mod world."""
     return list(range(rank, n_units, world))
+
+
+def run_job(engine, captures, units, rank: int = 0, world: int = 1, gather: bool = True, device=None) -> np.ndarray:
+    """Process this rank's share of `units` and return the frames of the WHOLE job in reference order
+    (identical on every rank and for every world size).  `captures(c)` returns capture c as a
+    complex64 array (host) -- only called for captures this rank needs.  Two shards are kept in flight."""
+    mine = [units[i] for i in assign_round_robin(len(units), rank, world)]
+    out, pending = [], 0
+    cache, alive = {}, []                # `alive`: buffers of the batches still in flight (host->device copies are async)
+    for u in mine:
+        c = u["capture"]
+        if c not in cache:
+            cache.clear()
+            cache[c] = captures(c)
+        x = cache[c][u["lo"]: u["hi"]]
+        if pending == 2:
+            out.append(engine.poll())
+            alive.pop(0)
+            pending -= 1
+        alive.append(x)
+        engine.process(x, shard=dict(pre_samples=u["pre_samples"], body_samples=u["body_samples"],
+                                     first_window=u["first_window"], first_capture_id=c))
+        pending += 1
+    while pending:
+        out.append(engine.poll())
+        pending -= 1
+    frames = np.concatenate(out) if out else np.zeros(0, dtype=FRAME_DTYPE)
+    if gather and world > 1:
+        frames = allgather_frames(frames, device)
+    return sort_reference_order(frames)
 
 
 def allgather_frames(frames: np.ndarray, device=None) -> np.ndarray:

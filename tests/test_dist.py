@@ -1,0 +1,102 @@
+"""Multi-GPU host logic on CPU: world_size-2 (and 3) gloo process groups, a content-digest engine in
+place of the CUDA engine.  The job result (frames in reference order) must be identical for every
+world size and equal to the single-process result; the all-gather carries ragged counts."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from snout_b200 import _abi, dist as sdist, stream
+
+
+def _captures(c):
+    rng = np.random.default_rng(100 + c)
+    n = 8192 * 21 + 1234
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+
+def _job(rank, world):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_engine import ContentEngine
+    eng = ContentEngine("ble_nb", channel=37, max_samples=8192 * 4 + 128 + 2048)
+    units = sdist.plan_job(3, len(_captures(0)), eng, units_per_shard=4)
+    return sdist.run_job(eng, _captures, units, rank, world), units, eng
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    r, w, _ = sdist.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    frames, units, eng = _job(rank, world)
+    q.put((rank, frames.tobytes(), len(eng.calls)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_job_result_is_identical_for_any_world_size(world):
+    import torch.multiprocessing as mp
+    single, units, eng1 = _job(0, 1)
+    assert len(units) == 3 * 6 and len(eng1.calls) == len(units)
+    # every window of every capture exactly once, digest of the right samples
+    assert len(single) == 3 * 22
+    for c in range(3):
+        x = _captures(c)
+        fc = single[single["capture_id"] == c]
+        assert list(fc["window"]) == list(range(22))
+        for f in fc:
+            s = int(f["window"]) * 8192
+            assert bytes(f["bytes"][: f["len"]]) == x[s: s + 2].tobytes()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    calls = [r[2] for r in res]
+    assert sum(calls) == len(units) and max(calls) - min(calls) <= 1          # round robin, no duplicates
+    for _, blob, _ in res:
+        assert blob == single.tobytes()                                       # identical on every rank, = world 1
+
+
+def test_allgather_single_process_is_identity():
+    f = np.zeros(3, _abi.FRAME_DTYPE)
+    assert sdist.allgather_frames(f) is f
+    assert sdist.assign_round_robin(7, 1, 3) == [1, 4]
+
+
+def test_sort_reference_order():
+    f = np.zeros(5, _abi.FRAME_DTYPE)
+    f["capture_id"] = [1, 0, 0, 0, 0]
+    f["proto"] = [3, 2, 3, 3, 3]
+    f["channel"] = [0, 11, 5, 5, 4]
+    f["window"] = [0, 0, 2, 1, 9]
+    s = sdist.sort_reference_order(f)
+    assert list(zip(s["capture_id"], s["proto"], s["channel"], s["window"])) == \
+           [(0, 3, 4, 9), (0, 3, 5, 1), (0, 3, 5, 2), (0, 2, 11, 0), (1, 3, 0, 0)]
+
+
+def test_plan_job_does_not_depend_on_world():
+    from fake_engine import ContentEngine
+    eng = ContentEngine("mixed_wb56", max_samples=(2 * 65536 + 40960 + 16512) * 24, zb_segment=65536, zb_prehalo=4096)
+    units = sdist.plan_job(2, 24 * 65536 * 5 + 240, eng)
+    assert [u["first_window"] for u in units if u["capture"] == 0] == [0, 16, 32]
+    assert all(u["pre_samples"] in (0, 40960 * 24) for u in units)
+    cover = sorted(i for w in (4,) for r in range(w) for i in sdist.assign_round_robin(len(units), r, w))
+    assert cover == list(range(len(units)))

@@ -14,51 +14,7 @@ import pytest
 from snout_b200 import _abi, btle_cli, chanplan, formats, stream
 
 
-MARK = [0x40, 6, 1, 2, 3, 4, 5, 6, 0xAA, 0xBB, 0xCC]       # ADV_IND, TxAdd=1, PloadL6, AdvA, CRC
-
-
-class RecordingEngine:
-    """Quacks like RxEngine for ShardStreamer: records every process() call, checks the queue
-    discipline of snrx_process / snrx_poll, returns one marker frame per shard."""
-
-    def __init__(self, mode="ble_nb", channel=37, max_samples=0, zb_segment=0, zb_prehalo=0, **kw):
-        self.mode, self.channel, self.kw = mode, channel, kw
-        self.wideband = mode in ("ble_wb40", "zb_wb16", "mixed_wb56")
-        self.decim = 24 if self.wideband else 1
-        self.n_ble = {"ble_nb": 1, "ble_wb40": 40, "mixed_wb56": 40}.get(mode, 0)
-        self.n_zb = {"zb_nb": 1, "zb_wb16": 16, "mixed_wb56": 16}.get(mode, 0)
-        self.cfg = _abi.Config()
-        self.cfg.max_samples, self.cfg.zb_segment, self.cfg.zb_prehalo = max_samples, zb_segment, zb_prehalo
-        self.calls, self.queue, self.max_queue, self.closed = [], [], 0, False
-
-    def process(self, iq, shard=None):
-        assert len(self.queue) < 2, "third batch queued"
-        assert len(iq) <= self.cfg.max_samples and len(iq) % self.decim == 0
-        self.calls.append((np.array(iq, copy=True), dict(shard)))
-        f = np.zeros(1, _abi.FRAME_DTYPE)
-        body0 = shard["first_window"] * 8192
-        f["sample_index"], f["window"], f["channel"] = body0, shard["first_window"], self.channel
-        f["proto"] = 3 if self.n_ble else 2
-        f["len"], f["crc_ok"], f["access_addr"], f["lqi"] = 11, 1, 0x8E89BED6, 255
-        f["bytes"][0, :11] = MARK
-        self.queue.append(f)
-        self.max_queue = max(self.max_queue, len(self.queue))
-        return self
-
-    def poll(self, copy=True):
-        return self.queue.pop(0)
-
-    def alloc_host(self, n):
-        class Buf:
-            def __init__(self, n):
-                self.array = np.zeros(n, np.complex64)
-
-            def free(self):
-                self.array = None
-        return Buf(n)
-
-    def close(self):
-        self.closed = True
+from fake_engine import MARK, RecordingEngine
 
 
 def _check_cover(eng, x, decim, unit, pre, post):
