@@ -173,13 +173,12 @@ SNRX_HD void ble_fill_frame(snrx_frame_t& f, const Cand& c, const Dec& d, const 
 
 // Sliding access-address correlation.  One warp per (capture, channel, chunk of 32 words); each
 // lane owns one word of each phase stream and obtains the following word from its neighbour by
-// warp shuffle.  COUNT pass writes hits per chunk, FILL pass writes the candidates at the
-// scanned offsets, ascending in s.
-template <bool FILL>
+// warp shuffle.  Writes the hit masks (bit i of hits[phase j][word w] = a 32-symbol window starting
+// at slot 32 (w-1) + i of phase j matches) and the number of hits per chunk; after the prefix sum
+// k_aa_fill turns the masks into the candidate list, ascending in s, without atomics or a sort.
 __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ bits, BitsLayout lay, BleParams p,
-                                                   uint32_t n_chunks, uint32_t* counts,
-                                                   const uint32_t* __restrict__ offsets, Cand* __restrict__ cands,
-                                                   uint32_t cand_cap) {
+                                                   uint32_t n_chunks, uint32_t* __restrict__ counts,
+                                                   uint32_t* __restrict__ hits_out) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t n_items = p.n_captures * p.n_channels * n_chunks;
@@ -187,17 +186,16 @@ __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ 
     const uint32_t mask_hi = p.aa_mask & ~((1u << z) - 1u);
     for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
          item += gridDim.x * warps_per_block) {
-        if (FILL && counts[item] == 0u) continue;                   // nothing found here by the count pass
         const uint32_t chunk = item % n_chunks;
         const uint32_t ch = (item / n_chunks) % p.n_channels;
         const uint32_t cap = item / (n_chunks * p.n_channels);
         const uint32_t w = chunk * 32 + lane;                       // word owned by this lane
         const bool valid = (w + 1) < lay.words_per_phase;
-        uint32_t hits[4];
         int cnt = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t* pw = bits + lay.index(cap, ch, j, 0);
+            const size_t base = lay.index(cap, ch, j, 0);
+            const uint32_t* pw = bits + base;
             uint32_t lo = valid ? __ldg(pw + w) : 0u;
             uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
             if (lane == 31) hi = (w + 1 < lay.words_per_phase) ? __ldg(pw + w + 1) : 0u;
@@ -207,39 +205,59 @@ __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ 
             // positions whose first sample lies beyond the capture carry no data
             const int nvalid = ((p.n_out - 1 - j) >> 2) - 32 * ((int)w - 1) + 1;
             if (nvalid <= 0) hj = 0u; else if (nvalid < 32) hj &= (1u << nvalid) - 1u;
-            hits[j] = hj;
+            if (w < lay.words_per_phase) hits_out[base + w] = hj;
             cnt += __popc(hj);
         }
-        const uint32_t any = __ballot_sync(0xffffffffu, cnt != 0);
-        if (!FILL) {
-            int tot = cnt;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-            if (lane == 0) counts[item] = (uint32_t)tot;
-        } else if (any) {
-            // exclusive prefix over lanes
-            int pre = cnt;
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) counts[item] = (uint32_t)cnt;
+    }
+}
+
+// Candidate list from the hit masks.  One warp per chunk that has hits; lanes own words, an exclusive
+// prefix over the lanes gives each lane its write position, slots then phases in ascending sample order.
+__global__ void __launch_bounds__(256) k_aa_fill(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ hits_in,
+                                                 BitsLayout lay, BleParams p, uint32_t n_chunks,
+                                                 const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                 Cand* __restrict__ cands, uint32_t cand_cap) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_per_block = blockDim.x >> 5;
+    const uint32_t n_items = p.n_captures * p.n_channels * n_chunks;
+    for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
+         item += gridDim.x * warps_per_block) {
+        if (counts[item] == 0u) continue;                           // warp-uniform
+        const uint32_t chunk = item % n_chunks;
+        const uint32_t ch = (item / n_chunks) % p.n_channels;
+        const uint32_t cap = item / (n_chunks * p.n_channels);
+        const uint32_t w = chunk * 32 + lane;
+        uint32_t hits[4];
+        int cnt = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-            pre -= cnt;
-            uint32_t dst = offsets[item] + (uint32_t)pre;
-            if (cnt) {
-                for (int i = 0; i < 32; i++) {
+        for (int j = 0; j < 4; j++) {
+            hits[j] = (w < lay.words_per_phase) ? __ldg(hits_in + lay.index(cap, ch, j, w)) : 0u;
+            cnt += __popc(hits[j]);
+        }
+        int pre = cnt;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if ((hits[j] >> i) & 1u) {
-                            const int t = 32 * ((int)w - 1) + i;
-                            const uint32_t* pw = bits + lay.index(cap, ch, j, 0);
-                            uint32_t r = slots32(pw, t);
-                            uint32_t d = (r ^ p.aa) & p.aa_mask;
-                            if (dst < cand_cap) {
-                                Cand c;
-                                c.s = 4 * t + j; c.ch_idx = (uint16_t)ch; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = cap;
-                                cands[dst] = c;
-                            }
-                            dst++;
-                        }
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+        pre -= cnt;
+        uint32_t dst = offsets[item] + (uint32_t)pre;
+        uint32_t any = hits[0] | hits[1] | hits[2] | hits[3];
+        while (any) {
+            const int i = __ffs(any) - 1;
+            any &= any - 1u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if ((hits[j] >> i) & 1u) {
+                    const int t = 32 * ((int)w - 1) + i;
+                    const uint32_t r = slots32(bits + lay.index(cap, ch, j, 0), t);
+                    const uint32_t d = (r ^ p.aa) & p.aa_mask;
+                    if (dst < cand_cap) {
+                        Cand c;
+                        c.s = 4 * t + j; c.ch_idx = (uint16_t)ch; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = cap;
+                        cands[dst] = c;
                     }
+                    dst++;
                 }
             }
         }

@@ -30,26 +30,41 @@ struct DevBuf {
 
 }  // namespace
 
+// One "lane" per output slot: a complete working set with its own stream, so that the latency-bound tail of
+// batch i (search, decode, resolve, export) overlaps the FP32-bound front end of batch i+1.
+struct Lane {
+    cudaStream_t stream = nullptr;      // front end (channelizer / slicer): low priority, fills the machine
+    cudaStream_t tail = nullptr;        // everything after it: high priority, so its small latency-bound kernels are
+                                        // dispatched ahead of the other lane's queued channelizer tiles
+    snrx_frame_t* frames = nullptr;     // pinned + mapped host copy, frame_cap records
+    snrx_frame_t* d_frames = nullptr;   // device copy the kernels write
+    uint32_t* totals = nullptr;         // pinned: [0] BLE frames [1] candidates [2] Zigbee frames
+    uint32_t* d_totals = nullptr;       // device: same layout
+    cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_done = nullptr, ev_in = nullptr;
+    cudaEvent_t ev_handoff = nullptr;
+    bool pending = false, done = false;
+    uint32_t caps = 0, n_out = 0, n_frames = 0; uint64_t n_in = 0; int launches = 0;
+    // BLE working set
+    float2* d_x = nullptr; size_t d_x_bytes = 0;          // staging of host input
+    uint32_t* d_bits = nullptr; size_t d_bits_bytes = 0;
+    uint32_t* d_hits = nullptr;                            // access-address hit masks, same layout as d_bits
+    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
+    uint32_t *d_wcounts = nullptr, *d_woffsets = nullptr;
+    Cand* d_cands = nullptr;
+    Dec* d_decs = nullptr;
+    int8_t* d_q8 = nullptr; size_t d_q8_bytes = 0;
+    float2* d_cf = nullptr; size_t d_cf_bytes = 0;
+    ZbState zb;
+    std::vector<cudaEvent_t> ev_chunks;
+};
+
 struct snrx_handle {
     snrx_config_t cfg{};
     int device = 0;
-    cudaStream_t stream = nullptr;       // compute stream (own or caller supplied)
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t user_stream = nullptr;  // stream the caller produces device input on (snrx_set_stream), or null
     cudaStream_t copy_stream = nullptr;  // H2D staging
-    cudaStream_t export_stream = nullptr; // frames device -> pinned host, overlapped with the next batch
-    // Output ring: snrx_process(i+1) may be queued before snrx_poll(i), so the GPU never idles between
-    // batches.  Frames are stored by the kernels straight into host-mapped pinned memory (zero copy).
-    struct OutSlot {
-        snrx_frame_t* frames = nullptr;     // pinned + mapped host copy, frame_cap records
-        snrx_frame_t* d_frames = nullptr;   // device copy the kernels write
-        cudaEvent_t ev_compute = nullptr, ev_exported = nullptr;
-        uint32_t* totals = nullptr;         // pinned: [0] BLE frames [1] candidates [2] Zigbee frames
-        cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_done = nullptr;
-        bool pending = false, done = false;
-        uint32_t caps = 0, n_out = 0, n_frames = 0; uint64_t n_in = 0; int launches = 0;
-    } slot[2];
+    Lane lane[2];
     uint64_t seq_process = 0, seq_poll = 0;
-    std::vector<cudaEvent_t> ev_chunks;
     int sm_count = 148;
     std::string err;
 
@@ -66,25 +81,15 @@ struct snrx_handle {
     uint32_t cand_cap = 0, frame_cap = 0;
     int pfb_nt = 16;
 
-    // device memory
-    float2* d_x = nullptr; size_t d_x_bytes = 0;          // staging of host input
-    uint32_t* d_bits = nullptr; size_t d_bits_bytes = 0;
-    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
-    uint32_t *d_wcounts = nullptr, *d_woffsets = nullptr;
-    Cand* d_cands = nullptr;
-    Dec* d_decs = nullptr;
-    uint32_t* d_totals = nullptr;        // [0] frames, [1] candidates, [2] zigbee frames (gathered at poll)
+    // constants on the device
     uint32_t *d_crc_tab = nullptr, *d_whiten = nullptr;
     int32_t* d_ble_channels = nullptr;
     float *d_taps_rho = nullptr, *d_taps_flat = nullptr;
-    int8_t* d_q8 = nullptr; size_t d_q8_bytes = 0;
-    float2* d_cf = nullptr; size_t d_cf_bytes = 0;
-    ZbState zb;
 
     // last batch
     bool batch_valid = false;
-    uint32_t b_caps = 0; uint64_t b_n_in = 0; uint32_t b_n_out = 0; uint32_t b_windows = 0;
-    uint32_t b_aa_items = 0, b_w_items = 0;
+    int last_lane = 0;
+    uint32_t b_caps = 0; uint64_t b_n_in = 0; uint32_t b_n_out = 0;
     snrx_stats_t stats{};
     int launches = 0;
 };
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __res
                                                        snrx_frame_t* __restrict__ dst_host, uint32_t* __restrict__ totals_host,
                                                        uint32_t frame_cap) {
     uint32_t n = totals_dev[0] + totals_dev[2];
-    if (n > frame_cap) n = frame_cap;
+    if (n > frame_cap) n = frame_cap;                      // few CTAs: this kernel is PCIe bound and must leave the SMs to the other lane
     const size_t n16 = (size_t)n * (sizeof(snrx_frame_t) / 16);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst_host);
@@ -234,23 +239,23 @@ int snrx_pfb_prototype(int mode, uint32_t taps, double* out) {
 void snrx_destroy(snrx_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    void* bufs[] = {h->d_x, h->d_bits, h->d_counts, h->d_offsets, h->d_scratch, h->d_wcounts, h->d_woffsets,
-                    h->d_cands, h->d_decs, h->d_totals, h->d_crc_tab, h->d_whiten, h->d_ble_channels,
-                    h->d_taps_rho, h->d_taps_flat, h->d_q8, h->d_cf};
+    for (auto& ln : h->lane) { if (ln.stream) cudaStreamSynchronize(ln.stream); if (ln.tail) cudaStreamSynchronize(ln.tail); }
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    void* bufs[] = {h->d_crc_tab, h->d_whiten, h->d_ble_channels, h->d_taps_rho, h->d_taps_flat};
     for (void* b : bufs) if (b) cudaFree(b);
-    zb_free(h->zb);
-    for (auto& sl : h->slot) {
-        if (sl.frames) cudaFreeHost(sl.frames);
-        if (sl.d_frames) cudaFree(sl.d_frames);
-        for (cudaEvent_t e : {sl.ev_compute, sl.ev_exported}) if (e) cudaEventDestroy(e);
-        if (sl.totals) cudaFreeHost(sl.totals);
-        for (cudaEvent_t e : {sl.ev_start, sl.ev_front0, sl.ev_front, sl.ev_done}) if (e) cudaEventDestroy(e);
+    for (auto& ln : h->lane) {
+        void* lb[] = {ln.d_x, ln.d_bits, ln.d_hits, ln.d_counts, ln.d_offsets, ln.d_scratch, ln.d_wcounts, ln.d_woffsets,
+                      ln.d_cands, ln.d_decs, ln.d_totals, ln.d_q8, ln.d_cf, ln.d_frames};
+        for (void* b : lb) if (b) cudaFree(b);
+        zb_free(ln.zb);
+        if (ln.frames) cudaFreeHost(ln.frames);
+        if (ln.totals) cudaFreeHost(ln.totals);
+        for (cudaEvent_t e : {ln.ev_start, ln.ev_front0, ln.ev_front, ln.ev_done, ln.ev_in, ln.ev_handoff}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : ln.ev_chunks) cudaEventDestroy(e);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.tail) cudaStreamDestroy(ln.tail);
     }
-    for (cudaEvent_t e : h->ev_chunks) cudaEventDestroy(e);
-    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->export_stream) cudaStreamDestroy(h->export_stream);
     delete h;
 }
 
@@ -267,17 +272,14 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
     if (!h) return fail(nullptr, SNRX_ENOMEM, "host allocation failed");
     h->cfg = *cfg;
     h->device = cfg->device;
-#define CKD(call) do { int r__ = (call); if (r__ != SNRX_OK) { g_err = h->err; snrx_destroy(h); return r__; } } while (0)
+#define CKD(call) do { int r__ = (call); if (r__ != SNRX_OK) return r__; } while (0)
     auto body = [&]() -> int {
         CK(cudaSetDevice(h->device));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sm_count = prop.multiProcessorCount;
         if (prop.major < 10) return fail(h, SNRX_ENODEV, "libsnoutrx is built for sm_100a (B200) only");
-        CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&h->export_stream, cudaStreamNonBlocking));
-        h->stream = h->own_stream;
 
         snrx_config_t& c = h->cfg;
         switch (c.mode) {
@@ -309,35 +311,11 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         h->frame_cap = c.max_frames;
         h->cand_cap = std::max<uint32_t>(1u << 16, 4 * c.max_frames);
 
-        CKD(dev_alloc(h, &h->d_totals, 24));
-        for (auto& sl : h->slot) {
-            CK(cudaHostAlloc((void**)&sl.frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap, cudaHostAllocMapped));
-            CK(cudaHostAlloc((void**)&sl.totals, 8 * sizeof(uint32_t), cudaHostAllocMapped));
-            CK(cudaEventCreate(&sl.ev_start));
-            CK(cudaEventCreate(&sl.ev_front0));
-            CK(cudaEventCreate(&sl.ev_front));
-            CK(cudaEventCreate(&sl.ev_done));
-            CK(cudaEventCreateWithFlags(&sl.ev_compute, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&sl.ev_exported, cudaEventDisableTiming));
-            CK(cudaMalloc((void**)&sl.d_frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap));
-        }
-
         if (h->has_ble) {
             const uint32_t tiles = div_up(h->max_out, kTileT);
             h->wpp = kBitsLeadWords + tiles + kBitsTailWords;
             h->n_chunks = div_up(h->wpp - 1, 32);
             h->max_windows = div_up(h->max_out, kWindow);
-            h->d_bits_bytes = (size_t)h->max_caps * h->n_ble_ch * 4 * h->wpp * sizeof(uint32_t);
-            CK(cudaMalloc((void**)&h->d_bits, h->d_bits_bytes));
-            const size_t aa_items = (size_t)h->max_caps * h->n_ble_ch * h->n_chunks;
-            const size_t w_items = (size_t)h->max_caps * h->n_ble_ch * h->max_windows;
-            CKD(dev_alloc(h, &h->d_counts, aa_items + 1));
-            CKD(dev_alloc(h, &h->d_offsets, aa_items + 1));
-            CKD(dev_alloc(h, &h->d_wcounts, w_items + 1));
-            CKD(dev_alloc(h, &h->d_woffsets, w_items + 1));
-            CKD(dev_alloc(h, &h->d_scratch, scan_scratch_items(std::max(aa_items, w_items))));
-            CKD(dev_alloc(h, &h->d_cands, h->cand_cap));
-            CKD(dev_alloc(h, &h->d_decs, h->cand_cap));
             uint32_t crc[256], wh[40 * 11];
             make_crc_table(crc);
             make_whiten_table(wh);
@@ -364,25 +342,55 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
                 CK(cudaFuncSetAttribute(k_pfb_ble<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<32>::kSmemBytes));
                 CK(cudaFuncSetAttribute(k_pfb_ble<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<32>::kSmemBytes));
             }
-            if (c.flags & SNRX_F_KEEP_STREAMS) {
-                h->d_q8_bytes = (size_t)h->max_caps * h->n_ble_ch * h->max_out * 2;
-                CK(cudaMalloc((void**)&h->d_q8, h->d_q8_bytes));
+        }
+        for (auto& ln : h->lane) {
+            int prio_lo = 0, prio_hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CK(cudaStreamCreateWithPriority(&ln.stream, cudaStreamNonBlocking, prio_lo));
+            CK(cudaStreamCreateWithPriority(&ln.tail, cudaStreamNonBlocking, prio_hi));
+            CK(cudaEventCreateWithFlags(&ln.ev_handoff, cudaEventDisableTiming));
+            CK(cudaHostAlloc((void**)&ln.frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap, cudaHostAllocMapped));
+            CK(cudaHostAlloc((void**)&ln.totals, 8 * sizeof(uint32_t), cudaHostAllocMapped));
+            CK(cudaEventCreate(&ln.ev_start));
+            CK(cudaEventCreate(&ln.ev_front0));
+            CK(cudaEventCreate(&ln.ev_front));
+            CK(cudaEventCreate(&ln.ev_done));
+            CK(cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming));
+            CK(cudaMalloc((void**)&ln.d_frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap));
+            CKD(dev_alloc(h, &ln.d_totals, 8));
+            CK(cudaMemset(ln.d_totals, 0, 8 * sizeof(uint32_t)));
+            if (h->has_ble) {
+                ln.d_bits_bytes = (size_t)h->max_caps * h->n_ble_ch * 4 * h->wpp * sizeof(uint32_t);
+                CK(cudaMalloc((void**)&ln.d_bits, ln.d_bits_bytes));
+                CK(cudaMalloc((void**)&ln.d_hits, ln.d_bits_bytes));
+                const size_t aa_items = (size_t)h->max_caps * h->n_ble_ch * h->n_chunks;
+                const size_t w_items = (size_t)h->max_caps * h->n_ble_ch * h->max_windows;
+                CKD(dev_alloc(h, &ln.d_counts, aa_items + 1));
+                CKD(dev_alloc(h, &ln.d_offsets, aa_items + 1));
+                CKD(dev_alloc(h, &ln.d_wcounts, w_items + 1));
+                CKD(dev_alloc(h, &ln.d_woffsets, w_items + 1));
+                CKD(dev_alloc(h, &ln.d_scratch, scan_scratch_items(std::max(aa_items, w_items))));
+                CKD(dev_alloc(h, &ln.d_cands, h->cand_cap));
+                CKD(dev_alloc(h, &ln.d_decs, h->cand_cap));
+                if (c.flags & SNRX_F_KEEP_STREAMS) {
+                    ln.d_q8_bytes = (size_t)h->max_caps * h->n_ble_ch * h->max_out * 2;
+                    CK(cudaMalloc((void**)&ln.d_q8, ln.d_q8_bytes));
+                    if (h->wideband) {
+                        ln.d_cf_bytes = (size_t)h->max_caps * h->n_ble_ch * h->max_out * sizeof(float2);
+                        CK(cudaMalloc((void**)&ln.d_cf, ln.d_cf_bytes));
+                    }
+                }
+            }
+            if (h->has_zb) {
+                int r = zb_create(ln.zb, h->cfg, h->wideband, h->n_zb_ch, h->max_caps, h->max_out, h->sm_count, h->err);
+                if (r != SNRX_OK) return r;
                 if (h->wideband) {
-                    h->d_cf_bytes = (size_t)h->max_caps * h->n_ble_ch * h->max_out * sizeof(float2);
-                    CK(cudaMalloc((void**)&h->d_cf, h->d_cf_bytes));
+                    const double* proto = (c.pfb_taps == 384) ? SNRX_PFB_ZB_384 : SNRX_PFB_ZB_768;
+                    r = zb_wideband_init(ln.zb, h->cfg, proto, h->max_caps, h->max_out, h->err);
+                    if (r != SNRX_OK) return r;
                 }
             }
         }
-        if (h->has_zb) {
-            int r = zb_create(h->zb, h->cfg, h->wideband, h->n_zb_ch, h->max_caps, h->max_out, h->sm_count, h->err);
-            if (r != SNRX_OK) return r;
-            if (h->wideband) {
-                const double* proto = (c.pfb_taps == 384) ? SNRX_PFB_ZB_384 : SNRX_PFB_ZB_768;
-                r = zb_wideband_init(h->zb, h->cfg, proto, h->max_caps, h->max_out, h->err);
-                if (r != SNRX_OK) return r;
-            }
-        }
-        CK(cudaMemset(h->d_totals, 0, 24 * sizeof(uint32_t)));
         return SNRX_OK;
     };
     int r = body();
@@ -394,27 +402,25 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
 
 int snrx_set_stream(snrx_t* h, void* cuda_stream) {
     if (!h) return SNRX_EINVAL;
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->user_stream = (cudaStream_t)cuda_stream;
     return SNRX_OK;
 }
 
 int snrx_set_channel(snrx_t* h, int channel) {
     if (!h) return SNRX_EINVAL;
     if (h->wideband) return fail(h, SNRX_EINVAL, "set_channel applies to the narrow-band modes");
+    CK(cudaSetDevice(h->device));
+    for (auto& ln : h->lane) CK(cudaStreamSynchronize(ln.tail));         // queued batches keep the channel they were queued with
     if (h->has_ble) {
         if (channel < 0 || channel > 39) return fail(h, SNRX_EINVAL, "BLE channel 0..39");
-        CK(cudaSetDevice(h->device));
         int32_t chans[40];
         for (int i = 0; i < 40; i++) chans[i] = channel;
-        CK(cudaMemcpyAsync(h->d_ble_channels, chans, sizeof chans, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(h->d_ble_channels, chans, sizeof chans, cudaMemcpyHostToDevice));
     } else {
         if (channel < 11 || channel > 26) return fail(h, SNRX_EINVAL, "802.15.4 channel 11..26");
-        CK(cudaSetDevice(h->device));
         int32_t chans[16];
         for (int i = 0; i < 16; i++) chans[i] = channel;
-        CK(cudaMemcpyAsync(h->zb.d_channels, chans, sizeof chans, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        for (auto& ln : h->lane) CK(cudaMemcpy(ln.zb.d_channels, chans, sizeof chans, cudaMemcpyHostToDevice));
     }
     h->cfg.channel = channel;
     return SNRX_OK;
@@ -423,12 +429,12 @@ int snrx_set_channel(snrx_t* h, int channel) {
 int snrx_sync(snrx_t* h) {
     if (!h) return SNRX_EINVAL;
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
+    for (auto& ln : h->lane) { CK(cudaStreamSynchronize(ln.stream)); CK(cudaStreamSynchronize(ln.tail)); }
     return SNRX_OK;
 }
 
 // ------------------------------------------------------------------------------------ process
-static int launch_ble_front(snrx_handle* h, const float2* x, uint32_t caps, uint64_t n_in, uint64_t stride,
+static int launch_ble_front(snrx_handle* h, Lane& ln, const float2* x, uint32_t caps, uint64_t n_in, uint64_t stride,
                             uint32_t n_out, int tile_begin, int tile_end, BitsLayout lay) {
     const bool dbg = (h->cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
     if (h->wideband) {
@@ -436,25 +442,25 @@ static int launch_ble_front(snrx_handle* h, const float2* x, uint32_t caps, uint
         a.x = x; a.stride = stride; a.n_in = (int64_t)n_in; a.n_out = (int32_t)n_out;
         a.n_tiles = tile_end - tile_begin;
         a.taps_rho = h->d_taps_rho; a.scale = h->cfg.quant_scale;
-        a.bits = h->d_bits; a.lay = lay; a.dbg_q8 = h->d_q8; a.dbg_cf = h->d_cf;
+        a.bits = ln.d_bits; a.lay = lay; a.dbg_q8 = ln.d_q8; a.dbg_cf = ln.d_cf;
         a.tile0 = tile_begin;
         const dim3 grid((unsigned)(a.n_tiles) * caps);
         if (h->pfb_nt == 16) {
-            if (dbg) k_pfb_ble<16, true><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, h->stream>>>(a);
-            else k_pfb_ble<16, false><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, h->stream>>>(a);
+            if (dbg) k_pfb_ble<16, true><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, ln.stream>>>(a);
+            else k_pfb_ble<16, false><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, ln.stream>>>(a);
         } else {
-            if (dbg) k_pfb_ble<32, true><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, h->stream>>>(a);
-            else k_pfb_ble<32, false><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, h->stream>>>(a);
+            if (dbg) k_pfb_ble<32, true><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, ln.stream>>>(a);
+            else k_pfb_ble<32, false><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, ln.stream>>>(a);
         }
     } else {
         NbArgs a;
         a.x = reinterpret_cast<const float4*>(x); a.stride = stride; a.n = (int64_t)n_in;
         a.n_groups = (int32_t)div_up(n_in, 128); a.n_captures = caps; a.scale = h->cfg.quant_scale;
-        a.bits = h->d_bits; a.lay = lay; a.dbg_q8 = h->d_q8;
+        a.bits = ln.d_bits; a.lay = lay; a.dbg_q8 = ln.d_q8;
         const uint64_t items = (uint64_t)caps * a.n_groups;
         const int grid = grid_for(h, items, 8, 8);
-        if (dbg) k_ble_slice_nb<true><<<grid, 256, 0, h->stream>>>(a);
-        else k_ble_slice_nb<false><<<grid, 256, 0, h->stream>>>(a);
+        if (dbg) k_ble_slice_nb<true><<<grid, 256, 0, ln.stream>>>(a);
+        else k_ble_slice_nb<false><<<grid, 256, 0, ln.stream>>>(a);
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -471,10 +477,12 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     if ((((uintptr_t)iq) & 15) || (n_captures > 1 && (stride_samples & 1))) return fail(h, SNRX_EINVAL, "captures must be 16-byte aligned (even stride)");
     if (h->wideband && (n_samples % kPfbD) != 0) return fail(h, SNRX_EINVAL, "wideband captures must hold a multiple of 24 samples");
     CK(cudaSetDevice(h->device));
-    snrx_handle::OutSlot& sl = h->slot[h->seq_process & 1];
-    if (sl.pending) return fail(h, SNRX_ESTATE, "two batches already queued: snrx_poll the oldest first");
+    const int li = (int)(h->seq_process & 1);
+    Lane& ln = h->lane[li];
+    if (ln.pending) return fail(h, SNRX_ESTATE, "two batches already queued: snrx_poll the oldest first");
     h->launches = 0;
-    // this slot's previous export (two batches ago) has been polled, hence finished: its buffers are free
+    // this lane's previous batch (two batches ago) has been polled, hence finished: its buffers are free
+    cudaStream_t st = ln.stream;
 
     const uint32_t n_out = (uint32_t)(n_samples / h->decim);
     uint32_t pre_out = 0, body_out = n_out, first_window = 0, first_capture = 0;
@@ -498,8 +506,12 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         }
     }
 
-    CK(cudaEventRecord(sl.ev_start, h->stream));
-    CK(cudaMemsetAsync(h->d_totals, 0, 8 * sizeof(uint32_t), h->stream));
+    if (is_device_ptr && h->user_stream) {          // device input is produced on the caller's stream
+        CK(cudaEventRecord(ln.ev_in, h->user_stream));
+        CK(cudaStreamWaitEvent(st, ln.ev_in, 0));
+    }
+    CK(cudaEventRecord(ln.ev_start, st));
+    CK(cudaMemsetAsync(ln.d_totals, 0, 8 * sizeof(uint32_t), st));
 
     // ---- input: device pointer as is, host pointer staged in chunks overlapped with the front end
     const float2* x = reinterpret_cast<const float2*>(iq);
@@ -508,12 +520,12 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     const uint64_t chunk_samples = 4ull << 20;                      // 32 MiB per copy
     if (staged) {
         const size_t need = (size_t)n_captures * n_samples * sizeof(float2);
-        if (need > h->d_x_bytes) {
-            if (h->d_x) { cudaFree(h->d_x); h->d_x = nullptr; h->d_x_bytes = 0; }
-            CK(cudaMalloc((void**)&h->d_x, need));
-            h->d_x_bytes = need;
+        if (need > ln.d_x_bytes) {
+            if (ln.d_x) { cudaFree(ln.d_x); ln.d_x = nullptr; ln.d_x_bytes = 0; }
+            CK(cudaMalloc((void**)&ln.d_x, need));
+            ln.d_x_bytes = need;
         }
-        x = h->d_x;
+        x = ln.d_x;
         x_stride = n_samples;
     }
 
@@ -522,25 +534,23 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         const uint32_t tiles = div_up(n_out, kTileT);
         lay.words_per_phase = kBitsLeadWords + tiles + kBitsTailWords;
         lay.n_channels = h->n_ble_ch;
-        CK(cudaMemsetAsync(h->d_bits, 0, (size_t)n_captures * h->n_ble_ch * 4 * lay.words_per_phase * sizeof(uint32_t), h->stream));
+        CK(cudaMemsetAsync(ln.d_bits, 0, (size_t)n_captures * h->n_ble_ch * 4 * lay.words_per_phase * sizeof(uint32_t), st));
     }
 
     if (staged) {
-        CK(cudaEventRecord(sl.ev_front0, h->stream));
-        // copy stream must not start overwriting the staging buffer before earlier work on the compute stream finished
-        CK(cudaEventRecord(sl.ev_front, h->stream));
-        CK(cudaStreamWaitEvent(h->copy_stream, sl.ev_front, 0));
+        CK(cudaEventRecord(ln.ev_front0, st));
+        // the copy stream serialises the staging copies of both lanes (one PCIe link anyway)
         size_t ev_i = 0;
         for (uint32_t c = 0; c < n_captures; c++) {
             const float2* src = reinterpret_cast<const float2*>(iq) + (size_t)c * stride_samples;
-            float2* dst = h->d_x + (size_t)c * n_samples;
+            float2* dst = ln.d_x + (size_t)c * n_samples;
             int tile_done = 0;
             for (uint64_t off = 0; off < n_samples; off += chunk_samples) {
                 const uint64_t len = std::min<uint64_t>(chunk_samples, n_samples - off);
                 CK(cudaMemcpyAsync(dst + off, src + off, len * sizeof(float2), cudaMemcpyHostToDevice, h->copy_stream));
-                if (ev_i >= h->ev_chunks.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->ev_chunks.push_back(e); }
-                CK(cudaEventRecord(h->ev_chunks[ev_i], h->copy_stream));
-                CK(cudaStreamWaitEvent(h->stream, h->ev_chunks[ev_i], 0));
+                if (ev_i >= ln.ev_chunks.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.ev_chunks.push_back(e); }
+                CK(cudaEventRecord(ln.ev_chunks[ev_i], h->copy_stream));
+                CK(cudaStreamWaitEvent(st, ln.ev_chunks[ev_i], 0));
                 ev_i++;
                 if (h->has_ble && h->wideband && !h->has_zb && n_captures == 1) {
                     // launch the channelizer on the tiles whose input has fully arrived
@@ -548,7 +558,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
                     const bool last = (have == n_samples);
                     int tile_end = last ? (int)div_up(n_out, kTileStride) : (int)(((int64_t)(have / kPfbD) - kTileT) / kTileStride);
                     if (tile_end > tile_done) {
-                        int r = launch_ble_front(h, x, 1, n_samples, x_stride, n_out, tile_done, tile_end, lay);
+                        int r = launch_ble_front(h, ln, x, 1, n_samples, x_stride, n_out, tile_done, tile_end, lay);
                         if (r != SNRX_OK) return r;
                         tile_done = tile_end;
                     }
@@ -560,11 +570,14 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     if (h->has_ble) {
         const bool pipelined = staged && h->wideband && !h->has_zb && n_captures == 1;
         if (!pipelined) {
-            CK(cudaEventRecord(sl.ev_front0, h->stream));
-            int r = launch_ble_front(h, x, n_captures, n_samples, x_stride, n_out, 0, (int)div_up(n_out, h->wideband ? kTileStride : kTileT), lay);
+            CK(cudaEventRecord(ln.ev_front0, st));
+            int r = launch_ble_front(h, ln, x, n_captures, n_samples, x_stride, n_out, 0, (int)div_up(n_out, h->wideband ? kTileStride : kTileT), lay);
             if (r != SNRX_OK) return r;
         }
-        CK(cudaEventRecord(sl.ev_front, h->stream));
+        CK(cudaEventRecord(ln.ev_front, st));
+        CK(cudaEventRecord(ln.ev_handoff, st));
+        st = ln.tail;                                  // the rest of the batch runs on the high-priority stream
+        CK(cudaStreamWaitEvent(st, ln.ev_handoff, 0));
 
         BleParams p{};
         p.aa = h->cfg.access_addr;
@@ -582,53 +595,52 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         const uint32_t w_items = n_captures * h->n_ble_ch * (uint32_t)p.n_windows;
 
         const int g_aa = grid_for(h, aa_items, 8, 8);
-        k_aa_search<false><<<g_aa, 256, 0, h->stream>>>(h->d_bits, lay, p, n_chunks, h->d_counts, nullptr, nullptr, 0);
-        h->launches += 1 + exclusive_scan(h->d_counts, aa_items, h->d_offsets, h->d_scratch, h->stream);
-        k_aa_search<true><<<g_aa, 256, 0, h->stream>>>(h->d_bits, lay, p, n_chunks, h->d_counts, h->d_offsets, h->d_cands, h->cand_cap);
-        k_ble_decode<<<h->sm_count * 16, 128, 0, h->stream>>>(h->d_bits, lay, p, h->d_offsets + aa_items, h->cand_cap, h->d_cands,
-                                                          h->d_decs, h->d_crc_tab, h->d_whiten, h->d_ble_channels);
+        k_aa_search<<<g_aa, 256, 0, st>>>(ln.d_bits, lay, p, n_chunks, ln.d_counts, ln.d_hits);
+        h->launches += 1 + exclusive_scan(ln.d_counts, aa_items, ln.d_offsets, ln.d_scratch, st);
+        k_aa_fill<<<g_aa, 256, 0, st>>>(ln.d_bits, ln.d_hits, lay, p, n_chunks, ln.d_counts, ln.d_offsets, ln.d_cands, h->cand_cap);
+        k_ble_decode<<<h->sm_count * 16, 128, 0, st>>>(ln.d_bits, lay, p, ln.d_offsets + aa_items, h->cand_cap, ln.d_cands,
+                                                   ln.d_decs, h->d_crc_tab, h->d_whiten, h->d_ble_channels);
         const int g_w = grid_for(h, w_items, 256, 8);
-        k_ble_resolve<false><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, h->d_wcounts, nullptr,
-                                                        nullptr, 0, h->d_ble_channels, h->cand_cap);
-        h->launches += 3 + exclusive_scan(h->d_wcounts, w_items, h->d_woffsets, h->d_scratch, h->stream);
-        k_ble_resolve<true><<<g_w, 256, 0, h->stream>>>(h->d_cands, h->d_decs, h->d_offsets, n_chunks, p, h->d_wcounts, h->d_woffsets,
-                                                       sl.d_frames, h->frame_cap, h->d_ble_channels, h->cand_cap);
+        k_ble_resolve<false><<<g_w, 256, 0, st>>>(ln.d_cands, ln.d_decs, ln.d_offsets, n_chunks, p, ln.d_wcounts, nullptr,
+                                                 nullptr, 0, h->d_ble_channels, h->cand_cap);
+        h->launches += 3 + exclusive_scan(ln.d_wcounts, w_items, ln.d_woffsets, ln.d_scratch, st);
+        k_ble_resolve<true><<<g_w, 256, 0, st>>>(ln.d_cands, ln.d_decs, ln.d_offsets, n_chunks, p, ln.d_wcounts, ln.d_woffsets,
+                                                ln.d_frames, h->frame_cap, h->d_ble_channels, h->cand_cap);
         h->launches += 1;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->d_totals + 0, h->d_woffsets + w_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
-        CK(cudaMemcpyAsync(h->d_totals + 1, h->d_offsets + aa_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
-        h->b_aa_items = aa_items;
-        h->b_w_items = w_items;
+        CK(cudaMemcpyAsync(ln.d_totals + 0, ln.d_woffsets + w_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(ln.d_totals + 1, ln.d_offsets + aa_items, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    }
+    if (h->has_zb && !h->has_ble) {
+        CK(cudaEventRecord(ln.ev_handoff, st));        // Zigbee only: front end and chains all on the tail stream
+        st = ln.tail;
+        CK(cudaStreamWaitEvent(st, ln.ev_handoff, 0));
     }
     if (h->has_zb) {
         const uint32_t first_segment = (uint32_t)(((uint64_t)first_window * kWindow) / h->cfg.zb_segment);
-        int r = zb_process(h->zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_segment,
-                           first_capture, sl.d_frames, h->frame_cap, h->d_totals, h->has_ble, h->stream, h->sm_count,
+        int r = zb_process(ln.zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_segment,
+                           first_capture, ln.d_frames, h->frame_cap, ln.d_totals, h->has_ble, st, h->sm_count,
                            h->launches, h->err);
         if (r != SNRX_OK) return r;
-        if (!h->has_ble) { CK(cudaEventRecord(sl.ev_front0, h->stream)); CK(cudaEventRecord(sl.ev_front, h->stream)); }
+        if (!h->has_ble) { CK(cudaEventRecord(ln.ev_front0, st)); CK(cudaEventRecord(ln.ev_front, st)); }
     }
-    // totals of this batch are snapshotted so that the next batch may reset d_totals while the export runs
-    CK(cudaMemcpyAsync(h->d_totals + 8 + 8 * (h->seq_process & 1), h->d_totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaEventRecord(sl.ev_compute, h->stream));
-    // export: device frame list -> pinned host memory on a side stream (overlaps the next batch's front end)
-    CK(cudaStreamWaitEvent(h->export_stream, sl.ev_compute, 0));
-    k_export_frames<<<h->sm_count * 2, 256, 0, h->export_stream>>>(sl.d_frames, h->d_totals + 8 + 8 * (h->seq_process & 1), sl.frames,
-                                                                 sl.totals, h->frame_cap);
+    // export: device frame list -> pinned host memory; on this lane's stream, so it overlaps the other lane's front end
+    k_export_frames<<<32, 256, 0, st>>>(ln.d_frames, ln.d_totals, ln.frames, ln.totals, h->frame_cap);
     h->launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(sl.ev_done, h->export_stream));
-    sl.pending = true; sl.done = false;
-    sl.caps = n_captures; sl.n_in = n_samples; sl.n_out = n_out; sl.launches = h->launches;
+    CK(cudaEventRecord(ln.ev_done, st));
+    ln.pending = true; ln.done = false;
+    ln.caps = n_captures; ln.n_in = n_samples; ln.n_out = n_out; ln.launches = h->launches;
     h->seq_process++;
     h->b_caps = n_captures; h->b_n_in = n_samples; h->b_n_out = n_out;
     h->batch_valid = true;
+    h->last_lane = li;
     return SNRX_OK;
 }
 
 // wait for the oldest queued batch, fill its stats; does not consume it
-static int finish_oldest(snrx_handle* h, snrx_handle::OutSlot** out_slot) {
-    snrx_handle::OutSlot& sl = h->slot[h->seq_poll & 1];
+static int finish_oldest(snrx_handle* h, Lane** out_lane) {
+    Lane& sl = h->lane[h->seq_poll & 1];
     if (!sl.pending) return fail(h, SNRX_ESTATE, "snrx_poll without a queued batch");
     if (!sl.done) {
         CK(cudaSetDevice(h->device));
@@ -653,13 +665,13 @@ static int finish_oldest(snrx_handle* h, snrx_handle::OutSlot** out_slot) {
         h->stats.gpu_ms = ms;
         h->stats.gpu_ms_frontend = msf;
     }
-    *out_slot = &sl;
+    *out_lane = &sl;
     return SNRX_OK;
 }
 
 int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
     if (!h) return SNRX_EINVAL;
-    snrx_handle::OutSlot* sl = nullptr;
+    Lane* sl = nullptr;
     int r = finish_oldest(h, &sl);
     if (r != SNRX_OK) return r;
     if (n_out) *n_out = sl->n_frames;
@@ -673,7 +685,7 @@ int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
 
 int snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out) {
     if (!h) return SNRX_EINVAL;
-    snrx_handle::OutSlot* sl = nullptr;
+    Lane* sl = nullptr;
     int r = finish_oldest(h, &sl);
     if (r != SNRX_OK) return r;
     if (frames) *frames = sl->frames;
@@ -685,11 +697,9 @@ int snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out) {
 
 int snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev) {
     if (!h || !h->batch_valid) return SNRX_ESTATE;
-    snrx_handle::OutSlot& sl = h->slot[(h->seq_process + 1) & 1];      // slot of the most recent snrx_process
-    void* dp = nullptr;
-    dp = sl.d_frames;
-    if (frames_dev) *frames_dev = dp;
-    if (count_dev) *count_dev = h->d_totals;
+    Lane& sl = h->lane[h->last_lane];                                   // lane of the most recent snrx_process
+    if (frames_dev) *frames_dev = sl.d_frames;
+    if (count_dev) *count_dev = sl.d_totals;
     return SNRX_OK;
 }
 
@@ -702,28 +712,30 @@ int snrx_stats(snrx_t* h, snrx_stats_t* s) {
 int snrx_debug_stage(snrx_t* h, int stage, void* out, uint64_t cap_bytes, uint64_t* n_bytes) {
     if (!h || !h->batch_valid) return SNRX_ESTATE;
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));
+    Lane& ln = h->lane[h->last_lane];                                    // streams of the most recent snrx_process
+    CK(cudaStreamSynchronize(ln.stream));
+    CK(cudaStreamSynchronize(ln.tail));
     const void* src = nullptr;
     uint64_t bytes = 0;
     switch (stage) {
         case SNRX_STAGE_BLE_Q8:
-            if (!h->d_q8) return fail(h, SNRX_ESTATE, "create the engine with SNRX_F_KEEP_STREAMS");
-            src = h->d_q8; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 2; break;
+            if (!ln.d_q8) return fail(h, SNRX_ESTATE, "create the engine with SNRX_F_KEEP_STREAMS");
+            src = ln.d_q8; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 2; break;
         case SNRX_STAGE_CHAN_CF32:
             if (h->cfg.mode == SNRX_MODE_ZB_WB16) {
-                int r = zb_debug_stage(h->zb, stage, h->b_caps, h->b_n_out, &src, &bytes);
+                int r = zb_debug_stage(ln.zb, stage, h->b_caps, h->b_n_out, &src, &bytes);
                 if (r != SNRX_OK) return fail(h, r, "create the engine with SNRX_F_KEEP_STREAMS");
                 break;
             }
-            if (!h->d_cf) return fail(h, SNRX_ESTATE, "create a wideband engine with SNRX_F_KEEP_STREAMS");
-            src = h->d_cf; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 8; break;
+            if (!ln.d_cf) return fail(h, SNRX_ESTATE, "create a wideband engine with SNRX_F_KEEP_STREAMS");
+            src = ln.d_cf; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 8; break;
         case SNRX_STAGE_BLE_BITS: {
-            if (!h->d_bits) return SNRX_ESTATE;
+            if (!ln.d_bits) return SNRX_ESTATE;
             const uint32_t wpp = kBitsLeadWords + div_up(h->b_n_out, kTileT) + kBitsTailWords;
-            src = h->d_bits; bytes = (uint64_t)h->b_caps * h->n_ble_ch * 4 * wpp * 4; break;
+            src = ln.d_bits; bytes = (uint64_t)h->b_caps * h->n_ble_ch * 4 * wpp * 4; break;
         }
         default: {
-            int r = zb_debug_stage(h->zb, stage, h->b_caps, h->b_n_out, &src, &bytes);
+            int r = zb_debug_stage(ln.zb, stage, h->b_caps, h->b_n_out, &src, &bytes);
             if (r != SNRX_OK) return fail(h, r, "stage not available in this mode");
         }
     }
