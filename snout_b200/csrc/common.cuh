@@ -56,6 +56,54 @@ SNRX_HD float f_div(float a, float b) {
     volatile float r = a / b; return r;
 #endif
 }
+// ---- packed pairs: sm_100 issues two FP32 operations on a 64-bit register pair as ONE instruction
+// (PTX fma/add/mul.rn.f32x2 -> SASS FFMA2/FADD2/FMUL2; ptxas folds operand swaps, per-half negation and
+// scalar broadcast into the instruction).  Same FP32-pipe time as two scalar ops but half the issue
+// slots -- and the channelizer is issue bound.  Each half is an IEEE-754 round-to-nearest operation,
+// so the host statement below (tests/emu) is bit-identical.
+#if defined(__CUDACC__)
+SNRX_HD float2 f2_fma(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+    unsigned long long ra, rb, rc, rd;
+    float2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+SNRX_HD float2 f2_add(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    unsigned long long ra, rb, rd;
+    float2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+#else
+    return make_float2(f_add(a.x, b.x), f_add(a.y, b.y));
+#endif
+}
+SNRX_HD float2 f2_mul(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+    unsigned long long ra, rb, rd;
+    float2 d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+#else
+    return make_float2(f_mul(a.x, b.x), f_mul(a.y, b.y));
+#endif
+}
+#endif
+
 SNRX_HD double d_mul(double a, double b) {
 #ifdef __CUDA_ARCH__
     return __dmul_rn(a, b);

@@ -4,7 +4,8 @@
 // Everything is resolved at compile time: the recursion is template recursion, all array
 // indices are constants after unrolling (so the arrays live in registers) and the twiddles are
 // constexpr values that end up as FFMA immediates.  Radix-2 decimation in time below a single
-// radix-3 stage; butterflies use the 6-FMA form  out0 = E + w O, out1 = 2E - out0.
+// radix-3 stage; butterflies use the form  out0 = E + w O, out1 = 2E - out0, written on (re, im) register
+// pairs so that each complex multiply-add is 2-3 packed FFMA2 instructions (common.cuh f2_*).
 #pragma once
 #include "common.cuh"
 
@@ -46,23 +47,27 @@ template <int NUM, int DEN> struct Tw {
     static constexpr float s = (float)detail::cx_sin_frac(NUM, DEN);
 };
 
+// complex values as register pairs; every helper below is one packed instruction
+SNRX_HD float2 P(const cf& x) { return make_float2(x.r, x.i); }
+SNRX_HD float2 Psw(const cf& x) { return make_float2(x.i, x.r); }          // swapped halves: folded into the operand
+SNRX_HD cf C(const float2& x) { return cf{x.x, x.y}; }
+
 // out0 = e + w*o ; out1 = e - w*o   with w = exp(+j 2 pi K / N)
 template <int K, int N>
 SNRX_HD void bfly(const cf& e, const cf& o, cf& out0, cf& out1) {
     constexpr int k = ((K % N) + N) % N;
     if constexpr (k == 0) {
-        out0.r = f_add(e.r, o.r); out0.i = f_add(e.i, o.i);
-        out1.r = f_sub(e.r, o.r); out1.i = f_sub(e.i, o.i);
-    } else if constexpr (4 * k == N) {          // w = +j
-        out0.r = f_sub(e.r, o.i); out0.i = f_add(e.i, o.r);
-        out1.r = f_add(e.r, o.i); out1.i = f_sub(e.i, o.r);
+        out0 = C(f2_add(P(e), P(o)));
+        out1 = C(f2_fma(P(o), make_float2(-1.0f, -1.0f), P(e)));
+    } else if constexpr (4 * k == N) {          // w = +j: w*o = (-o.i, o.r)
+        out0 = C(f2_fma(Psw(o), make_float2(-1.0f, 1.0f), P(e)));
+        out1 = C(f2_fma(Psw(o), make_float2(1.0f, -1.0f), P(e)));
     } else {
         constexpr float c = Tw<k, N>::c, s = Tw<k, N>::s;
-        float r0 = f_fma(c, o.r, f_fma(-s, o.i, e.r));
-        float i0 = f_fma(c, o.i, f_fma(s, o.r, e.i));
-        out0.r = r0; out0.i = i0;
-        out1.r = f_fma(2.0f, e.r, -r0);
-        out1.i = f_fma(2.0f, e.i, -i0);
+        const float2 t = f2_fma(make_float2(-s, s), Psw(o), P(e));
+        const float2 r0 = f2_fma(make_float2(c, c), P(o), t);
+        out0 = C(r0);
+        out1 = C(f2_fma(make_float2(2.0f, 2.0f), P(e), make_float2(-r0.x, -r0.y)));
     }
 }
 
@@ -100,7 +105,7 @@ SNRX_HD cf twmul(const cf& x) {
         return cf{x.i, -x.r};
     } else {
         constexpr float c = Tw<k, N>::c, s = Tw<k, N>::s;
-        return cf{f_fma(c, x.r, f_mul(-s, x.i)), f_fma(c, x.i, f_mul(s, x.r))};
+        return C(f2_fma(make_float2(c, c), P(x), f2_mul(make_float2(-s, s), Psw(x))));
     }
 }
 
@@ -112,19 +117,17 @@ struct Idft3xQ {
     template <int K1>
     SNRX_HD static void combine(const cf* f0, const cf* f1, const cf* f2, cf* out) {
         constexpr float h = 0.86602540378443864676f;   // sqrt(3)/2
-        cf a = f0[K1];
-        cf b = twmul<K1, N>(f1[K1]);
-        cf c = twmul<2 * K1, N>(f2[K1]);
-        cf s{f_add(b.r, c.r), f_add(b.i, c.i)};
-        cf d{f_sub(b.r, c.r), f_sub(b.i, c.i)};
-        out[K1].r = f_add(a.r, s.r);
-        out[K1].i = f_add(a.i, s.i);
-        cf m{f_fma(-0.5f, s.r, a.r), f_fma(-0.5f, s.i, a.i)};
-        // k2 = 1: a + w b + w^2 c, w = exp(+j 2pi/3) = -1/2 + j h  ->  m + j h d
-        out[K1 + Q].r = f_fma(-h, d.i, m.r);
-        out[K1 + Q].i = f_fma(h, d.r, m.i);
-        out[K1 + 2 * Q].r = f_fma(h, d.i, m.r);
-        out[K1 + 2 * Q].i = f_fma(-h, d.r, m.i);
+        const float2 a = P(f0[K1]);
+        const cf bb = twmul<K1, N>(f1[K1]);
+        const cf cc = twmul<2 * K1, N>(f2[K1]);
+        const float2 s = f2_add(P(bb), P(cc));
+        const float2 d = f2_fma(P(cc), make_float2(-1.0f, -1.0f), P(bb));
+        out[K1] = C(f2_add(a, s));
+        const float2 m = f2_fma(make_float2(-0.5f, -0.5f), s, a);
+        // k2 = 1: a + w b + w^2 c, w = exp(+j 2pi/3) = -1/2 + j h  ->  m + j h d ;  k2 = 2: m - j h d
+        const float2 dsw = make_float2(d.y, d.x);
+        out[K1 + Q] = C(f2_fma(make_float2(-h, h), dsw, m));
+        out[K1 + 2 * Q] = C(f2_fma(make_float2(h, -h), dsw, m));
         if constexpr (K1 + 1 < Q) combine<K1 + 1>(f0, f1, f2, out);
     }
     SNRX_HD static void run(const cf* in, cf* out) {

@@ -12,20 +12,24 @@
 // followed, per channel, by the int8-grid quantiser and the reference's one-sample
 // cross-product slicer (btle_rx.c:1357-1361); only ONE BIT per channel sample leaves the SM.
 //
-// One CTA (192 threads) computes 128 channel-rate samples x 40 channels from 3048 + L input
-// samples and emits the 127 slicer decisions that have their successor inside the tile (tiles
-// advance by 127 samples, so tiles are independent: no carry, no stitch pass):
-//   phase 0  cp.async stages the input tile into shared memory in 3 KiB pieces (coalesced 16-byte
-//            copies, one per thread and piece); the tile is laid out flat with a 64-byte skew
-//            every 384 samples so that phase 1 is bank-conflict free;
-//   phase 1  FIR: thread (rho, chunk) owns decimated sequence X_rho[c] = x[24 c - rho] and 16
-//            consecutive output times; taps of that rho live in registers, each loaded sample
-//            feeds up to 16 FMAs (register sliding window);
-//   phase 2  one thread per output time runs the fully unrolled 48-point inverse DFT in
-//            registers (fft.cuh), applies the bin rotation, quantises;
-//   phase 3  neighbour samples by warp shuffle, cross product, __ballot_sync -> bit masks,
-//            de-interleaved into the 4 sample phases, assembled into words in shared memory and
-//            OR-ed into the global bit streams.
+// One WARP computes 32 channel-rate samples x 40 channels end to end; a CTA is W such warps (default
+// 2: 64 samples from 1512 + L input samples) that share only the staged input tile and the one
+// column the slicer needs from the next warp.  Tiles advance by 32 W - 1 samples (the last sample
+// of a tile has no successor inside it), so tiles are independent: no carry, no stitch pass.
+//   phase 0  cp.async stages the input tile into shared memory (coalesced 16-byte copies); the tile
+//            is laid out flat with a 64-byte skew every 192 samples so that phase 1 is bank-conflict
+//            free; one __syncthreads, the only CTA-wide barrier before the bit hand-over;
+//   phase 1  FIR, per warp: lane (rho mod 8, chunk) owns decimated sequence X_rho[c] = x[24 c - rho]
+//            and 8 consecutive output times, three passes cover rho = 0..23 (branches rho, rho+24);
+//            taps of that rho live in registers, each loaded sample feeds up to 16 FMAs (register
+//            sliding window); results go to the warp's private V[48][32] (+1 pad) tile;
+//   phase 2  __syncwarp, then one lane per output time runs the fully unrolled 48-point inverse DFT
+//            in registers (fft.cuh), applies the bin rotation, quantises;
+//   phase 3  neighbour samples by warp shuffle (lane 31: first column of the next warp, through
+//            shared memory), cross product, __ballot_sync -> bit masks, de-interleaved into the 4
+//            sample phases, assembled into words in shared memory and OR-ed into the global bit streams.
+// Every warp is busy in every phase and warps only meet at two barriers per tile, so the SM's
+// schedulers always have 8-10 independent instruction streams (ncu: profiles/).
 #pragma once
 #include "common.cuh"
 #include "fft.cuh"
@@ -35,9 +39,8 @@ namespace snrx {
 constexpr int kPfbD = 24;
 constexpr int kTileT = 128;                    // channel-rate samples computed per tile
 constexpr int kTileStride = 127;               // samples whose slicer bit the tile emits (needs y[m+1])
-constexpr int kChunkT = 16;                    // output times per FIR thread
-constexpr int kFirThreads = 24 * (kTileT / kChunkT);   // 192
-constexpr int kVStride = 193;                  // float2 per V row: 128 + 8*8 skew columns + 1
+constexpr int kChunkT = 8;                     // output times per FIR lane and pass
+constexpr int kVStride = 33;                   // float2 per row of a warp's V[48][32] tile (odd: conflict free)
 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23: (x + kMagic) - kMagic == rint(x)
 
 // BLE bank: even bin 2q (q = 0..47) -> BLE channel number, or -1 (bins +-41..+-47 MHz carry no channel)
@@ -53,12 +56,22 @@ SNRX_HD constexpr int ble_channel_of_q(int q) {
 template <int TT>
 SNRX_HD constexpr int xs_pos(int ip) { return ip + 8 * ((ip + 12) / (24 * TT)); }
 
-template <int NT, int TT = 16> struct PfbGeom {
+template <int NT, int TT = 16, int T = kTileT> struct PfbGeom {
     static constexpr int kHist = 24 * NT;                              // L: 384 or 768
-    static constexpr int kTileIn = kHist + kPfbD * (kTileT - 1) + 2;   // samples i' = 0 .. kTileIn-1 (even count)
+    static constexpr int kTileIn = kHist + kPfbD * (T - 1) + 2;        // samples i' = 0 .. kTileIn-1 (even count)
     static constexpr int kPieces = (kTileIn + 12 + 24 * TT - 1) / (24 * TT);   // skew periods touched
     static constexpr int kXsLen = xs_pos<TT>(kTileIn) + 8;             // float2
-    static constexpr int kSmemBytes = (kXsLen + 48 * kVStride) * 8 + 40 * 4 * 2 * 4 + 4 * 48 * 8;   // BLE kernel
+};
+
+// BLE kernel: W warps per CTA, 32 output times per warp
+template <int NT, int W> struct PfbBleGeom {
+    static constexpr int kT = 32 * W;                                  // channel-rate samples computed per tile
+    static constexpr int kStride = kT - 1;                             // samples whose slicer bit the tile emits
+    static constexpr int kThreads = 32 * W;
+    using G = PfbGeom<NT, kChunkT, kT>;
+    static constexpr int kVWarp = 48 * kVStride;                       // float2 per warp
+    static constexpr int kSmemBytes = (G::kXsLen + W * kVWarp + W * 48) * 8 + 40 * 4 * 2 * 4;
+    static constexpr int kCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) < 16 ? (227 * 1024) / (kSmemBytes + 1024) : 16;
 };
 
 // FIR of one thread.  xb = &xs[xs_pos-base of this thread], see fir_base().  acc[a][e] accumulates
@@ -81,8 +94,7 @@ SNRX_HD void pfb_fir_thread(const float2* xb, int s0 /* 8 if rho <= 12 else 0 */
         for (int e = 0; e < TT; e++) {
             const int d = e - u;
             if (d >= 0 && d < NT) {
-                acc[d % A][e].x = f_fma(g[d], x.x, acc[d % A][e].x);
-                acc[d % A][e].y = f_fma(g[d], x.y, acc[d % A][e].y);
+                acc[d % A][e] = f2_fma(make_float2(g[d], g[d]), x, acc[d % A][e]);
             }
         }
     }
@@ -95,8 +107,6 @@ SNRX_HD int fir_base(int rho, int q) {
     return PfbGeom<NT, TT>::kHist + 24 * TT * q - rho + 8 * (PfbGeom<NT, TT>::kHist / (24 * TT) + q);
 }
 
-SNRX_HD constexpr int v_col(int m) { return m + 8 * (m / 16); }
-
 SNRX_HD float quant_fused(float y, float scale_signed) {
     float t = f_fma(y, scale_signed, kMagic);
     t = fminf(fmaxf(t, kMagic - 128.0f), kMagic + 127.0f);
@@ -106,11 +116,11 @@ SNRX_HD float quant_fused(float y, float scale_signed) {
 // 48-point inverse DFT of one output time + rotation + quantisation, in place:
 // on return y[q] holds the quantised (I, Q) of even bin 2q as integer-valued floats.
 // s_even / s_odd: quantiser scale with the sign of (-1)^(q m) folded in (0 beyond the capture end).
-SNRX_HD void pfb_dft48_quant(const float2* vcol /* &V[0][v_col(m)] */, cf (&y)[48], float s_even, float s_odd,
+SNRX_HD void pfb_dft48_quant(const float2* vcol /* &V[0][lane] of the warp tile */, cf (&y)[48], float s_even, float s_odd,
                              cf (&raw)[48], bool keep_raw) {
     cf v[48];
 #pragma unroll
-    for (int r = 0; r < 48; r++) { float2 t = vcol[r * kVStride]; v[r].r = t.x; v[r].i = t.y; }
+    for (int r = 0; r < 48; r++) { float2 t = vcol[r * kVStride]; v[r].r = t.x; v[r].i = t.y; }   // vcol = &V[0][lane]
     Idft3xQ<48>::run(v, y);
 #pragma unroll
     for (int q = 0; q < 48; q++) {
@@ -158,21 +168,17 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
 }
 
 // Stage tile samples i' = 0 .. kTileIn-1 (capture samples x0 + i') into the skewed tile: piece p holds
-// i' in [24 TT p - 12, 24 TT (p+1) - 12) at position i' + 8 p; each thread copies one 16-byte pair per piece.
-template <int NT, int TT, int THREADS>
+// i' in [24 TT p - 12, 24 TT (p+1) - 12) at position i' + 8 p; 16-byte copies (one sample pair each).
+template <class G, int TT, int THREADS>
 __device__ __forceinline__ void pfb_stage_tile(float2* xs, const float2* xcap, int64_t x0, int64_t n_in, int tid) {
-    using G = PfbGeom<NT, TT>;
-    constexpr int kPer = 24 * TT;
-    static_assert(kPer / 2 <= THREADS, "one pair per thread and piece");
-    if (tid < kPer / 2) {
-#pragma unroll
-        for (int p = 0; p < G::kPieces; p++) {
-            const int ip = kPer * p - 12 + 2 * tid;
-            if (ip >= 0 && ip < G::kTileIn) {
-                const int64_t i = x0 + ip;
-                const bool ok = (i >= 0) && (i + 1 < n_in);
-                cp_async16(xs + ip + 8 * p, xcap + (ok ? i : 0), ok);
-            }
+    constexpr int kPer = 24 * TT, kPairs = kPer / 2;
+    for (int idx = tid; idx < G::kPieces * kPairs; idx += THREADS) {
+        const int p = idx / kPairs, t = idx - p * kPairs;
+        const int ip = kPer * p - 12 + 2 * t;
+        if (ip >= 0 && ip < G::kTileIn) {
+            const int64_t i = x0 + ip;
+            const bool ok = (i >= 0) && (i + 1 < n_in);
+            cp_async16(xs + ip + 8 * p, xcap + (ok ? i : 0), ok);
         }
     }
 }
@@ -192,77 +198,82 @@ struct PfbBleArgs {
     float2* dbg_cf;           // [cap][40][n_out] or null
 };
 
-template <int NT, bool DEBUG>
-__global__ void __launch_bounds__(kFirThreads, 2) k_pfb_ble(PfbBleArgs a) {
-    using G = PfbGeom<NT>;
+template <int NT, int W, bool DEBUG>
+__global__ void __launch_bounds__(32 * W, PfbBleGeom<NT, W>::kCtasPerSm) k_pfb_ble(PfbBleArgs a) {
+    using B = PfbBleGeom<NT, W>;
+    using G = typename B::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);
-    float2* V = xs + G::kXsLen;                                            // [48][kVStride]
-    uint32_t* wordbuf = reinterpret_cast<uint32_t*>(V + 48 * kVStride);    // [40][4][2]
-    float2* edge = reinterpret_cast<float2*>(wordbuf + 320);               // [4][48] first lane of each warp
+    float2* Vall = xs + G::kXsLen;                                         // [W][48][kVStride]
+    float2* edge = Vall + W * B::kVWarp;                                   // [W][48] first column of each warp
+    uint32_t* wordbuf = reinterpret_cast<uint32_t*>(edge + W * 48);        // [40][4][2]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = a.tile0 + (int)(blockIdx.x % a.n_tiles);
     const int cap = blockIdx.x / a.n_tiles;
     const float2* xcap = a.x + (size_t)cap * a.stride;
-    const int g_first = kTileStride * tile;                                // first channel sample of the tile
+    const int g_first = B::kStride * tile;                                 // first channel sample of the tile
+    float2* V = Vall + wid * B::kVWarp;
 
     // ---- phase 0: stage the input tile
-    pfb_stage_tile<NT, kChunkT, kFirThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, tid);
-    const int rho = 8 * (wid % 3) + (lane & 7);
-    const int q = 4 * (wid / 3) + (lane >> 3);
-    float g[NT];
-#pragma unroll
-    for (int d = 0; d < NT; d++) g[d] = __ldg(a.taps_rho + rho * NT + d);   // taps of this thread's rho
-    for (int i = tid; i < 320; i += kFirThreads) wordbuf[i] = 0u;
+    pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, tid);
+    for (int i = tid; i < 320; i += B::kThreads) wordbuf[i] = 0u;
     cp_async_commit_wait_all();
     __syncthreads();
 
-    // ---- phase 1: FIR -> V[r][v_col(m)]
+    // ---- phase 1: FIR of this warp's 32 output times -> V[r][m]
     {
-        float2 acc[2][kChunkT];
-        pfb_fir_thread<NT, 2, kChunkT>(xs + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+        const int rl = lane & 7, c = lane >> 3, q = 4 * wid + c;           // q: chunk of 8 output times inside the tile
+#pragma unroll 1
+        for (int gi = 0; gi < 3; gi++) {
+            const int rho = 8 * gi + rl;
+            float g[NT];
 #pragma unroll
-        for (int e = 0; e < kChunkT; e++) {
-            V[rho * kVStride + 24 * q + e] = acc[0][e];
-            V[(rho + 24) * kVStride + 24 * q + e] = acc[1][e];
+            for (int d = 0; d < NT; d++) g[d] = __ldg(a.taps_rho + rho * NT + d);
+            float2 acc[2][kChunkT];
+            pfb_fir_thread<NT, 2, kChunkT>(xs + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+#pragma unroll
+            for (int e = 0; e < kChunkT; e++) {
+                V[rho * kVStride + 8 * c + e] = acc[0][e];
+                V[(rho + 24) * kVStride + 8 * c + e] = acc[1][e];
+            }
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase 2: 48-point inverse DFT + rotation + quantiser, one thread per output time
-    if (wid < 4) {
-        cf y[48];
-        const int m = tid;                                   // 0..127
-        const int mg = g_first + m;                          // channel-rate sample index in the capture
-        {
-            const float s = (mg < a.n_out) ? a.scale : 0.0f;
-            cf raw[48];
-            pfb_dft48_quant(V + v_col(m), y, s, (mg & 1) ? -s : s, raw, DEBUG);
-            if (DEBUG && m < kTileStride && mg < a.n_out) {
+    // ---- phase 2: 48-point inverse DFT + rotation + quantiser, one lane per output time
+    cf y[48];
+    const int m = tid;                                       // 0 .. 32 W - 1
+    const int mg = g_first + m;                              // channel-rate sample index in the capture
+    {
+        const float s = (mg < a.n_out) ? a.scale : 0.0f;
+        cf raw[48];
+        pfb_dft48_quant(V + lane, y, s, (mg & 1) ? -s : s, raw, DEBUG);
+        if (DEBUG && m < B::kStride && mg < a.n_out) {
 #pragma unroll
-                for (int qq = 0; qq < 48; qq++) {
-                    const int ch = ble_channel_of_q(qq);
-                    if (ch >= 0) {
-                        const size_t o = ((size_t)cap * 40 + ch) * (size_t)a.n_out + mg;
-                        if (a.dbg_q8) { a.dbg_q8[2 * o] = (int8_t)y[qq].r; a.dbg_q8[2 * o + 1] = (int8_t)y[qq].i; }
-                        if (a.dbg_cf) {
-                            const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
-                            a.dbg_cf[o] = make_float2(raw[qq].r * sg, raw[qq].i * sg);
-                        }
+            for (int qq = 0; qq < 48; qq++) {
+                const int ch = ble_channel_of_q(qq);
+                if (ch >= 0) {
+                    const size_t o = ((size_t)cap * 40 + ch) * (size_t)a.n_out + mg;
+                    if (a.dbg_q8) { a.dbg_q8[2 * o] = (int8_t)y[qq].r; a.dbg_q8[2 * o + 1] = (int8_t)y[qq].i; }
+                    if (a.dbg_cf) {
+                        const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
+                        a.dbg_cf[o] = make_float2(raw[qq].r * sg, raw[qq].i * sg);
                     }
                 }
             }
-            if (lane == 0) {
-#pragma unroll
-                for (int qq = 0; qq < 48; qq++) edge[wid * 48 + qq] = make_float2(y[qq].r, y[qq].i);
-            }
         }
-        asm volatile("bar.sync 1, 128;\n" ::);                // only the 4 DFT warps exchange edges
+        if (lane == 0) {
+#pragma unroll
+            for (int qq = 0; qq < 48; qq++) edge[wid * 48 + qq] = make_float2(y[qq].r, y[qq].i);
+        }
+    }
+    __syncthreads();                                          // edges visible (and nobody still reads xs / V of others)
 
-        // ---- phase 3: slicer bits.  b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0   (btle_rx.c:1357-1361)
+    // ---- phase 3: slicer bits.  b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0   (btle_rx.c:1357-1361)
+    {
         uint32_t mine0 = 0, mine1 = 0;        // masks of the channels this lane will de-interleave
-        const float2* nextw = edge + ((wid + 1) & 3) * 48;
+        const float2* nextw = edge + ((wid + 1) % W) * 48;
 #pragma unroll
         for (int qq = 0; qq < 48; qq++) {
             if (ble_channel_of_q(qq) < 0) continue;
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(kFirThreads, 2) k_pfb_ble(PfbBleArgs a) {
             uint32_t mask = __ballot_sync(0xffffffffu, cross > 0.0f);
             if (qq < 32) { if (lane == qq) mine0 = mask; } else { if (lane == qq - 32) mine1 = mask; }
         }
-        if (wid == 3) { mine0 &= 0x7FFFFFFFu; mine1 &= 0x7FFFFFFFu; }     // sample 127 has no successor in this tile
+        if (wid == W - 1) { mine0 &= 0x7FFFFFFFu; mine1 &= 0x7FFFFFFFu; }   // the tile's last sample has no successor in it
         // lane L de-interleaves bin q = L (and q = L + 32) into the tile's two-word windows
 #pragma unroll
         for (int half = 0; half < 2; half++) {
@@ -283,11 +294,11 @@ __global__ void __launch_bounds__(kFirThreads, 2) k_pfb_ble(PfbBleArgs a) {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const BitPlace bp = bit_place(g_first, wid, j);
-                    const uint32_t B = compress4(mk >> bp.sh);
-                    if (B) {
+                    const uint32_t Bm = compress4(mk >> bp.sh);
+                    if (Bm) {
                         uint32_t* w2 = wordbuf + (ch * 4 + j) * 2;
-                        atomicOr(w2 + bp.word, B << bp.off);
-                        if (bp.off > 24) atomicOr(w2 + bp.word + 1, B >> (32 - bp.off));
+                        atomicOr(w2 + bp.word, Bm << bp.off);
+                        if (bp.off > 24) atomicOr(w2 + bp.word + 1, Bm >> (32 - bp.off));
                     }
                 }
             }
@@ -296,7 +307,7 @@ __global__ void __launch_bounds__(kFirThreads, 2) k_pfb_ble(PfbBleArgs a) {
     __syncthreads();
     {
         const uint32_t wbase = (uint32_t)(((g_first >> 2) + 32) >> 5);
-        for (int i = tid; i < 320; i += kFirThreads) {
+        for (int i = tid; i < 320; i += B::kThreads) {
             const uint32_t v = wordbuf[i];
             if (v) atomicOr(a.bits + a.lay.index(cap, i >> 3, (i >> 1) & 3, wbase + (i & 1)), v);
         }

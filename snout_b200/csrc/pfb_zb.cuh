@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kZbFirThreads, 1) k_pfb_zb(PfbZbArgs a) {
     const float2* xcap = a.x + (size_t)cap * a.stride;
     const int g_first = kTileStride * tile;                            // tiles advance by 127 samples (see pfb.cuh)
 
-    pfb_stage_tile<NT, kZbChunkT, kZbFirThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, tid);
+    pfb_stage_tile<G, kZbChunkT, kZbFirThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, tid);
     for (int i = tid; i < 257; i += kZbFirThreads) tab[i] = a.atan_tab[i];
     // 12 warps: warp = (rho group of 8) x (4 chunks of 8 output times)
     const int rho = 8 * (wid % 3) + (lane & 7);

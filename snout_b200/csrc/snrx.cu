@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -80,6 +81,7 @@ struct snrx_handle {
     uint32_t max_windows = 0;
     uint32_t cand_cap = 0, frame_cap = 0;
     int pfb_nt = 16;
+    int ble_w = 2;                       // warps per CTA of the BLE channelizer: tile = 32 w samples, stride 32 w - 1
 
     // constants on the device
     uint32_t *d_crc_tab = nullptr, *d_whiten = nullptr;
@@ -180,6 +182,33 @@ int grid_for(snrx_handle* h, uint64_t items, int per_block, int blocks_per_sm) {
 }
 
 }  // namespace
+
+template <int NT, int W>
+static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint32_t caps) {
+    using B = PfbBleGeom<NT, W>;
+    if (!a) {
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        return SNRX_OK;
+    }
+    const dim3 grid((unsigned)(a->n_tiles) * caps);
+    if (h->cfg.flags & SNRX_F_KEEP_STREAMS) k_pfb_ble<NT, W, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
+    else k_pfb_ble<NT, W, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
+    return SNRX_OK;
+}
+static int pfb_ble_dispatch(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint32_t caps) {
+    const int key = h->pfb_nt * 10 + h->ble_w;
+    switch (key) {
+        case 161: return pfb_ble_go<16, 1>(h, a, st, caps);
+        case 162: return pfb_ble_go<16, 2>(h, a, st, caps);
+        case 164: return pfb_ble_go<16, 4>(h, a, st, caps);
+        case 321: return pfb_ble_go<32, 1>(h, a, st, caps);
+        case 322: return pfb_ble_go<32, 2>(h, a, st, caps);
+        case 324: return pfb_ble_go<32, 4>(h, a, st, caps);
+    }
+    return fail(h, SNRX_EINVAL, "no channelizer instance for this configuration");
+}
+static int ble_tile_stride(const snrx_handle* h) { return h->wideband ? 32 * h->ble_w - 1 : kTileT; }
 
 // device frame list -> host-mapped pinned memory, fully coalesced 16-byte stores; also publishes the totals
 __global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __restrict__ src, const uint32_t* __restrict__ totals_dev,
@@ -337,10 +366,10 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
                 CKD(dev_alloc(h, &h->d_taps_flat, L));
                 CK(cudaMemcpy(h->d_taps_rho, rho.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
                 CK(cudaMemcpy(h->d_taps_flat, flat.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
-                CK(cudaFuncSetAttribute(k_pfb_ble<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<16>::kSmemBytes));
-                CK(cudaFuncSetAttribute(k_pfb_ble<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<16>::kSmemBytes));
-                CK(cudaFuncSetAttribute(k_pfb_ble<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<32>::kSmemBytes));
-                CK(cudaFuncSetAttribute(k_pfb_ble<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbGeom<32>::kSmemBytes));
+                if (const char* e = getenv("SNRX_PFB_WARPS")) h->ble_w = atoi(e);        // tuning knob; results do not depend on it
+                if (h->ble_w != 1 && h->ble_w != 2 && h->ble_w != 4) return fail(h, SNRX_EINVAL, "SNRX_PFB_WARPS must be 1, 2 or 4");
+                int r = pfb_ble_dispatch(h, nullptr, nullptr, 0);                          // sets the shared-memory attributes
+                if (r != SNRX_OK) return r;
             }
         }
         for (auto& ln : h->lane) {
@@ -444,14 +473,8 @@ static int launch_ble_front(snrx_handle* h, Lane& ln, const float2* x, uint32_t 
         a.taps_rho = h->d_taps_rho; a.scale = h->cfg.quant_scale;
         a.bits = ln.d_bits; a.lay = lay; a.dbg_q8 = ln.d_q8; a.dbg_cf = ln.d_cf;
         a.tile0 = tile_begin;
-        const dim3 grid((unsigned)(a.n_tiles) * caps);
-        if (h->pfb_nt == 16) {
-            if (dbg) k_pfb_ble<16, true><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, ln.stream>>>(a);
-            else k_pfb_ble<16, false><<<grid, kFirThreads, PfbGeom<16>::kSmemBytes, ln.stream>>>(a);
-        } else {
-            if (dbg) k_pfb_ble<32, true><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, ln.stream>>>(a);
-            else k_pfb_ble<32, false><<<grid, kFirThreads, PfbGeom<32>::kSmemBytes, ln.stream>>>(a);
-        }
+        int r = pfb_ble_dispatch(h, &a, ln.stream, caps);
+        if (r != SNRX_OK) return r;
     } else {
         NbArgs a;
         a.x = reinterpret_cast<const float4*>(x); a.stride = stride; a.n = (int64_t)n_in;
@@ -556,7 +579,8 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
                     // launch the channelizer on the tiles whose input has fully arrived
                     const uint64_t have = off + len;
                     const bool last = (have == n_samples);
-                    int tile_end = last ? (int)div_up(n_out, kTileStride) : (int)(((int64_t)(have / kPfbD) - kTileT) / kTileStride);
+                    const int ts = ble_tile_stride(h);
+                    int tile_end = last ? (int)div_up(n_out, ts) : (int)(((int64_t)(have / kPfbD) - (ts + 1)) / ts);
                     if (tile_end > tile_done) {
                         int r = launch_ble_front(h, ln, x, 1, n_samples, x_stride, n_out, tile_done, tile_end, lay);
                         if (r != SNRX_OK) return r;
@@ -571,7 +595,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         const bool pipelined = staged && h->wideband && !h->has_zb && n_captures == 1;
         if (!pipelined) {
             CK(cudaEventRecord(ln.ev_front0, st));
-            int r = launch_ble_front(h, ln, x, n_captures, n_samples, x_stride, n_out, 0, (int)div_up(n_out, h->wideband ? kTileStride : kTileT), lay);
+            int r = launch_ble_front(h, ln, x, n_captures, n_samples, x_stride, n_out, 0, (int)div_up(n_out, ble_tile_stride(h)), lay);
             if (r != SNRX_OK) return r;
         }
         CK(cudaEventRecord(ln.ev_front, st));

@@ -40,77 +40,83 @@ int emu_ble_channel_of_q(int q) { return ble_channel_of_q(q); }
 
 }  // extern "C"
 
-// ---- one tile of k_pfb_ble<NT, *>, phases 0..3 ------------------------------------------------
+// ---- one tile of k_pfb_ble<NT, W, *>, phases 0..3 ---------------------------------------------
 // x: capture cf32 (n_in samples).  Outputs: words[40][4][2] (to be OR-ed at word index wbase + half),
-// q8[40][128][2] (int8), raw[40][128] cf32 for samples g_first .. g_first+127.
-template <int NT>
+// q8[40][T][2] (int8), raw[40][T] cf32 for samples g_first .. g_first+T-1, T = 32 W.
+template <int NT, int W>
 static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
                      float scale, uint32_t* words, int* wbase_out, int8_t* q8, float* raw_out) {
-    using G = PfbGeom<NT>;
+    using B = PfbBleGeom<NT, W>;
+    using G = typename B::G;
+    constexpr int T = B::kT;
     std::vector<float2> xs(G::kXsLen, make_float2(0.f, 0.f));
-    std::vector<float2> V(48 * kVStride, make_float2(0.f, 0.f));
-    const int g_first = kTileStride * tile;
+    std::vector<float2> V(W * B::kVWarp, make_float2(0.f, 0.f));
+    const int g_first = B::kStride * tile;
     const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
-    constexpr int kPer = 24 * kChunkT;
-    for (int tid = 0; tid < kPer / 2; tid++)
-        for (int p = 0; p < G::kPieces; p++) {
-            const int ip = kPer * p - 12 + 2 * tid;
-            if (ip >= 0 && ip < G::kTileIn) {
-                const int64_t i = x0 + ip;
-                const bool ok = (i >= 0) && (i + 1 < n_in);
-                for (int k = 0; k < 2; k++)
-                    xs[ip + 8 * p + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
-            }
-        }
-    for (int tid = 0; tid < kFirThreads; tid++) {
-        const int lane = tid & 31, wid = tid >> 5;
-        const int rho = 8 * (wid % 3) + (lane & 7), q = 4 * (wid / 3) + (lane >> 3);
-        float g[NT];
-        for (int d = 0; d < NT; d++) g[d] = taps_rho[rho * NT + d];
-        float2 acc[2][kChunkT];
-        pfb_fir_thread<NT, 2, kChunkT>(xs.data() + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
-        for (int e = 0; e < kChunkT; e++) {
-            V[rho * kVStride + 24 * q + e] = acc[0][e];
-            V[(rho + 24) * kVStride + 24 * q + e] = acc[1][e];
+    constexpr int kPer = 24 * kChunkT, kPairs = kPer / 2;
+    for (int idx = 0; idx < G::kPieces * kPairs; idx++) {              // pfb_stage_tile
+        const int p = idx / kPairs, t = idx - p * kPairs;
+        const int ip = kPer * p - 12 + 2 * t;
+        if (ip >= 0 && ip < G::kTileIn) {
+            const int64_t i = x0 + ip;
+            const bool ok = (i >= 0) && (i + 1 < n_in);
+            for (int k = 0; k < 2; k++)
+                xs[ip + 8 * p + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
         }
     }
-    std::vector<cf> Y(kTileT * 48);
-    for (int m = 0; m < kTileT; m++) {
+    for (int tid = 0; tid < B::kThreads; tid++) {                      // phase 1
+        const int lane = tid & 31, wid = tid >> 5;
+        const int rl = lane & 7, c = lane >> 3, q = 4 * wid + c;
+        float2* Vw = V.data() + wid * B::kVWarp;
+        for (int gi = 0; gi < 3; gi++) {
+            const int rho = 8 * gi + rl;
+            float g[NT];
+            for (int d = 0; d < NT; d++) g[d] = taps_rho[rho * NT + d];
+            float2 acc[2][kChunkT];
+            pfb_fir_thread<NT, 2, kChunkT>(xs.data() + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
+            for (int e = 0; e < kChunkT; e++) {
+                Vw[rho * kVStride + 8 * c + e] = acc[0][e];
+                Vw[(rho + 24) * kVStride + 8 * c + e] = acc[1][e];
+            }
+        }
+    }
+    std::vector<cf> Y(T * 48);
+    for (int m = 0; m < T; m++) {                                      // phase 2
         const int mg = g_first + m;
         const float s = (mg < n_out) ? scale : 0.0f;
         cf y[48], raw[48];
-        pfb_dft48_quant(V.data() + v_col(m), y, s, (mg & 1) ? -s : s, raw, true);
+        pfb_dft48_quant(V.data() + (m >> 5) * B::kVWarp + (m & 31), y, s, (mg & 1) ? -s : s, raw, true);
         for (int qq = 0; qq < 48; qq++) {
             Y[m * 48 + qq] = y[qq];
             const int ch = ble_channel_of_q(qq);
             if (ch >= 0) {
-                q8[(ch * kTileT + m) * 2] = (int8_t)y[qq].r;
-                q8[(ch * kTileT + m) * 2 + 1] = (int8_t)y[qq].i;
+                q8[(ch * T + m) * 2] = (int8_t)y[qq].r;
+                q8[(ch * T + m) * 2 + 1] = (int8_t)y[qq].i;
                 const float sg = ((qq & 1) && (mg & 1)) ? -1.0f : 1.0f;
-                raw_out[(ch * kTileT + m) * 2] = raw[qq].r * sg;
-                raw_out[(ch * kTileT + m) * 2 + 1] = raw[qq].i * sg;
+                raw_out[(ch * T + m) * 2] = raw[qq].r * sg;
+                raw_out[(ch * T + m) * 2 + 1] = raw[qq].i * sg;
             }
         }
     }
     memset(words, 0, sizeof(uint32_t) * 320);
     *wbase_out = ((g_first >> 2) + 32) >> 5;
-    for (int wid = 0; wid < 4; wid++) {
+    for (int wid = 0; wid < W; wid++) {                                // phase 3
         for (int qq = 0; qq < 48; qq++) {
             const int ch = ble_channel_of_q(qq);
             if (ch < 0) continue;
             uint32_t mask = 0;
             for (int lane = 0; lane < 32; lane++) {
                 const int m = 32 * wid + lane;
-                if (m + 1 >= kTileT) continue;                       // sample 127 has no successor in the tile
+                if (m + 1 >= T) continue;                            // the tile's last sample has no successor in it
                 const cf a = Y[m * 48 + qq], b = Y[(m + 1) * 48 + qq];
                 if (f_fma(a.r, b.i, -f_mul(b.r, a.i)) > 0.0f) mask |= 1u << lane;
             }
             for (int j = 0; j < 4; j++) {
                 const BitPlace bp = bit_place(g_first, wid, j);
-                const uint32_t B = compress4(mask >> bp.sh);
+                const uint32_t Bm = compress4(mask >> bp.sh);
                 uint32_t* w2 = words + (ch * 4 + j) * 2;
-                w2[bp.word] |= B << bp.off;
-                if (bp.off > 24) w2[bp.word + 1] |= B >> (32 - bp.off);
+                w2[bp.word] |= Bm << bp.off;
+                if (bp.off > 24) w2[bp.word + 1] |= Bm >> (32 - bp.off);
             }
         }
     }
@@ -170,12 +176,15 @@ void emu_pfb_zb_tile(int nt, const float* x, int64_t n_in, int n_out, int tile, 
 }
 int emu_zb_bin_of_slot(int c) { return zb_bin_of_slot(c); }
 
-int emu_pfb_tile_stride(void) { return kTileStride; }
+int emu_pfb_tile_stride(void) { return kTileStride; }          // Zigbee kernel
 
-void emu_pfb_ble_tile(int nt, const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
+// BLE kernel with w warps per CTA: tile of 32 w samples, stride 32 w - 1
+void emu_pfb_ble_tile(int nt, int w, const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
                       float scale, uint32_t* words, int* wbase, int8_t* q8, float* raw) {
-    if (nt == 16) pfb_tile<16>(x, n_in, n_out, tile, taps_rho, scale, words, wbase, q8, raw);
-    else pfb_tile<32>(x, n_in, n_out, tile, taps_rho, scale, words, wbase, q8, raw);
+#define GO(NT, W) pfb_tile<NT, W>(x, n_in, n_out, tile, taps_rho, scale, words, wbase, q8, raw)
+    if (nt == 16) { if (w == 1) GO(16, 1); else if (w == 2) GO(16, 2); else GO(16, 4); }
+    else { if (w == 1) GO(32, 1); else if (w == 2) GO(32, 2); else GO(32, 4); }
+#undef GO
 }
 
 // ---- narrow-band slicer: whole capture -> phase words (layout of BitsLayout, 1 channel) --------

@@ -103,8 +103,8 @@ def test_back_end_shard_origin(emu, oracle_mod):
     assert_frames_equal(got, want, what="shard")
 
 
-@pytest.mark.parametrize("nt,name", [(16, "BLE_384"), (32, "BLE_768")])
-def test_pfb_tile_kernel(emu, oracle_mod, nt, name):
+@pytest.mark.parametrize("nt,name,warps", [(16, "BLE_384", 2), (32, "BLE_768", 2), (16, "BLE_384", 4), (16, "BLE_384", 1)])
+def test_pfb_tile_kernel(emu, oracle_mod, nt, name, warps):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     from gen_tables import PFB_DESIGNS, kaiser_lowpass
     h = kaiser_lowpass(*PFB_DESIGNS[name])
@@ -115,7 +115,8 @@ def test_pfb_tile_kernel(emu, oracle_mod, nt, name):
     x = np.ascontiguousarray(cap.iq)[: 24 * 8192 - 24 * 40]          # ragged: n_out = 8152, last tile partial
     n_in = len(x)
     n_out = n_in // 24
-    stride = emu.emu_pfb_tile_stride()
+    T = 32 * warps
+    stride = T - 1
     tiles = (n_out + stride - 1) // stride
     wpp = 1 + (n_out + 127) // 128 + 16
     bits = np.zeros((40, 4, wpp), dtype=np.uint32)
@@ -124,17 +125,17 @@ def test_pfb_tile_kernel(emu, oracle_mod, nt, name):
     xf = x.view(np.float32)
     for t in range(tiles):
         w = np.zeros(320, dtype=np.uint32)
-        q = np.zeros((40, 128, 2), dtype=np.int8)
-        r = np.zeros((40, 128), dtype=np.complex64)
+        q = np.zeros((40, T, 2), dtype=np.int8)
+        r = np.zeros((40, T), dtype=np.complex64)
         wb = ctypes.c_int(0)
-        emu.emu_pfb_ble_tile(nt, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), ctypes.c_float(100.0), P(w), ctypes.byref(wb), P(q), P(r))
+        emu.emu_pfb_ble_tile(nt, warps, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), ctypes.c_float(100.0), P(w), ctypes.byref(wb), P(q), P(r))
         w = w.reshape(40, 4, 2)
         bits[:, :, wb.value] |= w[:, :, 0]
         bits[:, :, wb.value + 1] |= w[:, :, 1]
-        if t:                                                        # sample 127 of a tile == sample 0 of the next
+        if t:                                                        # last sample of a tile == sample 0 of the next
             assert np.array_equal(q8[:, t * stride], q[:, 0])
-        q8[:, t * stride:t * stride + 128] = q
-        raw[:, t * stride:t * stride + 128] = r
+        q8[:, t * stride:t * stride + T] = q
+        raw[:, t * stride:t * stride + T] = r
     assert not q8[:, n_out:].any()                                   # beyond the capture: zeros
     q8, raw = q8[:, :n_out], raw[:, :n_out]
     yd = oracle_mod.pfb(x, h, [chanplan.ble_channel_bin(c) for c in range(40)])

@@ -7,7 +7,4 @@ echo "launch list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_pfb_ble -s 2 -c 1 -o gpurun_out/prof_pfb -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_pfb.log 2>&1
 echo "full capture rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_aa_search -s 4 -c 2 -o gpurun_out/prof_aa -f \
-    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_aa.log 2>&1
-echo "aa capture rc=$?"
 ls -la gpurun_out
