@@ -49,6 +49,13 @@ SNRX_HD float f_sub(float a, float b) {
     volatile float r = a - b; return r;
 #endif
 }
+SNRX_HD float f_sat(float a) {             // clamp to [0, 1]; folds into the producing FFMA as .SAT on the device
+#ifdef __CUDA_ARCH__
+    return __saturatef(a);
+#else
+    return fminf(fmaxf(a, 0.0f), 1.0f);
+#endif
+}
 SNRX_HD float f_div(float a, float b) {
 #ifdef __CUDA_ARCH__
     return __fdiv_rn(a, b);

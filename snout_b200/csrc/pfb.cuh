@@ -107,10 +107,16 @@ SNRX_HD int fir_base(int rho, int q) {
     return PfbGeom<NT, TT>::kHist + 24 * TT * q - rho + 8 * (PfbGeom<NT, TT>::kHist / (24 * TT) + q);
 }
 
-SNRX_HD float quant_fused(float y, float scale_signed) {
-    float t = f_fma(y, scale_signed, kMagic);
-    t = fminf(fmaxf(t, kMagic - 128.0f), kMagic + 127.0f);
-    return f_sub(t, kMagic);
+// Quantiser of the wideband path: q = clamp(rint(y * scale), -128, 127) evaluated as
+//   u = sat(y * (scale/255) + 128/255)          one FFMA.SAT per component: the clamp is free
+//   q = rint(255 u) - 128                        (255 u + (1.5 * 2^23 - 128)) - 1.5 * 2^23, packed
+// u carries one extra rounding (<= 2^-25, i.e. 8e-6 of a quantiser step): part of this engine's definition of
+// its quantised channel streams (SNRX_STAGE_BLE_Q8), on which frame parity is stated.
+SNRX_HD float2 quant_pair(float2 y, float s255 /* +-scale/255, 0 beyond the capture end */) {
+    const float ux = f_sat(f_fma(y.x, s255, 128.0f / 255.0f));
+    const float uy = f_sat(f_fma(y.y, s255, 128.0f / 255.0f));
+    const float2 t = f2_fma(make_float2(ux, uy), make_float2(255.0f, 255.0f), make_float2(kMagic - 128.0f, kMagic - 128.0f));
+    return f2_add(t, make_float2(-kMagic, -kMagic));
 }
 
 // 48-point inverse DFT of one output time + rotation + quantisation, in place:
@@ -122,12 +128,11 @@ SNRX_HD void pfb_dft48_quant(const float2* vcol /* &V[0][lane] of the warp tile 
 #pragma unroll
     for (int r = 0; r < 48; r++) { float2 t = vcol[r * kVStride]; v[r].r = t.x; v[r].i = t.y; }   // vcol = &V[0][lane]
     Idft3xQ<48>::run(v, y);
+    const float se = f_mul(s_even, 1.0f / 255.0f), so = f_mul(s_odd, 1.0f / 255.0f);
 #pragma unroll
     for (int q = 0; q < 48; q++) {
-        const float s = (q & 1) ? s_odd : s_even;
         if (keep_raw) raw[q] = y[q];
-        y[q].r = quant_fused(y[q].r, s);
-        y[q].i = quant_fused(y[q].i, s);
+        y[q] = C(quant_pair(P(y[q]), (q & 1) ? so : se));
     }
 }
 
@@ -167,11 +172,50 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
     asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
+__device__ __forceinline__ void cp_async16_full(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+
 // Stage tile samples i' = 0 .. kTileIn-1 (capture samples x0 + i') into the skewed tile: piece p holds
 // i' in [24 TT p - 12, 24 TT (p+1) - 12) at position i' + 8 p; 16-byte copies (one sample pair each).
+// Interior tiles (the whole tile inside the capture) take a fully unrolled path whose offsets are
+// compile-time constants; tiles that touch either end of the capture zero-fill through the generic loop.
 template <class G, int TT, int THREADS>
 __device__ __forceinline__ void pfb_stage_tile(float2* xs, const float2* xcap, int64_t x0, int64_t n_in, int tid) {
     constexpr int kPer = 24 * TT, kPairs = kPer / 2;
+    if (x0 >= 0 && x0 + G::kTileIn <= n_in) {
+        if constexpr (THREADS % kPairs == 0) {
+            constexpr int R = THREADS / kPairs;                 // pieces covered per sweep of the CTA
+            const int pp = tid / kPairs, t = tid - pp * kPairs;
+            const int ip_t = kPer * pp - 12 + 2 * t;            // this thread's i' in sweep 0
+            const float2* src = xcap + x0 + ip_t;
+            float2* dst = xs + ip_t + 8 * pp;
+#pragma unroll
+            for (int k = 0; k * R < G::kPieces; k++) {
+                const int ip = ip_t + kPer * R * k;
+                const bool ok = (k > 0 || ip >= 0) && ((k + 1) * R * kPer - 12 <= G::kTileIn || ip < G::kTileIn);
+                if (ok) cp_async16_full(dst + (kPer + 8) * R * k, src + kPer * R * k);
+            }
+        } else {
+            const float2* src = xcap + x0 + 2 * tid;
+            float2* dst = xs + 2 * tid;
+#pragma unroll
+            for (int p = 0; p < G::kPieces; p++) {
+#pragma unroll
+                for (int t0 = 0; t0 < kPairs; t0 += THREADS) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int ip0 = kPer * p - 12 + 2 * t0;      // compile-time; this thread copies i' = ip0 + 2 tid
+                    bool ok = true;
+                    if (t0 + THREADS > kPairs) ok = ok && (t0 + tid < kPairs);
+                    if (ip0 < 0) ok = ok && (ip0 + 2 * tid >= 0);
+                    if (ip0 + 2 * (THREADS - 1) >= G::kTileIn) ok = ok && (ip0 + 2 * tid < G::kTileIn);
+                    if (ok) cp_async16_full(dst + ip0 + 8 * p, src + ip0);
+                }
+            }
+        }
+        return;
+    }
     for (int idx = tid; idx < G::kPieces * kPairs; idx += THREADS) {
         const int p = idx / kPairs, t = idx - p * kPairs;
         const int ip = kPer * p - 12 + 2 * t;
@@ -224,7 +268,7 @@ __global__ void __launch_bounds__(32 * W, PfbBleGeom<NT, W>::kCtasPerSm) k_pfb_b
     // ---- phase 1: FIR of this warp's 32 output times -> V[r][m]
     {
         const int rl = lane & 7, c = lane >> 3, q = 4 * wid + c;           // q: chunk of 8 output times inside the tile
-#pragma unroll 1
+#pragma unroll
         for (int gi = 0; gi < 3; gi++) {
             const int rho = 8 * gi + rl;
             float g[NT];
@@ -306,10 +350,16 @@ __global__ void __launch_bounds__(32 * W, PfbBleGeom<NT, W>::kCtasPerSm) k_pfb_b
     }
     __syncthreads();
     {
-        const uint32_t wbase = (uint32_t)(((g_first >> 2) + 32) >> 5);
-        for (int i = tid; i < 320; i += B::kThreads) {
-            const uint32_t v = wordbuf[i];
-            if (v) atomicOr(a.bits + a.lay.index(cap, i >> 3, (i >> 1) & 3, wbase + (i & 1)), v);
+        // (channel, phase) = i >> 1 is the row of the bit-stream matrix [cap][40][4][words_per_phase]
+        uint32_t* row0 = a.bits + a.lay.index(cap, 0, 0, (uint32_t)(((g_first >> 2) + 32) >> 5));
+        const uint32_t wpp = a.lay.words_per_phase;
+#pragma unroll
+        for (int i0 = 0; i0 < 320; i0 += B::kThreads) {
+            const int i = i0 + tid;
+            if (i0 + B::kThreads <= 320 || i < 320) {
+                const uint32_t v = wordbuf[i];
+                if (v) atomicOr(row0 + (size_t)(i >> 1) * wpp + (i & 1), v);
+            }
         }
     }
 }
