@@ -138,7 +138,7 @@ typedef struct snrx_stats {
 
 /* debug stages for snrx_debug_stage() */
 #define SNRX_STAGE_BLE_Q8      1  /* int8 I,Q quantised channel streams [cap][ch][n][2]      */
-#define SNRX_STAGE_BLE_BITS    2  /* uint32 sliced bit words [cap][ch][phase][words]         */
+#define SNRX_STAGE_BLE_BITS    2  /* uint32 slicer bit words [cap][ch][words], sample order  */
 #define SNRX_STAGE_CHAN_CF32   3  /* cf32 channel streams [cap][ch][n] (WB modes)             */
 #define SNRX_STAGE_ZB_DISC     4  /* f32 discriminator minus DC [cap][ch][stride] (stride = bytes/(4*cap*ch)) */
 #define SNRX_STAGE_ZB_CHIPS    5  /* f32 soft chips [chain][chips_cap], chain = (cap, ch, segment)  */

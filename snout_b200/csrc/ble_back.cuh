@@ -14,20 +14,12 @@
 //
 // The kernels work on bits only: the slicer decision b[n] = (I[n]Q[n+1] - I[n+1]Q[n]) > 0 is all
 // that search_unique_bits() and demod_byte() ever look at, so the front ends (narrow-band slicer,
-// wideband channelizer) hand over one bit per channel-rate sample, phase-deinterleaved:
-// word w of phase j holds samples n = 4*(32*(w-1) + i) + j in bit i.
+// wideband channelizer) hand over one bit per channel-rate sample in natural order (BitsLayout,
+// common.cuh): bit (n & 31) of word kBitsLeadWords + (n >> 5) is the decision of sample n.
 #pragma once
 #include "common.cuh"
 
 namespace snrx {
-
-SNRX_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
-#ifdef __CUDA_ARCH__
-    return __funnelshift_r(lo, hi, sh);
-#else
-    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
-#endif
-}
 
 SNRX_HD int hi_bit_plus1(uint32_t d) {   // 0 for d == 0, else index of highest set bit + 1
 #ifdef __CUDA_ARCH__
@@ -46,19 +38,20 @@ SNRX_HD int aa_virtual_bits(uint32_t aa, uint32_t mask) {
     return z;
 }
 
-// Sliding correlation over one 32-slot word of one phase stream, bit-parallel over the 32 start
-// positions ("shift-and"): bit i of the result is set when the 32 symbol-spaced decisions starting
-// at slot (32*(w-1) + i) equal the access address in every masked position >= z (full matches and
-// the "virtual" matches that are usable only at a search origin).  After access-address bit p has
-// been applied, a random position survives with probability 2^-(p+1); `keep_going` lets a warp
+// Sliding correlation over the 32 start positions held by one word of a bit stream, bit-parallel
+// ("shift-and"): bit i of the result is set when the 32 symbol-spaced decisions (every 4th sample)
+// starting at the word's sample i equal the access address in every masked position >= z (full matches
+// and the "virtual" matches that are usable only at a search origin).  w[0] is the word itself, w[1..4]
+// the four that follow: access-address bit p is compared with the stream shifted by 4p samples.  After
+// bit p has been applied a random position survives with probability 2^-(p+1); `keep_going` lets a warp
 // stop as soon as none of its lanes has a survivor.
 template <class KEEP>
-SNRX_HD uint32_t aa_word_hits(uint32_t lo, uint32_t hi, uint32_t aa, uint32_t mask_hi /* mask & ~((1<<z)-1) */,
+SNRX_HD uint32_t aa_word_hits(const uint32_t (&w)[5], uint32_t aa, uint32_t mask_hi /* mask & ~((1<<z)-1) */,
                               KEEP keep_going) {
     uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
     for (int p = 0; p < 32; p++) {
-        const uint32_t s = funnel_r(lo, hi, p);                       // bit i = decision of slot i + p
+        const uint32_t s = (p & 7) ? funnel_r(w[p >> 3], w[(p >> 3) + 1], 4 * (p & 7)) : w[p >> 3];   // bit i = sample i + 4p
         const uint32_t want0 = ((aa >> p) & 1u) - 1u;                 // all ones when AA bit p is 0
         const uint32_t dont_care = ((mask_hi >> p) & 1u) - 1u;        // all ones when position p is not compared
         m &= (s ^ want0) | dont_care;
@@ -67,34 +60,28 @@ SNRX_HD uint32_t aa_word_hits(uint32_t lo, uint32_t hi, uint32_t aa, uint32_t ma
     return m;
 }
 
-// 32 consecutive symbol decisions of one phase stream starting at slot t (t >= -32)
-SNRX_HD uint32_t slots32(const uint32_t* phase_words, int t) {
-    int w = (t + 32) >> 5, sh = (t + 32) & 31;
-    return funnel_r(phase_words[w], phase_words[w + 1], sh);
-}
-
 // Finish the decode of a candidate from its de-whitened 4-byte chunks (chunk c = bytes 4c..4c+3
-// counted from the PDU header).  Mirrors receiver() btle_rx.c:2066-2125.
-SNRX_HD void ble_finish(const uint32_t* chunk /*[11]*/, bool adv_channel, uint32_t crc_init_internal,
+// counted from the PDU header).  Mirrors receiver() btle_rx.c:2066-2125.  Written with compile-time
+// indices only (the byte loop is unrolled and predicated) so that one GPU thread per candidate keeps
+// everything in registers.
+SNRX_HD void ble_finish(const uint32_t (&chunk)[11], bool adv_channel, uint32_t crc_init_internal,
                         const uint32_t* crc_tab, Dec& d) {
-    uint8_t* b = d.bytes;
+    uint32_t* bw = reinterpret_cast<uint32_t*>(d.bytes);            // Dec::bytes is 4-byte aligned
 #pragma unroll
-    for (int c = 0; c < 11; c++) {
-        uint32_t v = chunk[c];
-        b[4 * c] = (uint8_t)v; b[4 * c + 1] = (uint8_t)(v >> 8);
-        b[4 * c + 2] = (uint8_t)(v >> 16); b[4 * c + 3] = (uint8_t)(v >> 24);
-    }
-    int len = adv_channel ? (b[1] & 0x3F) : (b[1] & 0x1F);     // btle_rx.c:1794 / 1776
+    for (int c = 0; c < 11; c++) bw[c] = chunk[c];
+    const int b1 = (int)((chunk[0] >> 8) & 0xFFu);
+    const int len = adv_channel ? (b1 & 0x3F) : (b1 & 0x1F);        // btle_rx.c:1794 / 1776
     d.len = (uint8_t)len;
     d.emit = (uint8_t)(adv_channel ? (len >= 6 && len <= 37) : 1);   // btle_rx.c:2096
-    uint32_t crc = crc_init_internal;
-    uint32_t recv = 0;
-    d.crc_ok = 0;
-    if (d.emit) {
-        for (int i = 0; i < len + 2; i++) crc = (crc_tab[(crc ^ b[i]) & 0xFF] ^ (crc >> 8)) & 0xFFFFFFu;
-        recv = (uint32_t)b[len + 2] | ((uint32_t)b[len + 3] << 8) | ((uint32_t)b[len + 4] << 16);
-        d.crc_ok = (uint8_t)(crc == recv);
+    uint32_t crc = crc_init_internal, recv = 0;
+#pragma unroll
+    for (int i = 0; i < 42; i++) {
+        const uint32_t byte = (chunk[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+        const int k = i - (len + 2);
+        if (k < 0) crc = (crc_tab[(crc ^ byte) & 0xFFu] ^ (crc >> 8)) & 0xFFFFFFu;       // crc_update, btle_rx.c:1137-1148
+        else if (k < 3) recv |= byte << (8 * k);                                        // crc_check, btle_rx.c:1826-1848
     }
+    d.crc_ok = (uint8_t)(d.emit && crc == recv);
 }
 
 // Replay of receiver() for one 8192-IQ window starting at local sample W.
@@ -171,11 +158,11 @@ SNRX_HD void ble_fill_frame(snrx_frame_t& f, const Cand& c, const Dec& d, const 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------ kernels
 
-// Sliding access-address correlation.  One warp per (capture, channel, chunk of 32 words); each
-// lane owns one word of each phase stream and obtains the following word from its neighbour by
-// warp shuffle.  Writes the hit masks (bit i of hits[phase j][word w] = a 32-symbol window starting
-// at slot 32 (w-1) + i of phase j matches) and the number of hits per chunk; after the prefix sum
-// k_aa_fill turns the masks into the candidate list, ascending in s, without atomics or a sort.
+// Sliding access-address correlation.  One warp per (capture, channel, chunk of 32 words); each lane
+// owns one word (32 start positions) and reads the four words that follow it.  Writes the hit masks
+// (bit i of hits[w] = the 32 symbols starting at sample 32 (w - kBitsLeadWords) + i match) and the number
+// of hits per chunk; after the prefix sum k_aa_fill turns the masks into the candidate list, ascending in
+// s, without atomics or a sort.
 __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ bits, BitsLayout lay, BleParams p,
                                                    uint32_t n_chunks, uint32_t* __restrict__ counts,
                                                    uint32_t* __restrict__ hits_out) {
@@ -184,30 +171,23 @@ __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ 
     const uint32_t n_items = p.n_captures * p.n_channels * n_chunks;
     const int z = aa_virtual_bits(p.aa, p.aa_mask);
     const uint32_t mask_hi = p.aa_mask & ~((1u << z) - 1u);
+    const uint32_t nw = lay.words_per_stream;
     for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
          item += gridDim.x * warps_per_block) {
         const uint32_t chunk = item % n_chunks;
         const uint32_t ch = (item / n_chunks) % p.n_channels;
         const uint32_t cap = item / (n_chunks * p.n_channels);
         const uint32_t w = chunk * 32 + lane;                       // word owned by this lane
-        const bool valid = (w + 1) < lay.words_per_phase;
-        int cnt = 0;
+        const uint32_t* pw = bits + lay.index(cap, ch, 0);
+        uint32_t ww[5];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const size_t base = lay.index(cap, ch, j, 0);
-            const uint32_t* pw = bits + base;
-            uint32_t lo = valid ? __ldg(pw + w) : 0u;
-            uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1);
-            if (lane == 31) hi = (w + 1 < lay.words_per_phase) ? __ldg(pw + w + 1) : 0u;
-            uint32_t hj = aa_word_hits(valid ? lo : 0u, valid ? hi : 0u, p.aa, mask_hi,
-                                       [](uint32_t m) { return __any_sync(0xffffffffu, m != 0u) != 0; });
-            if (!valid) hj = 0u;
-            // positions whose first sample lies beyond the capture carry no data
-            const int nvalid = ((p.n_out - 1 - j) >> 2) - 32 * ((int)w - 1) + 1;
-            if (nvalid <= 0) hj = 0u; else if (nvalid < 32) hj &= (1u << nvalid) - 1u;
-            if (w < lay.words_per_phase) hits_out[base + w] = hj;
-            cnt += __popc(hj);
-        }
+        for (int d = 0; d < 5; d++) ww[d] = (w + d < nw) ? __ldg(pw + w + d) : 0u;
+        uint32_t h = aa_word_hits(ww, p.aa, mask_hi, [](uint32_t m) { return __any_sync(0xffffffffu, m != 0u) != 0; });
+        // start positions beyond the capture carry no data
+        const int nvalid = p.n_out - 32 * ((int)w - kBitsLeadWords);
+        if (nvalid <= 0 || w >= nw) h = 0u; else if (nvalid < 32) h &= (1u << nvalid) - 1u;
+        if (w < nw) hits_out[lay.index(cap, ch, w)] = h;
+        int cnt = __popc(h);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) counts[item] = (uint32_t)cnt;
@@ -215,7 +195,7 @@ __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ 
 }
 
 // Candidate list from the hit masks.  One warp per chunk that has hits; lanes own words, an exclusive
-// prefix over the lanes gives each lane its write position, slots then phases in ascending sample order.
+// prefix over the lanes gives each lane its write position; bit order is sample order.
 __global__ void __launch_bounds__(256) k_aa_fill(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ hits_in,
                                                  BitsLayout lay, BleParams p, uint32_t n_chunks,
                                                  const uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
@@ -230,43 +210,32 @@ __global__ void __launch_bounds__(256) k_aa_fill(const uint32_t* __restrict__ bi
         const uint32_t ch = (item / n_chunks) % p.n_channels;
         const uint32_t cap = item / (n_chunks * p.n_channels);
         const uint32_t w = chunk * 32 + lane;
-        uint32_t hits[4];
-        int cnt = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            hits[j] = (w < lay.words_per_phase) ? __ldg(hits_in + lay.index(cap, ch, j, w)) : 0u;
-            cnt += __popc(hits[j]);
-        }
+        uint32_t hits = (w < lay.words_per_stream) ? __ldg(hits_in + lay.index(cap, ch, w)) : 0u;
+        const int cnt = __popc(hits);
         int pre = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
         pre -= cnt;
         uint32_t dst = offsets[item] + (uint32_t)pre;
-        uint32_t any = hits[0] | hits[1] | hits[2] | hits[3];
-        while (any) {
-            const int i = __ffs(any) - 1;
-            any &= any - 1u;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if ((hits[j] >> i) & 1u) {
-                    const int t = 32 * ((int)w - 1) + i;
-                    const uint32_t r = slots32(bits + lay.index(cap, ch, j, 0), t);
-                    const uint32_t d = (r ^ p.aa) & p.aa_mask;
-                    if (dst < cand_cap) {
-                        Cand c;
-                        c.s = 4 * t + j; c.ch_idx = (uint16_t)ch; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = cap;
-                        cands[dst] = c;
-                    }
-                    dst++;
-                }
+        const uint32_t* pw = bits + lay.index(cap, ch, 0);
+        while (hits) {
+            const int i = __ffs(hits) - 1;
+            hits &= hits - 1u;
+            const int s = 32 * ((int)w - kBitsLeadWords) + i;
+            const uint32_t d = (symbols32(pw, s) ^ p.aa) & p.aa_mask;
+            if (dst < cand_cap) {
+                Cand c;
+                c.s = s; c.ch_idx = (uint16_t)ch; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = cap;
+                cands[dst] = c;
             }
+            dst++;
         }
     }
 }
 
-// One warp per candidate: lanes 0..10 each pull 32 symbol decisions (4 bytes) of the frame out of
-// the candidate's phase stream and de-whiten them; lane 0 gathers them by shuffle, applies the
-// header rules and runs the CRC-24.
+// One THREAD per candidate: pulls the 11 x 32 symbol decisions of the longest possible frame out of the
+// bit stream (45 consecutive words), de-whitens them, applies the header rules and runs the CRC-24 from
+// a shared-memory table.
 __global__ void __launch_bounds__(128) k_ble_decode(const uint32_t* __restrict__ bits, BitsLayout lay, BleParams p,
                                                     const uint32_t* __restrict__ n_cands_dev, uint32_t cand_cap,
                                                     const Cand* __restrict__ cands, Dec* __restrict__ decs,
@@ -276,27 +245,31 @@ __global__ void __launch_bounds__(128) k_ble_decode(const uint32_t* __restrict__
     __shared__ uint32_t crc_s[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) crc_s[i] = crc_tab[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps_per_block = blockDim.x >> 5;
     uint32_t n = *n_cands_dev;
     if (n > cand_cap) n = cand_cap;
-    for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < n; k += gridDim.x * warps_per_block) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const Cand c = cands[k];
-        const int j = ((c.s % 4) + 4) % 4;
-        const int t0 = (c.s - j) / 4;                                 // slot of AA bit 0 (may be -1)
         const int chn = channel_numbers[c.ch_idx];
-        const uint32_t* pw = bits + lay.index(c.cap, c.ch_idx, j, 0);
-        uint32_t mine = 0;
-        if (lane < 11) mine = slots32(pw, t0 + 32 + 32 * lane) ^ whiten[chn * 11 + lane];
+        const uint32_t* pw = bits + lay.index(c.cap, c.ch_idx, 0);
+        // header starts 32 symbols = 128 samples after AA bit 0
+        const int n0 = c.s + 128 + 32 * kBitsLeadWords, w0 = n0 >> 5, sh = n0 & 31;
         uint32_t chunk[11];
+        uint32_t lo = __ldg(pw + w0);
 #pragma unroll
-        for (int q = 0; q < 11; q++) chunk[q] = __shfl_sync(0xffffffffu, mine, q);
-        if (lane == 0) {
-            Dec d;
-            d.s = c.s; d.resume = 0; d.vneed = c.vneed;
-            ble_finish(chunk, chn >= 37 && chn <= 39, p.crc_init_internal, crc_s, d);
-            decs[k] = d;
+        for (int q = 0; q < 11; q++) {
+            uint32_t r = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t hi = __ldg(pw + w0 + 4 * q + b + 1);
+                r |= compress4(funnel_r(lo, hi, sh)) << (8 * b);
+                lo = hi;
+            }
+            chunk[q] = r ^ __ldg(whiten + chn * 11 + q);
         }
+        Dec d;
+        d.s = c.s; d.resume = 0; d.vneed = c.vneed;
+        ble_finish(chunk, chn >= 37 && chn <= 39, p.crc_init_internal, crc_s, d);
+        decs[k] = d;
     }
 }
 

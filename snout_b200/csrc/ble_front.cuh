@@ -8,8 +8,9 @@
 // cross product below takes the same decision as the reference's `int` arithmetic).
 //
 // HBM-bound streaming kernel: 8 bytes in, 1 bit out per sample.  One warp turns 128 consecutive
-// samples (1 KiB, two 16-byte loads per lane) into the four phase words of one 32-symbol slot
-// group with four __ballot_sync.
+// samples (1 KiB, four coalesced 256-byte loads) into four words of the channel's bit stream (BitsLayout:
+// natural sample order) with four __ballot_sync; the successor of a word's last sample comes from lane 0
+// of the next word by warp shuffle.
 #pragma once
 #include "common.cuh"
 
@@ -28,8 +29,8 @@ SNRX_HD bool slicer_bit(float i0, float q0, float i1, float q1) {
 
 #if defined(__CUDACC__)
 struct NbArgs {
-    const float4* x;          // [n_captures][stride] cf32 viewed as float4 (2 samples)
-    uint64_t stride;          // samples between captures (even)
+    const float2* x;          // [n_captures][stride] cf32
+    uint64_t stride;          // samples between captures
     int64_t n;                // samples per capture
     int32_t n_groups;         // ceil(n / 128)
     uint32_t n_captures;
@@ -48,47 +49,31 @@ __global__ void __launch_bounds__(256) k_ble_slice_nb(NbArgs a) {
          item += (uint64_t)gridDim.x * warps_per_block) {
         const uint32_t cap = (uint32_t)(item / (uint64_t)a.n_groups);
         const int32_t grp = (int32_t)(item % (uint64_t)a.n_groups);
-        const float4* xc = a.x + (size_t)cap * (a.stride / 2);
-        const int64_t n0 = (int64_t)grp * 128 + 4 * lane;        // first of this lane's 4 samples
-        const float2* x2 = reinterpret_cast<const float2*>(xc);
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (n0 + 4 <= a.n) {                                      // streaming loads: every byte is used once
-            v0 = __ldcs(xc + n0 / 2);
-            v1 = __ldcs(xc + n0 / 2 + 1);
-        } else {                                                  // ragged end of the capture: zero fill
-            float2 t;
-            if (n0 + 0 < a.n) { t = __ldg(x2 + n0 + 0); v0.x = t.x; v0.y = t.y; }
-            if (n0 + 1 < a.n) { t = __ldg(x2 + n0 + 1); v0.z = t.x; v0.w = t.y; }
-            if (n0 + 2 < a.n) { t = __ldg(x2 + n0 + 2); v1.x = t.x; v1.y = t.y; }
-        }
-        float I[5], Q[5];
-        I[0] = quant_exact(v0.x, a.scale); Q[0] = quant_exact(v0.y, a.scale);
-        I[1] = quant_exact(v0.z, a.scale); Q[1] = quant_exact(v0.w, a.scale);
-        I[2] = quant_exact(v1.x, a.scale); Q[2] = quant_exact(v1.y, a.scale);
-        I[3] = quant_exact(v1.z, a.scale); Q[3] = quant_exact(v1.w, a.scale);
-        I[4] = __shfl_down_sync(0xffffffffu, I[0], 1);
-        Q[4] = __shfl_down_sync(0xffffffffu, Q[0], 1);
-        if (lane == 31) {                                         // first sample of the next group
-            const int64_t nn = n0 + 4;
-            float2 t = make_float2(0.f, 0.f);
-            if (nn < a.n) t = __ldg(x2 + nn);
-            I[4] = quant_exact(t.x, a.scale); Q[4] = quant_exact(t.y, a.scale);
-        }
-        if (DEBUG && a.dbg_q8) {
+        const float2* xc = a.x + (size_t)cap * a.stride;
+        const int64_t n0 = (int64_t)grp * 128 + lane;             // this lane's sample of word 0
+        float I[5], Q[5];                                         // [k]: sample n0 + 32 k; [4] only matters in lane 0
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (n0 + k < a.n) {
-                    const size_t o = ((size_t)cap * (size_t)a.n + (size_t)(n0 + k)) * 2;
-                    a.dbg_q8[o] = (int8_t)I[k]; a.dbg_q8[o + 1] = (int8_t)Q[k];
-                }
+        for (int k = 0; k < 5; k++) {
+            const int64_t n = n0 + 32 * k;
+            float2 t = make_float2(0.f, 0.f);                     // beyond the capture: zero fill
+            if ((k < 4 || lane == 0) && n < a.n) t = __ldcs(xc + n);   // streaming load: every byte is used once
+            I[k] = quant_exact(t.x, a.scale); Q[k] = quant_exact(t.y, a.scale);
+            if (DEBUG && a.dbg_q8 && k < 4 && n < a.n) {
+                const size_t o = ((size_t)cap * (size_t)a.n + (size_t)n) * 2;
+                a.dbg_q8[o] = (int8_t)I[k]; a.dbg_q8[o + 1] = (int8_t)Q[k];
             }
         }
         uint32_t w[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) w[j] = __ballot_sync(0xffffffffu, slicer_bit(I[j], Q[j], I[j + 1], Q[j + 1]));
+        for (int k = 0; k < 4; k++) {
+            float i1 = __shfl_sync(0xffffffffu, I[k], (lane + 1) & 31), q1 = __shfl_sync(0xffffffffu, Q[k], (lane + 1) & 31);
+            const float in = __shfl_sync(0xffffffffu, I[k + 1], 0), qn = __shfl_sync(0xffffffffu, Q[k + 1], 0);
+            if (lane == 31) { i1 = in; q1 = qn; }
+            w[k] = __ballot_sync(0xffffffffu, slicer_bit(I[k], Q[k], i1, q1));
+        }
         if (lane < 4) {
             const uint32_t out = lane == 0 ? w[0] : lane == 1 ? w[1] : lane == 2 ? w[2] : w[3];
-            a.bits[a.lay.index(cap, 0, lane, kBitsLeadWords + grp)] = out;
+            a.bits[a.lay.index(cap, 0, kBitsLeadWords + 4 * grp + lane)] = out;
         }
     }
 }

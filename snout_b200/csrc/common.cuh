@@ -132,19 +132,46 @@ constexpr int kWindow = SNRX_BLE_WINDOW;   // 8192 IQ per receiver() call, btle_
 constexpr int kSpanInt8 = 31 * 8 + 16384;  // receiver() buf_len, btle_rx.c:2382
 constexpr int kDemodLimitInt8 = 19392;     // demod_buf_len, btle_rx.c:2025
 constexpr int kBleMaxBytes = 42;           // 2 header + 37 payload + 3 crc, btle_rx.c:1344
-constexpr int kBitsLeadWords = 1;          // slots -32..-1 (only slot -1 is ever read)
-constexpr int kBitsTailWords = 16;         // zero words after the last tile: a frame at the very end reads
-                                           // 32+16+8*40 = 368 slots = 11.5 words past its start
+constexpr int kBitsLeadWords = 4;          // samples -128..-1: zeros (history of a search origin, btle_rx.c:1377)
+constexpr int kBitsTailWords = 64;         // zero words after the capture: a frame at the very end reads
+                                           // 4*(32+16+8*40) = 1472 samples = 46 words past its start
 
-// Bit layout: for capture c, channel k, phase j: word w holds slots t = 32*(w-1) .. 32*(w-1)+31,
-// bit i of the word is the slicer decision of channel-rate sample n = 4*t + j.
+// Bit layout: one word stream per (capture, channel), samples in natural order: bit (n & 31) of word
+// kBitsLeadWords + (n >> 5) is the slicer decision of channel-rate sample n.  Symbol-spaced decisions
+// (stride 4 samples, btle_rx.c:1357-1361) are picked out where they are needed: by the funnel shifts of the
+// sliding correlation and, per candidate, by symbols32().
 struct BitsLayout {
-    uint32_t words_per_phase;   // kBitsLeadWords + tiles + kBitsTailWords
+    uint32_t words_per_stream;  // kBitsLeadWords + ceil(n_out / 32) + kBitsTailWords
     uint32_t n_channels;
-    SNRX_HD size_t index(uint32_t cap, uint32_t ch, uint32_t phase, uint32_t w) const {
-        return (((size_t)cap * n_channels + ch) * 4 + phase) * (size_t)words_per_phase + w;
+    SNRX_HD size_t index(uint32_t cap, uint32_t ch, uint32_t w) const {
+        return ((size_t)cap * n_channels + ch) * (size_t)words_per_stream + w;
     }
 };
+SNRX_HD constexpr uint32_t bits_words_for(uint32_t n_out) { return kBitsLeadWords + (n_out + 31) / 32 + kBitsTailWords; }
+
+SNRX_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {      // bits sh .. sh+31 of hi:lo, 0 <= sh < 32
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+// every 4th bit of x starting at bit 0 -> low 8 bits
+SNRX_HD uint32_t compress4(uint32_t x) {
+    x &= 0x11111111u;
+    x = (x | (x >> 3)) & 0x03030303u;
+    x = (x | (x >> 6)) & 0x000F000Fu;
+    x = (x | (x >> 12)) & 0x000000FFu;
+    return x;
+}
+// 32 symbol decisions (every 4th sample) starting at channel-rate sample s >= -128, LSB = first symbol
+SNRX_HD uint32_t symbols32(const uint32_t* stream_words, int s) {
+    const int n = s + 32 * kBitsLeadWords, w = n >> 5, sh = n & 31;
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) r |= compress4(funnel_r(stream_words[w + q], stream_words[w + q + 1], sh)) << (8 * q);
+    return r;
+}
 
 // An access-address hit found by the sliding correlation.
 struct Cand {

@@ -12,24 +12,22 @@
 // followed, per channel, by the int8-grid quantiser and the reference's one-sample
 // cross-product slicer (btle_rx.c:1357-1361); only ONE BIT per channel sample leaves the SM.
 //
-// One WARP computes 32 channel-rate samples x 40 channels end to end; a CTA is W such warps (default
-// 2: 64 samples from 1512 + L input samples) that share only the staged input tile and the one
-// column the slicer needs from the next warp.  Tiles advance by 32 W - 1 samples (the last sample
-// of a tile has no successor inside it), so tiles are independent: no carry, no stitch pass.
+// One WARP (= one CTA) computes 32 channel-rate samples x 40 channels end to end and emits the 31 slicer
+// bits per channel whose successor sample it holds; tiles advance by 31 samples, so they are independent:
+// no carry, no stitch pass, no CTA-wide barrier.
 //   phase 0  cp.async stages the input tile into shared memory (coalesced 16-byte copies); the tile
-//            is laid out flat with a 64-byte skew every 192 samples so that phase 1 is bank-conflict
-//            free; one __syncthreads, the only CTA-wide barrier before the bit hand-over;
-//   phase 1  FIR, per warp: lane (rho mod 8, chunk) owns decimated sequence X_rho[c] = x[24 c - rho]
-//            and 8 consecutive output times, three passes cover rho = 0..23 (branches rho, rho+24);
-//            taps of that rho live in registers, each loaded sample feeds up to 16 FMAs (register
-//            sliding window); results go to the warp's private V[48][32] (+1 pad) tile;
-//   phase 2  __syncwarp, then one lane per output time runs the fully unrolled 48-point inverse DFT
-//            in registers (fft.cuh), applies the bin rotation, quantises;
-//   phase 3  neighbour samples by warp shuffle (lane 31: first column of the next warp, through
-//            shared memory), cross product, __ballot_sync -> bit masks, de-interleaved into the 4
-//            sample phases, assembled into words in shared memory and OR-ed into the global bit streams.
-// Every warp is busy in every phase and warps only meet at two barriers per tile, so the SM's
-// schedulers always have 8-10 independent instruction streams (ncu: profiles/).
+//            is laid out flat with a 64-byte skew every 192 samples so that phase 1 is bank-conflict free;
+//   phase 1  FIR: lane (rho mod 8, chunk) owns decimated sequence X_rho[c] = x[24 c - rho] and 8 consecutive
+//            output times, three passes cover rho = 0..23 (branches rho, rho+24); taps of that rho live in
+//            registers, each loaded sample feeds up to 16 FMAs (register sliding window); results go to
+//            the V[24][32] tile of float4 = (branch rho, branch rho + 24) with 16-byte stores;
+//   phase 2  __syncwarp, then one lane per output time loads its column (24 x 16 bytes) and runs the fully
+//            unrolled 48-point inverse DFT in registers (fft.cuh), applies the bin rotation, quantises
+//            the 40 bins that carry a channel;
+//   phase 3  successor samples by warp shuffle, cross product, sign bit shifted into a per-lane word
+//            (bit = channel); two 32x32 bit-matrix transposes by shuffle turn them into per-channel
+//            words (bit = time), which lanes OR into the global bit streams (natural sample order).
+// ncu: profiles/.
 #pragma once
 #include "common.cuh"
 #include "fft.cuh"
@@ -63,15 +61,16 @@ template <int NT, int TT = 16, int T = kTileT> struct PfbGeom {
     static constexpr int kXsLen = xs_pos<TT>(kTileIn) + 8;             // float2
 };
 
-// BLE kernel: W warps per CTA, 32 output times per warp
-template <int NT, int W> struct PfbBleGeom {
-    static constexpr int kT = 32 * W;                                  // channel-rate samples computed per tile
-    static constexpr int kStride = kT - 1;                             // samples whose slicer bit the tile emits
-    static constexpr int kThreads = 32 * W;
+// BLE kernel: one warp per CTA, 32 output times, 31 emitted decisions
+template <int NT> struct PfbBleGeom {
+    static constexpr int kT = 32;                                      // channel-rate samples computed per tile
+    static constexpr int kStride = 31;                                 // samples whose slicer bit the tile emits
+    static constexpr int kThreads = 32;
     using G = PfbGeom<NT, kChunkT, kT>;
-    static constexpr int kVWarp = 48 * kVStride;                       // float2 per warp
-    static constexpr int kSmemBytes = (G::kXsLen + W * kVWarp + W * 48) * 8 + 40 * 4 * 2 * 4;
-    static constexpr int kCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) < 16 ? (227 * 1024) / (kSmemBytes + 1024) : 16;
+    static constexpr int kXsBytes = ((G::kXsLen * 8 + 15) / 16) * 16;
+    static constexpr int kVRow = 33;                                   // float4 per row of V[24][32] (odd: conflict free)
+    static constexpr int kSmemBytes = kXsBytes + 24 * kVRow * 16;
+    static constexpr int kCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) < 24 ? (227 * 1024) / (kSmemBytes + 1024) : 24;
 };
 
 // FIR of one thread.  xb = &xs[xs_pos-base of this thread], see fir_base().  acc[a][e] accumulates
@@ -119,45 +118,54 @@ SNRX_HD float2 quant_pair(float2 y, float s255 /* +-scale/255, 0 beyond the capt
     return f2_add(t, make_float2(-kMagic, -kMagic));
 }
 
-// 48-point inverse DFT of one output time + rotation + quantisation, in place:
-// on return y[q] holds the quantised (I, Q) of even bin 2q as integer-valued floats.
+// 48-point inverse DFT of one output time + rotation + quantisation:
+// on return y[q] holds the quantised (I, Q) of even bin 2q as integer-valued floats for the 40 bins that
+// carry a BLE channel (the other 8 are never computed: dead code for the compiler).
 // s_even / s_odd: quantiser scale with the sign of (-1)^(q m) folded in (0 beyond the capture end).
-SNRX_HD void pfb_dft48_quant(const float2* vcol /* &V[0][lane] of the warp tile */, cf (&y)[48], float s_even, float s_odd,
+SNRX_HD void pfb_dft48_quant(const float4* vcol /* &V[0][lane] */, int v_row, cf (&y)[48], float s_even, float s_odd,
                              cf (&raw)[48], bool keep_raw) {
     cf v[48];
 #pragma unroll
-    for (int r = 0; r < 48; r++) { float2 t = vcol[r * kVStride]; v[r].r = t.x; v[r].i = t.y; }   // vcol = &V[0][lane]
+    for (int r = 0; r < 24; r++) {
+        const float4 t = vcol[r * v_row];
+        v[r].r = t.x; v[r].i = t.y; v[r + 24].r = t.z; v[r + 24].i = t.w;
+    }
     Idft3xQ<48>::run(v, y);
     const float se = f_mul(s_even, 1.0f / 255.0f), so = f_mul(s_odd, 1.0f / 255.0f);
 #pragma unroll
     for (int q = 0; q < 48; q++) {
+        if (ble_channel_of_q(q) < 0) { y[q] = cf{0.f, 0.f}; if (keep_raw) raw[q] = cf{0.f, 0.f}; continue; }
         if (keep_raw) raw[q] = y[q];
         y[q] = C(quant_pair(P(y[q]), (q & 1) ? so : se));
     }
 }
 
-// Where the slicer bits of one warp go.  A tile starts at channel sample g_first = 127*tile; warp
-// w holds decisions of samples g0 = g_first + 32 w + lane.  For sample phase j the 8 lanes
-// sh + 4 i (sh = (j - g0) & 3) are consecutive symbol slots t0 .. t0+7 of phase stream j.
-struct BitPlace { int sh; int word; int off; };
-SNRX_HD BitPlace bit_place(int g_first, int w, int j) {
-    const int g0 = g_first + 32 * w;
-    BitPlace b;
-    b.sh = (j - g0) & 3;
-    const int t0 = (g0 + b.sh) >> 2;
-    const int wbase = ((g_first >> 2) + 32) >> 5;
-    b.word = ((t0 + 32) >> 5) - wbase;          // 0 or 1 (+1 when the 8 bits straddle a word)
-    b.off = t0 & 31;
-    return b;
+// The 40 used bins in the order the slicer packs them: slot L of word A (L = 0..23) and of word B (L = 0..15)
+SNRX_HD constexpr int ble_q_of_slot_a(int L) { return L < 21 ? L : L + 8; }     // q = 0..20, 29..31
+SNRX_HD constexpr int ble_q_of_slot_b(int L) { return 32 + L; }                 // q = 32..47
+
+// Slicer decision b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0 (btle_rx.c:1357-1361) as the sign bit of
+// 0.5 - cross: the operands are integers of magnitude <= 128, so 0.5 - cross is exact and never zero.
+SNRX_HD uint32_t slicer_sign(float i0, float q0, float i1, float q1) {
+    const float t = f_fma(i1, q0, f_fma(-i0, q1, 0.5f));
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__float_as_int(t);
+#else
+    uint32_t u; memcpy(&u, &t, 4); return u;
+#endif
+}
+SNRX_HD uint32_t shift_in_sign(uint32_t acc, uint32_t sign_word) {   // (acc << 1) | (sign_word >> 31): one SHF
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(sign_word, acc, 1);
+#else
+    return (acc << 1) | (sign_word >> 31);
+#endif
 }
 
-// every 4th bit of x starting at bit 0 -> low 8 bits
-SNRX_HD uint32_t compress4(uint32_t x) {
-    x &= 0x11111111u;
-    x = (x | (x >> 3)) & 0x03030303u;
-    x = (x | (x >> 6)) & 0x000F000Fu;
-    x = (x | (x >> 12)) & 0x000000FFu;
-    return x;
+// One step of the 32x32 bit-matrix transpose across a warp (rows = lanes, columns = bits): exchange with
+// lane ^ j the off-diagonal j x j blocks.  m = columns whose bit j is clear.
+SNRX_HD uint32_t transpose_step(uint32_t x, uint32_t y /* value of lane ^ j */, int lane, int j, uint32_t m) {
+    return (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
 }
 
 #if defined(__CUDACC__)
@@ -242,58 +250,55 @@ struct PfbBleArgs {
     float2* dbg_cf;           // [cap][40][n_out] or null
 };
 
-template <int NT, int W, bool DEBUG>
-__global__ void __launch_bounds__(32 * W, PfbBleGeom<NT, W>::kCtasPerSm) k_pfb_ble(PfbBleArgs a) {
-    using B = PfbBleGeom<NT, W>;
+template <int NT, bool DEBUG>
+__global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbBleArgs a) {
+    using B = PfbBleGeom<NT>;
     using G = typename B::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);
-    float2* Vall = xs + G::kXsLen;                                         // [W][48][kVStride]
-    float2* edge = Vall + W * B::kVWarp;                                   // [W][48] first column of each warp
-    uint32_t* wordbuf = reinterpret_cast<uint32_t*>(edge + W * 48);        // [40][4][2]
+    float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [24][kVRow]
 
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int lane = threadIdx.x;
     const int tile = a.tile0 + (int)(blockIdx.x % a.n_tiles);
     const int cap = blockIdx.x / a.n_tiles;
     const float2* xcap = a.x + (size_t)cap * a.stride;
     const int g_first = B::kStride * tile;                                 // first channel sample of the tile
-    float2* V = Vall + wid * B::kVWarp;
 
     // ---- phase 0: stage the input tile
-    pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, tid);
-    for (int i = tid; i < 320; i += B::kThreads) wordbuf[i] = 0u;
+    pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, lane);
     cp_async_commit_wait_all();
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase 1: FIR of this warp's 32 output times -> V[r][m]
+    // ---- phase 1: FIR of the 32 output times -> V[rho][m] = (branch rho, branch rho + 24)
     {
-        const int rl = lane & 7, c = lane >> 3, q = 4 * wid + c;           // q: chunk of 8 output times inside the tile
+        const int rl = lane & 7, c = lane >> 3;                            // c: chunk of 8 output times
 #pragma unroll
         for (int gi = 0; gi < 3; gi++) {
             const int rho = 8 * gi + rl;
             float g[NT];
+            const float4* gp = reinterpret_cast<const float4*>(a.taps_rho + rho * NT);
 #pragma unroll
-            for (int d = 0; d < NT; d++) g[d] = __ldg(a.taps_rho + rho * NT + d);
-            float2 acc[2][kChunkT];
-            pfb_fir_thread<NT, 2, kChunkT>(xs + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
-#pragma unroll
-            for (int e = 0; e < kChunkT; e++) {
-                V[rho * kVStride + 8 * c + e] = acc[0][e];
-                V[(rho + 24) * kVStride + 8 * c + e] = acc[1][e];
+            for (int d = 0; d < NT / 4; d++) {
+                const float4 t = __ldg(gp + d);
+                g[4 * d] = t.x; g[4 * d + 1] = t.y; g[4 * d + 2] = t.z; g[4 * d + 3] = t.w;
             }
+            float2 acc[2][kChunkT];
+            pfb_fir_thread<NT, 2, kChunkT>(xs + fir_base<NT, kChunkT>(rho, c), rho <= 12 ? 8 : 0, g, acc);
+#pragma unroll
+            for (int e = 0; e < kChunkT; e++)
+                V[rho * B::kVRow + 8 * c + e] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
         }
     }
     __syncwarp();
 
     // ---- phase 2: 48-point inverse DFT + rotation + quantiser, one lane per output time
     cf y[48];
-    const int m = tid;                                       // 0 .. 32 W - 1
-    const int mg = g_first + m;                              // channel-rate sample index in the capture
+    const int mg = g_first + lane;                           // channel-rate sample index in the capture
     {
         const float s = (mg < a.n_out) ? a.scale : 0.0f;
         cf raw[48];
-        pfb_dft48_quant(V + lane, y, s, (mg & 1) ? -s : s, raw, DEBUG);
-        if (DEBUG && m < B::kStride && mg < a.n_out) {
+        pfb_dft48_quant(V + lane, B::kVRow, y, s, (mg & 1) ? -s : s, raw, DEBUG);
+        if (DEBUG && lane < B::kStride && mg < a.n_out) {
 #pragma unroll
             for (int qq = 0; qq < 48; qq++) {
                 const int ch = ble_channel_of_q(qq);
@@ -307,58 +312,46 @@ __global__ void __launch_bounds__(32 * W, PfbBleGeom<NT, W>::kCtasPerSm) k_pfb_b
                 }
             }
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int qq = 0; qq < 48; qq++) edge[wid * 48 + qq] = make_float2(y[qq].r, y[qq].i);
-        }
     }
-    __syncthreads();                                          // edges visible (and nobody still reads xs / V of others)
 
-    // ---- phase 3: slicer bits.  b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0   (btle_rx.c:1357-1361)
+    // ---- phase 3: slicer bits (btle_rx.c:1357-1361), transposed to one word per channel, OR-ed into the streams
     {
-        uint32_t mine0 = 0, mine1 = 0;        // masks of the channels this lane will de-interleave
-        const float2* nextw = edge + ((wid + 1) % W) * 48;
+        uint32_t wa = 0, wb = 0;                             // bit L = decision of slot L (ble_q_of_slot_a / _b) at time `lane`
 #pragma unroll
-        for (int qq = 0; qq < 48; qq++) {
-            if (ble_channel_of_q(qq) < 0) continue;
-            float i1 = __shfl_down_sync(0xffffffffu, y[qq].r, 1);
-            float q1 = __shfl_down_sync(0xffffffffu, y[qq].i, 1);
-            if (lane == 31) { const float2 n = nextw[qq]; i1 = n.x; q1 = n.y; }
-            const float cross = f_fma(y[qq].r, q1, -f_mul(i1, y[qq].i));
-            uint32_t mask = __ballot_sync(0xffffffffu, cross > 0.0f);
-            if (qq < 32) { if (lane == qq) mine0 = mask; } else { if (lane == qq - 32) mine1 = mask; }
+        for (int L = 23; L >= 0; L--) {
+            const int qq = ble_q_of_slot_a(L);
+            const float i1 = __shfl_down_sync(0xffffffffu, y[qq].r, 1), q1 = __shfl_down_sync(0xffffffffu, y[qq].i, 1);
+            wa = shift_in_sign(wa, slicer_sign(y[qq].r, y[qq].i, i1, q1));
         }
-        if (wid == W - 1) { mine0 &= 0x7FFFFFFFu; mine1 &= 0x7FFFFFFFu; }   // the tile's last sample has no successor in it
-        // lane L de-interleaves bin q = L (and q = L + 32) into the tile's two-word windows
+#pragma unroll
+        for (int L = 15; L >= 0; L--) {
+            const int qq = ble_q_of_slot_b(L);
+            const float i1 = __shfl_down_sync(0xffffffffu, y[qq].r, 1), q1 = __shfl_down_sync(0xffffffffu, y[qq].i, 1);
+            wb = shift_in_sign(wb, slicer_sign(y[qq].r, y[qq].i, i1, q1));
+        }
+        // rows = times (lanes), columns = slots  ->  rows = slots, columns = times
+        {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, wb, 16);
+            wb = (wb & 0xFFFFu) | (o << 16);                 // lanes 0..15: times 0..15 | times 16..31 of slots 0..15
+        }
+        wa = transpose_step(wa, __shfl_xor_sync(0xffffffffu, wa, 16), lane, 16, 0x0000FFFFu);
+#pragma unroll
+        for (int j = 8; j >= 1; j >>= 1) {
+            const uint32_t m = j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+            wa = transpose_step(wa, __shfl_xor_sync(0xffffffffu, wa, j), lane, j, m);
+            wb = transpose_step(wb, __shfl_xor_sync(0xffffffffu, wb, j), lane, j, m);
+        }
+        // lane L now holds the 32 decisions (bit = time) of slot L; the tile's last sample has no successor in it
+        const uint32_t wi = (uint32_t)kBitsLeadWords + ((uint32_t)g_first >> 5);
+        const int off = g_first & 31;
 #pragma unroll
         for (int half = 0; half < 2; half++) {
-            const int ch = ble_channel_of_q(lane + 32 * half);
-            const uint32_t mk = half ? mine1 : mine0;
-            if (ch >= 0 && (half == 0 || lane < 16)) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const BitPlace bp = bit_place(g_first, wid, j);
-                    const uint32_t Bm = compress4(mk >> bp.sh);
-                    if (Bm) {
-                        uint32_t* w2 = wordbuf + (ch * 4 + j) * 2;
-                        atomicOr(w2 + bp.word, Bm << bp.off);
-                        if (bp.off > 24) atomicOr(w2 + bp.word + 1, Bm >> (32 - bp.off));
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    {
-        // (channel, phase) = i >> 1 is the row of the bit-stream matrix [cap][40][4][words_per_phase]
-        uint32_t* row0 = a.bits + a.lay.index(cap, 0, 0, (uint32_t)(((g_first >> 2) + 32) >> 5));
-        const uint32_t wpp = a.lay.words_per_phase;
-#pragma unroll
-        for (int i0 = 0; i0 < 320; i0 += B::kThreads) {
-            const int i = i0 + tid;
-            if (i0 + B::kThreads <= 320 || i < 320) {
-                const uint32_t v = wordbuf[i];
-                if (v) atomicOr(row0 + (size_t)(i >> 1) * wpp + (i & 1), v);
+            const uint32_t mk = (half ? wb : wa) & 0x7FFFFFFFu;
+            if (lane < (half ? 16 : 24) && mk) {
+                const int ch = ble_channel_of_q(half ? ble_q_of_slot_b(lane) : ble_q_of_slot_a(lane));
+                uint32_t* dst = a.bits + a.lay.index(cap, ch, wi);
+                atomicOr(dst, mk << off);
+                if (off > 1 && (mk >> (32 - off))) atomicOr(dst + 1, mk >> (32 - off));
             }
         }
     }

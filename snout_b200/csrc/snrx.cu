@@ -76,12 +76,11 @@ struct snrx_handle {
     uint64_t max_in = 0;                 // input samples per capture
     uint32_t max_caps = 1;
     uint32_t max_out = 0;                // channel-rate samples per capture
-    uint32_t wpp = 0;                    // bit words per phase stream
-    uint32_t n_chunks = 0;               // aa-search chunks per phase stream
+    uint32_t wpp = 0;                    // words per (capture, channel) bit stream
+    uint32_t n_chunks = 0;               // aa-search chunks (32 words) per bit stream
     uint32_t max_windows = 0;
     uint32_t cand_cap = 0, frame_cap = 0;
     int pfb_nt = 16;
-    int ble_w = 2;                       // warps per CTA of the BLE channelizer: tile = 32 w samples, stride 32 w - 1
 
     // constants on the device
     uint32_t *d_crc_tab = nullptr, *d_whiten = nullptr;
@@ -183,32 +182,28 @@ int grid_for(snrx_handle* h, uint64_t items, int per_block, int blocks_per_sm) {
 
 }  // namespace
 
-template <int NT, int W>
+template <int NT>
 static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint32_t caps) {
-    using B = PfbBleGeom<NT, W>;
+    using B = PfbBleGeom<NT>;
     if (!a) {
-        CK(cudaFuncSetAttribute(k_pfb_ble<NT, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
-        CK(cudaFuncSetAttribute(k_pfb_ble<NT, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         return SNRX_OK;
     }
     const dim3 grid((unsigned)(a->n_tiles) * caps);
-    if (h->cfg.flags & SNRX_F_KEEP_STREAMS) k_pfb_ble<NT, W, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
-    else k_pfb_ble<NT, W, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
+    if (h->cfg.flags & SNRX_F_KEEP_STREAMS) k_pfb_ble<NT, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
+    else k_pfb_ble<NT, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
     return SNRX_OK;
 }
 static int pfb_ble_dispatch(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint32_t caps) {
-    const int key = h->pfb_nt * 10 + h->ble_w;
-    switch (key) {
-        case 161: return pfb_ble_go<16, 1>(h, a, st, caps);
-        case 162: return pfb_ble_go<16, 2>(h, a, st, caps);
-        case 164: return pfb_ble_go<16, 4>(h, a, st, caps);
-        case 321: return pfb_ble_go<32, 1>(h, a, st, caps);
-        case 322: return pfb_ble_go<32, 2>(h, a, st, caps);
-        case 324: return pfb_ble_go<32, 4>(h, a, st, caps);
+    switch (h->pfb_nt) {
+        case 16: return pfb_ble_go<16>(h, a, st, caps);
+        case 32: return pfb_ble_go<32>(h, a, st, caps);
     }
     return fail(h, SNRX_EINVAL, "no channelizer instance for this configuration");
 }
-static int ble_tile_stride(const snrx_handle* h) { return h->wideband ? 32 * h->ble_w - 1 : kTileT; }
+static int ble_tile_stride(const snrx_handle* h) { return h->wideband ? PfbBleGeom<16>::kStride : kTileT; }
 
 // device frame list -> host-mapped pinned memory, fully coalesced 16-byte stores; also publishes the totals
 __global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __restrict__ src, const uint32_t* __restrict__ totals_dev,
@@ -341,9 +336,8 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         h->cand_cap = std::max<uint32_t>(1u << 16, 4 * c.max_frames);
 
         if (h->has_ble) {
-            const uint32_t tiles = div_up(h->max_out, kTileT);
-            h->wpp = kBitsLeadWords + tiles + kBitsTailWords;
-            h->n_chunks = div_up(h->wpp - 1, 32);
+            h->wpp = bits_words_for(h->max_out);
+            h->n_chunks = div_up(h->wpp, 32);
             h->max_windows = div_up(h->max_out, kWindow);
             uint32_t crc[256], wh[40 * 11];
             make_crc_table(crc);
@@ -366,8 +360,6 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
                 CKD(dev_alloc(h, &h->d_taps_flat, L));
                 CK(cudaMemcpy(h->d_taps_rho, rho.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
                 CK(cudaMemcpy(h->d_taps_flat, flat.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
-                if (const char* e = getenv("SNRX_PFB_WARPS")) h->ble_w = atoi(e);        // tuning knob; results do not depend on it
-                if (h->ble_w != 1 && h->ble_w != 2 && h->ble_w != 4) return fail(h, SNRX_EINVAL, "SNRX_PFB_WARPS must be 1, 2 or 4");
                 int r = pfb_ble_dispatch(h, nullptr, nullptr, 0);                          // sets the shared-memory attributes
                 if (r != SNRX_OK) return r;
             }
@@ -389,7 +381,7 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
             CKD(dev_alloc(h, &ln.d_totals, 8));
             CK(cudaMemset(ln.d_totals, 0, 8 * sizeof(uint32_t)));
             if (h->has_ble) {
-                ln.d_bits_bytes = (size_t)h->max_caps * h->n_ble_ch * 4 * h->wpp * sizeof(uint32_t);
+                ln.d_bits_bytes = (size_t)h->max_caps * h->n_ble_ch * h->wpp * sizeof(uint32_t);
                 CK(cudaMalloc((void**)&ln.d_bits, ln.d_bits_bytes));
                 CK(cudaMalloc((void**)&ln.d_hits, ln.d_bits_bytes));
                 const size_t aa_items = (size_t)h->max_caps * h->n_ble_ch * h->n_chunks;
@@ -477,7 +469,7 @@ static int launch_ble_front(snrx_handle* h, Lane& ln, const float2* x, uint32_t 
         if (r != SNRX_OK) return r;
     } else {
         NbArgs a;
-        a.x = reinterpret_cast<const float4*>(x); a.stride = stride; a.n = (int64_t)n_in;
+        a.x = x; a.stride = stride; a.n = (int64_t)n_in;
         a.n_groups = (int32_t)div_up(n_in, 128); a.n_captures = caps; a.scale = h->cfg.quant_scale;
         a.bits = ln.d_bits; a.lay = lay; a.dbg_q8 = ln.d_q8;
         const uint64_t items = (uint64_t)caps * a.n_groups;
@@ -554,10 +546,9 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
 
     BitsLayout lay{};
     if (h->has_ble) {
-        const uint32_t tiles = div_up(n_out, kTileT);
-        lay.words_per_phase = kBitsLeadWords + tiles + kBitsTailWords;
+        lay.words_per_stream = bits_words_for(n_out);
         lay.n_channels = h->n_ble_ch;
-        CK(cudaMemsetAsync(ln.d_bits, 0, (size_t)n_captures * h->n_ble_ch * 4 * lay.words_per_phase * sizeof(uint32_t), st));
+        CK(cudaMemsetAsync(ln.d_bits, 0, (size_t)n_captures * h->n_ble_ch * lay.words_per_stream * sizeof(uint32_t), st));
     }
 
     if (staged) {
@@ -614,7 +605,7 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         p.first_capture = first_capture;
         p.n_captures = n_captures;
         p.n_channels = h->n_ble_ch;
-        const uint32_t n_chunks = div_up(lay.words_per_phase - 1, 32);
+        const uint32_t n_chunks = div_up(lay.words_per_stream, 32);
         const uint32_t aa_items = n_captures * h->n_ble_ch * n_chunks;
         const uint32_t w_items = n_captures * h->n_ble_ch * (uint32_t)p.n_windows;
 
@@ -755,8 +746,7 @@ int snrx_debug_stage(snrx_t* h, int stage, void* out, uint64_t cap_bytes, uint64
             src = ln.d_cf; bytes = (uint64_t)h->b_caps * h->n_ble_ch * h->b_n_out * 8; break;
         case SNRX_STAGE_BLE_BITS: {
             if (!ln.d_bits) return SNRX_ESTATE;
-            const uint32_t wpp = kBitsLeadWords + div_up(h->b_n_out, kTileT) + kBitsTailWords;
-            src = ln.d_bits; bytes = (uint64_t)h->b_caps * h->n_ble_ch * 4 * wpp * 4; break;
+            src = ln.d_bits; bytes = (uint64_t)h->b_caps * h->n_ble_ch * bits_words_for(h->b_n_out) * 4; break;
         }
         default: {
             int r = zb_debug_stage(ln.zb, stage, h->b_caps, h->b_n_out, &src, &bytes);

@@ -194,7 +194,7 @@ class RxEngine:
         if stage == _abi.STAGE_CHAN_CF32:
             return raw.view(np.complex64).reshape(caps, self.n_zb if self.mode == MODE_ZB_WB16 else self.n_ble, n_out)
         if stage == _abi.STAGE_BLE_BITS:
-            return raw.view(np.uint32).reshape(caps, self.n_ble, 4, -1)
+            return raw.view(np.uint32).reshape(caps, self.n_ble, -1)
         if stage in (_abi.STAGE_ZB_DISC, _abi.STAGE_ZB_F):
             return raw.view(np.float32).reshape(caps, self.n_zb, -1)[:, :, :n_out]
         if stage == _abi.STAGE_ZB_NCHIPS:

@@ -40,17 +40,17 @@ int emu_ble_channel_of_q(int q) { return ble_channel_of_q(q); }
 
 }  // extern "C"
 
-// ---- one tile of k_pfb_ble<NT, W, *>, phases 0..3 ---------------------------------------------
-// x: capture cf32 (n_in samples).  Outputs: words[40][4][2] (to be OR-ed at word index wbase + half),
-// q8[40][T][2] (int8), raw[40][T] cf32 for samples g_first .. g_first+T-1, T = 32 W.
-template <int NT, int W>
+// ---- one tile of k_pfb_ble<NT, *>, phases 0..3 --------------------------------------------------
+// x: capture cf32 (n_in samples).  Outputs: words[40] = the 31 decisions of samples g_first .. g_first+30
+// (bit = time), q8[40][32][2] (int8), raw[40][32] cf32 for samples g_first .. g_first+31.
+template <int NT>
 static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
-                     float scale, uint32_t* words, int* wbase_out, int8_t* q8, float* raw_out) {
-    using B = PfbBleGeom<NT, W>;
+                     float scale, uint32_t* words, int8_t* q8, float* raw_out) {
+    using B = PfbBleGeom<NT>;
     using G = typename B::G;
     constexpr int T = B::kT;
     std::vector<float2> xs(G::kXsLen, make_float2(0.f, 0.f));
-    std::vector<float2> V(W * B::kVWarp, make_float2(0.f, 0.f));
+    std::vector<float4> V(24 * B::kVRow, make_float4(0.f, 0.f, 0.f, 0.f));
     const int g_first = B::kStride * tile;
     const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
     constexpr int kPer = 24 * kChunkT, kPairs = kPer / 2;
@@ -64,20 +64,16 @@ static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const fl
                 xs[ip + 8 * p + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
         }
     }
-    for (int tid = 0; tid < B::kThreads; tid++) {                      // phase 1
-        const int lane = tid & 31, wid = tid >> 5;
-        const int rl = lane & 7, c = lane >> 3, q = 4 * wid + c;
-        float2* Vw = V.data() + wid * B::kVWarp;
+    for (int lane = 0; lane < 32; lane++) {                            // phase 1
+        const int rl = lane & 7, c = lane >> 3;
         for (int gi = 0; gi < 3; gi++) {
             const int rho = 8 * gi + rl;
             float g[NT];
             for (int d = 0; d < NT; d++) g[d] = taps_rho[rho * NT + d];
             float2 acc[2][kChunkT];
-            pfb_fir_thread<NT, 2, kChunkT>(xs.data() + fir_base<NT, kChunkT>(rho, q), rho <= 12 ? 8 : 0, g, acc);
-            for (int e = 0; e < kChunkT; e++) {
-                Vw[rho * kVStride + 8 * c + e] = acc[0][e];
-                Vw[(rho + 24) * kVStride + 8 * c + e] = acc[1][e];
-            }
+            pfb_fir_thread<NT, 2, kChunkT>(xs.data() + fir_base<NT, kChunkT>(rho, c), rho <= 12 ? 8 : 0, g, acc);
+            for (int e = 0; e < kChunkT; e++)
+                V[rho * B::kVRow + 8 * c + e] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
         }
     }
     std::vector<cf> Y(T * 48);
@@ -85,7 +81,7 @@ static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const fl
         const int mg = g_first + m;
         const float s = (mg < n_out) ? scale : 0.0f;
         cf y[48], raw[48];
-        pfb_dft48_quant(V.data() + (m >> 5) * B::kVWarp + (m & 31), y, s, (mg & 1) ? -s : s, raw, true);
+        pfb_dft48_quant(V.data() + m, B::kVRow, y, s, (mg & 1) ? -s : s, raw, true);
         for (int qq = 0; qq < 48; qq++) {
             Y[m * 48 + qq] = y[qq];
             const int ch = ble_channel_of_q(qq);
@@ -98,28 +94,35 @@ static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const fl
             }
         }
     }
-    memset(words, 0, sizeof(uint32_t) * 320);
-    *wbase_out = ((g_first >> 2) + 32) >> 5;
-    for (int wid = 0; wid < W; wid++) {                                // phase 3
-        for (int qq = 0; qq < 48; qq++) {
-            const int ch = ble_channel_of_q(qq);
-            if (ch < 0) continue;
-            uint32_t mask = 0;
-            for (int lane = 0; lane < 32; lane++) {
-                const int m = 32 * wid + lane;
-                if (m + 1 >= T) continue;                            // the tile's last sample has no successor in it
-                const cf a = Y[m * 48 + qq], b = Y[(m + 1) * 48 + qq];
-                if (f_fma(a.r, b.i, -f_mul(b.r, a.i)) > 0.0f) mask |= 1u << lane;
-            }
-            for (int j = 0; j < 4; j++) {
-                const BitPlace bp = bit_place(g_first, wid, j);
-                const uint32_t Bm = compress4(mask >> bp.sh);
-                uint32_t* w2 = words + (ch * 4 + j) * 2;
-                w2[bp.word] |= Bm << bp.off;
-                if (bp.off > 24) w2[bp.word + 1] |= Bm >> (32 - bp.off);
-            }
+    // phase 3: per-lane slot words, then the shuffle transposes
+    uint32_t wa[32], wb[32];
+    for (int lane = 0; lane < 32; lane++) {
+        const int nx = lane < 31 ? lane + 1 : lane;                    // __shfl_down: lane 31 reads itself
+        uint32_t a = 0, b = 0;
+        for (int L = 23; L >= 0; L--) {
+            const int qq = ble_q_of_slot_a(L);
+            a = shift_in_sign(a, slicer_sign(Y[lane * 48 + qq].r, Y[lane * 48 + qq].i, Y[nx * 48 + qq].r, Y[nx * 48 + qq].i));
         }
+        for (int L = 15; L >= 0; L--) {
+            const int qq = ble_q_of_slot_b(L);
+            b = shift_in_sign(b, slicer_sign(Y[lane * 48 + qq].r, Y[lane * 48 + qq].i, Y[nx * 48 + qq].r, Y[nx * 48 + qq].i));
+        }
+        wa[lane] = a; wb[lane] = b;
     }
+    auto xchg = [](uint32_t* w, int j, uint32_t m) {
+        uint32_t o[32];
+        for (int lane = 0; lane < 32; lane++) o[lane] = transpose_step(w[lane], w[lane ^ j], lane, j, m);
+        memcpy(w, o, sizeof o);
+    };
+    { uint32_t o[32]; for (int lane = 0; lane < 32; lane++) o[lane] = (wb[lane] & 0xFFFFu) | (wb[lane ^ 16] << 16); memcpy(wb, o, sizeof o); }
+    xchg(wa, 16, 0x0000FFFFu);
+    for (int j = 8; j >= 1; j >>= 1) {
+        const uint32_t m = j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
+        xchg(wa, j, m); xchg(wb, j, m);
+    }
+    memset(words, 0, sizeof(uint32_t) * 40);
+    for (int L = 0; L < 24; L++) words[ble_channel_of_q(ble_q_of_slot_a(L))] = wa[L] & 0x7FFFFFFFu;
+    for (int L = 0; L < 16; L++) words[ble_channel_of_q(ble_q_of_slot_b(L))] = wb[L] & 0x7FFFFFFFu;
 }
 
 // ---- one tile of k_pfb_zb<NT, *>: f[g_first+1 .. g_first+127] for 16 channels, rotated streams for debug
@@ -178,66 +181,57 @@ int emu_zb_bin_of_slot(int c) { return zb_bin_of_slot(c); }
 
 int emu_pfb_tile_stride(void) { return kTileStride; }          // Zigbee kernel
 
-// BLE kernel with w warps per CTA: tile of 32 w samples, stride 32 w - 1
-void emu_pfb_ble_tile(int nt, int w, const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
-                      float scale, uint32_t* words, int* wbase, int8_t* q8, float* raw) {
-#define GO(NT, W) pfb_tile<NT, W>(x, n_in, n_out, tile, taps_rho, scale, words, wbase, q8, raw)
-    if (nt == 16) { if (w == 1) GO(16, 1); else if (w == 2) GO(16, 2); else GO(16, 4); }
-    else { if (w == 1) GO(32, 1); else if (w == 2) GO(32, 2); else GO(32, 4); }
-#undef GO
+// BLE channelizer tile (one warp): 32 samples computed, 31 decisions emitted
+int emu_pfb_ble_stride(void) { return PfbBleGeom<16>::kStride; }
+void emu_pfb_ble_tile(int nt, const float* x, int64_t n_in, int n_out, int tile, const float* taps_rho,
+                      float scale, uint32_t* words, int8_t* q8, float* raw) {
+    if (nt == 16) pfb_tile<16>(x, n_in, n_out, tile, taps_rho, scale, words, q8, raw);
+    else pfb_tile<32>(x, n_in, n_out, tile, taps_rho, scale, words, q8, raw);
 }
 
-// ---- narrow-band slicer: whole capture -> phase words (layout of BitsLayout, 1 channel) --------
-void emu_ble_slice_nb(const float* x, int64_t n, float scale, uint32_t* bits, uint32_t wpp, int8_t* q8) {
-    memset(bits, 0, sizeof(uint32_t) * 4 * wpp);
+int emu_bits_words_for(int n_out) { return (int)bits_words_for((uint32_t)n_out); }
+int emu_bits_lead_words(void) { return kBitsLeadWords; }
+
+// ---- narrow-band slicer: whole capture -> bit stream words (BitsLayout, 1 channel) --------------
+void emu_ble_slice_nb(const float* x, int64_t n, float scale, uint32_t* bits, uint32_t nw, int8_t* q8) {
+    memset(bits, 0, sizeof(uint32_t) * nw);
     auto qv = [&](int64_t k, int c) -> float { return k < n ? quant_exact(x[2 * k + c], scale) : quant_exact(0.f, scale); };
     for (int64_t k = 0; k < n; k++) {
         if (q8) { q8[2 * k] = (int8_t)qv(k, 0); q8[2 * k + 1] = (int8_t)qv(k, 1); }
-        if (slicer_bit(qv(k, 0), qv(k, 1), qv(k + 1, 0), qv(k + 1, 1))) {
-            const int64_t t = k / 4; const int j = (int)(k % 4);
-            bits[(size_t)j * wpp + (size_t)((t + 32) >> 5)] |= 1u << ((t + 32) & 31);
-        }
+        if (slicer_bit(qv(k, 0), qv(k, 1), qv(k + 1, 0), qv(k + 1, 1)))
+            bits[(size_t)kBitsLeadWords + (size_t)(k >> 5)] |= 1u << (k & 31);
     }
 }
 
 // ---- BLE back end over one (capture, channel) bit stream: aa search, decode, resolve -----------
-int emu_ble_back(const uint32_t* bits, uint32_t wpp, int n_out, int m_origin, int n_windows, uint32_t first_window,
+int emu_ble_back(const uint32_t* bits, uint32_t nw, int n_out, int m_origin, int n_windows, uint32_t first_window,
                  int channel, uint32_t aa, uint32_t aa_mask, uint32_t crc_init_internal, const uint32_t* crc_tab,
                  const uint32_t* whiten /*[40][11]*/, snrx_frame_t* out, int cap, int* n_cands_out) {
-    BitsLayout lay; lay.words_per_phase = wpp; lay.n_channels = 1;
     BleParams p{};
     p.aa = aa; p.aa_mask = aa_mask; p.crc_init_internal = crc_init_internal; p.n_out = n_out; p.m_origin = m_origin;
     p.n_windows = n_windows; p.first_window = first_window; p.first_capture = 0; p.n_captures = 1; p.n_channels = 1;
     const int z = aa_virtual_bits(aa, aa_mask);
     const uint32_t mask_hi = aa_mask & ~((1u << z) - 1u);
     std::vector<Cand> cands;
-    for (uint32_t w = 0; w + 1 < wpp; w++) {
-        uint32_t hits[4];
-        for (int j = 0; j < 4; j++) {
-            const uint32_t* pw = bits + lay.index(0, 0, j, 0);
-            uint32_t hj = aa_word_hits(pw[w], pw[w + 1], aa, mask_hi, [](uint32_t m) { return m != 0u; });
-            const int nvalid = ((n_out - 1 - j) >> 2) - 32 * ((int)w - 1) + 1;
-            if (nvalid <= 0) hj = 0u; else if (nvalid < 32) hj &= (1u << nvalid) - 1u;
-            hits[j] = hj;
-        }
+    for (uint32_t w = 0; w < nw; w++) {                                // k_aa_search + k_aa_fill
+        uint32_t ww[5];
+        for (int d = 0; d < 5; d++) ww[d] = (w + d < nw) ? bits[w + d] : 0u;
+        uint32_t h = aa_word_hits(ww, aa, mask_hi, [](uint32_t m) { return m != 0u; });
+        const int nvalid = n_out - 32 * ((int)w - kBitsLeadWords);
+        if (nvalid <= 0) h = 0u; else if (nvalid < 32) h &= (1u << nvalid) - 1u;
         for (int i = 0; i < 32; i++)
-            for (int j = 0; j < 4; j++)
-                if ((hits[j] >> i) & 1u) {
-                    const int t = 32 * ((int)w - 1) + i;
-                    const uint32_t* pw = bits + lay.index(0, 0, j, 0);
-                    uint32_t d = (slots32(pw, t) ^ aa) & aa_mask;
-                    Cand c; c.s = 4 * t + j; c.ch_idx = 0; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = 0;
-                    cands.push_back(c);
-                }
+            if ((h >> i) & 1u) {
+                const int s = 32 * ((int)w - kBitsLeadWords) + i;
+                const uint32_t d = (symbols32(bits, s) ^ aa) & aa_mask;
+                Cand c; c.s = s; c.ch_idx = 0; c.vneed = (uint8_t)hi_bit_plus1(d); c.pad = 0; c.cap = 0;
+                cands.push_back(c);
+            }
     }
     std::vector<Dec> decs(cands.size());
-    for (size_t k = 0; k < cands.size(); k++) {
+    for (size_t k = 0; k < cands.size(); k++) {                        // k_ble_decode
         const Cand c = cands[k];
-        const int j = ((c.s % 4) + 4) % 4;
-        const int t0 = (c.s - j) / 4;
-        const uint32_t* pw = bits + lay.index(0, 0, j, 0);
         uint32_t chunk[11];
-        for (int q = 0; q < 11; q++) chunk[q] = slots32(pw, t0 + 32 + 32 * q) ^ whiten[channel * 11 + q];
+        for (int q = 0; q < 11; q++) chunk[q] = symbols32(bits, c.s + 128 + 128 * q) ^ whiten[channel * 11 + q];
         Dec d; d.s = c.s; d.resume = 0; d.vneed = c.vneed;
         ble_finish(chunk, channel >= 37 && channel <= 39, crc_init_internal, crc_tab, d);
         decs[k] = d;

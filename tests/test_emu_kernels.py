@@ -38,8 +38,8 @@ def _back(emu, oracle_mod, bits, wpp, n_out, ch, m_origin=0, n_windows=None, fir
 def _slice_nb(emu, q_or_x, scale):
     x = np.ascontiguousarray(q_or_x, dtype=np.float32).reshape(-1)
     n = len(x) // 2
-    wpp = 1 + (n + 127) // 128 + 16
-    bits = np.zeros(4 * wpp, dtype=np.uint32)
+    wpp = emu.emu_bits_words_for(n)
+    bits = np.zeros(wpp, dtype=np.uint32)
     q8 = np.zeros((n, 2), dtype=np.int8)
     emu.emu_ble_slice_nb(P(x), ctypes.c_int64(n), ctypes.c_float(scale), P(bits), ctypes.c_uint32(wpp), P(q8))
     return bits, wpp, q8
@@ -103,39 +103,40 @@ def test_back_end_shard_origin(emu, oracle_mod):
     assert_frames_equal(got, want, what="shard")
 
 
-@pytest.mark.parametrize("nt,name,warps", [(16, "BLE_384", 2), (32, "BLE_768", 2), (16, "BLE_384", 4), (16, "BLE_384", 1)])
-def test_pfb_tile_kernel(emu, oracle_mod, nt, name, warps):
+@pytest.mark.parametrize("nt,name", [(16, "BLE_384"), (32, "BLE_768")])
+def test_pfb_tile_kernel(emu, oracle_mod, nt, name):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
     from gen_tables import PFB_DESIGNS, kaiser_lowpass
     h = kaiser_lowpass(*PFB_DESIGNS[name])
-    L = len(h)
     hf = h.astype(np.float32)
     rho = np.array([hf[r + 24 * d] for r in range(24) for d in range(nt)], dtype=np.float32)
     cap = synth.wideband_capture(seconds=0.0025, kind="ble", seed=4000, gap=(200, 2000))
     x = np.ascontiguousarray(cap.iq)[: 24 * 8192 - 24 * 40]          # ragged: n_out = 8152, last tile partial
     n_in = len(x)
     n_out = n_in // 24
-    T = 32 * warps
-    stride = T - 1
+    T, stride = 32, emu.emu_pfb_ble_stride()
+    assert stride == 31
     tiles = (n_out + stride - 1) // stride
-    wpp = 1 + (n_out + 127) // 128 + 16
-    bits = np.zeros((40, 4, wpp), dtype=np.uint32)
+    wpp, lead = emu.emu_bits_words_for(n_out), emu.emu_bits_lead_words()
+    bits = np.zeros((40, wpp), dtype=np.uint64)                      # 64-bit scratch so that shifted words can spill
     q8 = np.zeros((40, tiles * stride + 1, 2), dtype=np.int8)
     raw = np.zeros((40, tiles * stride + 1), dtype=np.complex64)
     xf = x.view(np.float32)
     for t in range(tiles):
-        w = np.zeros(320, dtype=np.uint32)
+        w = np.zeros(40, dtype=np.uint32)
         q = np.zeros((40, T, 2), dtype=np.int8)
         r = np.zeros((40, T), dtype=np.complex64)
-        wb = ctypes.c_int(0)
-        emu.emu_pfb_ble_tile(nt, warps, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), ctypes.c_float(100.0), P(w), ctypes.byref(wb), P(q), P(r))
-        w = w.reshape(40, 4, 2)
-        bits[:, :, wb.value] |= w[:, :, 0]
-        bits[:, :, wb.value + 1] |= w[:, :, 1]
+        emu.emu_pfb_ble_tile(nt, P(xf), ctypes.c_int64(n_in), n_out, t, P(rho), ctypes.c_float(100.0), P(w), P(q), P(r))
+        g0 = t * stride
+        wi, off = lead + (g0 >> 5), g0 & 31                          # what the kernel's two atomicOr do
+        sh = w.astype(np.uint64) << np.uint64(off)
+        bits[:, wi] |= sh & np.uint64(0xFFFFFFFF)
+        bits[:, wi + 1] |= sh >> np.uint64(32)
         if t:                                                        # last sample of a tile == sample 0 of the next
-            assert np.array_equal(q8[:, t * stride], q[:, 0])
-        q8[:, t * stride:t * stride + T] = q
-        raw[:, t * stride:t * stride + T] = r
+            assert np.array_equal(q8[:, g0], q[:, 0])
+        q8[:, g0:g0 + T] = q
+        raw[:, g0:g0 + T] = r
+    bits = bits.astype(np.uint32)
     assert not q8[:, n_out:].any()                                   # beyond the capture: zeros
     q8, raw = q8[:, :n_out], raw[:, :n_out]
     yd = oracle_mod.pfb(x, h, [chanplan.ble_channel_bin(c) for c in range(40)])
@@ -146,8 +147,8 @@ def test_pfb_tile_kernel(emu, oracle_mod, nt, name, warps):
     n_frames = 0
     for c in range(40):
         b2, _, _ = _slice_nb(emu, q8[c].astype(np.float32) / 128.0, 128.0)
-        assert np.array_equal(b2.reshape(4, wpp), bits[c]), f"slicer words of channel {c}"
-        got = _back(emu, oracle_mod, np.ascontiguousarray(bits[c]).reshape(-1), wpp, n_out, c)
+        assert np.array_equal(b2, bits[c]), f"slicer words of channel {c}"
+        got = _back(emu, oracle_mod, np.ascontiguousarray(bits[c]), wpp, n_out, c)
         assert_frames_equal(got, oracle_mod.ble_decode(q8[c], c), what=f"channel {c}")
         n_frames += len(got)
     assert n_frames > 100
