@@ -17,12 +17,14 @@
 // no carry, no stitch pass, no CTA-wide barrier.
 //   phase 0  cp.async stages the input tile into shared memory (coalesced 16-byte copies); the tile
 //            is laid out flat with a 64-byte skew every 192 samples so that phase 1 is bank-conflict free;
-//   phase 1  FIR: lane (rho mod 8, chunk) owns decimated sequence X_rho[c] = x[24 c - rho] and 8 consecutive
-//            output times, three passes cover rho = 0..23 (branches rho, rho+24); taps of that rho live in
-//            registers, each loaded sample feeds up to 16 FMAs (register sliding window); results go to
-//            the V[24][32] tile of float4 = (branch rho, branch rho + 24) with 16-byte stores;
-//   phase 2  __syncwarp, then one lane per output time loads its column (24 x 16 bytes) and runs the fully
-//            unrolled 48-point inverse DFT in registers (fft.cuh), applies the bin rotation, quantises
+//   phase 1  three passes gi = 0..2, each: FIR of branches r = gi + 3 rl (+24) -- lane (rl, chunk) owns the
+//            decimated sequence X_rho[c] = x[24 c - rho], rho = gi + 3 rl, and 8 consecutive output times; the
+//            taps of that rho live in registers and each loaded sample feeds up to 16 FMAs (register sliding
+//            window) -- then a 4 KB transpose through shared memory (16-byte stores/loads, XOR swizzle) and,
+//            one lane per output time, the 16-point inverse DFT over the branches r = gi (mod 3), in
+//            registers.  Keeping only one third of the branch outputs in shared memory at a time is what
+//            lets 16 warps share an SM;
+//   phase 2  radix-3 combination of the three 16-point transforms (fft.cuh), bin rotation, quantisation of
 //            the 40 bins that carry a channel;
 //   phase 3  successor samples by warp shuffle, cross product, sign bit shifted into a per-lane word
 //            (bit = channel); two 32x32 bit-matrix transposes by shuffle turn them into per-channel
@@ -68,9 +70,9 @@ template <int NT> struct PfbBleGeom {
     static constexpr int kThreads = 32;
     using G = PfbGeom<NT, kChunkT, kT>;
     static constexpr int kXsBytes = ((G::kXsLen * 8 + 15) / 16) * 16;
-    static constexpr int kVRow = 33;                                   // float4 per row of V[24][32] (odd: conflict free)
-    static constexpr int kSmemBytes = kXsBytes + 24 * kVRow * 16;
-    static constexpr int kCtasPerSm = (227 * 1024) / (kSmemBytes + 1024) < 24 ? (227 * 1024) / (kSmemBytes + 1024) : 24;
+    static constexpr int kVBytes = 8 * 32 * 16;                        // V[8][32] float4 = (branch r2 = rl, r2 = rl + 8) of one pass
+    static constexpr int kSmemBytes = kXsBytes + kVBytes;
+    static constexpr int kCtasPerSm = (228 * 1024) / (kSmemBytes + 1024) < 16 ? (228 * 1024) / (kSmemBytes + 1024) : 16;
 };
 
 // FIR of one thread.  xb = &xs[xs_pos-base of this thread], see fir_base().  acc[a][e] accumulates
@@ -118,19 +120,27 @@ SNRX_HD float2 quant_pair(float2 y, float s255 /* +-scale/255, 0 beyond the capt
     return f2_add(t, make_float2(-kMagic, -kMagic));
 }
 
-// 48-point inverse DFT of one output time + rotation + quantisation:
+// V tile of one FIR pass: row rl (0..7), column = output time, float4 = (branch r2 = rl, branch r2 = rl + 8)
+// of the pass's 16-point transform; the column is XOR-swizzled with the row so that both the FIR lanes'
+// stores (8 rows at one column) and the DFT lanes' loads (one row, 32 columns) are bank-conflict free.
+SNRX_HD constexpr int v_pos(int row, int col) { return row * 32 + (col ^ row); }
+
+// One lane's column of the pass -> the 16 inputs of IdftPow2<16, 1>
+SNRX_HD void pfb_load_col16(const float4* V, int lane, cf (&v)[16]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const float4 t = V[v_pos(r, lane)];
+        v[r].r = t.x; v[r].i = t.y; v[r + 8].r = t.z; v[r + 8].i = t.w;
+    }
+}
+
+// Radix-3 combination of the three 16-point transforms + rotation + quantisation:
 // on return y[q] holds the quantised (I, Q) of even bin 2q as integer-valued floats for the 40 bins that
 // carry a BLE channel (the other 8 are never computed: dead code for the compiler).
 // s_even / s_odd: quantiser scale with the sign of (-1)^(q m) folded in (0 beyond the capture end).
-SNRX_HD void pfb_dft48_quant(const float4* vcol /* &V[0][lane] */, int v_row, cf (&y)[48], float s_even, float s_odd,
-                             cf (&raw)[48], bool keep_raw) {
-    cf v[48];
-#pragma unroll
-    for (int r = 0; r < 24; r++) {
-        const float4 t = vcol[r * v_row];
-        v[r].r = t.x; v[r].i = t.y; v[r + 24].r = t.z; v[r + 24].i = t.w;
-    }
-    Idft3xQ<48>::run(v, y);
+SNRX_HD void pfb_combine_quant(const cf (&f0)[16], const cf (&f1)[16], const cf (&f2)[16], cf (&y)[48], float s_even,
+                               float s_odd, cf (&raw)[48], bool keep_raw) {
+    Idft3xQ<48>::template combine<0>(f0, f1, f2, y);
     const float se = f_mul(s_even, 1.0f / 255.0f), so = f_mul(s_odd, 1.0f / 255.0f);
 #pragma unroll
     for (int q = 0; q < 48; q++) {
@@ -256,7 +266,7 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     using G = typename B::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);
-    float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [24][kVRow]
+    float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [8][32], see v_pos()
 
     const int lane = threadIdx.x;
     const int tile = a.tile0 + (int)(blockIdx.x % a.n_tiles);
@@ -269,12 +279,13 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     cp_async_commit_wait_all();
     __syncwarp();
 
-    // ---- phase 1: FIR of the 32 output times -> V[rho][m] = (branch rho, branch rho + 24)
+    // ---- phase 1: three passes of FIR (branches r = gi mod 3) -> transpose -> 16-point inverse DFT
+    cf f[3][16];
     {
         const int rl = lane & 7, c = lane >> 3;                            // c: chunk of 8 output times
 #pragma unroll
         for (int gi = 0; gi < 3; gi++) {
-            const int rho = 8 * gi + rl;
+            const int rho = gi + 3 * rl;
             float g[NT];
             const float4* gp = reinterpret_cast<const float4*>(a.taps_rho + rho * NT);
 #pragma unroll
@@ -286,18 +297,22 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
             pfb_fir_thread<NT, 2, kChunkT>(xs + fir_base<NT, kChunkT>(rho, c), rho <= 12 ? 8 : 0, g, acc);
 #pragma unroll
             for (int e = 0; e < kChunkT; e++)
-                V[rho * B::kVRow + 8 * c + e] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
+                V[v_pos(rl, 8 * c + e)] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
+            __syncwarp();
+            cf v16[16];
+            pfb_load_col16(V, lane, v16);
+            __syncwarp();                                                  // V is rewritten by the next pass
+            IdftPow2<16, 1>::run(v16, f[gi]);
         }
     }
-    __syncwarp();
 
-    // ---- phase 2: 48-point inverse DFT + rotation + quantiser, one lane per output time
+    // ---- phase 2: radix-3 combination + rotation + quantiser, one lane per output time
     cf y[48];
     const int mg = g_first + lane;                           // channel-rate sample index in the capture
     {
         const float s = (mg < a.n_out) ? a.scale : 0.0f;
         cf raw[48];
-        pfb_dft48_quant(V + lane, B::kVRow, y, s, (mg & 1) ? -s : s, raw, DEBUG);
+        pfb_combine_quant(f[0], f[1], f[2], y, s, (mg & 1) ? -s : s, raw, DEBUG);
         if (DEBUG && lane < B::kStride && mg < a.n_out) {
 #pragma unroll
             for (int qq = 0; qq < 48; qq++) {

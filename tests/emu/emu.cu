@@ -50,7 +50,7 @@ static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const fl
     using G = typename B::G;
     constexpr int T = B::kT;
     std::vector<float2> xs(G::kXsLen, make_float2(0.f, 0.f));
-    std::vector<float4> V(24 * B::kVRow, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<float4> V(8 * 32, make_float4(0.f, 0.f, 0.f, 0.f));
     const int g_first = B::kStride * tile;
     const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
     constexpr int kPer = 24 * kChunkT, kPairs = kPer / 2;
@@ -64,24 +64,32 @@ static void pfb_tile(const float* x, int64_t n_in, int n_out, int tile, const fl
                 xs[ip + 8 * p + k] = ok ? make_float2(x[2 * (i + k)], x[2 * (i + k) + 1]) : make_float2(0.f, 0.f);
         }
     }
-    for (int lane = 0; lane < 32; lane++) {                            // phase 1
-        const int rl = lane & 7, c = lane >> 3;
-        for (int gi = 0; gi < 3; gi++) {
-            const int rho = 8 * gi + rl;
+    std::vector<cf> F(T * 3 * 16);                                     // f[gi][16] of every lane
+    for (int gi = 0; gi < 3; gi++) {                                   // phase 1
+        for (int lane = 0; lane < 32; lane++) {
+            const int rl = lane & 7, c = lane >> 3;
+            const int rho = gi + 3 * rl;
             float g[NT];
             for (int d = 0; d < NT; d++) g[d] = taps_rho[rho * NT + d];
             float2 acc[2][kChunkT];
             pfb_fir_thread<NT, 2, kChunkT>(xs.data() + fir_base<NT, kChunkT>(rho, c), rho <= 12 ? 8 : 0, g, acc);
             for (int e = 0; e < kChunkT; e++)
-                V[rho * B::kVRow + 8 * c + e] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
+                V[v_pos(rl, 8 * c + e)] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
+        }
+        for (int lane = 0; lane < 32; lane++) {
+            cf v16[16], f16[16];
+            pfb_load_col16(V.data(), lane, v16);
+            IdftPow2<16, 1>::run(v16, f16);
+            for (int k = 0; k < 16; k++) F[(lane * 3 + gi) * 16 + k] = f16[k];
         }
     }
     std::vector<cf> Y(T * 48);
     for (int m = 0; m < T; m++) {                                      // phase 2
         const int mg = g_first + m;
         const float s = (mg < n_out) ? scale : 0.0f;
-        cf y[48], raw[48];
-        pfb_dft48_quant(V.data() + m, B::kVRow, y, s, (mg & 1) ? -s : s, raw, true);
+        cf y[48], raw[48], f0[16], f1[16], f2[16];
+        for (int k = 0; k < 16; k++) { f0[k] = F[(m * 3 + 0) * 16 + k]; f1[k] = F[(m * 3 + 1) * 16 + k]; f2[k] = F[(m * 3 + 2) * 16 + k]; }
+        pfb_combine_quant(f0, f1, f2, y, s, (mg & 1) ? -s : s, raw, true);
         for (int qq = 0; qq < 48; qq++) {
             Y[m * 48 + qq] = y[qq];
             const int ch = ble_channel_of_q(qq);
