@@ -29,9 +29,14 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (engine mode, BASELINE config, description)
     "ble_wb40": ("ble_wb40", "configs[3]", "BLE all 40 channels: 96 Msps wideband capture PFB-channelized into 40 GFSK receivers"),
+    "zb_wb16": ("zb_wb16", "configs[2]", "Zigbee all 16 channels: 96 Msps wideband capture PFB-channelized into 16 O-QPSK receivers"),
+    "mixed_wb56": ("mixed_wb56", "configs[4] (one capture)", "mixed BLE+Zigbee 96 Msps capture: 40 GFSK + 16 O-QPSK receivers"),
     "ble_nb": ("ble_nb", "configs[0]", "BLE advertising channel 37: 4 Msps cf32, 1e7 samples"),
     "zb_nb": ("zb_nb", "configs[1]", "Zigbee 802.15.4 channel 11: 4 Msps O-QPSK capture, 1e7 samples"),
 }
+
+
+WIDEBAND = {"ble_wb40": "ble", "zb_wb16": "zigbee", "mixed_wb56": "mixed"}
 
 
 def peaks():
@@ -85,8 +90,8 @@ class ClockSampler:
 
 def make_capture(workload, seconds_base, seed):
     from snout_b200 import synth
-    if workload == "ble_wb40":
-        base = synth.wideband_capture(seconds=seconds_base, kind="ble", seed=seed, esn0_db=25.0)
+    if workload in WIDEBAND:
+        base = synth.wideband_capture(seconds=seconds_base, kind=WIDEBAND[workload], seed=seed, esn0_db=25.0)
         return base.iq, len(base.truth)
     if workload == "ble_nb":
         c = synth.ble_capture(n=10_000_000, channel=37, seed=1001, esn0_db=30.0)
@@ -104,12 +109,22 @@ def cpu_path(workload, sample, min_seconds=0.0):
     oracle.build(native=True)
     cores = os.cpu_count() or 1
     kind = "port"
-    h = _abi.pfb_prototype(_abi.MODE_BLE_WB40, 384) if workload == "ble_wb40" else None
+    h = _abi.pfb_prototype(_abi.MODE_BLE_WB40, 384) if workload in ("ble_wb40", "mixed_wb56") else None
+    hz = _abi.pfb_prototype(_abi.MODE_ZB_WB16, 384) if workload in ("zb_wb16", "mixed_wb56") else None
     bins = [chanplan.ble_channel_bin(c) for c in range(40)]
+    zbins = [chanplan.zigbee_channel_bin(c) for c in range(11, 27)]
     t0 = time.perf_counter()
     frames, done = 0, 0
     while True:
-        if workload == "ble_wb40":
+        if workload in ("zb_wb16", "mixed_wb56"):
+            # CPU statement of the wideband Zigbee path: float channelizer (OpenMP) + the restated GNU Radio chain
+            # and the packet sink, one channel per thread
+            y = oracle.pfb(sample, hz, zbins, fast=True)
+            def zone(c):
+                return len(oracle.zb_receive(y[c], 11 + c))
+            with ThreadPoolExecutor(cores) as ex:
+                frames = sum(ex.map(zone, range(16)))
+        if workload in ("ble_wb40", "mixed_wb56"):
             # channelizer: no reference counterpart (the reference retunes one 4 Msps channel at a time), CPU
             # statement = oracle/pfb_oracle.c with OpenMP over all cores; per-channel decode = the port of
             # btle_rx.c's receiver(), one channel per thread
@@ -117,7 +132,9 @@ def cpu_path(workload, sample, min_seconds=0.0):
             def one(c):
                 return len(oracle.ble_decode(oracle.ble_quantize(y[c], 100.0), c, impl="port"))
             with ThreadPoolExecutor(cores) as ex:
-                frames = sum(ex.map(one, range(40)))
+                frames = (frames if workload == "mixed_wb56" else 0) + sum(ex.map(one, range(40)))
+        elif workload == "zb_wb16":
+            pass
         elif workload == "ble_nb":
             kind = "reference" if oracle.have_ref("btle_ref") else "port"
             q = oracle.ble_quantize(sample, 128.0)
@@ -205,13 +222,13 @@ def main():
     dev = torch.device("cuda", local)
 
     base, n_truth = make_capture(args.workload, args.base_seconds, 4000 + 37 * rank)
-    tiles = args.tiles if args.workload == "ble_wb40" else 1
+    tiles = args.tiles if args.workload in WIDEBAND else 1
     n = len(base) * tiles
     pinned = _abi.PinnedBuffer(n, np.complex64)
     for i in range(tiles):
         pinned.array[i * len(base):(i + 1) * len(base)] = base
     x_dev = torch.from_numpy(pinned.array).to(dev)                   # resident input, larger than L2 for the wideband run
-    eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps if mode == "ble_wb40" else 0, device=local,
+    eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps if args.workload in WIDEBAND else 0, device=local,
                    channel=None, max_frames=1 << 18)
 
     def barrier():
@@ -265,25 +282,53 @@ def main():
         ms = float(t.item())
     value = world * n * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- end to end: pinned host buffer in, frames out, every step
-    for _ in range(2):
-        eng.run(pinned)
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(args.steps):
-        fr = eng.run(pinned)
-        d2h += fr.nbytes + 32
+    # ---- end to end: pinned host buffer in, frames out, every step.  Same two-deep software pipeline a streaming
+    #      caller uses (process, process, poll, ...): the H2D copy of batch i+1 overlaps the decode tail of batch i.
+    def run_e2e(buf, k):
+        d2h, nfr = 0, 0
+        eng.process(buf)
+        for i in range(k):
+            if i + 1 < k:
+                eng.process(buf)
+            fr = eng.poll(copy=True)
+            d2h += fr.nbytes + 32
+            nfr = len(fr)
+            if world > 1:
+                sdist.allgather_frames(fr, dev)
+        torch.cuda.synchronize()
+        return d2h, nfr
+
+    def time_e2e(buf):
+        run_e2e(buf, 2)
+        barrier()
+        t0 = time.perf_counter()
+        d2h, nfr = run_e2e(buf, args.steps)
+        dt = time.perf_counter() - t0
         if world > 1:
-            sdist.allgather_frames(fr, dev)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as d
-        t = torch.tensor([e2e_s], device=dev)
-        d.all_reduce(t, op=d.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = world * n * args.steps / e2e_s / 1e6
+            import torch.distributed as d
+            t = torch.tensor([dt], device=dev)
+            d.all_reduce(t, op=d.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * n * args.steps / dt / 1e6, d2h, nfr
+
+    e2e, d2h, _ = time_e2e(pinned)
+    # the same capture as an 8-bit digitiser delivers it (interleaved int8 I,Q = the HackRF transfer format the
+    # reference consumes, btle_rx.c:204,489-498) through snrx_process_sc8: a quarter of the PCIe bytes
+    e2e_sc8 = None
+    if args.workload in WIDEBAND or args.workload == "ble_nb":
+        peak_amp = float(np.abs(pinned.array[: len(base)]).max())
+        pinned8 = _abi.PinnedBuffer((n, 2), np.int8)
+        q = np.clip(np.rint(base.view(np.float32).reshape(-1, 2) * (100.0 / peak_amp)), -128, 127).astype(np.int8)
+        for i in range(tiles):
+            pinned8.array[i * len(base):(i + 1) * len(base)] = q
+        if args.workload in WIDEBAND:                      # keep the per-channel int8 amplitude of the cf32 run
+            eng.close()
+            eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps, device=local, max_frames=1 << 18,
+                           quant_scale=100.0 * 1.28 * peak_amp)
+        v8, d2h8, nfr8 = time_e2e(pinned8)
+        e2e_sc8 = {"value": v8, "unit": unit, "h2d_bytes_per_step": int(n * 2), "d2h_bytes_per_step": int(d2h8 / args.steps),
+                   "frames_per_step": int(nfr8),
+                   "note": "same capture quantised to interleaved int8 I,Q (full scale = 1.28 x peak), RxEngine.run via snrx_process_sc8"}
 
     if rank != 0:
         return 0
@@ -295,17 +340,18 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": f"synthetic: {args.base_seconds}s seeded GFSK capture with AWGN, tiled x{tiles}; random frames on every channel",
         "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "samples_per_step_per_gpu": int(n),
-                   "input_bytes_per_step_per_gpu": int(n * 8), "pfb_taps": args.taps if mode == "ble_wb40" else None,
+                   "input_bytes_per_step_per_gpu": int(n * 8), "pfb_taps": args.taps if args.workload in WIDEBAND else None,
                    "l2": "input (%.0f MB) larger than L2; no flush needed" % (n * 8 / 1e6),
                    "frames_per_step": int(frames_per_step), "timed": "K x (process + poll), two batches in flight, frames land in pinned host memory; CUDA events on the engine stream"},
         "frames_per_s": frames_per_step * args.steps / (ms * 1e-3),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(d2h / args.steps),
-                "note": "RxEngine.run(pinned host buffer): chunked H2D overlapped with the channelizer, frames read back"},
+                "note": "RxEngine.process/poll on a pinned host cf32 buffer, two batches in flight: chunked H2D overlapped with the channelizer, frames copied out"},
+        "e2e_sc8": e2e_sc8,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "kernel": "k_pfb_ble (channelizer+slicer)" if mode == "ble_wb40" else "front-end kernel",
+                     "kernel": "k_pfb_ble (channelizer+slicer)" if mode == "ble_wb40" else "front-end kernels (stats.gpu_ms_frontend)",
                      "algorithmic_bytes_per_launch": int(n * 8), "kernel_ms": fms,
                      "note": "8 B per input sample (one cf32 read); the fused channelizer is FP32-pipe limited, see DESIGN.md"},
     }
@@ -314,7 +360,7 @@ def main():
         line["roofline"]["traffic"] = tr[0]
         line["roofline"]["traffic_source"] = f"profiles/{tr[1]} (ncu --set full, dram read+write of one launch)"
     if world == 1 and not args.no_cpu_baseline:
-        sample = base[: min(len(base), 4_800_000)] if args.workload == "ble_wb40" else base
+        sample = base[: min(len(base), 4_800_000)] if args.workload in WIDEBAND else base
         dt, done, frames, cores, kind = cpu_path(args.workload, sample, min_seconds=args.cpu_seconds)
         line["cpu_baseline"] = {"value": done / dt / 1e6, "unit": unit, "cores": cores, "kind": kind,
                                 "sample": f"{done} samples = a {len(sample)}-sample slice of the same capture repeated for "

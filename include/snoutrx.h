@@ -31,6 +31,9 @@
  *       Wideband modes additionally run the 96 Msps polyphase channelizer,
  *       which has no counterpart in the reference (it retunes one channel at
  *       a time: snout/util/btle.py:62, snout/core/radio.py:415).
+ *   snrx_process_sc8
+ *       the same with the reference's native sample format: int8 I,Q as delivered by
+ *       hackrf_transfer.buffer to rx_callback() (btle_rx.c:489-498, IQ_TYPE btle_rx.c:204).
  *   snrx_poll
  *       BLE   : the printf()/fflush() of one line per frame (btle_rx.c:2137-2145,
  *               2383) that snout/core/pcontroller.py:115-131 reads back.
@@ -184,6 +187,15 @@ typedef struct snrx_shard {
 int  snrx_process(snrx_t* h, const float* iq, uint32_t n_captures,
                   uint64_t n_samples, uint64_t stride_samples,
                   const snrx_shard_t* shard, int is_device_ptr);
+
+/* snrx_process for captures stored as interleaved signed 8-bit I,Q -- the transfer format of the HackRF the
+ * reference receives from (IQ_TYPE int8_t, btle_rx.c:204; rx_callback() copies exactly these bytes into the ring,
+ * btle_rx.c:489-498).  Sample value x = q / 128 (exact), so with the narrow-band default quant_scale = 128 the
+ * BLE path sees the reference's own int8 samples.  A quarter of the host->device bytes of cf32.  `iq` 16-byte
+ * aligned, even stride for batches; sizes and strides count complex samples as in snrx_process. */
+int  snrx_process_sc8(snrx_t* h, const int8_t* iq, uint32_t n_captures,
+                      uint64_t n_samples, uint64_t stride_samples,
+                      const snrx_shard_t* shard, int is_device_ptr);
 
 /* Up to two batches may be queued (snrx_process, snrx_process, snrx_poll, ...): results are
  * collected oldest first.  snrx_poll waits for the oldest queued batch; *n_out = its number of

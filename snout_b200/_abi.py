@@ -66,6 +66,7 @@ SYMBOLS = [
     ("snrx_create", c_int, [POINTER(c_void_p), POINTER(Config)]),
     ("snrx_destroy", None, [c_void_p]),
     ("snrx_process", c_int, [c_void_p, c_void_p, c_uint32, c_uint64, c_uint64, POINTER(Shard), c_int]),
+    ("snrx_process_sc8", c_int, [c_void_p, c_void_p, c_uint32, c_uint64, c_uint64, POINTER(Shard), c_int]),
     ("snrx_poll", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_poll_view", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
     ("snrx_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),

@@ -71,7 +71,7 @@ template <int NT> struct PfbBleGeom {
     using G = PfbGeom<NT, kChunkT, kT>;
     static constexpr int kXsBytes = ((G::kXsLen * 8 + 15) / 16) * 16;
     static constexpr int kVBytes = 8 * 32 * 16;                        // V[8][32] float4 = (branch r2 = rl, r2 = rl + 8) of one pass
-    static constexpr int kSmemBytes = kXsBytes + kVBytes;
+    static constexpr int kSmemBytes = kXsBytes + kVBytes + 16;         // + the staging mbarrier
     static constexpr int kCtasPerSm = (228 * 1024) / (kSmemBytes + 1024) < 16 ? (228 * 1024) / (kSmemBytes + 1024) : 16;
 };
 
@@ -195,6 +195,54 @@ __device__ __forceinline__ void cp_async16_full(void* smem_dst, const void* gsrc
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
 }
 
+// ---- bulk (TMA) staging: one cp.async.bulk per skew piece, completion on an mbarrier.  The bytes go
+// L2 -> shared memory through the async proxy: no LSU wavefronts, no per-lane address arithmetic.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Interior tile (entirely inside the capture): lane p < kPieces copies piece p -- tile samples
+// i' in [24 TT p - 12, 24 TT (p+1) - 12) clipped to [0, kTileIn), stored at i' + 8 p.  All sizes and
+// addresses are multiples of 16 bytes (kTileIn, 24 TT and the tile origin are even).
+template <class G, int TT>
+__device__ __forceinline__ void pfb_stage_tile_bulk(float2* xs, const float2* xtile /* sample i' = 0 */, uint64_t* bar, int lane) {
+    constexpr int kPer = 24 * TT;
+    static_assert(G::kPieces <= 32 && G::kTileIn % 2 == 0, "one lane per piece");
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)(G::kTileIn * sizeof(float2)));
+    }
+    __syncwarp();
+    if (lane < G::kPieces) {
+        const int lo = lane == 0 ? 0 : kPer * lane - 12;
+        const int hi = min(kPer * (lane + 1) - 12, G::kTileIn);
+        bulk_g2s(xs + lo + 8 * lane, xtile + lo, (uint32_t)((hi - lo) * sizeof(float2)), bar);
+    }
+}
+
 // Stage tile samples i' = 0 .. kTileIn-1 (capture samples x0 + i') into the skewed tile: piece p holds
 // i' in [24 TT p - 12, 24 TT (p+1) - 12) at position i' + 8 p; 16-byte copies (one sample pair each).
 // Interior tiles (the whole tile inside the capture) take a fully unrolled path whose offsets are
@@ -252,7 +300,8 @@ struct PfbBleArgs {
     int32_t n_out;            // channel-rate samples per capture (n_in / 24)
     int32_t n_tiles;          // tiles of this launch
     int32_t tile0;            // first tile of this launch
-    const float* taps_rho;    // [24][NT]: taps_rho[rho*NT + d] = h[rho + 24 d]
+    const float4* taps_pass;  // [3][NT/4][8] float4: element (gi, d4, rl) = h[rho + 24 (4 d4 + 0..3)], rho = gi + 3 rl --
+                              // the 8 FIR rows of a pass read 128 contiguous bytes per load
     float scale;              // quantiser scale
     uint32_t* bits;           // zero-initialised; tiles OR their words in
     BitsLayout lay;
@@ -267,6 +316,7 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);
     float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [8][32], see v_pos()
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
 
     const int lane = threadIdx.x;
     const int tile = a.tile0 + (int)(blockIdx.x % a.n_tiles);
@@ -274,10 +324,18 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     const float2* xcap = a.x + (size_t)cap * a.stride;
     const int g_first = B::kStride * tile;                                 // first channel sample of the tile
 
-    // ---- phase 0: stage the input tile
-    pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, (int64_t)kPfbD * g_first - G::kHist, a.n_in, lane);
-    cp_async_commit_wait_all();
-    __syncwarp();
+    // ---- phase 0: stage the input tile (bulk copies for interior tiles, zero-filling cp.async at the capture ends)
+    {
+        const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
+        if (x0 >= 0 && x0 + G::kTileIn <= a.n_in) {
+            pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
+            mbar_wait(bar, 0);
+        } else {
+            pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, x0, a.n_in, lane);
+            cp_async_commit_wait_all();
+            __syncwarp();
+        }
+    }
 
     // ---- phase 1: three passes of FIR (branches r = gi mod 3) -> transpose -> 16-point inverse DFT
     cf f[3][16];
@@ -287,10 +345,10 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
         for (int gi = 0; gi < 3; gi++) {
             const int rho = gi + 3 * rl;
             float g[NT];
-            const float4* gp = reinterpret_cast<const float4*>(a.taps_rho + rho * NT);
+            const float4* gp = a.taps_pass + gi * (NT / 4) * 8 + rl;
 #pragma unroll
             for (int d = 0; d < NT / 4; d++) {
-                const float4 t = __ldg(gp + d);
+                const float4 t = __ldg(gp + 8 * d);
                 g[4 * d] = t.x; g[4 * d + 1] = t.y; g[4 * d + 2] = t.z; g[4 * d + 3] = t.w;
             }
             float2 acc[2][kChunkT];

@@ -46,7 +46,8 @@ struct Lane {
     bool pending = false, done = false;
     uint32_t caps = 0, n_out = 0, n_frames = 0; uint64_t n_in = 0; int launches = 0;
     // BLE working set
-    float2* d_x = nullptr; size_t d_x_bytes = 0;          // staging of host input
+    float2* d_x = nullptr; size_t d_x_bytes = 0;          // staging of host input / cf32 image of sc8 input
+    int8_t* d_x8 = nullptr; size_t d_x8_bytes = 0;        // staging of sc8 host input
     uint32_t* d_bits = nullptr; size_t d_bits_bytes = 0;
     uint32_t* d_hits = nullptr;                            // access-address hit masks, same layout as d_bits
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
@@ -85,7 +86,7 @@ struct snrx_handle {
     // constants on the device
     uint32_t *d_crc_tab = nullptr, *d_whiten = nullptr;
     int32_t* d_ble_channels = nullptr;
-    float *d_taps_rho = nullptr, *d_taps_flat = nullptr;
+    float *d_taps_rho = nullptr, *d_taps_flat = nullptr, *d_taps_pass = nullptr;
 
     // last batch
     bool batch_valid = false;
@@ -218,6 +219,26 @@ __global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __res
     if (blockIdx.x == 0 && threadIdx.x < 8) totals_host[threadIdx.x] = totals_dev[threadIdx.x];
 }
 
+// Interleaved signed 8-bit I,Q (the HackRF transfer format the reference consumes: IQ_TYPE int8_t, btle_rx.c:204,
+// filled by rx_callback btle_rx.c:489-498) -> cf32 with x = q / 128, exact in FP32.  One sample pair per thread:
+// 4-byte loads and 16-byte stores, both coalesced.  n = samples per capture, strides in samples.
+__global__ void __launch_bounds__(256) k_sc8_to_cf32(const int8_t* __restrict__ src, uint64_t src_stride, float2* __restrict__ dst,
+                                                     uint64_t dst_stride, uint64_t n, uint32_t n_captures) {
+    const uint64_t pairs = (n + 1) / 2;
+    const uint64_t total = pairs * n_captures;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t c = i / pairs, p = i - c * pairs;
+        const int8_t* s = src + 2 * (c * src_stride + 2 * p);
+        float2* d = dst + c * dst_stride + 2 * p;
+        if (2 * p + 1 < n) {
+            const char4 q = __ldcs(reinterpret_cast<const char4*>(s));
+            __stcs(reinterpret_cast<float4*>(d), make_float4(q.x * 0.0078125f, q.y * 0.0078125f, q.z * 0.0078125f, q.w * 0.0078125f));
+        } else {
+            d[0] = make_float2(s[0] * 0.0078125f, s[1] * 0.0078125f);
+        }
+    }
+}
+
 extern "C" {
 
 int snrx_abi_version(void) { return SNRX_ABI_VERSION; }
@@ -265,10 +286,10 @@ void snrx_destroy(snrx_t* h) {
     cudaSetDevice(h->device);
     for (auto& ln : h->lane) { if (ln.stream) cudaStreamSynchronize(ln.stream); if (ln.tail) cudaStreamSynchronize(ln.tail); }
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    void* bufs[] = {h->d_crc_tab, h->d_whiten, h->d_ble_channels, h->d_taps_rho, h->d_taps_flat};
+    void* bufs[] = {h->d_crc_tab, h->d_whiten, h->d_ble_channels, h->d_taps_rho, h->d_taps_flat, h->d_taps_pass};
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& ln : h->lane) {
-        void* lb[] = {ln.d_x, ln.d_bits, ln.d_hits, ln.d_counts, ln.d_offsets, ln.d_scratch, ln.d_wcounts, ln.d_woffsets,
+        void* lb[] = {ln.d_x, ln.d_x8, ln.d_bits, ln.d_hits, ln.d_counts, ln.d_offsets, ln.d_scratch, ln.d_wcounts, ln.d_woffsets,
                       ln.d_cands, ln.d_decs, ln.d_totals, ln.d_q8, ln.d_cf, ln.d_frames};
         for (void* b : lb) if (b) cudaFree(b);
         zb_free(ln.zb);
@@ -360,6 +381,12 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
                 CKD(dev_alloc(h, &h->d_taps_flat, L));
                 CK(cudaMemcpy(h->d_taps_rho, rho.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
                 CK(cudaMemcpy(h->d_taps_flat, flat.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
+                // per-pass layout of k_pfb_ble: [gi][d4][rl][4] = h[rho + 24 (4 d4 + k)], rho = gi + 3 rl
+                std::vector<float> pass(L);
+                for (int gi = 0; gi < 3; gi++) for (int d4 = 0; d4 < NT / 4; d4++) for (int rl = 0; rl < 8; rl++) for (int k = 0; k < 4; k++)
+                    pass[((gi * (NT / 4) + d4) * 8 + rl) * 4 + k] = flat[(gi + 3 * rl) + 24 * (4 * d4 + k)];
+                CKD(dev_alloc(h, &h->d_taps_pass, L));
+                CK(cudaMemcpy(h->d_taps_pass, pass.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
                 int r = pfb_ble_dispatch(h, nullptr, nullptr, 0);                          // sets the shared-memory attributes
                 if (r != SNRX_OK) return r;
             }
@@ -462,7 +489,7 @@ static int launch_ble_front(snrx_handle* h, Lane& ln, const float2* x, uint32_t 
         PfbBleArgs a;
         a.x = x; a.stride = stride; a.n_in = (int64_t)n_in; a.n_out = (int32_t)n_out;
         a.n_tiles = tile_end - tile_begin;
-        a.taps_rho = h->d_taps_rho; a.scale = h->cfg.quant_scale;
+        a.taps_pass = reinterpret_cast<const float4*>(h->d_taps_pass); a.scale = h->cfg.quant_scale;
         a.bits = ln.d_bits; a.lay = lay; a.dbg_q8 = ln.d_q8; a.dbg_cf = ln.d_cf;
         a.tile0 = tile_begin;
         int r = pfb_ble_dispatch(h, &a, ln.stream, caps);
@@ -482,8 +509,12 @@ static int launch_ble_front(snrx_handle* h, Lane& ln, const float2* x, uint32_t 
     return SNRX_OK;
 }
 
-int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_samples, uint64_t stride_samples,
-                 const snrx_shard_t* shard, int is_device_ptr) {
+}  // extern "C"
+
+enum { kFmtCf32 = 0, kFmtSc8 = 1 };
+
+static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures, uint64_t n_samples, uint64_t stride_samples,
+                        const snrx_shard_t* shard, int is_device_ptr) {
     if (!h || !iq) return SNRX_EINVAL;
     if (n_captures == 0 || n_samples == 0) return fail(h, SNRX_EINVAL, "empty batch");
     if (n_captures > h->max_caps || n_samples > h->max_in) return fail(h, SNRX_ERANGE, "batch exceeds max_captures/max_samples");
@@ -528,20 +559,37 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
     CK(cudaEventRecord(ln.ev_start, st));
     CK(cudaMemsetAsync(ln.d_totals, 0, 8 * sizeof(uint32_t), st));
 
-    // ---- input: device pointer as is, host pointer staged in chunks overlapped with the front end
+    // ---- input: cf32 device pointer as is; host pointer staged in chunks overlapped with the front end;
+    //      sc8 input (host or device) is expanded to cf32 in ln.d_x by k_sc8_to_cf32, chunk by chunk
     const float2* x = reinterpret_cast<const float2*>(iq);
     uint64_t x_stride = stride_samples;
     const bool staged = !is_device_ptr;
-    const uint64_t chunk_samples = 4ull << 20;                      // 32 MiB per copy
-    if (staged) {
-        const size_t need = (size_t)n_captures * n_samples * sizeof(float2);
+    const bool sc8 = (fmt == kFmtSc8);
+    const uint64_t chunk_samples = sc8 ? (8ull << 20) : (4ull << 20);   // 16 MiB (sc8) / 32 MiB (cf32) per copy
+    const size_t in_elem = sc8 ? 2 : sizeof(float2);                // bytes per input sample
+    if (staged || sc8) {
+        x_stride = n_samples + (n_samples & 1);                     // captures stay 16-byte aligned
+        const size_t need = (size_t)n_captures * x_stride * sizeof(float2);
         if (need > ln.d_x_bytes) {
             if (ln.d_x) { cudaFree(ln.d_x); ln.d_x = nullptr; ln.d_x_bytes = 0; }
             CK(cudaMalloc((void**)&ln.d_x, need));
             ln.d_x_bytes = need;
         }
         x = ln.d_x;
-        x_stride = n_samples;
+    }
+    if (staged && sc8) {
+        const size_t need = (size_t)n_captures * x_stride * 2;
+        if (need > ln.d_x8_bytes) {
+            if (ln.d_x8) { cudaFree(ln.d_x8); ln.d_x8 = nullptr; ln.d_x8_bytes = 0; }
+            CK(cudaMalloc((void**)&ln.d_x8, need));
+            ln.d_x8_bytes = need;
+        }
+    }
+    if (sc8 && !staged) {                                           // device sc8: one expansion pass over the batch
+        k_sc8_to_cf32<<<h->sm_count * 8, 256, 0, st>>>(reinterpret_cast<const int8_t*>(iq), stride_samples, ln.d_x, x_stride,
+                                                       n_samples, n_captures);
+        h->launches++;
+        CK(cudaGetLastError());
     }
 
     BitsLayout lay{};
@@ -556,16 +604,22 @@ int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_sam
         // the copy stream serialises the staging copies of both lanes (one PCIe link anyway)
         size_t ev_i = 0;
         for (uint32_t c = 0; c < n_captures; c++) {
-            const float2* src = reinterpret_cast<const float2*>(iq) + (size_t)c * stride_samples;
-            float2* dst = ln.d_x + (size_t)c * n_samples;
+            const char* src = reinterpret_cast<const char*>(iq) + (size_t)c * stride_samples * in_elem;
+            char* dst = sc8 ? reinterpret_cast<char*>(ln.d_x8) + (size_t)c * x_stride * in_elem
+                            : reinterpret_cast<char*>(ln.d_x + (size_t)c * x_stride);
             int tile_done = 0;
             for (uint64_t off = 0; off < n_samples; off += chunk_samples) {
                 const uint64_t len = std::min<uint64_t>(chunk_samples, n_samples - off);
-                CK(cudaMemcpyAsync(dst + off, src + off, len * sizeof(float2), cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaMemcpyAsync(dst + off * in_elem, src + off * in_elem, len * in_elem, cudaMemcpyHostToDevice, h->copy_stream));
                 if (ev_i >= ln.ev_chunks.size()) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ln.ev_chunks.push_back(e); }
                 CK(cudaEventRecord(ln.ev_chunks[ev_i], h->copy_stream));
                 CK(cudaStreamWaitEvent(st, ln.ev_chunks[ev_i], 0));
                 ev_i++;
+                if (sc8) {                                          // chunk_samples is even: pairs never straddle chunks
+                    k_sc8_to_cf32<<<h->sm_count * 4, 256, 0, st>>>(reinterpret_cast<const int8_t*>(dst) + off * 2, 0,
+                                                                   ln.d_x + (size_t)c * x_stride + off, 0, len, 1);
+                    h->launches++;
+                }
                 if (h->has_ble && h->wideband && !h->has_zb && n_captures == 1) {
                     // launch the channelizer on the tiles whose input has fully arrived
                     const uint64_t have = off + len;
@@ -682,6 +736,18 @@ static int finish_oldest(snrx_handle* h, Lane** out_lane) {
     }
     *out_lane = &sl;
     return SNRX_OK;
+}
+
+extern "C" {
+
+int snrx_process(snrx_t* h, const float* iq, uint32_t n_captures, uint64_t n_samples, uint64_t stride_samples,
+                 const snrx_shard_t* shard, int is_device_ptr) {
+    return process_impl(h, iq, kFmtCf32, n_captures, n_samples, stride_samples, shard, is_device_ptr);
+}
+
+int snrx_process_sc8(snrx_t* h, const int8_t* iq, uint32_t n_captures, uint64_t n_samples, uint64_t stride_samples,
+                     const snrx_shard_t* shard, int is_device_ptr) {
+    return process_impl(h, iq, kFmtSc8, n_captures, n_samples, stride_samples, shard, is_device_ptr);
 }
 
 int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {

@@ -111,7 +111,9 @@ class RxEngine:
     # ------------------------------------------------------------------ data path
     def process(self, iq, shard: dict | None = None, n_samples: int | None = None, stride: int = 0):
         """Queue one batch.  `iq`: complex64 numpy array [n] or [captures, n] (host memory), a
-        _abi.PinnedBuffer, or a torch CUDA tensor of complex64 [n] / [captures, n]."""
+        _abi.PinnedBuffer, or a torch CUDA tensor of complex64 [n] / [captures, n].  int8 arrays / tensors
+        with a trailing axis of 2 ([n, 2] or [captures, n, 2]: interleaved I,Q as a HackRF delivers them,
+        btle_rx.c:489-498) take the sc8 entry point; their sample value is q / 128."""
         sh = None
         if shard:
             sh = Shard(int(shard.get("pre_samples", 0)), int(shard.get("body_samples", 0)),
@@ -123,25 +125,36 @@ class RxEngine:
             if not iq.is_cuda:
                 iq = iq.numpy()
             else:
-                assert iq.dtype == torch.complex64 and iq.is_contiguous()
-                caps = 1 if iq.dim() == 1 else iq.shape[0]
-                n = iq.shape[-1] if n_samples is None else n_samples
-                st = stride or iq.shape[-1]
+                assert iq.is_contiguous()
+                if iq.dtype == torch.int8:
+                    assert iq.shape[-1] == 2, "sc8 input is [..., n, 2] (I, Q)"
+                    fn, shape = self.lib.snrx_process_sc8, iq.shape[:-1]
+                else:
+                    assert iq.dtype == torch.complex64
+                    fn, shape = self.lib.snrx_process, iq.shape
+                caps = 1 if len(shape) == 1 else shape[0]
+                n = shape[-1] if n_samples is None else n_samples
+                st = stride or shape[-1]
                 self.set_stream(torch.cuda.current_stream(iq.device).cuda_stream)
                 self._keepalive = iq
-                self._check(self.lib.snrx_process(self.handle, c_void_p(iq.data_ptr()), caps, n, st,
-                                                  byref(sh) if sh else None, 1))
+                self._check(fn(self.handle, c_void_p(iq.data_ptr()), caps, n, st, byref(sh) if sh else None, 1))
                 self._last = (caps, n)
                 return self
         a = np.asarray(iq)
-        if a.dtype != np.complex64 or not a.flags.c_contiguous:
-            a = np.ascontiguousarray(a, dtype=np.complex64)
-        caps = 1 if a.ndim == 1 else a.shape[0]
-        n = a.shape[-1] if n_samples is None else n_samples
-        st = stride or a.shape[-1]
+        if a.dtype == np.int8:
+            if a.shape[-1] != 2:
+                raise ValueError("sc8 input is [..., n, 2] (I, Q)")
+            a = np.ascontiguousarray(a)
+            fn, shape = self.lib.snrx_process_sc8, a.shape[:-1]
+        else:
+            if a.dtype != np.complex64 or not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a, dtype=np.complex64)
+            fn, shape = self.lib.snrx_process, a.shape
+        caps = 1 if len(shape) == 1 else shape[0]
+        n = shape[-1] if n_samples is None else n_samples
+        st = stride or shape[-1]
         self._keepalive = a
-        self._check(self.lib.snrx_process(self.handle, a.ctypes.data_as(c_void_p), caps, n, st,
-                                          byref(sh) if sh else None, 0))
+        self._check(fn(self.handle, a.ctypes.data_as(c_void_p), caps, n, st, byref(sh) if sh else None, 0))
         self._last = (caps, n)
         return self
 
@@ -167,8 +180,11 @@ class RxEngine:
     def run(self, iq, **kw) -> np.ndarray:
         return self.process(iq, **kw).poll()
 
-    def alloc_host(self, n_samples: int) -> _abi.PinnedBuffer:
-        """Page-locked complex64 staging buffer (snrx_host_alloc) for full-rate host->device copies."""
+    def alloc_host(self, n_samples: int, sc8: bool = False) -> _abi.PinnedBuffer:
+        """Page-locked staging buffer (snrx_host_alloc) for full-rate host->device copies: complex64 [n], or
+        int8 [n, 2] with sc8=True."""
+        if sc8:
+            return _abi.PinnedBuffer((int(n_samples), 2), np.int8)
         return _abi.PinnedBuffer(int(n_samples), np.complex64)
 
     def stats(self) -> dict:

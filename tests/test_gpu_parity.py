@@ -90,6 +90,50 @@ def test_ble_nb_batch_ragged_and_edge_cases(Engine, oracle_mod):
             e.run(np.zeros(n + 2, np.complex64))          # over capacity -> SNRX_ERANGE, loudly
 
 
+def test_ble_nb_sc8_golden_capture(Engine, golden):
+    """snrx_process_sc8: the reference's own sample format (int8 I,Q, btle_rx.c:204,489-498) goes in as is."""
+    g = golden("btle_sample_iq_4msps.npz")
+    with Engine("ble_nb", channel=37, max_samples=len(g["iq"]), keep_streams=True) as e:
+        got = e.run(g["iq"])                                     # int8 [n, 2]
+        assert np.array_equal(e.debug_stage(_abi.STAGE_BLE_Q8)[0, 0], g["iq"])
+        assert e.stats()["kernel_launches"] >= 7                 # + the sc8 expansion kernel
+    assert list(got["sample_index"]) == [97892, 501906, 905891]
+    assert_frames_equal(got, g["frames"], what="golden capture (sc8) vs reference output")
+
+
+def test_sc8_equals_cf32_all_paths(Engine):
+    """int8 input q and cf32 input q/128 give identical frames: host and device pointers, batches with odd
+    lengths and strides, wideband (pipelined staging) and Zigbee."""
+    import torch
+    rng = np.random.default_rng(3)
+    n = 8192 * 6 + 777                       # odd
+    caps = [synth.ble_capture(n=n, channel=5, seed=700 + i, esn0_db=30, gap=(100, 1200)).iq for i in range(3)]
+    q = np.stack([np.clip(np.rint(c.view(np.float32).reshape(-1, 2) * 128.0), -128, 127).astype(np.int8) for c in caps])
+    x = (q.astype(np.float32) / 128.0).view(np.complex64).reshape(3, n)
+    qp = np.zeros((3, n + 1, 2), np.int8)     # odd length inside an even stride (captures must stay 16-byte aligned)
+    qp[:, :n] = q
+    xp = np.zeros((3, n + 1), np.complex64)
+    xp[:, :n] = x
+    with Engine("ble_nb", channel=5, max_samples=n, max_captures=3) as e:
+        want = e.run(xp, n_samples=n, stride=n + 1)
+        assert len(want) > 10
+        assert_frames_equal(e.run(qp, n_samples=n, stride=n + 1), want, what="sc8 host batch")
+        assert_frames_equal(e.run(torch.from_numpy(qp).cuda(), n_samples=n, stride=n + 1), want, what="sc8 device batch")
+        with pytest.raises(_abi.SnrxError):
+            e.run(q)                                            # odd stride: captures not aligned -> refused loudly
+    wb = synth.wideband_capture(seconds=0.02, kind="mixed", seed=5200, esn0_db=25.0, gap=(400, 5000))
+    peak = float(np.abs(wb.iq).max())        # an 8-bit wideband digitiser: full scale just above the peak of the sum
+    q = np.clip(np.rint(wb.iq.view(np.float32).reshape(-1, 2) * (100.0 / peak)), -128, 127).astype(np.int8)
+    x = (q.astype(np.float32) / 128.0).view(np.complex64).reshape(-1)
+    for mode in ("ble_wb40", "mixed_wb56"):
+        with Engine(mode, max_samples=len(x), zb_segment=16384, quant_scale=128.0 * peak) as e:
+            want = e.run(x)
+            assert len(want) > 20, mode
+            assert_frames_equal(e.run(q), want, what=f"{mode}: sc8 host")
+            assert_frames_equal(e.run(torch.from_numpy(q).cuda()), want, what=f"{mode}: sc8 device")
+    del rng
+
+
 def test_ble_nb_device_pointer_equals_host_pointer(Engine):
     import torch
     cap = synth.ble_capture(n=300_000, channel=37, seed=11, esn0_db=30)
