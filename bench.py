@@ -351,7 +351,9 @@ def main():
         "e2e_sc8": e2e_sc8,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "kernel": "k_pfb_ble (channelizer+slicer)" if mode == "ble_wb40" else "front-end kernels (stats.gpu_ms_frontend)",
+                     "kernel": {"ble_wb40": "k_pfb_ble (channelizer+slicer)", "zb_wb16": "k_pfb_zb_warp (channelizer+discriminator)",
+                                "mixed_wb56": "k_pfb_ble (channelizer+slicer; the Zigbee front end runs after it on the tail stream)",
+                                "ble_nb": "k_ble_slice_nb", "zb_nb": "k_zb_quad"}[mode],
                      "algorithmic_bytes_per_launch": int(n * 8), "kernel_ms": fms,
                      "note": "8 B per input sample (one cf32 read); the fused channelizer is FP32-pipe limited, see DESIGN.md"},
     }

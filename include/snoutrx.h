@@ -105,6 +105,12 @@ typedef struct snrx_frame {
     uint8_t  bytes[132];    /* BLE: header|payload|crc (de-whitened); Zigbee: PSDU incl. FCS */
 } snrx_frame_t;
 
+/* Default Zigbee chain geometry: one clock-recovery + packet-sink chain per 8192 channel-rate samples
+ * (2 ms, the BLE window length), started 4096 samples early.  Part of the parity contract: the oracle
+ * runs the same segments. */
+#define SNRX_ZB_SEGMENT_DEFAULT 8192
+#define SNRX_ZB_PREHALO_DEFAULT 4096
+
 typedef struct snrx_config {
     uint32_t abi_version;    /* must be SNRX_ABI_VERSION                                   */
     int32_t  device;         /* CUDA device ordinal                                        */
@@ -117,8 +123,8 @@ typedef struct snrx_config {
     uint64_t max_samples;    /* capacity: input samples per capture                        */
     uint32_t max_captures;   /* capacity: captures per snrx_process batch                  */
     uint32_t max_frames;     /* capacity: frames per snrx_process batch                    */
-    uint32_t zb_segment;     /* Zigbee: chain segment body, channel-rate samples (0 = default 65536) */
-    uint32_t zb_prehalo;     /* Zigbee: chain warm-up, channel-rate samples (0 = default 4096)    */
+    uint32_t zb_segment;     /* Zigbee: chain segment body, channel-rate samples (0 = SNRX_ZB_SEGMENT_DEFAULT) */
+    uint32_t zb_prehalo;     /* Zigbee: chain warm-up, channel-rate samples (0 = SNRX_ZB_PREHALO_DEFAULT)   */
     uint32_t pfb_taps;       /* WB: prototype length, 384 or 768 (0 = default 384)         */
     uint32_t flags;          /* SNRX_F_*                                                   */
     uint32_t access_mask;    /* BLE `-m`: access-address bits that take part in the match

@@ -228,7 +228,7 @@ def zb_chain(z: np.ndarray, begin: int, end: int, body_lo: int, body_hi: int, ch
     return out[:nf.value].copy(), chips[:min(n, maxchips)], pos[:min(n, maxchips)]
 
 
-def zb_receive(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = 65536,
+def zb_receive(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = 8192,
                prehalo: int = 4096, cap: int = 1 << 16) -> np.ndarray:
     x = np.ascontiguousarray(iq_cf32, dtype=np.complex64)
     out = _frames(cap)
@@ -239,7 +239,7 @@ def zb_receive(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, segm
     return out[:n].copy()
 
 
-def zb_receive_z(z: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = 65536,
+def zb_receive_z(z: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = 8192,
                  prehalo: int = 4096, cap: int = 1 << 16) -> np.ndarray:
     z = _f32(z)
     out = _frames(cap)
@@ -248,7 +248,7 @@ def zb_receive_z(z: np.ndarray, channel: int = 11, threshold: int = 10, segment:
     return out[:n].copy()
 
 
-def zb_time(iq_cf32: np.ndarray, channel: int = 11, segment: int = 65536, prehalo: int = 4096, reps: int = 1):
+def zb_time(iq_cf32: np.ndarray, channel: int = 11, segment: int = 8192, prehalo: int = 4096, reps: int = 1):
     x = np.ascontiguousarray(iq_cf32, dtype=np.complex64)
     nf = c_int(0)
     lib = _lib("port")

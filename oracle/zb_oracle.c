@@ -308,7 +308,8 @@ int64_t zb_oracle_chain(const float* z, int64_t begin, int64_t end, int64_t body
     zb_sink_t sink;
     zb_sink_init(&sink, threshold);
     int64_t nchips = 0;
-    while (mm.ii + 8 <= end) {
+    /* stop at the post halo, or once past the body with the sink searching: a later sync belongs to the next chain */
+    while (mm.ii + 8 <= end && !(mm.ii >= body_hi && sink.state == 0)) {
         int64_t pos = mm.ii;
         float soft = mm_step(&mm, z);
         if (chips_out && nchips < chips_cap) { chips_out[nchips] = soft; if (chip_pos_out) chip_pos_out[nchips] = pos; }

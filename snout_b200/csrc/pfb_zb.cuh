@@ -160,11 +160,142 @@ __device__ __forceinline__ void zb_disc_all(const cf (&y)[16], const float2* nex
     if constexpr (C + 1 < 16) zb_disc_all<C + 1>(y, next_warp_first, lane, tab, out);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// One-warp tiles (same shape as k_pfb_ble, pfb.cuh): a warp computes 32 channel-rate samples of all 16
+// channels end to end and writes the 31 discriminator values whose predecessor it holds; tiles advance by 31
+// samples, so they are independent -- no CTA-wide barrier, 17 KB of shared memory, ~12 warps per SM.
+//   phase 0  bulk (TMA) staging of the skewed input tile;
+//   phase 1  three passes gi = 0..2: FIR of the 32 branches r = gi + 3 r2 (lane (rl, chunk) owns rho = gi + 3 rl,
+//            i.e. r2 = rl + 8 a, a = 0..3, and 8 output times), an 8 KB transpose through shared memory,
+//            one 32-point inverse DFT per lane (= output time), of which only the 16 bins that carry a channel
+//            are ever used: the radix-3 combination y_k += W96^(k gi) F_gi[k mod 32] is accumulated pass by pass;
+//   phase 2  successor sample by warp shuffle, cross product, table atan2, coalesced store of f.
+// Arithmetic per output is the same sequence of operations as k_pfb_zb (pfb_fir_thread, IdftPow2<32>,
+// f0 + W f1 + W^2 f2), so tests/emu's statement of the tile covers both.
+template <int NT> struct PfbZbWarpGeom {
+    static constexpr int kT = 32, kStride = 31, kThreads = 32;
+    using G = PfbGeom<NT, kChunkT, kT>;
+    static constexpr int kXsBytes = ((G::kXsLen * 8 + 15) / 16) * 16;
+    static constexpr int kVBytes = 2 * 8 * 32 * 16;                    // two float4 planes [8][32]: (a0, a1) and (a2, a3)
+    static constexpr int kSmemBytes = kXsBytes + kVBytes + 16;
+    static constexpr int kCtasPerSm = (228 * 1024) / (kSmemBytes + 1024) < 12 ? (228 * 1024) / (kSmemBytes + 1024) : 12;
+};
+
+template <int GI, int C>
+SNRX_HD void pfb_zb_accumulate(const cf (&f)[32], cf (&y)[16]) {
+    constexpr int k = zb_bin_of_slot(C), k1 = k % 32;
+    if constexpr (GI == 0) {
+        y[C] = f[k1];
+    } else {
+        const cf t = twmul<GI * k, 96>(f[k1]);
+        y[C].r = f_add(y[C].r, t.r);
+        y[C].i = f_add(y[C].i, t.i);
+    }
+    if constexpr (C + 1 < 16) pfb_zb_accumulate<GI, C + 1>(f, y);
+}
+
+struct PfbZbWarpArgs {
+    const float2* x; uint64_t stride; int64_t n_in; int32_t n_out; int32_t n_tiles;
+    const float4* taps_pass;   // [3][NT/4][8] float4, as PfbBleArgs::taps_pass
+    float* f; size_t f_stride; // [cap][16][f_stride]
+    const float* atan_tab;     // [257] global (L1 resident)
+    float2* dbg_cf;            // [cap][16][n_out] rotated channel streams, or null
+};
+
+template <int NT, bool DEBUG>
+__global__ void __launch_bounds__(32, PfbZbWarpGeom<NT>::kCtasPerSm) k_pfb_zb_warp(PfbZbWarpArgs a) {
+    using B = PfbZbWarpGeom<NT>;
+    using G = typename B::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* xs = reinterpret_cast<float2*>(smem_raw);
+    float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
+
+    const int lane = threadIdx.x;
+    const int tile = (int)(blockIdx.x % a.n_tiles);
+    const int cap = blockIdx.x / a.n_tiles;
+    const float2* xcap = a.x + (size_t)cap * a.stride;
+    const int g_first = B::kStride * tile;
+    {
+        const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
+        if (x0 >= 0 && x0 + G::kTileIn <= a.n_in) {
+            pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
+            mbar_wait(bar, 0);
+        } else {
+            pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, x0, a.n_in, lane);
+            cp_async_commit_wait_all();
+            __syncwarp();
+        }
+    }
+
+    cf y[16];
+    {
+        const int rl = lane & 7, c = lane >> 3;
+#pragma unroll
+        for (int gi = 0; gi < 3; gi++) {
+            const int rho = gi + 3 * rl;
+            float g[NT];
+            const float4* gp = a.taps_pass + gi * (NT / 4) * 8 + rl;
+#pragma unroll
+            for (int d = 0; d < NT / 4; d++) {
+                const float4 t = __ldg(gp + 8 * d);
+                g[4 * d] = t.x; g[4 * d + 1] = t.y; g[4 * d + 2] = t.z; g[4 * d + 3] = t.w;
+            }
+            {
+                float2 acc[4][kChunkT];
+                pfb_fir_thread<NT, 4, kChunkT>(xs + fir_base<NT, kChunkT>(rho, c), rho <= 12 ? 8 : 0, g, acc);
+#pragma unroll
+                for (int e = 0; e < kChunkT; e++) {
+                    V[v_pos(rl, 8 * c + e)] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
+                    V[256 + v_pos(rl, 8 * c + e)] = make_float4(acc[2][e].x, acc[2][e].y, acc[3][e].x, acc[3][e].y);
+                }
+            }
+            __syncwarp();
+            cf v32[32], f[32];
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                const float4 t0 = V[v_pos(r, lane)], t1 = V[256 + v_pos(r, lane)];
+                v32[r].r = t0.x; v32[r].i = t0.y; v32[r + 8].r = t0.z; v32[r + 8].i = t0.w;
+                v32[r + 16].r = t1.x; v32[r + 16].i = t1.y; v32[r + 24].r = t1.z; v32[r + 24].i = t1.w;
+            }
+            __syncwarp();                                                  // V is rewritten by the next pass
+            IdftPow2<32, 1>::run(v32, f);
+            if (gi == 0) pfb_zb_accumulate<0, 0>(f, y);
+            else if (gi == 1) pfb_zb_accumulate<1, 0>(f, y);
+            else pfb_zb_accumulate<2, 0>(f, y);
+        }
+    }
+
+    const int mg = g_first + lane;
+    if (DEBUG && a.dbg_cf && lane < B::kStride && mg < a.n_out) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const int rot = (zb_bin_of_slot(c) * (mg & 3)) & 3;
+            const float rr = rot == 0 ? y[c].r : rot == 1 ? y[c].i : rot == 2 ? -y[c].r : -y[c].i;
+            const float ii = rot == 0 ? y[c].i : rot == 1 ? -y[c].r : rot == 2 ? -y[c].i : y[c].r;
+            a.dbg_cf[((size_t)cap * 16 + c) * (size_t)a.n_out + mg] = make_float2(rr, ii);
+        }
+    }
+    float out[16];
+    zb_disc_all<0>(y, reinterpret_cast<const float2*>(xs) /* lane 31's successor is not in the tile: value unused */,
+                   lane, a.atan_tab, out);
+    const int n = mg + 1;                                                   // f[n] pairs y[n] with y[n-1]
+    if (lane < B::kStride && n < a.n_out) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) a.f[((size_t)cap * 16 + c) * a.f_stride + n] = out[c];
+    }
+    if (mg == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; c++) a.f[((size_t)cap * 16 + c) * a.f_stride] = 0.0f;       // x[-1] = 0 -> atan2(0,0)
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 inline int zb_wideband_init(ZbState& s, const snrx_config_t& cfg, const double* proto, uint32_t max_caps, uint32_t max_out,
                             std::string& err) {
     const int L = (int)cfg.pfb_taps, NT = L / 24;
     s.wb_nt = NT;
+    { const char* e = getenv("SNRX_ZB_PFB"); s.wb_cta_kernel = e && std::string(e) == "cta"; }   // A/B switch: the 384-thread tile kernel
     std::vector<float> flat(L), rho(L);
     for (int n = 0; n < L; n++) flat[n] = (float)proto[n];
     for (int r = 0; r < 24; r++) for (int d = 0; d < NT; d++) rho[r * NT + d] = flat[r + 24 * d];
@@ -172,6 +303,17 @@ inline int zb_wideband_init(ZbState& s, const snrx_config_t& cfg, const double* 
     ZCK(cudaMalloc((void**)&s.d_wb_taps_flat, sizeof(float) * L));
     ZCK(cudaMemcpy(s.d_wb_taps_rho, rho.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
     ZCK(cudaMemcpy(s.d_wb_taps_flat, flat.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
+    {
+        std::vector<float> pass(L);
+        for (int gi = 0; gi < 3; gi++) for (int d4 = 0; d4 < NT / 4; d4++) for (int rl = 0; rl < 8; rl++) for (int k = 0; k < 4; k++)
+            pass[((gi * (NT / 4) + d4) * 8 + rl) * 4 + k] = flat[(gi + 3 * rl) + 24 * (4 * d4 + k)];
+        ZCK(cudaMalloc((void**)&s.d_wb_taps_pass, sizeof(float) * L));
+        ZCK(cudaMemcpy(s.d_wb_taps_pass, pass.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
+    }
+    ZCK(cudaFuncSetAttribute(k_pfb_zb_warp<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbZbWarpGeom<16>::kSmemBytes));
+    ZCK(cudaFuncSetAttribute(k_pfb_zb_warp<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbZbWarpGeom<16>::kSmemBytes));
+    ZCK(cudaFuncSetAttribute(k_pfb_zb_warp<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbZbWarpGeom<32>::kSmemBytes));
+    ZCK(cudaFuncSetAttribute(k_pfb_zb_warp<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbZbWarpGeom<32>::kSmemBytes));
     ZCK(cudaFuncSetAttribute(k_pfb_zb<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbZbGeom<16>::kSmemBytes));
     ZCK(cudaFuncSetAttribute(k_pfb_zb<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbZbGeom<16>::kSmemBytes));
     ZCK(cudaFuncSetAttribute(k_pfb_zb<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PfbZbGeom<32>::kSmemBytes));
@@ -183,13 +325,31 @@ inline int zb_wideband_init(ZbState& s, const snrx_config_t& cfg, const double* 
 
 inline int zb_wideband_front(ZbState& s, const snrx_config_t& cfg, const float2* x, uint32_t n_captures, uint64_t n_samples,
                              uint64_t stride, uint32_t n_out, cudaStream_t st, int& launches, std::string& err) {
+    const bool dbg = (cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
+    if (!s.wb_cta_kernel) {
+        PfbZbWarpArgs a;
+        a.x = x; a.stride = stride; a.n_in = (int64_t)n_samples; a.n_out = (int32_t)n_out;
+        a.n_tiles = (int32_t)std::max<uint32_t>(1u, (n_out - 1 + 30) / 31);
+        a.taps_pass = reinterpret_cast<const float4*>(s.d_wb_taps_pass);
+        a.f = s.d_f; a.f_stride = s.stride; a.atan_tab = s.d_atan; a.dbg_cf = s.d_wb_cf;
+        const dim3 grid((unsigned)a.n_tiles * n_captures);
+        if (s.wb_nt == 16) {
+            if (dbg) k_pfb_zb_warp<16, true><<<grid, 32, PfbZbWarpGeom<16>::kSmemBytes, st>>>(a);
+            else k_pfb_zb_warp<16, false><<<grid, 32, PfbZbWarpGeom<16>::kSmemBytes, st>>>(a);
+        } else {
+            if (dbg) k_pfb_zb_warp<32, true><<<grid, 32, PfbZbWarpGeom<32>::kSmemBytes, st>>>(a);
+            else k_pfb_zb_warp<32, false><<<grid, 32, PfbZbWarpGeom<32>::kSmemBytes, st>>>(a);
+        }
+        launches++;
+        ZCK(cudaGetLastError());
+        return SNRX_OK;
+    }
     PfbZbArgs a;
     a.x = x; a.stride = stride; a.n_in = (int64_t)n_samples; a.n_out = (int32_t)n_out;
     a.n_tiles = (int32_t)std::max<uint32_t>(1u, (n_out - 1 + kTileStride - 1) / kTileStride); a.tile0 = 0;
     a.taps_rho = s.d_wb_taps_rho;
     a.f = s.d_f; a.f_stride = s.stride; a.atan_tab = s.d_atan; a.dbg_cf = s.d_wb_cf;
     const dim3 grid((unsigned)a.n_tiles * n_captures);
-    const bool dbg = (cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
     if (s.wb_nt == 16) {
         if (dbg) k_pfb_zb<16, true><<<grid, kZbFirThreads, PfbZbGeom<16>::kSmemBytes, st>>>(a);
         else k_pfb_zb<16, false><<<grid, kZbFirThreads, PfbZbGeom<16>::kSmemBytes, st>>>(a);

@@ -342,8 +342,8 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         if (c.max_captures == 0) c.max_captures = 1;
         if (c.max_samples == 0) c.max_samples = h->wideband ? 96000000ull : 10000000ull;
         if (c.max_frames == 0) c.max_frames = 1u << 17;
-        if (c.zb_segment == 0) c.zb_segment = 65536;
-        if (c.zb_prehalo == 0) c.zb_prehalo = 4096;
+        if (c.zb_segment == 0) c.zb_segment = SNRX_ZB_SEGMENT_DEFAULT;
+        if (c.zb_prehalo == 0) c.zb_prehalo = SNRX_ZB_PREHALO_DEFAULT;
         if (c.pfb_taps == 0) c.pfb_taps = 384;
         if (c.pfb_taps != 384 && c.pfb_taps != 768) return fail(h, SNRX_EINVAL, "pfb_taps must be 384 or 768");
         h->pfb_nt = (int)c.pfb_taps / 24;
@@ -548,7 +548,8 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
             if (((uint64_t)first_window * kWindow) % seg) return fail(h, SNRX_EINVAL, "Zigbee shards: the body must start on the segment grid");
             const uint32_t need = (SNRX_IIR_MEMORY_BLOCKS + 1) * SNRX_IIR_BLOCK + h->cfg.zb_prehalo;   // +1: the first block of a
             // buffer holds a discriminator sample without history (and the channelizer start-up), so its end value is off
-            if (first_window != 0 && pre_out < need) return fail(h, SNRX_EINVAL, "Zigbee shards: pre halo shorter than 36864 + zb_prehalo channel samples");
+            // (a buffer that starts at capture sample 0 holds the whole history there is)
+            if (first_window != 0 && pre_out < need && (uint64_t)first_window * kWindow != pre_out) return fail(h, SNRX_EINVAL, "Zigbee shards: pre halo shorter than 36864 + zb_prehalo channel samples");
         }
     }
 
@@ -687,11 +688,11 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
     }
     if (h->has_zb) {
         const uint32_t first_segment = (uint32_t)(((uint64_t)first_window * kWindow) / h->cfg.zb_segment);
+        if (!h->has_ble) CK(cudaEventRecord(ln.ev_front0, st));
         int r = zb_process(ln.zb, h->cfg, x, n_captures, n_samples, x_stride, n_out, pre_out, body_out, first_segment,
                            first_capture, ln.d_frames, h->frame_cap, ln.d_totals, h->has_ble, st, h->sm_count,
-                           h->launches, h->err);
+                           h->launches, h->err, h->has_ble ? nullptr : ln.ev_front);
         if (r != SNRX_OK) return r;
-        if (!h->has_ble) { CK(cudaEventRecord(ln.ev_front0, st)); CK(cudaEventRecord(ln.ev_front, st)); }
     }
     // export: device frame list -> pinned host memory; on this lane's stream, so it overlaps the other lane's front end
     k_export_frames<<<32, 256, 0, st>>>(ln.d_frames, ln.d_totals, ln.frames, ln.totals, h->frame_cap);

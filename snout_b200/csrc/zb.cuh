@@ -100,7 +100,7 @@ struct ZbSink {
     int byte, nibble_idx;
     int frame_len, got;
     unsigned lqi_sum, lqi_n;
-    int64_t sync_pos;
+    int32_t sync_pos;
 };
 
 SNRX_HD void zb_sink_search(ZbSink& s) { s.state = 0; s.reg = 0; s.preamble_cnt = 0; s.chip_cnt = 0; s.byte = 0; }
@@ -123,7 +123,7 @@ SNRX_HD int zb_decode_symbol(ZbSink& s, const uint32_t* map, int threshold) {   
 }
 
 // push one hard chip; returns 1 when a frame is complete (psdu[0..got))
-SNRX_HD int zb_sink_push(ZbSink& s, int chip, int64_t pos, const uint32_t* map, int threshold, uint8_t* psdu) {
+SNRX_HD int zb_sink_push(ZbSink& s, int chip, int32_t pos, const uint32_t* map, int threshold, uint8_t* psdu) {
     s.reg = (s.reg << 1) | (uint32_t)(chip & 1);
     if (s.state == 0) {                                           // STATE_SYNC_SEARCH :176-245
         if (s.preamble_cnt > 0) s.chip_cnt++;
@@ -191,14 +191,25 @@ SNRX_HD double zb_iir_fold(const double* ends, int b, double decay) {
     return carry;
 }
 
-struct ZbMm { float mu, omega, last; int64_t ii; };
+struct ZbMm { float mu, omega, last; int32_t ii; };     // ii: position in the stream (n_out < 2^31)
 
-SNRX_HD float zb_mm_step(ZbMm& st, const float* z, const float* taps /*[129][8]*/) {
+// row of the MMSE interpolator table for the fractional delay mu: rint(mu * 128).  mu * 128 lies in [0, 128],
+// so adding 1.5 * 2^23 rounds it to the nearest integer (ties to even, exactly rintf) in the low mantissa bits:
+// one FADD instead of a conversion on the chain's critical path.
+SNRX_HD int zb_mm_row(float mu) {
+    const float t = f_add(f_mul(mu, (float)SNRX_MMSE_NSTEPS), 12582912.0f);
+#ifdef __CUDA_ARCH__
+    return __float_as_int(t) & 0x1FF;
+#else
+    uint32_t u; memcpy(&u, &t, 4); return (int)(u & 0x1FFu);
+#endif
+}
+
+// one Mueller-Mueller step on the 8 samples in[0..8) = z[ii .. ii+8) with the interpolator row t = taps[zb_mm_row(mu)];
+// returns the soft chip
+SNRX_HD float zb_mm_step(ZbMm& st, const float (&in)[8], const float (&t)[8]) {
     const float omega_mid = 2.0f, gain_omega = 0.000225f, gain_mu = 0.03f;
     const float omega_lim = 2.0f * 0.0002f;
-    const float* in = z + st.ii;
-    const int imu = (int)rintf(f_mul(st.mu, (float)SNRX_MMSE_NSTEPS));
-    const float* t = taps + imu * SNRX_MMSE_NTAPS;
     const float p0 = f_mul(t[0], in[0]), p1 = f_mul(t[1], in[1]), p2 = f_mul(t[2], in[2]), p3 = f_mul(t[3], in[3]);
     const float p4 = f_mul(t[4], in[4]), p5 = f_mul(t[5], in[5]), p6 = f_mul(t[6], in[6]), p7 = f_mul(t[7], in[7]);
     const float s01 = f_add(p0, p1), s23 = f_add(p2, p3), s45 = f_add(p4, p5), s67 = f_add(p6, p7);
@@ -214,10 +225,24 @@ SNRX_HD float zb_mm_step(ZbMm& st, const float* z, const float* taps /*[129][8]*
     const float g = f_mul(gain_mu, mm);
     const float m2 = f_add(f_add(st.mu, st.omega), g);
     const float fl = floorf(m2);
-    st.ii += (int64_t)fl;
+    st.ii += (int32_t)fl;
     st.mu = f_sub(m2, fl);
     return out;
 }
+
+// where a chain reads its samples from: straight from the stream (host stepping harness) ...
+struct ZbDirectSrc {
+    const float* z;
+    const float* taps;     // [129][8]
+    SNRX_HD void get8(int32_t ii, float (&in)[8]) const {
+#pragma unroll
+        for (int k = 0; k < 8; k++) in[k] = z[ii + k];
+    }
+    SNRX_HD void row(int r, float (&t)[8]) const {
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = taps[r * SNRX_MMSE_NTAPS + k];
+    }
+};
 
 struct ZbChainParams {
     int32_t n_out;            // channel-rate samples per capture in the buffer
@@ -232,31 +257,39 @@ struct ZbChainParams {
     size_t z_stride;          // floats between (capture, channel) streams
 };
 
-// One chain.  z: stream of this (capture, channel).  Frames are written to slots[0..), returns count.
-SNRX_HD uint32_t zb_run_chain(const float* z, const ZbChainParams& p, int seg, const float* taps, const uint32_t* map,
+// One chain.  src: samples of this (capture, channel) stream.  Frames are written to slots[0..), returns count.
+// The chain ends at the post halo, or as soon as it has passed its body with the sink back in the search
+// state: a sync found from there on completes at a position >= hi and belongs to the next segment, so
+// nothing this chain could still report is lost (oracle/zb_oracle.c zb_oracle_chain stops at the same step).
+template <class Src>
+SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const uint32_t* map,
                               int channel_number, uint32_t capture_id, snrx_frame_t* slots, float* chips_dbg,
                               int64_t chips_cap, int64_t* nchips_out) {
-    const int64_t lo = (int64_t)p.origin + (int64_t)seg * p.segment;
-    int64_t hi = lo + p.segment;
-    const int64_t body_end = (int64_t)p.origin + p.body;
+    // all positions are < n_out + segment + post halo < 2^31 (zb_create bounds max_out)
+    const int32_t lo = p.origin + seg * p.segment;
+    int32_t hi = lo + p.segment;
+    const int32_t body_end = p.origin + p.body;
     if (hi > body_end) hi = body_end;
-    int64_t begin = lo - p.prehalo; if (begin < 0) begin = 0;
-    int64_t end = hi + kZbPostHalo; if (end > p.n_out) end = p.n_out;
+    int32_t begin = lo - p.prehalo; if (begin < 0) begin = 0;
+    int32_t end = hi + kZbPostHalo; if (end > p.n_out) end = p.n_out;
     ZbMm mm; mm.mu = 0.5f; mm.omega = 2.0f; mm.last = 0.0f; mm.ii = begin;
     ZbSink sink; zb_sink_init(sink);
     uint8_t psdu[128];
     uint32_t nf = 0;
-    int64_t nchips = 0;
-    while (mm.ii + 8 <= end) {
-        const int64_t pos = mm.ii;
-        const float soft = zb_mm_step(mm, z, taps);
+    int32_t nchips = 0;
+    while (mm.ii + 8 <= end && !(mm.ii >= hi && sink.state == 0)) {
+        const int32_t pos = mm.ii;
+        float in[8], t[8];
+        src.row(zb_mm_row(mm.mu), t);
+        src.get8(pos, in);
+        const float soft = zb_mm_step(mm, in, t);
         if (chips_dbg && nchips < chips_cap) chips_dbg[nchips] = soft;
         nchips++;
         if (zb_sink_push(sink, soft > 0.0f, pos, map, p.threshold, psdu)) {
             if (sink.sync_pos >= lo && sink.sync_pos < hi) {
                 if (nf < p.slots_per_chain) {
                     snrx_frame_t& f = slots[nf];
-                    f.sample_index = (sink.sync_pos - p.origin) + (int64_t)p.first_segment * p.segment;
+                    f.sample_index = (int64_t)(sink.sync_pos - p.origin) + (int64_t)p.first_segment * p.segment;
                     f.capture_id = capture_id;
                     f.window = p.first_segment + (uint32_t)seg;
                     f.channel = (uint16_t)channel_number;
@@ -314,16 +347,42 @@ struct ZbIirArgs {
     const double* pw;     // [4096] (1-alpha)^(i+1)
 };
 
-__global__ void __launch_bounds__(128) k_zb_iir_sum(ZbIirArgs a) {
+// A (stream, block) unit is one thread's 4096-sample serial recurrence.  Its samples are contiguous and
+// 128-byte aligned, so the thread streams them as float4 with the next 32 samples (8 loads) already in
+// flight while the current 32 go through the dependent double-precision chain.
+constexpr int kIirPf = 8;             // float4 loads in flight per thread
+
+__global__ void __launch_bounds__(64) k_zb_iir_sum(ZbIirArgs a) {
     const uint32_t total = a.n_streams * (uint32_t)a.n_blocks;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const uint32_t s = idx / (uint32_t)a.n_blocks, b = idx % (uint32_t)a.n_blocks;
-        const float* f = a.f + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
-        const int len = min(SNRX_IIR_BLOCK, a.n - (int)b * SNRX_IIR_BLOCK);
-        double l = 0.0;
-        for (int i = 0; i < len; i++) l = d_add(d_mul(SNRX_IIR_ALPHA, (double)f[i]), d_mul(SNRX_IIR_BETA, l));
-        a.block_end[idx] = l;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // consecutive threads take different streams (DRAM page spread, as in k_zb_chain)
+    const uint32_t b = idx / a.n_streams, s = idx % a.n_streams;
+    const float* f = a.f + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
+    const int len = min(SNRX_IIR_BLOCK, a.n - (int)b * SNRX_IIR_BLOCK);
+    const int n4 = len >> 2;
+    const float4* f4 = reinterpret_cast<const float4*>(f);
+    double l = 0.0;
+    float4 cur[kIirPf], nxt[kIirPf];
+#pragma unroll
+    for (int k = 0; k < kIirPf; k++) nxt[k] = (k < n4) ? __ldcs(f4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i4 = 0; i4 < n4; i4 += kIirPf) {
+#pragma unroll
+        for (int k = 0; k < kIirPf; k++) cur[k] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < kIirPf; k++) nxt[k] = (i4 + kIirPf + k < n4) ? __ldcs(f4 + i4 + kIirPf + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < kIirPf; k++) {
+            if (i4 + k < n4) {
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].x), d_mul(SNRX_IIR_BETA, l));
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].y), d_mul(SNRX_IIR_BETA, l));
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].z), d_mul(SNRX_IIR_BETA, l));
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].w), d_mul(SNRX_IIR_BETA, l));
+            }
+        }
     }
+    for (int i = n4 << 2; i < len; i++) l = d_add(d_mul(SNRX_IIR_ALPHA, (double)f[i]), d_mul(SNRX_IIR_BETA, l));
+    a.block_end[(size_t)s * a.n_blocks + b] = l;
 }
 
 // carried state entering block b: folded from the SNRX_IIR_MEMORY_BLOCKS preceding blocks (all full
@@ -338,48 +397,157 @@ __global__ void __launch_bounds__(128) k_zb_iir_carry(ZbIirArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(128) k_zb_dc(ZbIirArgs a) {
+__global__ void __launch_bounds__(64) k_zb_dc(ZbIirArgs a) {
+    __shared__ double pw_s[SNRX_IIR_BLOCK];                   // (1-alpha)^(i+1): same index for every thread -> broadcast
+    for (int i = threadIdx.x; i < SNRX_IIR_BLOCK; i += blockDim.x) pw_s[i] = a.pw[i];
+    __syncthreads();
     const uint32_t total = a.n_streams * (uint32_t)a.n_blocks;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const uint32_t s = idx / (uint32_t)a.n_blocks, b = idx % (uint32_t)a.n_blocks;
-        const float* f = a.f + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
-        float* z = a.z + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
-        const int len = min(SNRX_IIR_BLOCK, a.n - (int)b * SNRX_IIR_BLOCK);
-        const double carry = a.carry_in[idx];
-        double l = 0.0;
-        for (int i = 0; i < len; i++) {
-            const float fv = f[i];
-            l = d_add(d_mul(SNRX_IIR_ALPHA, (double)fv), d_mul(SNRX_IIR_BETA, l));
-            const double y = d_add(l, d_mul(a.pw[i], carry));
-            z[i] = f_sub(fv, (float)y);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const uint32_t b = idx / a.n_streams, s = idx % a.n_streams;
+    const float* f = a.f + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
+    float* z = a.z + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
+    const int len = min(SNRX_IIR_BLOCK, a.n - (int)b * SNRX_IIR_BLOCK);
+    const int n4 = len >> 2;
+    const float4* f4 = reinterpret_cast<const float4*>(f);
+    float4* z4 = reinterpret_cast<float4*>(z);
+    const double carry = a.carry_in[(size_t)s * a.n_blocks + b];
+    double l = 0.0;
+    float4 cur[kIirPf], nxt[kIirPf];
+#pragma unroll
+    for (int k = 0; k < kIirPf; k++) nxt[k] = (k < n4) ? __ldcs(f4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i4 = 0; i4 < n4; i4 += kIirPf) {
+#pragma unroll
+        for (int k = 0; k < kIirPf; k++) cur[k] = nxt[k];
+#pragma unroll
+        for (int k = 0; k < kIirPf; k++) nxt[k] = (i4 + kIirPf + k < n4) ? __ldcs(f4 + i4 + kIirPf + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < kIirPf; k++) {
+            if (i4 + k < n4) {
+                const int i = (i4 + k) << 2;
+                float4 o;
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].x), d_mul(SNRX_IIR_BETA, l));
+                o.x = f_sub(cur[k].x, (float)d_add(l, d_mul(pw_s[i], carry)));
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].y), d_mul(SNRX_IIR_BETA, l));
+                o.y = f_sub(cur[k].y, (float)d_add(l, d_mul(pw_s[i + 1], carry)));
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].z), d_mul(SNRX_IIR_BETA, l));
+                o.z = f_sub(cur[k].z, (float)d_add(l, d_mul(pw_s[i + 2], carry)));
+                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].w), d_mul(SNRX_IIR_BETA, l));
+                o.w = f_sub(cur[k].w, (float)d_add(l, d_mul(pw_s[i + 3], carry)));
+                z4[i4 + k] = o;
+            }
         }
+    }
+    for (int i = n4 << 2; i < len; i++) {
+        const float fv = f[i];
+        l = d_add(d_mul(SNRX_IIR_ALPHA, (double)fv), d_mul(SNRX_IIR_BETA, l));
+        z[i] = f_sub(fv, (float)d_add(l, d_mul(pw_s[i], carry)));
     }
 }
 
-__global__ void __launch_bounds__(64) k_zb_chain(const float* __restrict__ z, ZbChainParams p,
+// ... or, on the device, through a per-thread ring in shared memory that cp.async keeps kZbAhead samples
+// ahead of the chain.  The M&M loop is one long dependent chain per thread; with the samples already on
+// chip its step costs shared-memory latency instead of an L2 / HBM round trip every few steps.
+// Layout: ring row r of lane l at ring[r * 32 + l] -> every access of a warp is bank-conflict free whatever
+// the lanes' positions; rows 0..7 are mirrored at kZbRing.. so the 8 taps never wrap.
+constexpr int kZbRing = 128;          // samples held per chain (power of two)
+constexpr int kZbChunk = 16;          // samples per cp.async group
+constexpr int kZbAhead = 64;          // a group is waited for 3 groups (48 samples) after its issue
+constexpr int kZbChainThreads = 64;
+
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+struct ZbRingSrc {
+    const float* z;        // stream
+    uint32_t ring;         // shared-memory byte address of this lane's column
+    uint32_t taps;         // shared-memory byte address of the interpolator table (kept in a register: the
+                           // compiler would otherwise rebuild it from SR_CgaCtaId inside the loop)
+    int32_t begin;         // stream index of ring position 0
+    int32_t fetched;       // samples requested so far (relative to begin, multiple of kZbChunk)
+    int32_t last;          // last readable stream index (requests beyond it are clamped; never consumed)
+
+    __device__ __forceinline__ void issue() {
+        const int r = fetched & (kZbRing - 1);
+        const uint32_t dst = ring + (uint32_t)r * 128u;
+        const int32_t g0 = begin + fetched;
+        if (g0 + kZbChunk - 1 <= last) {
+            const float* g = z + g0;
+#pragma unroll
+            for (int k = 0; k < kZbChunk; k++) cp_async4(dst + 128u * k, g + k);
+            if (r == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) cp_async4(dst + 128u * (kZbRing + k), g + k);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kZbChunk; k++) cp_async4(dst + 128u * k, z + min(g0 + k, last));
+            if (r == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) cp_async4(dst + 128u * (kZbRing + k), z + min(g0 + k, last));
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        fetched += kZbChunk;
+    }
+    __device__ __forceinline__ void prime() {
+        while (fetched < 8 + kZbAhead) issue();
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    // the chain advances by at most 3 samples per step and one group brings 16, so one issue per step
+    // keeps `fetched >= rel + 8 + kZbAhead`; everything but the 3 newest groups has landed after the wait
+    __device__ __forceinline__ void get8(int32_t ii, float (&in)[8]) {
+        const int rel = ii - begin;
+        if (fetched < rel + 8 + kZbAhead) issue();
+        asm volatile("cp.async.wait_group 3;\n" ::: "memory");
+        const uint32_t p = ring + (uint32_t)(rel & (kZbRing - 1)) * 128u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(in[k]) : "r"(p + 128u * k));
+    }
+    __device__ __forceinline__ void row(int r, float (&t)[8]) const {
+        const uint32_t a = taps + (uint32_t)r * (SNRX_MMSE_NTAPS * 4);
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]) : "r"(a));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7]) : "r"(a + 16u));
+    }
+};
+
+__global__ void __launch_bounds__(kZbChainThreads) k_zb_chain(const float* __restrict__ z, ZbChainParams p,
                                                  const float* __restrict__ taps_g, ChipMap map_arg,
                                                  const int32_t* __restrict__ channel_numbers,
                                                  snrx_frame_t* __restrict__ slots, uint32_t* __restrict__ counts,
                                                  float* chips_dbg, int64_t chips_cap_per_chain, int64_t* nchips_dbg) {
-    __shared__ float taps[(SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS];
-    __shared__ uint32_t map[16];
+    __shared__ __align__(16) float taps[(SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS];
+    __shared__ float ring[(kZbChainThreads / 32) * (kZbRing + 8) * 32];
     for (int i = threadIdx.x; i < (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS; i += blockDim.x) taps[i] = taps_g[i];
-    if (threadIdx.x < 16) map[threadIdx.x] = map_arg.w[threadIdx.x];
     __syncthreads();
     const uint32_t total = p.n_captures * p.n_channels * (uint32_t)p.n_segments;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
+    const uint32_t* map = map_arg.w;            // kernel parameter: the chip words are constant-bank operands
     // consecutive threads take different streams so that a warp touches many DRAM pages at once
     const uint32_t seg = idx / (p.n_captures * p.n_channels);
     const uint32_t sc = idx % (p.n_captures * p.n_channels);
     const uint32_t cap = sc / p.n_channels, ch = sc % p.n_channels;
     const uint32_t chain = (cap * p.n_channels + ch) * (uint32_t)p.n_segments + seg;    // output order
-    const float* zs = z + (size_t)sc * p.z_stride;
+    ZbRingSrc src;
+    src.z = z + (size_t)sc * p.z_stride;
+    src.ring = (uint32_t)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * ((kZbRing + 8) * 32) + (threadIdx.x & 31));
+    src.taps = (uint32_t)__cvta_generic_to_shared(taps);
+    asm volatile("" : "+r"(src.ring), "+r"(src.taps));          // opaque: stay in registers
+    {
+        const int32_t lo = p.origin + (int32_t)seg * p.segment;
+        src.begin = lo - p.prehalo > 0 ? lo - p.prehalo : 0;                  // = the chain's first sample
+    }
+    src.fetched = 0;
+    src.last = p.n_out > 0 ? p.n_out - 1 : 0;
+    src.prime();
     int64_t nchips = 0;
-    const uint32_t nf = zb_run_chain(zs, p, (int)seg, taps, map, channel_numbers[ch], p.first_capture + cap,
+    const uint32_t nf = zb_run_chain(src, p, (int)seg, map, channel_numbers[ch], p.first_capture + cap,
                                      slots + (size_t)chain * p.slots_per_chain,
                                      chips_dbg ? chips_dbg + (size_t)chain * chips_cap_per_chain : nullptr,
                                      chips_cap_per_chain, &nchips);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     counts[chain] = nf < p.slots_per_chain ? nf : p.slots_per_chain;
     if (nchips_dbg) nchips_dbg[chain] = nchips;
 }
@@ -417,14 +585,15 @@ struct ZbState {
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
     uint32_t max_chains = 0, slots_per_chain = 0;
     float* d_chips = nullptr; int64_t* d_nchips = nullptr; int64_t chips_cap = 0;
-    float *d_wb_taps_rho = nullptr, *d_wb_taps_flat = nullptr; float2* d_wb_cf = nullptr; int wb_nt = 16;   // wideband front end
+    float *d_wb_taps_rho = nullptr, *d_wb_taps_flat = nullptr, *d_wb_taps_pass = nullptr; float2* d_wb_cf = nullptr; int wb_nt = 16;
+    bool wb_cta_kernel = false;   // wideband front end
     ChipMap map;
     uint32_t last_chains = 0;
 };
 
 inline void zb_free(ZbState& s) {
     void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_pw, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
-                    s.d_counts, s.d_offsets, s.d_scratch, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_cf};
+                    s.d_counts, s.d_offsets, s.d_scratch, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     s = ZbState();
 }
@@ -444,6 +613,7 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
                      uint32_t max_out, int sm_count, std::string& err) {
     (void)sm_count;
     s.n_ch = n_ch; s.max_caps = max_caps; s.max_out = max_out;
+    if ((uint64_t)max_out + cfg.zb_segment + kZbPostHalo >= (1ull << 31)) { err = "zigbee: capture too long for 32-bit chain positions"; return SNRX_ERANGE; }
     s.stride = ((size_t)max_out + 8 + 31) & ~(size_t)31;
     const size_t streams = (size_t)max_caps * n_ch;
     ZCK(cudaMalloc((void**)&s.d_f, streams * s.stride * sizeof(float)));
@@ -488,7 +658,7 @@ inline int zb_wideband_front(ZbState& s, const snrx_config_t& cfg, const float2*
 inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uint32_t n_captures, uint64_t n_samples,
                       uint64_t stride, uint32_t n_out, uint32_t pre_out, uint32_t body_out, uint32_t first_segment,
                       uint32_t first_capture, snrx_frame_t* frames, uint32_t frame_cap, uint32_t* totals, bool after_ble,
-                      cudaStream_t st, int sm_count, int& launches, std::string& err) {
+                      cudaStream_t st, int sm_count, int& launches, std::string& err, cudaEvent_t ev_front_done = nullptr) {
     const bool wideband = (cfg.mode != SNRX_MODE_ZB_NB);
     const uint32_t streams = n_captures * s.n_ch;
     if (wideband) {
@@ -503,14 +673,15 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
         k_zb_quad<<<grid, 256, 0, st>>>(q);
         launches++;
     }
+    if (ev_front_done) ZCK(cudaEventRecord(ev_front_done, st));      // front end = channelizer + discriminator (stats.gpu_ms_frontend)
     ZbIirArgs ia;
     ia.f = s.d_f; ia.z = s.d_z; ia.stride = s.stride; ia.n = (int32_t)n_out;
     ia.n_blocks = (int32_t)((n_out + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK); ia.n_streams = streams;
     ia.block_end = s.d_block_end; ia.carry_in = s.d_carry; ia.pw = s.d_pw;
     const uint32_t nb_total = streams * (uint32_t)ia.n_blocks;
-    k_zb_iir_sum<<<(nb_total + 127) / 128, 128, 0, st>>>(ia);
+    k_zb_iir_sum<<<(nb_total + 63) / 64, 64, 0, st>>>(ia);
     k_zb_iir_carry<<<(nb_total + 127) / 128, 128, 0, st>>>(ia);
-    k_zb_dc<<<(nb_total + 127) / 128, 128, 0, st>>>(ia);
+    k_zb_dc<<<(nb_total + 63) / 64, 64, 0, st>>>(ia);
     launches += 3;
 
     ZbChainParams p{};
@@ -522,7 +693,7 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     p.slots_per_chain = s.slots_per_chain; p.z_stride = s.stride;
     const uint32_t n_chains = streams * (uint32_t)p.n_segments;
     if (n_chains > s.max_chains) { err = "zigbee: more chains than capacity"; return SNRX_ERANGE; }
-    k_zb_chain<<<(n_chains + 63) / 64, 64, 0, st>>>(s.d_z, p, s.d_mmse, s.map, s.d_channels, s.d_slots, s.d_counts,
+    k_zb_chain<<<(n_chains + kZbChainThreads - 1) / kZbChainThreads, kZbChainThreads, 0, st>>>(s.d_z, p, s.d_mmse, s.map, s.d_channels, s.d_slots, s.d_counts,
                                                   s.d_chips, s.chips_cap, s.d_nchips);
     launches += 1 + exclusive_scan(s.d_counts, n_chains, s.d_offsets, s.d_scratch, st);
     k_zb_gather<<<std::max(1u, std::min<uint32_t>((n_chains + 3) / 4, (uint32_t)sm_count * 8)), 128, 0, st>>>(

@@ -26,7 +26,7 @@ BLE_PRE_HALO = 128
 BLE_POST_HALO = 2048
 
 
-def shard_geometry(n_ble: int, n_zb: int, zb_segment: int = 65536, zb_prehalo: int = 4096) -> tuple[int, int, int]:
+def shard_geometry(n_ble: int, n_zb: int, zb_segment: int = 8192, zb_prehalo: int = 4096) -> tuple[int, int, int]:
     """(unit, pre, post) in channel-rate samples for an engine with n_ble / n_zb receivers."""
     unit, pre, post = chanplan.BLE_WINDOW, 0, 0
     if n_ble:
@@ -73,7 +73,7 @@ class ShardStreamer:
     def __init__(self, engine, units_per_shard: int | None = None):
         self.eng = engine
         self.decim = engine.decim
-        self.unit, self.pre, self.post = shard_geometry(engine.n_ble, engine.n_zb, engine.cfg.zb_segment or 65536,
+        self.unit, self.pre, self.post = shard_geometry(engine.n_ble, engine.n_zb, engine.cfg.zb_segment or 8192,
                                                         engine.cfg.zb_prehalo or 4096)
         cap_in = int(engine.cfg.max_samples) or (96_000_000 if engine.wideband else 10_000_000)   # snrx_create defaults
         cap_ch = cap_in // self.decim

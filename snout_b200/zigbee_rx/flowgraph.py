@@ -130,8 +130,8 @@ class top_block:
             factory = RxEngine
         mode = "zb_wb16" if self._wideband else "zb_nb"
         decim = chanplan.WB_DECIM if self._wideband else 1
-        seg = self._zb_segment or 65536
-        nseg = self._segments or (4 if self._wideband else 16)
+        seg = self._zb_segment or 8192
+        nseg = self._segments or (262144 if self._wideband else 1048576) // seg
         try:
             eng = factory(mode, channel=self.channel, device=self._device, zb_segment=seg,
                           max_samples=(nseg * seg + 40960 + 16512) * decim)

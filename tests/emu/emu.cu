@@ -297,7 +297,8 @@ int emu_zb_chains(const float* z, int n_out, int origin, int body, int segment, 
     std::vector<snrx_frame_t> slots(p.slots_per_chain);
     int n = 0;
     for (int seg = 0; seg < p.n_segments; seg++) {
-        uint32_t nf = zb_run_chain(z, p, seg, &SNRX_MMSE_TAPS[0][0], map.w, channel, 0, slots.data(), nullptr, 0, nullptr);
+        ZbDirectSrc src{z, &SNRX_MMSE_TAPS[0][0]};
+        uint32_t nf = zb_run_chain(src, p, seg, map.w, channel, 0, slots.data(), nullptr, 0, nullptr);
         for (uint32_t k = 0; k < nf && k < p.slots_per_chain; k++) { if (n < cap) out[n] = slots[k]; n++; }
     }
     return n;

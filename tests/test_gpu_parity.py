@@ -241,26 +241,33 @@ def test_ble_wb40_shards_equal_whole(Engine):
 
 
 # ------------------------------------------------------------------------------------ Zigbee narrow band
+@pytest.mark.parametrize("segment", [0, 65536])
 @pytest.mark.parametrize("seed,esn0", [(2001, 30.0), (2002, 12.0), (2003, 9.0)])
-def test_zb_nb_parity(Engine, oracle_mod, seed, esn0):
+def test_zb_nb_parity(Engine, oracle_mod, seed, esn0, segment):
     cap = synth.zigbee_capture(n=1_000_000, channel=11, seed=seed, esn0_db=esn0)
-    with Engine("zb_nb", channel=11, max_samples=len(cap.iq), keep_streams=True) as e:
+    with Engine("zb_nb", channel=11, max_samples=len(cap.iq), keep_streams=True, zb_segment=segment) as e:
         got = e.run(cap.iq)
         f = e.debug_stage(_abi.STAGE_ZB_F)[0, 0]
         z = e.debug_stage(_abi.STAGE_ZB_DISC)[0, 0]
         nchips = e.debug_stage(_abi.STAGE_ZB_NCHIPS)
         chips = e.debug_stage(_abi.STAGE_ZB_CHIPS)
+    seg = segment or _abi.ZB_SEGMENT_DEFAULT
     fo = oracle_mod.zb_quad_demod(cap.iq)
     assert np.array_equal(f, fo)                                  # same table atan2, same op order: bit exact
     zo = oracle_mod.zb_dc_remove(fo)
     assert np.array_equal(z, zo)
-    want = oracle_mod.zb_receive(cap.iq, 11, segment=65536, prehalo=4096)
+    want = oracle_mod.zb_receive(cap.iq, 11, segment=seg, prehalo=4096)
     assert len(want) > 5
     assert_frames_equal(got, want, what=f"zigbee seed {seed}")
-    # soft chips of chain 3 (segment 3): identical count and values
-    lo, hi = 3 * 65536, 4 * 65536
-    _, c3, _ = oracle_mod.zb_chain(zo, lo - 4096, min(len(zo), hi + 16448), lo, hi, want_chips=True)
-    assert nchips[3] == len(c3) and np.array_equal(chips[3, : len(c3)], c3)
+    # soft chips of every chain (one per segment): identical count and values, including the step at which
+    # a chain stops (post halo, or past its body with the sink searching)
+    n_chains = -(-len(zo) // seg)
+    assert len(nchips) == n_chains
+    for k in range(n_chains):
+        lo, hi = k * seg, min(len(zo), (k + 1) * seg)
+        _, ck, _ = oracle_mod.zb_chain(zo, max(0, lo - 4096), min(len(zo), hi + 16448), lo, hi, want_chips=True)
+        assert nchips[k] == len(ck), (k, nchips[k], len(ck))
+        assert np.array_equal(chips[k, : len(ck)], ck), k
 
 
 def test_zb_nb_batch_and_set_channel(Engine, oracle_mod):

@@ -180,7 +180,7 @@ def test_zigbee_top_block_interface_xmlrpc_and_udp():
     port = _free_port()
     made = []
     x = np.zeros(65536 * 5 + 99, np.complex64)
-    tb = top_block(channel=11, xmlrpc_addr=("localhost", port), udp_dest=rx.getsockname(), segments_per_shard=2,
+    tb = top_block(channel=11, xmlrpc_addr=("localhost", port), udp_dest=rx.getsockname(), segments_per_shard=2, zb_segment=65536,
                    engine_factory=lambda m, **k: made.append(RecordingEngine(m, **k)) or made[-1], blocks=[x])
     srv = xmlrpc.client.ServerProxy(f"http://localhost:{port}")
     assert srv.get_channel() == 11 and srv.get_samp_rate() == 4000000
@@ -198,7 +198,7 @@ def test_zigbee_top_block_interface_xmlrpc_and_udp():
         assert d[:16] == bytes.fromhex("5246746104000101c30000000000803f") and p["dlt"] == 195 and p["qual"] == 1.0
         assert p["payload"] == bytes(MARK)
     # GnuradioPacket encapsulation of the older flowgraphs: first byte 2 -> GnuradioSocket.recv builds a GnuradioPacket
-    tb = top_block(channel=26, serve_xmlrpc=False, udp_dest=rx.getsockname(), encap="gnuradio", segments_per_shard=2,
+    tb = top_block(channel=26, serve_xmlrpc=False, udp_dest=rx.getsockname(), encap="gnuradio", segments_per_shard=2, zb_segment=65536,
                    engine_factory=lambda m, **k: RecordingEngine(m, **k), blocks=[x[:70000]])
     tb.start()
     d = rx.recvfrom(4096)[0]
