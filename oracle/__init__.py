@@ -210,22 +210,26 @@ def zb_dc_remove(f: np.ndarray) -> np.ndarray:
 
 
 def zb_chain(z: np.ndarray, begin: int, end: int, body_lo: int, body_hi: int, channel: int = 11,
-             threshold: int = 10, segment: int = 0, cap: int = 4096, want_chips: bool = False):
-    """One clock-recovery + sink chain.  Returns (frames, soft chips, chip positions)."""
+             threshold: int = 10, segment: int = 0, cap: int = 4096, want_chips: bool = False, hold: int = 0,
+             want_stop: bool = False):
+    """One clock-recovery + sink chain (sink held in its initial state until position `hold`).
+    Returns (frames, soft chips, chip positions[, stop position])."""
     z = _f32(z)
     out = _frames(cap)
     nf = c_int(0)
+    stop = c_int64(0)
     lib = _lib("port")
-    lib.zb_oracle_chain.restype = c_int64
+    lib.zb_oracle_chain_hold.restype = c_int64
     maxchips = (end - begin) // 2 + 64 if want_chips else 0
     chips = np.zeros(max(maxchips, 1), dtype=np.float32)
     pos = np.zeros(max(maxchips, 1), dtype=np.int64)
-    n = lib.zb_oracle_chain(_ptr(z), c_int64(begin), c_int64(end), c_int64(body_lo), c_int64(body_hi),
-                            c_int(threshold), c_int(channel), c_uint32(segment), _ptr(out), c_int(cap),
-                            ctypes.byref(nf), _ptr(chips) if want_chips else None,
-                            _ptr(pos) if want_chips else None, c_int64(maxchips))
+    n = lib.zb_oracle_chain_hold(_ptr(z), c_int64(begin), c_int64(end), c_int64(body_lo), c_int64(body_hi), c_int64(hold),
+                                 c_int(threshold), c_int(channel), c_uint32(segment), _ptr(out), c_int(cap),
+                                 ctypes.byref(nf), _ptr(chips) if want_chips else None,
+                                 _ptr(pos) if want_chips else None, c_int64(maxchips), ctypes.byref(stop))
     n = int(n)
-    return out[:nf.value].copy(), chips[:min(n, maxchips)], pos[:min(n, maxchips)]
+    res = (out[:nf.value].copy(), chips[:min(n, maxchips)], pos[:min(n, maxchips)])
+    return res + (int(stop.value),) if want_stop else res
 
 
 def zb_receive(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = 8192,

@@ -296,24 +296,27 @@ static inline float mm_step(zb_mm_t* st, const float* z) {
     return out;
 }
 
-/* Run one chain over z[begin, end): fresh clock recovery and sink state at `begin`,
- * frames whose SFD-completing chip lies at a position in [body_lo, body_hi) are kept.
+/* Run one chain over z[begin, end): fresh clock recovery at `begin`; the sink stays in its initial (search,
+ * empty register) state until the chain reaches position `hold` (0 = from the start) -- the state the
+ * sequential sink is in right after it finished a frame there.  Frames whose SFD-completing chip lies at a
+ * position in [body_lo, body_hi) are kept.  The chain stops at `end`, or once it has passed its body with
+ * the sink searching (a later sync belongs to the next chain).  *stop_out = max(position where it stopped,
+ * hold): up to there the receiver was busy with a frame of this chain (or an earlier one).
  * chips_out (optional) receives up to chips_cap soft chips, chip_pos_out their positions.
- * Returns the number of frames appended (n_frames in/out counts, stores at most cap). */
-int64_t zb_oracle_chain(const float* z, int64_t begin, int64_t end, int64_t body_lo, int64_t body_hi,
-                        int threshold, int channel, uint32_t segment,
-                        snrx_frame_t* out, int cap, int* n_frames,
-                        float* chips_out, int64_t* chip_pos_out, int64_t chips_cap) {
+ * Returns the number of chips (n_frames in/out counts, stores at most cap). */
+int64_t zb_oracle_chain_hold(const float* z, int64_t begin, int64_t end, int64_t body_lo, int64_t body_hi,
+                             int64_t hold, int threshold, int channel, uint32_t segment,
+                             snrx_frame_t* out, int cap, int* n_frames,
+                             float* chips_out, int64_t* chip_pos_out, int64_t chips_cap, int64_t* stop_out) {
     zb_mm_t mm = {0.5f, 2.0f, 0.0f, begin};
     zb_sink_t sink;
     zb_sink_init(&sink, threshold);
     int64_t nchips = 0;
-    /* stop at the post halo, or once past the body with the sink searching: a later sync belongs to the next chain */
     while (mm.ii + 8 <= end && !(mm.ii >= body_hi && sink.state == 0)) {
         int64_t pos = mm.ii;
         float soft = mm_step(&mm, z);
         if (chips_out && nchips < chips_cap) { chips_out[nchips] = soft; if (chip_pos_out) chip_pos_out[nchips] = pos; }
-        if (zb_sink_push(&sink, soft > 0.0f, nchips, pos)) {
+        if (pos >= hold && zb_sink_push(&sink, soft > 0.0f, nchips, pos)) {
             if (sink.sync_pos >= body_lo && sink.sync_pos < body_hi) {
                 if (*n_frames < cap) {
                     snrx_frame_t* f = &out[*n_frames];
@@ -335,14 +338,41 @@ int64_t zb_oracle_chain(const float* z, int64_t begin, int64_t end, int64_t body
         }
         nchips++;
     }
+    if (stop_out) *stop_out = mm.ii > hold ? mm.ii : hold;
     return nchips;
 }
 
-#define ZB_POST_HALO 16448      /* PHR + 127 bytes = 256 symbols * 64 samples + 64 */
+int64_t zb_oracle_chain(const float* z, int64_t begin, int64_t end, int64_t body_lo, int64_t body_hi,
+                        int threshold, int channel, uint32_t segment,
+                        snrx_frame_t* out, int cap, int* n_frames,
+                        float* chips_out, int64_t* chip_pos_out, int64_t chips_cap) {
+    return zb_oracle_chain_hold(z, begin, end, body_lo, body_hi, 0, threshold, channel, segment, out, cap, n_frames,
+                                chips_out, chip_pos_out, chips_cap, NULL);
+}
 
-/* Whole receive chain over one buffer of channel-rate cf32: DC tracker fresh at sample 0,
- * segments of `segment` samples, each chain starting `prehalo` samples early and running
- * ZB_POST_HALO samples past its body.  Frames are appended in (segment, position) order. */
+#define ZB_POST_HALO 16448      /* PHR + 127 bytes = 256 symbols * 64 samples + 64 */
+#define ZB_SINK_LEAD 1024       /* the sink starts this many samples before the body: SHR (640) + alignment slack */
+
+/* The chains of one stream.  Chain k covers the body [k*segment, (k+1)*segment): its clock recovery starts
+ * `prehalo` samples early (warm-up), its sink ZB_SINK_LEAD samples early (long enough to catch a preamble
+ * that began before the body, short enough that a chain starting inside a foreign frame rarely locks onto
+ * payload chips before its body), and it may run ZB_POST_HALO samples past its body to finish a frame.
+ * Chains are independent, so a time shard reproduces the whole-capture result bit for bit.  Frames are
+ * appended in (segment, position) order. */
+static int zb_chains(const float* z, int64_t n, int channel, int threshold, int64_t segment, int64_t prehalo,
+                     snrx_frame_t* out, int cap) {
+    int nf = 0;
+    uint32_t seg = 0;
+    for (int64_t lo = 0; lo < n; lo += segment, seg++) {
+        const int64_t hi = lo + segment < n ? lo + segment : n;
+        const int64_t begin = lo - prehalo > 0 ? lo - prehalo : 0;
+        const int64_t end = hi + ZB_POST_HALO < n ? hi + ZB_POST_HALO : n;
+        zb_oracle_chain_hold(z, begin, end, lo, hi, lo - ZB_SINK_LEAD, threshold, channel, seg, out, cap, &nf, NULL, NULL, 0, NULL);
+    }
+    return nf;
+}
+
+/* Whole receive chain over one buffer of channel-rate cf32: DC tracker fresh at sample 0, then the chains. */
 int zb_oracle_receive(const float* iq, int64_t n, int channel, int threshold,
                       int64_t segment, int64_t prehalo, snrx_frame_t* out, int cap) {
     float* f = (float*)malloc(sizeof(float) * (size_t)(n + 8));
@@ -350,14 +380,7 @@ int zb_oracle_receive(const float* iq, int64_t n, int channel, int threshold,
     if (!f || !z) { free(f); free(z); return -1; }
     zb_oracle_quad_demod(iq, n, f);
     zb_oracle_dc_remove(f, n, z);
-    int nf = 0;
-    uint32_t seg = 0;
-    for (int64_t lo = 0; lo < n; lo += segment, seg++) {
-        int64_t hi = lo + segment < n ? lo + segment : n;
-        int64_t begin = lo - prehalo > 0 ? lo - prehalo : 0;
-        int64_t end = hi + ZB_POST_HALO < n ? hi + ZB_POST_HALO : n;
-        zb_oracle_chain(z, begin, end, lo, hi, threshold, channel, seg, out, cap, &nf, NULL, NULL, 0);
-    }
+    int nf = zb_chains(z, n, channel, threshold, segment, prehalo, out, cap);
     free(f); free(z);
     return nf;
 }
@@ -365,15 +388,7 @@ int zb_oracle_receive(const float* iq, int64_t n, int channel, int threshold,
 /* same, on an already demodulated + DC-removed stream (used on GPU-produced streams) */
 int zb_oracle_receive_z(const float* z, int64_t n, int channel, int threshold,
                         int64_t segment, int64_t prehalo, snrx_frame_t* out, int cap) {
-    int nf = 0;
-    uint32_t seg = 0;
-    for (int64_t lo = 0; lo < n; lo += segment, seg++) {
-        int64_t hi = lo + segment < n ? lo + segment : n;
-        int64_t begin = lo - prehalo > 0 ? lo - prehalo : 0;
-        int64_t end = hi + ZB_POST_HALO < n ? hi + ZB_POST_HALO : n;
-        zb_oracle_chain(z, begin, end, lo, hi, threshold, channel, seg, out, cap, &nf, NULL, NULL, 0);
-    }
-    return nf;
+    return zb_chains(z, n, channel, threshold, segment, prehalo, out, cap);
 }
 
 double zb_oracle_time(const float* iq, int64_t n, int channel, int64_t segment, int64_t prehalo,

@@ -31,6 +31,8 @@ namespace snrx {
 
 constexpr int kZbPostHalo = 16448;          // PHR + 127 bytes = 256 symbols * 64 samples, + 64
 constexpr int kZbMinFrameSamples = 896;     // 10 SHR + 2 PHR + 2 PSDU symbols of 64 samples
+constexpr int kZbSinkLead = 1024;           // the sink starts this many samples before the body: SHR (640) + alignment
+                                            // slack; the clock recovery starts `prehalo` samples early (warm-up only)
 
 SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) {
     const float ya = fabsf(y), xa = fabsf(x);
@@ -272,6 +274,7 @@ SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const u
     if (hi > body_end) hi = body_end;
     int32_t begin = lo - p.prehalo; if (begin < 0) begin = 0;
     int32_t end = hi + kZbPostHalo; if (end > p.n_out) end = p.n_out;
+    const int32_t sink_from = lo - kZbSinkLead;
     ZbMm mm; mm.mu = 0.5f; mm.omega = 2.0f; mm.last = 0.0f; mm.ii = begin;
     ZbSink sink; zb_sink_init(sink);
     uint8_t psdu[128];
@@ -285,7 +288,7 @@ SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const u
         const float soft = zb_mm_step(mm, in, t);
         if (chips_dbg && nchips < chips_cap) chips_dbg[nchips] = soft;
         nchips++;
-        if (zb_sink_push(sink, soft > 0.0f, pos, map, p.threshold, psdu)) {
+        if (pos >= sink_from && zb_sink_push(sink, soft > 0.0f, pos, map, p.threshold, psdu)) {
             if (sink.sync_pos >= lo && sink.sync_pos < hi) {
                 if (nf < p.slots_per_chain) {
                     snrx_frame_t& f = slots[nf];
