@@ -231,6 +231,8 @@ def main():
     eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps if args.workload in WIDEBAND else 0, device=local,
                    channel=None, max_frames=1 << 18)
 
+    gather = sdist.FrameGather(dev, cap=1 << 15) if world > 1 else None
+
     def barrier():
         if world > 1:
             import torch.distributed as d
@@ -242,21 +244,29 @@ def main():
         the GPU never waits for the host.  Returns (frames of last step, front-end ms list, launches)."""
         front, launches, nfr, done = [], 0, 0, 0
         t0 = time.perf_counter()
+        pend = None
         eng.process(x_dev)
         while True:
             more = (done + 1 < k) or (time.perf_counter() - t0 < min_seconds)
             if more:
                 eng.process(x_dev)
             fr = eng.poll(copy=False)
+            nfr = len(fr)
             if world > 1:
-                fr = sdist.allgather_frames(fr, dev)
+                # the one exchange of the path: this step's records all-gathered over NVLink from the engine's HBM copy,
+                # asynchronously (it overlaps the next step); the previous step's gather is collected here
+                h = gather.start(fr, eng.polled_frames_device()[0])
+                if pend is not None:
+                    nfr = sum(pend.counts())
+                pend = h
             st = eng.stats()
             front.append(st["gpu_ms_frontend"])
             launches += st["kernel_launches"]
-            nfr = len(fr)
             done += 1
             if not more:
                 break
+        if pend is not None:
+            nfr = sum(pend.counts())
         return nfr, front, launches, done
 
     sampler = ClockSampler(local)
@@ -286,6 +296,7 @@ def main():
     #      caller uses (process, process, poll, ...): the H2D copy of batch i+1 overlaps the decode tail of batch i.
     def run_e2e(buf, k):
         d2h, nfr = 0, 0
+        pend = None
         eng.process(buf)
         for i in range(k):
             if i + 1 < k:
@@ -294,7 +305,12 @@ def main():
             d2h += fr.nbytes + 32
             nfr = len(fr)
             if world > 1:
-                sdist.allgather_frames(fr, dev)
+                h = gather.start(fr, eng.polled_frames_device()[0])
+                if pend is not None:
+                    pend.counts()
+                pend = h
+        if pend is not None:
+            pend.counts()
         torch.cuda.synchronize()
         return d2h, nfr
 

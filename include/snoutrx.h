@@ -213,9 +213,14 @@ int  snrx_process_sc8(snrx_t* h, const int8_t* iq, uint32_t n_captures,
 int  snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out);
 int  snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out);
 
-/* Device-visible pointers of the frame list / totals of the most recent snrx_process (the frame
- * list lives in host-mapped pinned memory). */
+/* Device-memory frame list / totals of the most recent snrx_process (valid once that batch has been
+ * polled; the kernels write the list in HBM and k_export_frames copies it to the pinned host buffer). */
 int  snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev);
+
+/* Device-memory copy of the frames of the batch most recently retired by snrx_poll / snrx_poll_view and
+ * their count: the send buffer of the multi-GPU frame all-gather (no host round trip).
+ * Valid until the second-next snrx_process. */
+int  snrx_polled_frames_device(snrx_t* h, const snrx_frame_t** frames_dev, uint32_t* n_out);
 
 int  snrx_set_channel(snrx_t* h, int channel);           /* NB modes */
 int  snrx_set_stream(snrx_t* h, void* cuda_stream);       /* run on a caller stream */

@@ -72,6 +72,7 @@ SYMBOLS = [
     ("snrx_poll", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_poll_view", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
     ("snrx_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
+    ("snrx_polled_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
     ("snrx_set_channel", c_int, [c_void_p, c_int]),
     ("snrx_set_stream", c_int, [c_void_p, c_void_p]),
     ("snrx_sync", c_int, [c_void_p]),

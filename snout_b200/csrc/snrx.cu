@@ -91,6 +91,7 @@ struct snrx_handle {
     // last batch
     bool batch_valid = false;
     int last_lane = 0;
+    int polled_lane = -1;                // lane of the batch most recently retired by snrx_poll / snrx_poll_view
     uint32_t b_caps = 0; uint64_t b_n_in = 0; uint32_t b_n_out = 0;
     snrx_stats_t stats{};
     int launches = 0;
@@ -760,6 +761,7 @@ int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
     if (out) {                                   // copying the frames out consumes the batch
         memcpy(out, sl->frames, sizeof(snrx_frame_t) * (size_t)std::min(cap, sl->n_frames));
         sl->pending = false;
+        h->polled_lane = (int)(sl - h->lane);
         h->seq_poll++;
     }
     return SNRX_OK;
@@ -773,7 +775,16 @@ int snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out) {
     if (frames) *frames = sl->frames;
     if (n_out) *n_out = sl->n_frames;
     sl->pending = false;
+    h->polled_lane = (int)(sl - h->lane);
     h->seq_poll++;
+    return SNRX_OK;
+}
+
+int snrx_polled_frames_device(snrx_t* h, const snrx_frame_t** frames_dev, uint32_t* n_out) {
+    if (!h || h->polled_lane < 0) return SNRX_ESTATE;
+    Lane& sl = h->lane[h->polled_lane];
+    if (frames_dev) *frames_dev = sl.d_frames;
+    if (n_out) *n_out = sl.n_frames;
     return SNRX_OK;
 }
 

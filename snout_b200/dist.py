@@ -113,6 +113,134 @@ def allgather_frames(frames: np.ndarray, device=None) -> np.ndarray:
     return np.concatenate(out) if out else frames[:0]
 
 
+class _DevView:
+    """Raw device memory as a CUDA-array-interface object (uint8 [n])."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class FrameGather:
+    """Pipelined all-gather of the per-step frame records (the one exchange of the path): ONE collective per
+    step on fixed-capacity device buffers, launched asynchronously on a side stream, so that it overlaps the next
+    step's kernels and the host never waits inside the step.  Each rank sends [header | records padded to `cap`];
+    the header carries its count.  The gathered records stay in device memory on every rank; `Pending.counts()`
+    reads back only the headers, `Pending.frames()` the records.  If a rank ever holds more than `cap` records the
+    step falls back to the exact two-phase `allgather_frames` and the capacity grows.
+
+        g = FrameGather(device); h = g.start(frames)   ...next step's work...   all_frames = h.frames()"""
+
+    def __init__(self, device=None, cap: int = 4096, depth: int = 2):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        nccl = dist.is_initialized() and dist.get_backend() == "nccl"
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+        self.device = device
+        self.cuda = device.type == "cuda"
+        self.cap, self.depth, self.slot = int(cap), depth, 0
+        self.stream = torch.cuda.Stream(device) if self.cuda else None
+        self.bufs = []
+        self.src_cache = {}
+        self.fallbacks = 0
+
+    def _alloc(self):
+        t, rec = self.torch, FRAME_DTYPE.itemsize
+        self.bufs = []
+        for _ in range(self.depth):
+            b = {"send": t.zeros((self.cap + 1, rec), dtype=t.uint8, device=self.device),
+                 "recv": t.zeros((self.world, self.cap + 1, rec), dtype=t.uint8, device=self.device),
+                 "host": t.zeros((self.cap + 1, rec), dtype=t.uint8),
+                 "hdr": t.zeros(1, dtype=t.int64), "counts": t.zeros(self.world, dtype=t.int64)}
+            b["send_flat"], b["recv_flat"] = b["send"].view(-1), b["recv"].view(-1)
+            b["send_hdr"] = b["send"][0, :8].view(t.int64)
+            b["recv_hdr"] = b["recv"][:, 0, :8]
+            if self.cuda:
+                for k in ("host", "hdr", "counts"):
+                    b[k] = b[k].pin_memory()
+                b["ev_copy"], b["ev_done"] = t.cuda.Event(), t.cuda.Event()
+            b["counts_u8"] = b["counts"].view(t.uint8).view(self.world, 8)
+            self.bufs.append(b)
+
+    class Pending:
+        def __init__(self, g, frames, work, buf):
+            self.g, self.local, self.work, self.buf = g, frames, work, buf
+            self.cap = g.cap                                   # capacity of the buffers this step was sent in
+            self._counts = None
+
+        def counts(self):
+            """Frames per rank (reads back the headers only)."""
+            if self._counts is None:
+                g = self.g
+                if g.world == 1:
+                    self._counts = [len(self.local)]
+                elif g.cuda:
+                    self.buf["ev_done"].synchronize()          # gather + header read-back were queued a step ago
+                    self._counts = self.buf["counts"].tolist()
+                else:
+                    self.work.wait()
+                    self._counts = self.buf["recv_hdr"].contiguous().view(g.torch.int64).reshape(-1).tolist()
+            return self._counts
+
+        def frames(self):
+            """All ranks' frames concatenated in rank order."""
+            g = self.g
+            if g.world == 1:
+                return self.local
+            c = self.counts()
+            if max(c) > self.cap:                                  # some rank overflowed the fixed buffers (every rank sees
+                g.fallbacks += 1                                   # the same counts): exact two-phase path, larger buffers
+                if 2 * max(c) > g.cap:
+                    g.cap = 2 * max(c)
+                    g.bufs = []
+                return allgather_frames(self.local, g.device)
+            recv = self.buf["recv"]
+            out = [recv[r, 1:1 + c[r]].cpu().numpy().reshape(-1).view(FRAME_DTYPE) for r in range(g.world)]
+            return np.concatenate(out) if out else self.local[:0]
+
+    def start(self, frames: np.ndarray, device_ptr: int = 0) -> "FrameGather.Pending":
+        """Launch the gather of this step's frames.  `device_ptr`: device address of the same records
+        (RxEngine.polled_frames_device()) -- then the send buffer is filled by a device-to-device copy and the
+        records never cross PCIe; otherwise they are staged from host memory.  A Pending must be collected
+        (counts() / frames()) before `depth` further steps have been started."""
+        t = self.torch
+        if self.world == 1:
+            return FrameGather.Pending(self, frames, None, None)
+        n = len(frames)
+        if not self.bufs:
+            self._alloc()
+        b = self.bufs[self.slot]
+        self.slot = (self.slot + 1) % self.depth
+        m = min(n, self.cap)
+        rec = FRAME_DTYPE.itemsize
+        if self.cuda:
+            b["hdr"][0] = n
+            with t.cuda.stream(self.stream):
+                b["send_hdr"].copy_(b["hdr"], non_blocking=True)
+                if m and device_ptr:
+                    src = self.src_cache.get(device_ptr)
+                    if src is None or src.numel() < m * rec:
+                        src = t.as_tensor(_DevView(device_ptr, max(m, self.cap) * rec), device=self.device)
+                        self.src_cache[device_ptr] = src
+                    b["send_flat"][rec:rec + m * rec].copy_(src[: m * rec], non_blocking=True)
+                elif m:
+                    b["host"][1:1 + m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
+                    b["send"][1:1 + m].copy_(b["host"][1:1 + m], non_blocking=True)
+                b["ev_copy"].record(self.stream)
+                self.dist.all_gather_into_tensor(b["recv_flat"], b["send_flat"], async_op=True).wait()   # stream-ordered, host does not block
+                b["counts_u8"].copy_(b["recv_hdr"], non_blocking=True)
+                b["ev_done"].record(self.stream)
+            b["ev_copy"].synchronize()            # the engine may reuse the lane and the staging rows from here on
+            return FrameGather.Pending(self, frames, None, b)
+        b["send_hdr"][0] = n
+        if m:
+            b["send"][1:1 + m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
+        work = self.dist.all_gather_into_tensor(b["recv_flat"], b["send_flat"], async_op=True)
+        return FrameGather.Pending(self, frames, work, b)
+
+
 def sort_reference_order(frames: np.ndarray) -> np.ndarray:
     order = np.lexsort((frames["sample_index"], frames["window"], frames["channel"],
                         255 - frames["proto"].astype(np.int32), frames["capture_id"]))

@@ -100,3 +100,50 @@ def test_plan_job_does_not_depend_on_world():
     assert all(u["pre_samples"] in (0, 40960 * 24) for u in units)
     cover = sorted(i for w in (4,) for r in range(w) for i in sdist.assign_round_robin(len(units), r, w))
     assert cover == list(range(len(units)))
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    sdist.init_from_env(backend="gloo")
+    g = sdist.FrameGather(cap=8)
+
+    def frames_of(r, step):
+        n = [3, 7, 0, 20][(r + step) % 4]                    # ragged, one empty, one beyond the capacity of 8
+        f = np.zeros(n, _abi.FRAME_DTYPE)
+        f["capture_id"], f["sample_index"], f["channel"] = r, np.arange(n) + 1000 * step, step
+        f["bytes"][:, 0] = r + 1
+        return f
+
+    out, pend = [], None
+    for step in range(5):                                    # two steps in flight: start step i, collect step i-1
+        h = g.start(frames_of(rank, step))
+        if pend is not None:
+            out.append((pend.counts(), pend.frames().tobytes()))
+        pend = h
+    out.append((pend.counts(), pend.frames().tobytes()))
+    want = [np.concatenate([frames_of(r, s) for r in range(world)]).tobytes() for s in range(5)]
+    q.put((rank, [o[1] for o in out] == want, [o[0] for o in out], g.fallbacks))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_frame_gather_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, same, counts, fallbacks in res:
+        assert same, rank
+        assert counts[0] == [3, 7] and counts[3] == [20, 3]
+        assert fallbacks >= 1                                 # the 20-frame step went through the exact two-phase path
+    single = sdist.FrameGather()
+    f = np.zeros(2, _abi.FRAME_DTYPE)
+    assert single.start(f).frames() is f and single.start(f).counts() == [2]
