@@ -245,26 +245,31 @@ def main():
         front, launches, nfr, done = [], 0, 0, 0
         t0 = time.perf_counter()
         pend = None
-        eng.process(x_dev)
-        while True:
-            more = (done + 1 < k) or (time.perf_counter() - t0 < min_seconds)
-            if more:
-                eng.process(x_dev)
+        queued = 0
+        for _ in range(min(2, max(k, 1))):
+            eng.process(x_dev)
+            queued += 1
+        while queued:
             fr = eng.poll(copy=False)
+            queued -= 1
+            done += 1
             nfr = len(fr)
+            h = None
             if world > 1:
-                # the one exchange of the path: this step's records all-gathered over NVLink from the engine's HBM copy,
-                # asynchronously (it overlaps the next step); the previous step's gather is collected here
-                h = gather.start(fr, eng.polled_frames_device()[0])
-                if pend is not None:
-                    nfr = sum(pend.counts())
-                pend = h
+                # the one exchange of the path: this step's records leave the engine's HBM frame list by a device-to-device
+                # copy; the lane is free again after it, so the next batch is queued BEFORE the collective is launched
+                h = gather.start(fr, *eng.polled_frames_device()[:2], defer=True)
             st = eng.stats()
+            if (done + queued < k) or (time.perf_counter() - t0 < min_seconds):
+                eng.process(x_dev)
+                queued += 1
+            if h is not None:
+                h.launch()                       # asynchronous NCCL all-gather over NVLink: overlaps the next step
+                if pend is not None:
+                    nfr = sum(pend.counts())     # collect the previous step's gather
+                pend = h
             front.append(st["gpu_ms_frontend"])
             launches += st["kernel_launches"]
-            done += 1
-            if not more:
-                break
         if pend is not None:
             nfr = sum(pend.counts())
         return nfr, front, launches, done
@@ -272,8 +277,26 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # warm-up: at least W steps and at least ~1.5 s under load so that nvidia-smi (100 ms period) sees the clocks
-    frames_per_step, _, _, _ = run_resident(args.warmup, min_seconds=1.5)
+    # warm-up: at least W steps and at least ~1.5 s under load so that nvidia-smi (100 ms period) sees the clocks.
+    # With several ranks the step COUNT must be the same everywhere (every step carries a collective), so the
+    # duration is turned into a count agreed by an all-reduce.
+    def steps_for(seconds, t_step):
+        if world == 1:
+            return 0
+        import torch.distributed as d
+        t = torch.tensor([t_step], device=dev)
+        d.all_reduce(t, op=d.ReduceOp.MAX)
+        return int(min(20000, max(1, seconds / max(float(t.item()), 1e-5))))
+
+    if world == 1:
+        frames_per_step, _, _, _ = run_resident(args.warmup, min_seconds=1.5)
+        t_est = 0.0
+    else:
+        t0 = time.perf_counter()
+        run_resident(args.warmup)
+        torch.cuda.synchronize()
+        t_est = (time.perf_counter() - t0) / args.warmup
+        frames_per_step, _, _, _ = run_resident(steps_for(1.5, t_est))
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -283,7 +306,10 @@ def main():
     assert done == args.steps
     ms = ev0.elapsed_time(ev1)
     # keep the load on for the clock sampler a little longer, then stop it
-    run_resident(3, min_seconds=0.5)
+    if world == 1:
+        run_resident(3, min_seconds=0.5)
+    else:
+        run_resident(steps_for(0.5, t_est))
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         import torch.distributed as d
@@ -295,17 +321,22 @@ def main():
     # ---- end to end: pinned host buffer in, frames out, every step.  Same two-deep software pipeline a streaming
     #      caller uses (process, process, poll, ...): the H2D copy of batch i+1 overlaps the decode tail of batch i.
     def run_e2e(buf, k):
-        d2h, nfr = 0, 0
-        pend = None
-        eng.process(buf)
-        for i in range(k):
-            if i + 1 < k:
-                eng.process(buf)
+        d2h, nfr, pend, queued, done = 0, 0, None, 0, 0
+        for _ in range(min(2, k)):
+            eng.process(buf)
+            queued += 1
+        while queued:
             fr = eng.poll(copy=True)
+            queued -= 1
+            done += 1
             d2h += fr.nbytes + 32
             nfr = len(fr)
-            if world > 1:
-                h = gather.start(fr, eng.polled_frames_device()[0])
+            h = gather.start(fr, *eng.polled_frames_device()[:2], defer=True) if world > 1 else None
+            if done + queued < k:
+                eng.process(buf)
+                queued += 1
+            if h is not None:
+                h.launch()
                 if pend is not None:
                     pend.counts()
                 pend = h

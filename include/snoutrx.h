@@ -217,9 +217,10 @@ int  snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out);
  * polled; the kernels write the list in HBM and k_export_frames copies it to the pinned host buffer). */
 int  snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev);
 
-/* Device-memory copy of the frames of the batch most recently retired by snrx_poll / snrx_poll_view and
- * their count: the send buffer of the multi-GPU frame all-gather (no host round trip).
- * Valid until the second-next snrx_process. */
+/* Device-memory list of the frames of the batch most recently retired by snrx_poll / snrx_poll_view and
+ * their count: the send buffer of the multi-GPU frame all-gather (no host round trip, no copy).
+ * The buffer holds max_frames records (those past the count are unspecified) and stays valid for two
+ * further snrx_process calls: it is overwritten by the third (each of the two lanes alternates between two lists). */
 int  snrx_polled_frames_device(snrx_t* h, const snrx_frame_t** frames_dev, uint32_t* n_out);
 
 int  snrx_set_channel(snrx_t* h, int channel);           /* NB modes */

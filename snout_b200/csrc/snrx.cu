@@ -38,7 +38,9 @@ struct Lane {
     cudaStream_t tail = nullptr;        // everything after it: high priority, so its small latency-bound kernels are
                                         // dispatched ahead of the other lane's queued channelizer tiles
     snrx_frame_t* frames = nullptr;     // pinned + mapped host copy, frame_cap records
-    snrx_frame_t* d_frames = nullptr;   // device copy the kernels write
+    snrx_frame_t* d_frames = nullptr;   // device list the kernels of the current batch write: one of d_frames_buf, alternating,
+    snrx_frame_t* d_frames_buf[2] = {nullptr, nullptr};   // so a polled batch's list stays valid for two further snrx_process calls
+    uint32_t uses = 0;
     uint32_t* totals = nullptr;         // pinned: [0] BLE frames [1] candidates [2] Zigbee frames
     uint32_t* d_totals = nullptr;       // device: same layout
     cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_done = nullptr, ev_in = nullptr;
@@ -92,6 +94,7 @@ struct snrx_handle {
     bool batch_valid = false;
     int last_lane = 0;
     int polled_lane = -1;                // lane of the batch most recently retired by snrx_poll / snrx_poll_view
+    const snrx_frame_t* polled_frames_dev = nullptr;   // its device frame list
     uint32_t b_caps = 0; uint64_t b_n_in = 0; uint32_t b_n_out = 0;
     snrx_stats_t stats{};
     int launches = 0;
@@ -291,7 +294,7 @@ void snrx_destroy(snrx_t* h) {
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& ln : h->lane) {
         void* lb[] = {ln.d_x, ln.d_x8, ln.d_bits, ln.d_hits, ln.d_counts, ln.d_offsets, ln.d_scratch, ln.d_wcounts, ln.d_woffsets,
-                      ln.d_cands, ln.d_decs, ln.d_totals, ln.d_q8, ln.d_cf, ln.d_frames};
+                      ln.d_cands, ln.d_decs, ln.d_totals, ln.d_q8, ln.d_cf, ln.d_frames_buf[0], ln.d_frames_buf[1]};
         for (void* b : lb) if (b) cudaFree(b);
         zb_free(ln.zb);
         if (ln.frames) cudaFreeHost(ln.frames);
@@ -405,7 +408,8 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
             CK(cudaEventCreate(&ln.ev_front));
             CK(cudaEventCreate(&ln.ev_done));
             CK(cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming));
-            CK(cudaMalloc((void**)&ln.d_frames, sizeof(snrx_frame_t) * (size_t)h->frame_cap));
+            for (auto& fb : ln.d_frames_buf) CK(cudaMalloc((void**)&fb, sizeof(snrx_frame_t) * (size_t)h->frame_cap));
+            ln.d_frames = ln.d_frames_buf[0];
             CKD(dev_alloc(h, &ln.d_totals, 8));
             CK(cudaMemset(ln.d_totals, 0, 8 * sizeof(uint32_t)));
             if (h->has_ble) {
@@ -560,6 +564,7 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
     }
     CK(cudaEventRecord(ln.ev_start, st));
     CK(cudaMemsetAsync(ln.d_totals, 0, 8 * sizeof(uint32_t), st));
+    ln.d_frames = ln.d_frames_buf[ln.uses++ & 1];
 
     // ---- input: cf32 device pointer as is; host pointer staged in chunks overlapped with the front end;
     //      sc8 input (host or device) is expanded to cf32 in ln.d_x by k_sc8_to_cf32, chunk by chunk
@@ -762,6 +767,7 @@ int snrx_poll(snrx_t* h, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
         memcpy(out, sl->frames, sizeof(snrx_frame_t) * (size_t)std::min(cap, sl->n_frames));
         sl->pending = false;
         h->polled_lane = (int)(sl - h->lane);
+        h->polled_frames_dev = sl->d_frames;
         h->seq_poll++;
     }
     return SNRX_OK;
@@ -776,15 +782,15 @@ int snrx_poll_view(snrx_t* h, const snrx_frame_t** frames, uint32_t* n_out) {
     if (n_out) *n_out = sl->n_frames;
     sl->pending = false;
     h->polled_lane = (int)(sl - h->lane);
+    h->polled_frames_dev = sl->d_frames;
     h->seq_poll++;
     return SNRX_OK;
 }
 
 int snrx_polled_frames_device(snrx_t* h, const snrx_frame_t** frames_dev, uint32_t* n_out) {
     if (!h || h->polled_lane < 0) return SNRX_ESTATE;
-    Lane& sl = h->lane[h->polled_lane];
-    if (frames_dev) *frames_dev = sl.d_frames;
-    if (n_out) *n_out = sl.n_frames;
+    if (frames_dev) *frames_dev = h->polled_frames_dev;
+    if (n_out) *n_out = h->lane[h->polled_lane].n_frames;
     return SNRX_OK;
 }
 

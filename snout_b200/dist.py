@@ -121,14 +121,18 @@ class _DevView:
 
 
 class FrameGather:
-    """Pipelined all-gather of the per-step frame records (the one exchange of the path): ONE collective per
-    step on fixed-capacity device buffers, launched asynchronously on a side stream, so that it overlaps the next
-    step's kernels and the host never waits inside the step.  Each rank sends [header | records padded to `cap`];
-    the header carries its count.  The gathered records stay in device memory on every rank; `Pending.counts()`
-    reads back only the headers, `Pending.frames()` the records.  If a rank ever holds more than `cap` records the
-    step falls back to the exact two-phase `allgather_frames` and the capacity grows.
+    """Pipelined all-gather of the per-step frame records (the one exchange of the path): a count all-gather and
+    ONE fixed-capacity record all-gather per step, launched asynchronously on a high-priority side stream, so that
+    they overlap the next step's kernels and the host never waits inside the step.  On GPUs the send buffer is the
+    engine's own HBM frame list (RxEngine.polled_frames_device(): no copy, the records never cross PCIe).  The
+    gathered records stay in device memory on every rank; `Pending.counts()` reads back only the counts,
+    `Pending.frames()` the records.  If a rank ever holds more than `cap` records the step falls back to the exact
+    two-phase `allgather_frames` and the capacity grows.
 
-        g = FrameGather(device); h = g.start(frames)   ...next step's work...   all_frames = h.frames()"""
+        g = FrameGather(device); h = g.start(frames, ptr, records)   ...next step...   all_frames = h.frames()
+
+    A Pending must be collected before `depth` further steps have been started (the engine keeps a polled frame
+    list valid for two further process() calls, include/snoutrx.h)."""
 
     def __init__(self, device=None, cap: int = 4096, depth: int = 2):
         import torch
@@ -141,7 +145,8 @@ class FrameGather:
         self.device = device
         self.cuda = device.type == "cuda"
         self.cap, self.depth, self.slot = int(cap), depth, 0
-        self.stream = torch.cuda.Stream(device) if self.cuda else None
+        # high priority: the collective must not queue behind the ~10^5 CTAs of the next step's channelizer
+        self.stream = torch.cuda.Stream(device, priority=-1) if self.cuda else None
         self.bufs = []
         self.src_cache = {}
         self.fallbacks = 0
@@ -150,38 +155,60 @@ class FrameGather:
         t, rec = self.torch, FRAME_DTYPE.itemsize
         self.bufs = []
         for _ in range(self.depth):
-            b = {"send": t.zeros((self.cap + 1, rec), dtype=t.uint8, device=self.device),
-                 "recv": t.zeros((self.world, self.cap + 1, rec), dtype=t.uint8, device=self.device),
-                 "host": t.zeros((self.cap + 1, rec), dtype=t.uint8),
-                 "hdr": t.zeros(1, dtype=t.int64), "counts": t.zeros(self.world, dtype=t.int64)}
+            b = {"send": t.zeros((self.cap, rec), dtype=t.uint8, device=self.device),
+                 "recv": t.zeros((self.world, self.cap, rec), dtype=t.uint8, device=self.device),
+                 "host": t.zeros((self.cap, rec), dtype=t.uint8),
+                 "cnt_host": t.zeros(1, dtype=t.int64), "cnts_host": t.zeros(self.world, dtype=t.int64),
+                 "cnt": t.zeros(1, dtype=t.int64, device=self.device),
+                 "cnts": t.zeros(self.world, dtype=t.int64, device=self.device)}
             b["send_flat"], b["recv_flat"] = b["send"].view(-1), b["recv"].view(-1)
-            b["send_hdr"] = b["send"][0, :8].view(t.int64)
-            b["recv_hdr"] = b["recv"][:, 0, :8]
             if self.cuda:
-                for k in ("host", "hdr", "counts"):
+                for k in ("host", "cnt_host", "cnts_host"):
                     b[k] = b[k].pin_memory()
                 b["ev_copy"], b["ev_done"] = t.cuda.Event(), t.cuda.Event()
-            b["counts_u8"] = b["counts"].view(t.uint8).view(self.world, 8)
             self.bufs.append(b)
 
     class Pending:
-        def __init__(self, g, frames, work, buf):
-            self.g, self.local, self.work, self.buf = g, frames, work, buf
+        def __init__(self, g, frames, buf, src):
+            self.g, self.local, self.buf, self.src = g, frames, buf, src
             self.cap = g.cap                                   # capacity of the buffers this step was sent in
             self._counts = None
+            self.launched = False
+            self.work = None
+
+        def launch(self):
+            """Queue the collectives (and the read-back of the counts) of a deferred start()."""
+            g, b = self.g, self.buf
+            if b is None or self.launched:
+                return self
+            self.launched = True
+            if g.cuda:
+                with g.torch.cuda.stream(g.stream):
+                    b["cnt"].copy_(b["cnt_host"], non_blocking=True)
+                    g.dist.all_gather_into_tensor(b["cnts"], b["cnt"], async_op=True).wait()      # stream-ordered: the host
+                    g.dist.all_gather_into_tensor(b["recv_flat"], self.src, async_op=True).wait()  # does not block
+                    b["cnts_host"].copy_(b["cnts"], non_blocking=True)
+                    b["ev_done"].record(g.stream)
+            else:
+                b["cnt"][0] = len(self.local)
+                self.work = [g.dist.all_gather_into_tensor(b["cnts"], b["cnt"], async_op=True),
+                             g.dist.all_gather_into_tensor(b["recv_flat"], self.src, async_op=True)]
+            return self
 
         def counts(self):
-            """Frames per rank (reads back the headers only)."""
+            """Frames per rank (reads back the counts only)."""
+            self.launch()
             if self._counts is None:
                 g = self.g
                 if g.world == 1:
                     self._counts = [len(self.local)]
                 elif g.cuda:
-                    self.buf["ev_done"].synchronize()          # gather + header read-back were queued a step ago
-                    self._counts = self.buf["counts"].tolist()
+                    self.buf["ev_done"].synchronize()          # the collectives were queued a step ago
+                    self._counts = self.buf["cnts_host"].tolist()
                 else:
-                    self.work.wait()
-                    self._counts = self.buf["recv_hdr"].contiguous().view(g.torch.int64).reshape(-1).tolist()
+                    for w in self.work:
+                        w.wait()
+                    self._counts = self.buf["cnts"].tolist()
             return self._counts
 
         def frames(self):
@@ -197,14 +224,15 @@ class FrameGather:
                     g.bufs = []
                 return allgather_frames(self.local, g.device)
             recv = self.buf["recv"]
-            out = [recv[r, 1:1 + c[r]].cpu().numpy().reshape(-1).view(FRAME_DTYPE) for r in range(g.world)]
+            out = [recv[r, :c[r]].cpu().numpy().reshape(-1).view(FRAME_DTYPE) for r in range(g.world)]
             return np.concatenate(out) if out else self.local[:0]
 
-    def start(self, frames: np.ndarray, device_ptr: int = 0) -> "FrameGather.Pending":
-        """Launch the gather of this step's frames.  `device_ptr`: device address of the same records
-        (RxEngine.polled_frames_device()) -- then the send buffer is filled by a device-to-device copy and the
-        records never cross PCIe; otherwise they are staged from host memory.  A Pending must be collected
-        (counts() / frames()) before `depth` further steps have been started."""
+    def start(self, frames: np.ndarray, device_ptr: int = 0, device_records: int = 0, defer: bool = False) -> "FrameGather.Pending":
+        """Launch the gather of this step's frames.  `device_ptr` / `device_records`: device address and capacity (in
+        records) of a device buffer that starts with the same records (RxEngine.polled_frames_device()); when it holds
+        at least `cap` records it is the send buffer itself.  Otherwise the records are copied device-to-device, or
+        staged from host memory when there is no device copy.  With defer=True the collectives are queued by
+        Pending.launch() -- the caller can queue its next batch first."""
         t = self.torch
         if self.world == 1:
             return FrameGather.Pending(self, frames, None, None)
@@ -215,30 +243,33 @@ class FrameGather:
         self.slot = (self.slot + 1) % self.depth
         m = min(n, self.cap)
         rec = FRAME_DTYPE.itemsize
+        src = b["send_flat"]
         if self.cuda:
-            b["hdr"][0] = n
-            with t.cuda.stream(self.stream):
-                b["send_hdr"].copy_(b["hdr"], non_blocking=True)
-                if m and device_ptr:
-                    src = self.src_cache.get(device_ptr)
-                    if src is None or src.numel() < m * rec:
-                        src = t.as_tensor(_DevView(device_ptr, max(m, self.cap) * rec), device=self.device)
-                        self.src_cache[device_ptr] = src
-                    b["send_flat"][rec:rec + m * rec].copy_(src[: m * rec], non_blocking=True)
-                elif m:
-                    b["host"][1:1 + m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
-                    b["send"][1:1 + m].copy_(b["host"][1:1 + m], non_blocking=True)
-                b["ev_copy"].record(self.stream)
-                self.dist.all_gather_into_tensor(b["recv_flat"], b["send_flat"], async_op=True).wait()   # stream-ordered, host does not block
-                b["counts_u8"].copy_(b["recv_hdr"], non_blocking=True)
-                b["ev_done"].record(self.stream)
-            b["ev_copy"].synchronize()            # the engine may reuse the lane and the staging rows from here on
-            return FrameGather.Pending(self, frames, None, b)
-        b["send_hdr"][0] = n
-        if m:
-            b["send"][1:1 + m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
-        work = self.dist.all_gather_into_tensor(b["recv_flat"], b["send_flat"], async_op=True)
-        return FrameGather.Pending(self, frames, work, b)
+            b["cnt_host"][0] = n
+            dev = None
+            if device_ptr:
+                key = (device_ptr, device_records)
+                dev = self.src_cache.get(key)
+                if dev is None:
+                    dev = t.as_tensor(_DevView(device_ptr, max(device_records, m) * rec), device=self.device)
+                    self.src_cache[key] = dev
+            if dev is not None and device_records >= self.cap:
+                src = dev[: self.cap * rec]                         # zero copy: the engine's frame list is the send buffer
+            elif m:
+                with t.cuda.stream(self.stream):
+                    if dev is not None:
+                        b["send_flat"][: m * rec].copy_(dev[: m * rec], non_blocking=True)
+                    else:
+                        b["host"][:m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
+                        b["send"][:m].copy_(b["host"][:m], non_blocking=True)
+                    b["ev_copy"].record(self.stream)
+                b["ev_copy"].synchronize()        # the engine may reuse the lane and the staging rows from here on
+        elif m:
+            b["send"][:m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
+        p = FrameGather.Pending(self, frames, b, src)
+        if not defer:
+            p.launch()
+        return p
 
 
 def sort_reference_order(frames: np.ndarray) -> np.ndarray:

@@ -192,12 +192,13 @@ class RxEngine:
         self._check(self.lib.snrx_stats(self.handle, byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
-    def polled_frames_device(self) -> tuple[int, int]:
-        """(device address, count) of the frames of the batch most recently returned by poll(): the HBM copy of the
-        list, valid until the second-next process() -- what dist.FrameGather sends over NVLink."""
+    def polled_frames_device(self) -> tuple[int, int, int]:
+        """(device address, capacity in records, count) of the frame list of the batch most recently returned by
+        poll(): the HBM list the kernels wrote, valid for two further process() calls -- what dist.FrameGather
+        sends over NVLink."""
         f, n = c_void_p(), c_uint32(0)
         self._check(self.lib.snrx_polled_frames_device(self.handle, byref(f), byref(n)))
-        return int(f.value or 0), int(n.value)
+        return int(f.value or 0), int(self.cfg.max_frames) or (1 << 17), int(n.value)   # 1 << 17: the library default
 
     def frames_device(self) -> tuple[int, int]:
         f, c = c_void_p(), c_void_p()

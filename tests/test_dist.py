@@ -117,7 +117,8 @@ def _gather_worker(rank, world, port, q):
 
     out, pend = [], None
     for step in range(5):                                    # two steps in flight: start step i, collect step i-1
-        h = g.start(frames_of(rank, step))
+        h = g.start(frames_of(rank, step), defer=(step % 2 == 1))     # deferred: copy now, collective on launch()
+        h.launch()
         if pend is not None:
             out.append((pend.counts(), pend.frames().tobytes()))
         pend = h

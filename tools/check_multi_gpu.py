@@ -29,7 +29,7 @@ def main():
         pend, got = None, []
         for step in range(4):
             fr = eng.process(x).poll(copy=True)
-            h = g.start(fr, eng.polled_frames_device()[0])
+            h = g.start(fr, *eng.polled_frames_device()[:2])
             if pend is not None:
                 got.append(pend.frames())
             pend = h
