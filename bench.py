@@ -159,7 +159,7 @@ def ncu_traffic(n_samples):
                 j = json.load(open(os.path.join(ROOT, "profiles", name)))
                 for l in j["launches"]:
                     if "k_pfb_ble" in l["kernel"] and abs(l["dram_read_bytes"] / (n_samples * 8) - 1) < 0.2:
-                        best = (l["traffic_bytes"], name)
+                        best = (l["traffic_bytes"], name, l.get("pipe_fma_cycles_pct"))
             except Exception:
                 pass
     return best
@@ -408,6 +408,10 @@ def main():
     if tr:
         line["roofline"]["traffic"] = tr[0]
         line["roofline"]["traffic_source"] = f"profiles/{tr[1]} (ncu --set full, dram read+write of one launch)"
+        if tr[2]:
+            line["roofline"]["fp32_fma_pipe_cycles_active_pct"] = tr[2]
+            line["roofline"]["note"] = ("8 B per input sample (one cf32 read). The binding unit is the FP32 FMA pipe: ncu "
+                                        "sm__pipe_fma_cycles_active of the same launch, committed in profiles/; see DESIGN.md 3, 6")
     if world == 1 and not args.no_cpu_baseline:
         sample = base[: min(len(base), 4_800_000)] if args.workload in WIDEBAND else base
         dt, done, frames, cores, kind = cpu_path(args.workload, sample, min_seconds=args.cpu_seconds)

@@ -423,3 +423,38 @@ def test_ble_wb40_batch_of_captures(Engine):
     assert len(want) > 300
     assert_frames_equal(got, want, what="batch of wideband captures")
     assert np.array_equal(got["capture_id"], want["capture_id"])
+
+
+# ------------------------------------------------------------------------------------ BASELINE full sizes (configs[2], [3])
+def _tile_frames(fr, k, tile_ch, lo_guard=0, hi_guard=0):
+    """Frames anchored in tile k (channel-rate tile length tile_ch), positions made tile relative."""
+    s = fr["sample_index"]
+    sel = fr[(s >= k * tile_ch + lo_guard) & (s < (k + 1) * tile_ch - hi_guard)].copy()
+    sel["sample_index"] -= k * tile_ch
+    sel["window"] -= (k * tile_ch) // 8192
+    return sel
+
+
+@pytest.mark.parametrize("mode,kind", [("ble_wb40", "ble"), ("zb_wb16", "zigbee")])
+def test_wideband_full_size_time_invariance(Engine, mode, kind):
+    """The bench workload at BASELINE size (0.98 s of 96 Msps = 94.4 M samples: a seeded 0.1-s capture tiled x10) checked
+    through a size-independent property: the tile length is a multiple of the BLE window / Zigbee segment / DC-block grids
+    and of the channelizer's decimation and rotation periods, so every tile that is preceded by a full tile must decode to
+    exactly the same records, shifted -- equal to the records of tile 1 of a 3-tile run (whose small-size parity against
+    the oracle the stage-wise tests establish).  The last 40 ms of the final tile are excluded (a frame there may run
+    past the capture end)."""
+    base = synth.wideband_capture(seconds=0.1, kind=kind, seed=4000, esn0_db=25.0).iq
+    tile_ch = len(base) // 24
+    assert tile_ch % 8192 == 0
+    with Engine(mode, max_samples=10 * len(base), max_frames=1 << 18) as e:
+        small = e.run(np.tile(base, 3))
+        ref = _tile_frames(small, 1, tile_ch)
+        assert len(ref) > (2000 if kind == "ble" else 100)
+        big = e.run(np.tile(base, 10))
+    assert len(big) > 9 * len(ref)
+    for k in range(1, 10):
+        guard = 160_000 if k == 9 else 0
+        got = _tile_frames(big, k, tile_ch, hi_guard=guard)
+        want = ref[ref["sample_index"] < tile_ch - guard]
+        key = lambda f: np.lexsort((f["sample_index"], f["window"], f["channel"]))   # noqa: E731
+        assert_frames_equal(got[key(got)], want[key(want)], what=f"{mode}: tile {k} of the full-size run vs tile 1 of 3")
