@@ -110,6 +110,11 @@ typedef struct snrx_frame {
  * runs the same segments. */
 #define SNRX_ZB_SEGMENT_DEFAULT 8192
 #define SNRX_ZB_PREHALO_DEFAULT 4096
+/* Span rule (also part of the contract): a CRC-failed 802.15.4 record whose sample_index lies inside the span of an
+ * earlier CRC-ok record of the same (capture, channel) -- (2 + 2 * len) * 64 samples after its sample_index -- is not
+ * reported: the reference's sequential packet sink is busy with that frame (packet_sink_scapy_impl.cc:247-359) and only
+ * a chain restarted inside it can lock onto its payload chips.  Applied inside every batch; a caller that concatenates
+ * time shards applies it once more across the shard boundary (snout_b200/stream.py zb_span_filter). */
 
 typedef struct snrx_config {
     uint32_t abi_version;    /* must be SNRX_ABI_VERSION                                   */

@@ -351,6 +351,25 @@ int64_t zb_oracle_chain(const float* z, int64_t begin, int64_t end, int64_t body
 }
 
 #define ZB_POST_HALO 16448      /* PHR + 127 bytes = 256 symbols * 64 samples + 64 */
+/* While the reference's sequential sink decodes a frame it cannot lock onto anything else.  A chain that starts inside a
+ * foreign frame can (payload chips that look like 0,7,A), so a CRC-failed record whose sync lies inside the span of an
+ * earlier CRC-ok record of the same stream -- PHR (2 symbols) + len bytes (2 symbols each) of 64 samples after the
+ * SFD-completing chip -- is an artefact of restarting the sink per segment and is not reported.  Records of one stream
+ * in position order, compacted in place; returns the number kept. */
+int zb_span_filter(snrx_frame_t* fr, int n) {
+    int64_t good_end = 0;
+    int w = 0;
+    for (int k = 0; k < n; k++) {
+        int keep = 1;
+        if (fr[k].crc_ok) {
+            int64_t e = fr[k].sample_index + (int64_t)(2 + 2 * fr[k].len) * 64;
+            if (e > good_end) good_end = e;
+        } else if (fr[k].sample_index < good_end) keep = 0;
+        if (keep) { if (w != k) fr[w] = fr[k]; w++; }
+    }
+    return w;
+}
+
 #define ZB_SINK_LEAD 1024       /* the sink starts this many samples before the body: SHR (640) + alignment slack */
 
 /* The chains of one stream.  Chain k covers the body [k*segment, (k+1)*segment): its clock recovery starts
@@ -369,6 +388,7 @@ static int zb_chains(const float* z, int64_t n, int channel, int threshold, int6
         const int64_t end = hi + ZB_POST_HALO < n ? hi + ZB_POST_HALO : n;
         zb_oracle_chain_hold(z, begin, end, lo, hi, lo - ZB_SINK_LEAD, threshold, channel, seg, out, cap, &nf, NULL, NULL, 0, NULL);
     }
+    if (out && nf <= cap) nf = zb_span_filter(out, nf);
     return nf;
 }
 

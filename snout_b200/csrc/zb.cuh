@@ -246,6 +246,12 @@ struct ZbDirectSrc {
     }
 };
 
+// Samples a frame occupies after its SFD-completing chip: PHR (2 symbols) + len bytes (2 symbols each), 64 samples per symbol.
+// While the reference's sequential sink decodes such a frame it cannot lock onto anything else, so a CRC-failed record whose
+// sync lies inside the span of an earlier CRC-ok record of the same stream is an artefact of restarting the sink per segment
+// and is not reported (k_zb_span_filter here, zb_span_filter in oracle/zb_oracle.c, stream.zb_span_filter across shards).
+SNRX_HD int64_t zb_frame_end(int64_t sample_index, int len) { return sample_index + (int64_t)(2 + 2 * len) * 64; }
+
 struct ZbChainParams {
     int32_t n_out;            // channel-rate samples per capture in the buffer
     int32_t origin;           // local index where segment `first_segment` starts (pre halo length)
@@ -266,7 +272,8 @@ struct ZbChainParams {
 template <class Src>
 SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const uint32_t* map,
                               int channel_number, uint32_t capture_id, snrx_frame_t* slots, float* chips_dbg,
-                              int64_t chips_cap, int64_t* nchips_out) {
+                              int64_t chips_cap, int64_t* nchips_out, int64_t* good_end_out = nullptr) {
+    int64_t good_end = 0;            // end (whole-capture index) of the last CRC-ok frame this chain reports
     // all positions are < n_out + segment + post halo < 2^31 (zb_create bounds max_out)
     const int32_t lo = p.origin + seg * p.segment;
     int32_t hi = lo + p.segment;
@@ -308,14 +315,31 @@ SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const u
                         f.crc_ok = (uint8_t)(c == (uint16_t)(psdu[sink.got - 2] | (psdu[sink.got - 1] << 8)));
                     }
                     for (int i = 0; i < 132; i++) f.bytes[i] = (i < sink.got) ? psdu[i] : 0;
+                    if (f.crc_ok) { const int64_t e = zb_frame_end(f.sample_index, sink.got); if (e > good_end) good_end = e; }
                 }
                 nf++;
             }
         }
     }
     if (nchips_out) *nchips_out = nchips;
+    if (good_end_out) *good_end_out = good_end;
     return nf;
 }
+
+// Filter of one chain's records given the ends of the CRC-ok frames of the `lookback` preceding chains of its stream.
+// Records are compacted in place; returns the number kept.
+SNRX_HD uint32_t zb_filter_chain(snrx_frame_t* slots, uint32_t n, int64_t good_end) {
+    uint32_t w = 0;
+    for (uint32_t k = 0; k < n; k++) {
+        const snrx_frame_t& f = slots[k];
+        bool keep = true;
+        if (f.crc_ok) { const int64_t e = zb_frame_end(f.sample_index, f.len); if (e > good_end) good_end = e; }
+        else if (f.sample_index < good_end) keep = false;
+        if (keep) { if (w != k) slots[w] = slots[k]; w++; }
+    }
+    return w;
+}
+SNRX_HD int zb_filter_lookback(int segment) { return (16384 + segment - 1) / segment + 1; }
 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------ kernels
@@ -519,6 +543,7 @@ __global__ void __launch_bounds__(kZbChainThreads) k_zb_chain(const float* __res
                                                  const float* __restrict__ taps_g, ChipMap map_arg,
                                                  const int32_t* __restrict__ channel_numbers,
                                                  snrx_frame_t* __restrict__ slots, uint32_t* __restrict__ counts,
+                                                 int64_t* __restrict__ good_end,
                                                  float* chips_dbg, int64_t chips_cap_per_chain, int64_t* nchips_dbg) {
     __shared__ __align__(16) float taps[(SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS];
     __shared__ float ring[(kZbChainThreads / 32) * (kZbRing + 8) * 32];
@@ -549,10 +574,25 @@ __global__ void __launch_bounds__(kZbChainThreads) k_zb_chain(const float* __res
     const uint32_t nf = zb_run_chain(src, p, (int)seg, map, channel_numbers[ch], p.first_capture + cap,
                                      slots + (size_t)chain * p.slots_per_chain,
                                      chips_dbg ? chips_dbg + (size_t)chain * chips_cap_per_chain : nullptr,
-                                     chips_cap_per_chain, &nchips);
+                                     chips_cap_per_chain, &nchips, good_end + chain);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     counts[chain] = nf < p.slots_per_chain ? nf : p.slots_per_chain;
     if (nchips_dbg) nchips_dbg[chain] = nchips;
+}
+
+// one thread per chain: drop the CRC-failed records that lie inside a CRC-ok frame of this or a preceding chain
+__global__ void __launch_bounds__(128) k_zb_span_filter(snrx_frame_t* __restrict__ slots, uint32_t slots_per_chain,
+                                                        uint32_t* __restrict__ counts, const int64_t* __restrict__ good_end,
+                                                        uint32_t n_chains, uint32_t n_segments, int lookback) {
+    const uint32_t chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= n_chains) return;
+    const uint32_t n = counts[chain];
+    if (n == 0) return;
+    const uint32_t seg = chain % n_segments;
+    int64_t ge = 0;
+    for (int j = 1; j <= lookback && (uint32_t)j <= seg; j++) { const int64_t e = good_end[chain - j]; if (e > ge) ge = e; }
+    const uint32_t w = zb_filter_chain(slots + (size_t)chain * slots_per_chain, n, ge);
+    if (w != n) counts[chain] = w;
 }
 
 __global__ void __launch_bounds__(128) k_zb_gather(const snrx_frame_t* __restrict__ slots, uint32_t slots_per_chain,
@@ -586,6 +626,7 @@ struct ZbState {
     int32_t* d_channels = nullptr;
     snrx_frame_t* d_slots = nullptr; size_t slots_bytes = 0;
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
+    int64_t* d_good_end = nullptr;
     uint32_t max_chains = 0, slots_per_chain = 0;
     float* d_chips = nullptr; int64_t* d_nchips = nullptr; int64_t chips_cap = 0;
     float *d_wb_taps_rho = nullptr, *d_wb_taps_flat = nullptr, *d_wb_taps_pass = nullptr; float2* d_wb_cf = nullptr; int wb_nt = 16;
@@ -596,7 +637,7 @@ struct ZbState {
 
 inline void zb_free(ZbState& s) {
     void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_pw, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
-                    s.d_counts, s.d_offsets, s.d_scratch, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
+                    s.d_counts, s.d_offsets, s.d_scratch, s.d_good_end, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     s = ZbState();
 }
@@ -644,6 +685,7 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     ZCK(cudaMalloc((void**)&s.d_counts, sizeof(uint32_t) * ((size_t)s.max_chains + 1)));
     ZCK(cudaMalloc((void**)&s.d_offsets, sizeof(uint32_t) * ((size_t)s.max_chains + 1)));
     ZCK(cudaMalloc((void**)&s.d_scratch, sizeof(uint32_t) * scan_scratch_items(s.max_chains)));
+    ZCK(cudaMalloc((void**)&s.d_good_end, sizeof(int64_t) * ((size_t)s.max_chains + 1)));
     if (cfg.flags & SNRX_F_KEEP_STREAMS) {
         s.chips_cap = ((int64_t)cfg.zb_segment + cfg.zb_prehalo + kZbPostHalo) / 2 + 64;
         ZCK(cudaMalloc((void**)&s.d_chips, sizeof(float) * (size_t)s.max_chains * (size_t)s.chips_cap));
@@ -697,8 +739,10 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     const uint32_t n_chains = streams * (uint32_t)p.n_segments;
     if (n_chains > s.max_chains) { err = "zigbee: more chains than capacity"; return SNRX_ERANGE; }
     k_zb_chain<<<(n_chains + kZbChainThreads - 1) / kZbChainThreads, kZbChainThreads, 0, st>>>(s.d_z, p, s.d_mmse, s.map, s.d_channels, s.d_slots, s.d_counts,
-                                                  s.d_chips, s.chips_cap, s.d_nchips);
-    launches += 1 + exclusive_scan(s.d_counts, n_chains, s.d_offsets, s.d_scratch, st);
+                                                  s.d_good_end, s.d_chips, s.chips_cap, s.d_nchips);
+    k_zb_span_filter<<<(n_chains + 127) / 128, 128, 0, st>>>(s.d_slots, s.slots_per_chain, s.d_counts, s.d_good_end, n_chains,
+                                                             (uint32_t)p.n_segments, zb_filter_lookback(p.segment));
+    launches += 2 + exclusive_scan(s.d_counts, n_chains, s.d_offsets, s.d_scratch, st);
     k_zb_gather<<<std::max(1u, std::min<uint32_t>((n_chains + 3) / 4, (uint32_t)sm_count * 8)), 128, 0, st>>>(
         s.d_slots, s.slots_per_chain, s.d_counts, s.d_offsets, n_chains, frames, frame_cap, totals, after_ble ? 1 : 0);
     launches++;

@@ -85,7 +85,8 @@ def run_job(engine, captures, units, rank: int = 0, world: int = 1, gather: bool
     frames = np.concatenate(out) if out else np.zeros(0, dtype=FRAME_DTYPE)
     if gather and world > 1:
         frames = allgather_frames(frames, device)
-    return sort_reference_order(frames)
+    from . import stream
+    return stream.zb_span_filter(sort_reference_order(frames))      # the span rule across shard (and rank) boundaries
 
 
 def allgather_frames(frames: np.ndarray, device=None) -> np.ndarray:

@@ -61,6 +61,34 @@ def plan_shards(n_samples: int, decim: int, unit: int, pre: int, post: int, unit
     return out
 
 
+def zb_span_filter(frames: np.ndarray, state: dict | None = None) -> np.ndarray:
+    """The 802.15.4 span rule across shard boundaries (include/snoutrx.h, csrc/zb.cuh k_zb_span_filter): a CRC-failed
+    record whose sync lies inside the span of an earlier CRC-ok record of the same (capture, channel) stream is dropped.
+    The engine applies the rule inside a batch; the CRC-ok frame that covers the first records of a time shard was
+    reported by the previous shard, so whoever concatenates shards applies it once more.  `frames`: records in stream
+    order per (capture, channel) (any interleaving of streams); `state` carries the end of the last CRC-ok frame of
+    every stream from call to call (streaming).  Idempotent; BLE records pass through."""
+    if len(frames) == 0:
+        return frames
+    zb = frames["proto"] == 2
+    if not zb.any():
+        return frames
+    keep = np.ones(len(frames), dtype=bool)
+    key = frames["capture_id"].astype(np.int64) * 65536 + frames["channel"].astype(np.int64)
+    ends = frames["sample_index"] + (2 + 2 * frames["len"].astype(np.int64)) * 64
+    for k in np.unique(key[zb]):
+        idx = np.nonzero(zb & (key == k))[0]
+        s = frames["sample_index"][idx]
+        ok = frames["crc_ok"][idx] == 1
+        e = np.where(ok, ends[idx], 0)
+        prev = state.get(int(k), 0) if state is not None else 0
+        before = np.maximum.accumulate(np.concatenate(([prev], e)))[:-1]      # end of the CRC-ok frames seen so far
+        keep[idx] = ok | (s >= before)
+        if state is not None:
+            state[int(k)] = int(max(prev, e.max()))
+    return frames if keep.all() else frames[keep]
+
+
 class ShardStreamer:
     """Push IQ blocks in, get frame arrays out, in stream order.
 
@@ -89,6 +117,11 @@ class ShardStreamer:
         self.body_start = 0              # channel-rate index of the body of the shard being filled
         self.in_flight = 0
         self.total_in = 0
+        self._zb_state = {}              # zb_span_filter state: the shards of a stream come back in order
+
+    def _poll(self) -> np.ndarray:
+        fr = self.eng.poll()
+        return zb_span_filter(fr, self._zb_state) if self.eng.n_zb else fr
 
     # absolute input-rate index of the first sample of the slot being filled
     def _lo(self) -> int:
@@ -132,11 +165,11 @@ class ShardStreamer:
             off += take
             if self.fill == self._target():
                 if self.in_flight == 2:              # the slot we are about to seed belongs to the oldest batch
-                    yield self.eng.poll()
+                    yield self._poll()
                     self.in_flight -= 1
                 self._launch(last=False)
                 if self.in_flight == 2:
-                    yield self.eng.poll()
+                    yield self._poll()
                     self.in_flight -= 1
                 self._advance()
 
@@ -145,11 +178,11 @@ class ShardStreamer:
         n_eff = self.fill - self.fill % self.decim
         if n_eff > self.body_start * self.decim - self._lo():          # anything past the pre halo
             if self.in_flight == 2:
-                yield self.eng.poll()
+                yield self._poll()
                 self.in_flight -= 1
             self._launch(last=True)
         while self.in_flight:
-            yield self.eng.poll()
+            yield self._poll()
             self.in_flight -= 1
         self.fill = 0
 

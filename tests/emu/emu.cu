@@ -294,12 +294,24 @@ int emu_zb_chains(const float* z, int n_out, int origin, int body, int segment, 
     p.n_captures = 1; p.n_channels = 1; p.threshold = threshold; p.slots_per_chain = segment / kZbMinFrameSamples + 2;
     p.z_stride = 0;
     ChipMap map = make_chip_map();
-    std::vector<snrx_frame_t> slots(p.slots_per_chain);
-    int n = 0;
+    // k_zb_chain: every chain into its own slots + the end of its CRC-ok frames
+    std::vector<snrx_frame_t> slots((size_t)p.slots_per_chain * p.n_segments);
+    std::vector<uint32_t> counts(p.n_segments);
+    std::vector<int64_t> good_end(p.n_segments);
     for (int seg = 0; seg < p.n_segments; seg++) {
         ZbDirectSrc src{z, &SNRX_MMSE_TAPS[0][0]};
-        uint32_t nf = zb_run_chain(src, p, seg, map.w, channel, 0, slots.data(), nullptr, 0, nullptr);
-        for (uint32_t k = 0; k < nf && k < p.slots_per_chain; k++) { if (n < cap) out[n] = slots[k]; n++; }
+        uint32_t nf = zb_run_chain(src, p, seg, map.w, channel, 0, slots.data() + (size_t)seg * p.slots_per_chain, nullptr, 0, nullptr,
+                                   &good_end[seg]);
+        counts[seg] = nf < p.slots_per_chain ? nf : p.slots_per_chain;
+    }
+    // k_zb_span_filter (one thread per chain), then k_zb_gather
+    const int lookback = zb_filter_lookback(segment);
+    int n = 0;
+    for (int seg = 0; seg < p.n_segments; seg++) {
+        int64_t ge = 0;
+        for (int j = 1; j <= lookback && j <= seg; j++) ge = std::max(ge, good_end[seg - j]);
+        const uint32_t w = zb_filter_chain(slots.data() + (size_t)seg * p.slots_per_chain, counts[seg], ge);
+        for (uint32_t k = 0; k < w; k++) { if (n < cap) out[n] = slots[(size_t)seg * p.slots_per_chain + k]; n++; }
     }
     return n;
 }

@@ -309,7 +309,8 @@ def test_zb_nb_shards_equal_whole(Engine, oracle_mod):
         with pytest.raises(_abi.SnrxError):          # pre halo too short for the tracker memory: refused
             e.run(x[65536 - 4096:].copy(), shard=dict(pre_samples=4096, body_samples=0, first_window=8))
     assert len(whole) > 40
-    assert_frames_equal(np.concatenate(parts), whole, what="zigbee: 3 time shards vs whole")
+    from snout_b200 import stream
+    assert_frames_equal(stream.zb_span_filter(np.concatenate(parts)), whole, what="zigbee: 3 time shards vs whole")
     assert_frames_equal(whole, oracle_mod.zb_receive(x, 17), what="whole vs oracle")
 
 
@@ -323,29 +324,27 @@ def test_zb_wb16_shards_equal_whole(Engine):
         for lo, hi, sh in _zb_shards(n_ch, 16384, [0, 4, 9, 13]):
             sh = {k: (v * 24 if k != "first_window" else v) for k, v in sh.items()}
             parts.append(e.run(x[lo * 24: hi * 24].copy(), shard=sh))
+    from snout_b200 import stream
     got = np.concatenate(parts)
     order = np.lexsort((got["sample_index"], got["window"], got["channel"]))
     assert len(whole) > 60
-    assert_frames_equal(got[order], whole, what="zigbee wideband: 3 time shards vs whole")
+    assert_frames_equal(stream.zb_span_filter(got[order]), whole, what="zigbee wideband: 3 time shards vs whole")
 
 
 def test_zb_nb_full_size_config2(Engine, oracle_mod):
-    """BASELINE config 2: 1e7 samples of channel 11.  With 64K-sample chain segments the decoded frames are exactly
-    the transmitted ones; with the default 8K segments every transmitted frame is recovered and the only extras are
-    CRC-failed syncs of chains that start inside a foreign frame -- both bit-exact with the oracle."""
+    """BASELINE config 2: 1e7 samples of channel 11.  At both segment sizes the decoded frames are exactly the transmitted
+    ones (what an unsegmented sequential receiver reports): the span rule removes the CRC-failed syncs of chains that
+    start inside a foreign frame."""
     cap = synth.zigbee_capture(n=10_000_000, channel=11, seed=2001, esn0_db=30.0)
     truth = [bytes(t.data) for t in cap.truth]
-    with Engine("zb_nb", channel=11, max_samples=10_000_000, zb_segment=65536) as e:
-        got = e.run(cap.iq)
-    assert_frames_equal(got, oracle_mod.zb_receive(cap.iq, 11, segment=65536), what="config 2, 64K segments")
-    assert [bytes(f["bytes"][:f["len"]]) for f in got] == truth
-    assert got["crc_ok"].all()
-    with Engine("zb_nb", channel=11, max_samples=10_000_000) as e:
-        got = e.run(cap.iq)
-    assert_frames_equal(got, oracle_mod.zb_receive(cap.iq, 11), what="config 2, default segments")
-    good = got[got["crc_ok"] == 1]
-    assert [bytes(f["bytes"][:f["len"]]) for f in good] == truth
-    assert len(got) - len(good) <= 5
+    unsegmented = oracle_mod.zb_receive(cap.iq, 11, segment=1 << 40)
+    for seg in (65536, 0):
+        with Engine("zb_nb", channel=11, max_samples=10_000_000, zb_segment=seg) as e:
+            got = e.run(cap.iq)
+        assert_frames_equal(got, oracle_mod.zb_receive(cap.iq, 11, segment=seg or _abi.ZB_SEGMENT_DEFAULT), what=f"config 2, segment {seg}")
+        assert [bytes(f["bytes"][:f["len"]]) for f in got] == truth
+        assert got["crc_ok"].all()
+        assert np.array_equal(got["bytes"], unsegmented["bytes"]) and np.array_equal(got["lqi"], unsegmented["lqi"])
 
 
 # ------------------------------------------------------------------------------------ Zigbee wideband / mixed
