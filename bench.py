@@ -153,8 +153,12 @@ def ncu_traffic(n_samples):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_pfb_ble launch from the committed ncu --set full
     summary (profiles/), valid when it was captured on this same workload size; else None."""
     best = None
-    for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
-        if name.startswith("r") and "_pfb_ncu" in name and name.endswith(".json"):
+    import re
+    def version(name):                   # r01_pfb_ncu_v10.json -> (1, 10): newest capture last
+        m = re.match(r"r(\d+)_pfb_ncu_v(\d+)\.json$", name)
+        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), key=version):
+        if version(name)[0] >= 0:
             try:
                 j = json.load(open(os.path.join(ROOT, "profiles", name)))
                 for l in j["launches"]:
