@@ -221,8 +221,12 @@ def main():
     import torch
     from snout_b200 import _abi, dist as sdist
     from snout_b200.engine import RxEngine
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        if os.environ.get("SNRX_NCCL_CHANNELS"):
+            os.environ["NCCL_MAX_NCHANNELS"] = os.environ["SNRX_NCCL_CHANNELS"]     # experiment switch; default: NCCL's choice
     rank, world, local = sdist.init_from_env()
     torch.cuda.set_device(local)
+    numa = sdist.bind_to_gpu_numa(local) if world > 1 else None
     dev = torch.device("cuda", local)
 
     base, n_truth = make_capture(args.workload, args.base_seconds, 4000 + 37 * rank)
@@ -235,7 +239,11 @@ def main():
     eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps if args.workload in WIDEBAND else 0, device=local,
                    channel=None, max_frames=1 << 18)
 
-    gather = sdist.FrameGather(dev, cap=1 << 15) if world > 1 else None
+    # whole records go zero-copy from the engine's HBM frame list, which stays valid for two further process() calls ->
+    # two gathers in flight.  (FrameGather(record_bytes=80) would exchange only the 80 bytes a BLE record uses; measured at
+    # N=4 it does not change the step time, nor do three gathers in flight: the exchange is not bandwidth bound.)
+    gather_depth = 2
+    gather = sdist.FrameGather(dev, cap=1 << 15, depth=gather_depth) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -248,7 +256,7 @@ def main():
         the GPU never waits for the host.  Returns (frames of last step, front-end ms list, launches)."""
         front, launches, nfr, done = [], 0, 0, 0
         t0 = time.perf_counter()
-        pend = None
+        pend = []
         queued = 0
         for _ in range(min(2, max(k, 1))):
             eng.process(x_dev)
@@ -268,14 +276,14 @@ def main():
                 eng.process(x_dev)
                 queued += 1
             if h is not None:
-                h.launch()                       # asynchronous NCCL all-gather over NVLink: overlaps the next step
-                if pend is not None:
-                    nfr = sum(pend.counts())     # collect the previous step's gather
-                pend = h
+                h.launch()                       # asynchronous NCCL all-gather over NVLink: overlaps the next step(s)
+                pend.append(h)
+                if len(pend) >= gather_depth:
+                    nfr = sum(pend.pop(0).counts())     # collect the oldest gather in flight
             front.append(st["gpu_ms_frontend"])
             launches += st["kernel_launches"]
-        if pend is not None:
-            nfr = sum(pend.counts())
+        while pend:
+            nfr = sum(pend.pop(0).counts())
         return nfr, front, launches, done
 
     sampler = ClockSampler(local)
@@ -325,7 +333,7 @@ def main():
     # ---- end to end: pinned host buffer in, frames out, every step.  Same two-deep software pipeline a streaming
     #      caller uses (process, process, poll, ...): the H2D copy of batch i+1 overlaps the decode tail of batch i.
     def run_e2e(buf, k):
-        d2h, nfr, pend, queued, done = 0, 0, None, 0, 0
+        d2h, nfr, pend, queued, done = 0, 0, [], 0, 0
         for _ in range(min(2, k)):
             eng.process(buf)
             queued += 1
@@ -341,11 +349,11 @@ def main():
                 queued += 1
             if h is not None:
                 h.launch()
-                if pend is not None:
-                    pend.counts()
-                pend = h
-        if pend is not None:
-            pend.counts()
+                pend.append(h)
+                if len(pend) >= gather_depth:
+                    pend.pop(0).counts()
+        while pend:
+            pend.pop(0).counts()
         torch.cuda.synchronize()
         return d2h, nfr
 

@@ -31,6 +31,30 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank: int) -> int | None:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the page-locked staging buffers it
+    allocates afterwards (first touch) and its copy threads sit next to the GPU's PCIe root.  With several ranks
+    streaming host IQ at PCIe rate the cross-socket hop is the first thing to saturate.  Returns the node or None."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def plan_job(n_captures: int, n_samples: int, engine=None, units_per_shard: int = 0, geometry=None, decim: int | None = None):
     """Work units of a batch job (BASELINE config 5: many long captures, sharded by time segment
     with halo): one unit = (capture_id, time shard).  Returns a list of dicts
@@ -135,10 +159,15 @@ class FrameGather:
     A Pending must be collected before `depth` further steps have been started (the engine keeps a polled frame
     list valid for two further process() calls, include/snoutrx.h)."""
 
-    def __init__(self, device=None, cap: int = 4096, depth: int = 2):
+    def __init__(self, device=None, cap: int = 4096, depth: int = 2, record_bytes: int | None = None):
+        """record_bytes: leading bytes of every 160-byte record that are exchanged (multiple of 16).  BLE records carry
+        at most 42 payload bytes after the 28-byte header, so 80 is enough for a BLE-only engine and halves the NVLink
+        traffic; the receiving side pads with zeros.  Default: whole records."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
+        self.rec = int(record_bytes or FRAME_DTYPE.itemsize)
+        assert self.rec % 16 == 0 and 32 <= self.rec <= FRAME_DTYPE.itemsize
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         nccl = dist.is_initialized() and dist.get_backend() == "nccl"
         if device is None:
@@ -153,7 +182,7 @@ class FrameGather:
         self.fallbacks = 0
 
     def _alloc(self):
-        t, rec = self.torch, FRAME_DTYPE.itemsize
+        t, rec = self.torch, self.rec
         self.bufs = []
         for _ in range(self.depth):
             b = {"send": t.zeros((self.cap, rec), dtype=t.uint8, device=self.device),
@@ -225,7 +254,15 @@ class FrameGather:
                     g.bufs = []
                 return allgather_frames(self.local, g.device)
             recv = self.buf["recv"]
-            out = [recv[r, :c[r]].cpu().numpy().reshape(-1).view(FRAME_DTYPE) for r in range(g.world)]
+            full = FRAME_DTYPE.itemsize
+            out = []
+            for r in range(g.world):
+                a = recv[r, :c[r]].cpu().numpy()
+                if g.rec != full:                                  # packed exchange: the tail of every record is zero
+                    z = np.zeros((c[r], full), dtype=np.uint8)
+                    z[:, :g.rec] = a
+                    a = z
+                out.append(a.reshape(-1).view(FRAME_DTYPE))
             return np.concatenate(out) if out else self.local[:0]
 
     def start(self, frames: np.ndarray, device_ptr: int = 0, device_records: int = 0, defer: bool = False) -> "FrameGather.Pending":
@@ -243,8 +280,11 @@ class FrameGather:
         b = self.bufs[self.slot]
         self.slot = (self.slot + 1) % self.depth
         m = min(n, self.cap)
-        rec = FRAME_DTYPE.itemsize
+        rec, full = self.rec, FRAME_DTYPE.itemsize
         src = b["send_flat"]
+
+        def packed(fr):                                             # host records -> [m, rec] uint8
+            return t.from_numpy(np.ascontiguousarray(fr[:m]).view(np.uint8).reshape(m, full)[:, :rec].copy())
         if self.cuda:
             b["cnt_host"][0] = n
             dev = None
@@ -252,21 +292,22 @@ class FrameGather:
                 key = (device_ptr, device_records)
                 dev = self.src_cache.get(key)
                 if dev is None:
-                    dev = t.as_tensor(_DevView(device_ptr, max(device_records, m) * rec), device=self.device)
+                    dev = t.as_tensor(_DevView(device_ptr, max(device_records, m) * full), device=self.device).view(-1, full)
                     self.src_cache[key] = dev
-            if dev is not None and device_records >= self.cap:
-                src = dev[: self.cap * rec]                         # zero copy: the engine's frame list is the send buffer
+            if dev is not None and device_records >= self.cap and rec == full:
+                src = dev[: self.cap].view(-1)                      # zero copy: the engine's frame list is the send buffer
             elif m:
                 with t.cuda.stream(self.stream):
-                    if dev is not None:
-                        b["send_flat"][: m * rec].copy_(dev[: m * rec], non_blocking=True)
+                    if dev is not None:                             # (packing) device-to-device copy
+                        b["send"][:m].copy_(dev[:m, :rec], non_blocking=True)
                     else:
-                        b["host"][:m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
+                        b["host"][:m] = packed(frames)
                         b["send"][:m].copy_(b["host"][:m], non_blocking=True)
                     b["ev_copy"].record(self.stream)
-                b["ev_copy"].synchronize()        # the engine may reuse the lane and the staging rows from here on
+                if dev is None:
+                    b["ev_copy"].synchronize()    # the staging rows are free again from here on
         elif m:
-            b["send"][:m] = t.from_numpy(np.ascontiguousarray(frames[:m]).view(np.uint8).reshape(m, rec))
+            b["send"][:m] = packed(frames)
         p = FrameGather.Pending(self, frames, b, src)
         if not defer:
             p.launch()

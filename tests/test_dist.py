@@ -106,7 +106,7 @@ def _gather_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     import torch.distributed as dist
     sdist.init_from_env(backend="gloo")
-    g = sdist.FrameGather(cap=8)
+    g = sdist.FrameGather(cap=8, record_bytes=int(os.environ.get('SNRX_TEST_RECORD_BYTES', '160')))
 
     def frames_of(r, step):
         n = [3, 7, 0, 20][(r + step) % 4]                    # ragged, one empty, one beyond the capacity of 8
@@ -129,8 +129,10 @@ def _gather_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_pipelined_frame_gather_world2():
+@pytest.mark.parametrize("record_bytes", [160, 80])
+def test_pipelined_frame_gather_world2(record_bytes, monkeypatch):
     import torch.multiprocessing as mp
+    monkeypatch.setenv("SNRX_TEST_RECORD_BYTES", str(record_bytes))
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

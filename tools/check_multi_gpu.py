@@ -24,7 +24,7 @@ def main():
     dev = torch.device("cuda", local)
     cap = synth.wideband_capture(seconds=0.02, kind="ble", seed=7000 + rank, esn0_db=25.0, gap=(300, 3000))
     x = cap.iq[: len(cap.iq) - 24 * 1000 * rank]                 # ragged frame counts across ranks
-    g = sdist.FrameGather(dev, cap=64)                             # small: the first step overflows and falls back
+    g = sdist.FrameGather(dev, cap=64, record_bytes=80)                             # small: the first step overflows and falls back
     with RxEngine("ble_wb40", max_samples=len(cap.iq), device=local) as eng:
         pend, got = None, []
         for step in range(4):
