@@ -266,18 +266,16 @@ def main():
             queued -= 1
             done += 1
             nfr = len(fr)
-            h = None
-            if world > 1:
-                # the one exchange of the path: this step's records leave the engine's HBM frame list by a device-to-device
-                # copy; the lane is free again after it, so the next batch is queued BEFORE the collective is launched
-                h = gather.start(fr, *eng.polled_frames_device()[:2], defer=True)
-            st = eng.stats()
+            # queue the next batch FIRST: everything below is host bookkeeping that must not delay the GPU.  (The polled
+            # batch's frame list and stats stay valid: each lane alternates two lists, include/snoutrx.h.)
             if (done + queued < k) or (time.perf_counter() - t0 < min_seconds):
                 eng.process(x_dev)
                 queued += 1
-            if h is not None:
-                h.launch()                       # asynchronous NCCL all-gather over NVLink: overlaps the next step(s)
-                pend.append(h)
+            st = eng.stats()
+            if world > 1:
+                # the one exchange of the path: this step's records go out of the engine's HBM frame list (zero copy) in an
+                # asynchronous NCCL all-gather over NVLink that overlaps the next step(s)
+                pend.append(gather.start(fr, *eng.polled_frames_device()[:2]))
                 if len(pend) >= gather_depth:
                     nfr = sum(pend.pop(0).counts())     # collect the oldest gather in flight
             front.append(st["gpu_ms_frontend"])
@@ -343,13 +341,11 @@ def main():
             done += 1
             d2h += fr.nbytes + 32
             nfr = len(fr)
-            h = gather.start(fr, *eng.polled_frames_device()[:2], defer=True) if world > 1 else None
             if done + queued < k:
                 eng.process(buf)
                 queued += 1
-            if h is not None:
-                h.launch()
-                pend.append(h)
+            if world > 1:
+                pend.append(gather.start(fr, *eng.polled_frames_device()[:2]))
                 if len(pend) >= gather_depth:
                     pend.pop(0).counts()
         while pend:

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- CPU oracles of the receive path.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
-may import this package.  Nothing under snout_b200/ does (tests/test_layout.py enforces it).
+may import this package.  Nothing under snout_b200/ does (tests/test_abi_layout.py enforces it).
 
 Two kinds of oracle live here:
 
