@@ -228,6 +228,59 @@ int  snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev);
  * further snrx_process calls: it is overwritten by the third (each of the two lanes alternates between two lists). */
 int  snrx_polled_frames_device(snrx_t* h, const snrx_frame_t** frames_dev, uint32_t* n_out);
 
+/* ---- advertising analytics on the decoded BLE records (what Snout does per btle_rx line:
+ * BtleMessage.fromraw message.py:205-237 -> BtlePDUPayload advertising.py:113-307 -> Device device.py) ---- */
+#define SNRX_ADV_FLAGS         0x0001  /* AD 0x01 present (ad_flags)                                   */
+#define SNRX_ADV_UUID128       0x0002  /* AD 0x06                                                      */
+#define SNRX_ADV_OOB           0x0004  /* AD 0x11 (oob_flags)                                          */
+#define SNRX_ADV_SERVICE_DATA  0x0008  /* AD 0x16 (service_uuid)                                       */
+#define SNRX_ADV_MANUFACTURER  0x0010  /* AD 0xff (company_id; Apple: apple_types / apple_action)      */
+#define SNRX_ADV_UNKNOWN       0x0020  /* some other AD type (unknown_type = the last one)             */
+#define SNRX_ADV_MALFORMED     0x0040  /* truncated where the reference parser raises / never returns  */
+#define SNRX_ADV_SENDER        0x0080  /* adv_a holds the sender address                               */
+
+typedef struct snrx_adv {           /* one per record of the batch, 32 bytes */
+    uint8_t  adv_a[6];      /* sender address as transmitted (btle_rx prints it reversed, btle_rx.c:1434-1441) */
+    uint8_t  pdu_type;      /* header & 0x0f; 0xff: not a BLE record                                  */
+    uint8_t  tx_add, rx_add;
+    uint8_t  adv_len;       /* bytes of AD structures (PDU types 0, 2, 4, 6)                           */
+    uint8_t  n_ad;          /* AD structures walked (AdvDataParser.get_ad_structure :74-91)            */
+    uint8_t  ad_flags;      /* AD 0x01 value (last one wins, as in the reference's dict)               */
+    uint16_t present;       /* SNRX_ADV_*                                                              */
+    uint16_t company_id;    /* AD 0xff company (word16be() of the reference is little endian), 0xffff none */
+    uint16_t service_uuid;  /* AD 0x16, 0xffff none                                                    */
+    uint8_t  unknown_type;
+    uint8_t  apple_action;  /* Apple Nearby (type 0x10) action code, 0xff none                         */
+    uint8_t  oob_flags;     /* AD 0x11 value                                                           */
+    uint8_t  reserved;
+    uint32_t apple_types;   /* bit t: Apple Continuity TLV type t (< 32) present (last Apple AD wins)   */
+    uint32_t frame;         /* index of the record in the batch                                        */
+} snrx_adv_t;
+
+typedef struct snrx_device {        /* one per sender (AdvA, TxAdd), 64 bytes */
+    uint8_t  adv_a[6];
+    uint8_t  tx_add;
+    uint8_t  ad_flags;      /* OR over its packets                                                     */
+    uint32_t packets, crc_ok;
+    uint64_t chan_mask;     /* bit c: seen on BLE channel c                                            */
+    int64_t  first_index, last_index;     /* channel-rate position of its first / last packet ...      */
+    uint32_t first_capture, last_capture; /* ... and their capture ids                                 */
+    uint16_t pdu_mask;      /* bit t: PDU type t seen                                                  */
+    uint16_t present;       /* OR of SNRX_ADV_* over its packets                                       */
+    uint16_t company_id;    /* of its latest packet with manufacturer data, 0xffff none                */
+    uint16_t reserved;
+    uint32_t apple_types;   /* OR over its packets                                                     */
+    uint32_t pad;
+} snrx_device_t;
+
+/* Summaries of the batch most recently retired by snrx_poll / snrx_poll_view (computed on the GPU from the device frame
+ * list; call before the second-next snrx_process).  out may be NULL (only folds the batch into the device table).
+ * *n_out = records of the batch (BLE and others; others have pdu_type 0xff). */
+int  snrx_ble_adv_summary(snrx_t* h, snrx_adv_t* out, uint32_t cap, uint32_t* n_out);
+/* The sender table accumulated by every snrx_ble_adv_summary call so far (unordered); reset != 0 clears it afterwards.
+ * SNRX_EOVERFLOW if more than 2^18 distinct senders were seen (the extra ones were not recorded). */
+int  snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_out, int reset);
+
 int  snrx_set_channel(snrx_t* h, int channel);           /* NB modes */
 int  snrx_set_stream(snrx_t* h, void* cuda_stream);       /* run on a caller stream */
 int  snrx_sync(snrx_t* h);

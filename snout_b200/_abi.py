@@ -60,6 +60,20 @@ class SnrxError(RuntimeError):
 
 
 # every symbol include/snoutrx.h declares: (name, restype, argtypes)
+# SURVEY 8(f) N1 records (include/snoutrx.h snrx_adv_t / snrx_device_t)
+ADV_FLAGS, ADV_UUID128, ADV_OOB, ADV_SERVICE_DATA, ADV_MANUFACTURER, ADV_UNKNOWN, ADV_MALFORMED, ADV_SENDER = (1 << i for i in range(8))
+ADV_DTYPE = np.dtype([
+    ("adv_a", "u1", (6,)), ("pdu_type", "u1"), ("tx_add", "u1"), ("rx_add", "u1"), ("adv_len", "u1"), ("n_ad", "u1"),
+    ("ad_flags", "u1"), ("present", "<u2"), ("company_id", "<u2"), ("service_uuid", "<u2"), ("unknown_type", "u1"),
+    ("apple_action", "u1"), ("oob_flags", "u1"), ("reserved", "u1"), ("apple_types", "<u4"), ("frame", "<u4"),
+], align=True)
+DEVICE_DTYPE = np.dtype([
+    ("adv_a", "u1", (6,)), ("tx_add", "u1"), ("ad_flags", "u1"), ("packets", "<u4"), ("crc_ok", "<u4"), ("chan_mask", "<u8"),
+    ("first_index", "<i8"), ("last_index", "<i8"), ("first_capture", "<u4"), ("last_capture", "<u4"), ("pdu_mask", "<u2"),
+    ("present", "<u2"), ("company_id", "<u2"), ("reserved", "<u2"), ("apple_types", "<u4"), ("pad", "<u4"),
+], align=True)
+assert ADV_DTYPE.itemsize == 32 and DEVICE_DTYPE.itemsize == 64
+
 SYMBOLS = [
     ("snrx_abi_version", c_int, []),
     ("snrx_strerror", c_char_p, [c_int]),
@@ -73,6 +87,8 @@ SYMBOLS = [
     ("snrx_poll_view", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
     ("snrx_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
     ("snrx_polled_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
+    ("snrx_ble_adv_summary", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
+    ("snrx_ble_devices", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32), c_int]),
     ("snrx_set_channel", c_int, [c_void_p, c_int]),
     ("snrx_set_stream", c_int, [c_void_p, c_void_p]),
     ("snrx_sync", c_int, [c_void_p]),

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "ble_adv.cuh"
 #include "ble_back.cuh"
 #include "ble_front.cuh"
 #include "common.cuh"
@@ -67,6 +68,13 @@ struct snrx_handle {
     int device = 0;
     cudaStream_t user_stream = nullptr;  // stream the caller produces device input on (snrx_set_stream), or null
     cudaStream_t copy_stream = nullptr;  // H2D staging
+    // advertising analytics, allocated by the first snrx_ble_adv_summary
+    cudaStream_t adv_stream = nullptr;
+    snrx_adv_t* d_adv = nullptr;
+    snrx::DevSlot* d_devtab = nullptr;
+    snrx_device_t* d_devout = nullptr;
+    uint32_t* d_adv_counters = nullptr;   // [0] records summarised (BLE), [1] new devices, [2] dropped (table full), [3] export count
+    uint32_t dev_count = 0, dev_dropped = 0;
     Lane lane[2];
     uint64_t seq_process = 0, seq_poll = 0;
     int sm_count = 148;
@@ -305,6 +313,8 @@ void snrx_destroy(snrx_t* h) {
         if (ln.tail) cudaStreamDestroy(ln.tail);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->adv_stream) { cudaStreamSynchronize(h->adv_stream); cudaStreamDestroy(h->adv_stream); }
+    { void* ab[] = {h->d_adv, h->d_devtab, h->d_devout, h->d_adv_counters}; for (void* b : ab) if (b) cudaFree(b); }
     delete h;
 }
 
@@ -799,6 +809,72 @@ int snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev) {
     Lane& sl = h->lane[h->last_lane];                                   // lane of the most recent snrx_process
     if (frames_dev) *frames_dev = sl.d_frames;
     if (count_dev) *count_dev = sl.d_totals;
+    return SNRX_OK;
+}
+
+constexpr uint32_t kDevSlots = 1u << 19;      // open addressing, at most 2^18 senders (load factor 1/2)
+
+static int adv_init(snrx_handle* h) {
+    if (h->adv_stream) return SNRX_OK;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMalloc((void**)&h->d_adv, sizeof(snrx_adv_t) * (size_t)h->frame_cap));
+    CK(cudaMalloc((void**)&h->d_devtab, sizeof(snrx::DevSlot) * (size_t)kDevSlots));
+    CK(cudaMalloc((void**)&h->d_devout, sizeof(snrx_device_t) * (size_t)(kDevSlots / 2)));
+    CK(cudaMalloc((void**)&h->d_adv_counters, 4 * sizeof(uint32_t)));
+    CK(cudaMemset(h->d_devtab, 0, sizeof(snrx::DevSlot) * (size_t)kDevSlots));
+    CK(cudaMemset(h->d_adv_counters, 0, 4 * sizeof(uint32_t)));
+    CK(cudaStreamCreateWithFlags(&h->adv_stream, cudaStreamNonBlocking));
+    return SNRX_OK;
+}
+
+int snrx_ble_adv_summary(snrx_t* h, snrx_adv_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h) return SNRX_EINVAL;
+    if (h->polled_lane < 0) return fail(h, SNRX_ESTATE, "snrx_ble_adv_summary needs a polled batch");
+    int r = adv_init(h);
+    if (r != SNRX_OK) return r;
+    CK(cudaSetDevice(h->device));
+    const uint32_t n = h->lane[h->polled_lane].n_frames;
+    if (n_out) *n_out = n;
+    if (n == 0) return SNRX_OK;
+    if (out && cap < n) return fail(h, SNRX_ERANGE, "summary buffer smaller than the batch");
+    cudaStream_t st = h->adv_stream;
+    if (h->dev_count >= kDevSlots / 2) return fail(h, SNRX_EOVERFLOW, "sender table full (2^18 devices)");
+    k_ble_adv_summary<<<(n + 255) / 256, 256, 0, st>>>(h->polled_frames_dev, n, h->d_adv, h->d_adv_counters + 0);
+    k_ble_adv_devices<<<(n + 255) / 256, 256, 0, st>>>(h->polled_frames_dev, h->d_adv, n, h->d_devtab, kDevSlots - 1, h->d_adv_counters + 1);
+    CK(cudaGetLastError());
+    uint32_t c[4];
+    CK(cudaMemcpyAsync(c, h->d_adv_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+    if (out) CK(cudaMemcpyAsync(out, h->d_adv, sizeof(snrx_adv_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    h->dev_count = c[1];
+    h->dev_dropped = c[2];
+    return SNRX_OK;
+}
+
+int snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_out, int reset) {
+    if (!h) return SNRX_EINVAL;
+    int r = adv_init(h);
+    if (r != SNRX_OK) return r;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->adv_stream;
+    const uint32_t n = h->dev_count;
+    if (n_out) *n_out = n;
+    if (out && n) {
+        if (cap < n) return fail(h, SNRX_ERANGE, "device buffer smaller than the table");
+        CK(cudaMemsetAsync(h->d_adv_counters + 3, 0, sizeof(uint32_t), st));
+        k_ble_adv_export<<<(kDevSlots + 255) / 256, 256, 0, st>>>(h->d_devtab, kDevSlots, h->d_devout, kDevSlots / 2, h->d_adv_counters + 3);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, h->d_devout, sizeof(snrx_device_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    const bool dropped = h->dev_dropped != 0;
+    if (reset) {
+        CK(cudaMemsetAsync(h->d_devtab, 0, sizeof(snrx::DevSlot) * (size_t)kDevSlots, st));
+        CK(cudaMemsetAsync(h->d_adv_counters, 0, 4 * sizeof(uint32_t), st));
+        CK(cudaStreamSynchronize(st));
+        h->dev_count = h->dev_dropped = 0;
+    }
+    if (dropped) return fail(h, SNRX_EOVERFLOW, "more than 2^18 distinct senders: some were not recorded");
     return SNRX_OK;
 }
 

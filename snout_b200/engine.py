@@ -200,6 +200,33 @@ class RxEngine:
         self._check(self.lib.snrx_polled_frames_device(self.handle, byref(f), byref(n)))
         return int(f.value or 0), int(self.cfg.max_frames) or (1 << 17), int(n.value)   # 1 << 17: the library default
 
+    # ------------------------------------------------------------------ advertising analytics
+    def adv_summary(self, want: bool = True) -> np.ndarray:
+        """Per-record summaries (sender, PDU type, AD-structure fields: _abi.ADV_DTYPE) of the batch most recently
+        returned by poll(), computed on the GPU from the HBM frame list; also folds the batch into the sender table.
+        This is what Snout builds per btle_rx line (BtleMessage.fromraw -> BtlePDUPayload, message.py:205-237,
+        advertising.py:113-307).  Call before the second-next process().  want=False only updates the table."""
+        n = c_uint32(0)
+        if not want:
+            self._check(self.lib.snrx_ble_adv_summary(self.handle, None, 0, byref(n)))
+            return np.zeros(0, dtype=_abi.ADV_DTYPE)
+        cap = int(self.cfg.max_frames) or (1 << 17)
+        out = np.zeros(cap, dtype=_abi.ADV_DTYPE)
+        self._check(self.lib.snrx_ble_adv_summary(self.handle, out.ctypes.data_as(c_void_p), cap, byref(n)))
+        return out[: n.value].copy()
+
+    def devices(self, reset: bool = False) -> np.ndarray:
+        """The sender table (one _abi.DEVICE_DTYPE row per (AdvA, TxAdd), sorted by address) accumulated over every
+        adv_summary() call: Snout's Device.get_unique bookkeeping (device.py:31-58) as packet counts, channel / PDU /
+        AD masks, first and last position, latest company id."""
+        n = c_uint32(0)
+        self._check(self.lib.snrx_ble_devices(self.handle, None, 0, byref(n), 0))
+        out = np.zeros(max(n.value, 1), dtype=_abi.DEVICE_DTYPE)
+        self._check(self.lib.snrx_ble_devices(self.handle, out.ctypes.data_as(c_void_p), len(out), byref(n), 1 if reset else 0))
+        out = out[: n.value]
+        key = out["adv_a"].astype(np.uint64) @ (np.uint64(256) ** np.arange(6, dtype=np.uint64)) + (out["tx_add"].astype(np.uint64) << np.uint64(48))
+        return out[np.argsort(key, kind="stable")]
+
     def frames_device(self) -> tuple[int, int]:
         f, c = c_void_p(), c_void_p()
         self._check(self.lib.snrx_frames_device(self.handle, byref(f), byref(c)))

@@ -10,6 +10,7 @@
 #include "../../snout_b200/csrc/ble_front.cuh"
 #include "../../snout_b200/csrc/fft.cuh"
 #include "../../snout_b200/csrc/pfb.cuh"
+#include "../../snout_b200/csrc/ble_adv.cuh"
 #include "../../snout_b200/csrc/zb.cuh"
 #include "../../snout_b200/csrc/pfb_zb.cuh"
 
@@ -315,5 +316,8 @@ int emu_zb_chains(const float* z, int n_out, int origin, int body, int segment, 
     }
     return n;
 }
+
+// one record through ble_adv_parse (k_ble_adv_summary's per-thread code)
+void emu_ble_adv_parse(const uint8_t* pdu, int len, snrx_adv_t* out) { ble_adv_parse(pdu, len, *out); out->frame = 0; }
 
 }  // extern "C"
