@@ -366,6 +366,20 @@ def main():
             dt = float(t.item())
         return world * n * args.steps / dt / 1e6, d2h, nfr
 
+    # SURVEY 8(f) N1 (outside the timed region): advertising summaries + sender table of one polled batch, on the GPU
+    analytics = None
+    if world == 1 and eng.n_ble:
+        fr = eng.process(x_dev).poll(copy=False)
+        eng.adv_summary(want=False)
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            eng.adv_summary(want=False)
+        dt = (time.perf_counter() - t0) / reps
+        n_dev = len(eng.devices(reset=True))
+        analytics = {"records_per_batch": int(len(fr)), "ms_per_batch": dt * 1e3, "records_per_s": len(fr) / dt, "senders": int(n_dev),
+                     "note": "snrx_ble_adv_summary (k_ble_adv_summary + k_ble_adv_devices + counter read-back), not part of value/e2e"}
+
     e2e, d2h, _ = time_e2e(pinned)
     # the same capture as an 8-bit digitiser delivers it (interleaved int8 I,Q = the HackRF transfer format the
     # reference consumes, btle_rx.c:204,489-498) through snrx_process_sc8: a quarter of the PCIe bytes
@@ -404,6 +418,7 @@ def main():
         "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(d2h / args.steps),
                 "note": "RxEngine.process/poll on a pinned host cf32 buffer, two batches in flight: chunked H2D overlapped with the channelizer, frames copied out"},
         "e2e_sc8": e2e_sc8,
+        "analytics": analytics,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
                      "kernel": {"ble_wb40": "k_pfb_ble (channelizer+slicer)", "zb_wb16": "k_pfb_zb_warp (channelizer+discriminator)",

@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(256) k_ble_adv_summary(const snrx_frame_t* __r
         atomicAdd(n_out, 1u);
     } else {
         ble_adv_parse(nullptr, 0, o);
+        o.present = 0;                      // not a BLE record: pdu_type 0xff, nothing else
     }
     o.frame = i;
     out[i] = o;
