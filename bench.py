@@ -243,7 +243,13 @@ def main():
     # two gathers in flight.  (FrameGather(record_bytes=80) would exchange only the 80 bytes a BLE record uses; measured at
     # N=4 it does not change the step time, nor do three gathers in flight: the exchange is not bandwidth bound.)
     gather_depth = 2
-    gather = sdist.FrameGather(dev, cap=1 << 15, depth=gather_depth) if world > 1 else None
+    gather, gather_kind = None, None
+    if world > 1:
+        # preferred: peer-to-peer pushes on the copy engines (no collective kernel beside the channelizer); NCCL otherwise
+        gather = None if os.environ.get("SNRX_GATHER", "peer") == "nccl" else sdist.PeerGather.available(dev)
+        gather_kind = "peer-to-peer copies over NVLink (dist.PeerGather)" if gather is not None else "NCCL all-gather (dist.FrameGather)"
+        if gather is None:
+            gather = sdist.FrameGather(dev, cap=1 << 15, depth=gather_depth)
 
     def barrier():
         if world > 1:
@@ -411,7 +417,7 @@ def main():
         "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "samples_per_step_per_gpu": int(n),
                    "input_bytes_per_step_per_gpu": int(n * 8), "pfb_taps": args.taps if args.workload in WIDEBAND else None,
                    "l2": "input (%.0f MB) larger than L2; no flush needed" % (n * 8 / 1e6),
-                   "frames_per_step": int(frames_per_step), "timed": "K x (process + poll), two batches in flight, frames land in pinned host memory; CUDA events on the engine stream"},
+                   "frames_per_step": int(frames_per_step), "frame_exchange": gather_kind, "timed": "K x (process + poll), two batches in flight, frames land in pinned host memory; CUDA events on the engine stream"},
         "frames_per_s": frames_per_step * args.steps / (ms * 1e-3),
         "gpu_launches": int(launches),
         "clocks": clocks,

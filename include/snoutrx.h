@@ -224,8 +224,9 @@ int  snrx_frames_device(snrx_t* h, void** frames_dev, void** count_dev);
 
 /* Device-memory list of the frames of the batch most recently retired by snrx_poll / snrx_poll_view and
  * their count: the send buffer of the multi-GPU frame all-gather (no host round trip, no copy).
- * The buffer holds max_frames records (those past the count are unspecified) and stays valid for two
- * further snrx_process calls: it is overwritten by the third (each of the two lanes alternates between two lists). */
+ * The buffer holds max_frames records (those past the count are unspecified); the 160 bytes in front of it hold
+ * {uint64 count, uint64 batch number (0, 1, ... per handle)}, so [header | records] can be sent as one block.  It stays
+ * valid for two further snrx_process calls: it is overwritten by the third (each of the two lanes alternates between two lists). */
 int  snrx_polled_frames_device(snrx_t* h, const snrx_frame_t** frames_dev, uint32_t* n_out);
 
 /* ---- advertising analytics on the decoded BLE records (what Snout does per btle_rx line:

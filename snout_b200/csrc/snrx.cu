@@ -221,9 +221,13 @@ static int ble_tile_stride(const snrx_handle* h) { return h->wideband ? PfbBleGe
 // device frame list -> host-mapped pinned memory, fully coalesced 16-byte stores; also publishes the totals
 __global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __restrict__ src, const uint32_t* __restrict__ totals_dev,
                                                        snrx_frame_t* __restrict__ dst_host, uint32_t* __restrict__ totals_host,
-                                                       uint32_t frame_cap) {
+                                                       uint32_t frame_cap, unsigned long long batch_no) {
     uint32_t n = totals_dev[0] + totals_dev[2];
     if (n > frame_cap) n = frame_cap;                      // few CTAs: this kernel is PCIe bound and must leave the SMs to the other lane
+    if (blockIdx.x == 0 && threadIdx.x == 0) {             // header in front of the device list (see the allocation)
+        unsigned long long* hdr = reinterpret_cast<unsigned long long*>(const_cast<snrx_frame_t*>(src) - 1);
+        hdr[0] = n; hdr[1] = batch_no;
+    }
     const size_t n16 = (size_t)n * (sizeof(snrx_frame_t) / 16);
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst_host);
@@ -302,7 +306,8 @@ void snrx_destroy(snrx_t* h) {
     for (void* b : bufs) if (b) cudaFree(b);
     for (auto& ln : h->lane) {
         void* lb[] = {ln.d_x, ln.d_x8, ln.d_bits, ln.d_hits, ln.d_counts, ln.d_offsets, ln.d_scratch, ln.d_wcounts, ln.d_woffsets,
-                      ln.d_cands, ln.d_decs, ln.d_totals, ln.d_q8, ln.d_cf, ln.d_frames_buf[0], ln.d_frames_buf[1]};
+                      ln.d_cands, ln.d_decs, ln.d_totals, ln.d_q8, ln.d_cf,
+                      ln.d_frames_buf[0] ? ln.d_frames_buf[0] - 1 : nullptr, ln.d_frames_buf[1] ? ln.d_frames_buf[1] - 1 : nullptr};
         for (void* b : lb) if (b) cudaFree(b);
         zb_free(ln.zb);
         if (ln.frames) cudaFreeHost(ln.frames);
@@ -418,7 +423,9 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
             CK(cudaEventCreate(&ln.ev_front));
             CK(cudaEventCreate(&ln.ev_done));
             CK(cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming));
-            for (auto& fb : ln.d_frames_buf) CK(cudaMalloc((void**)&fb, sizeof(snrx_frame_t) * (size_t)h->frame_cap));
+            // one record of room in front of every list: k_export_frames writes {uint64 count, uint64 batch number} there,
+            // so [header | records] can leave the GPU as one block (dist.PeerGather)
+            for (auto& fb : ln.d_frames_buf) { CK(cudaMalloc((void**)&fb, sizeof(snrx_frame_t) * ((size_t)h->frame_cap + 1))); fb += 1; }
             ln.d_frames = ln.d_frames_buf[0];
             CKD(dev_alloc(h, &ln.d_totals, 8));
             CK(cudaMemset(ln.d_totals, 0, 8 * sizeof(uint32_t)));
@@ -711,7 +718,7 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
         if (r != SNRX_OK) return r;
     }
     // export: device frame list -> pinned host memory; on this lane's stream, so it overlaps the other lane's front end
-    k_export_frames<<<32, 256, 0, st>>>(ln.d_frames, ln.d_totals, ln.frames, ln.totals, h->frame_cap);
+    k_export_frames<<<32, 256, 0, st>>>(ln.d_frames, ln.d_totals, ln.frames, ln.totals, h->frame_cap, (unsigned long long)h->seq_process);
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ln.ev_done, st));

@@ -314,6 +314,117 @@ class FrameGather:
         return p
 
 
+class PeerGather:
+    """The same exchange as FrameGather without a collective kernel: every rank pushes its [header | records] block (the
+    engine writes the header in front of its HBM frame list, include/snoutrx.h) straight into a receive slot in every
+    peer's HBM -- peer-to-peer copies over NVLink / NVSwitch on the copy engines, through buffers mapped with
+    torch.distributed._symmetric_memory -- followed by a stream-ordered signal per peer.  No SM-resident kernel waits for
+    the slowest rank beside the channelizer (an NCCL all-gather does: DESIGN.md 9).  Same interface as FrameGather
+    (start(frames, device_ptr, device_records, defer) -> Pending with launch() / counts() / frames()); `available()` tells
+    whether the symmetric-memory rendezvous works on this system -- callers fall back to FrameGather otherwise."""
+
+    SLOTS = 4
+
+    def __init__(self, device, cap: int = 1 << 15):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.torch, self.dist = torch, dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.device, self.cap, self.step = device, int(cap), 0
+        self.rec = FRAME_DTYPE.itemsize
+        self.slot_bytes = (self.cap + 1) * self.rec
+        self.buf = symm.empty(self.world * self.SLOTS * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        shape = (self.world, self.SLOTS, self.slot_bytes)
+        self.views = [self.hdl.get_buffer(r, shape, torch.uint8) for r in range(self.world)]     # views[p][src, slot, byte]
+        self.stream = torch.cuda.Stream(device, priority=-1)
+        self.hdr_host = [torch.zeros((self.world, 16), dtype=torch.uint8).pin_memory() for _ in range(self.SLOTS)]
+        self.ev_done = [torch.cuda.Event() for _ in range(self.SLOTS)]
+        self.src_cache = {}
+        self.fallbacks = 0
+        torch.cuda.synchronize(device)
+        dist.barrier()
+
+    @staticmethod
+    def available(device) -> "PeerGather | None":
+        """Try to set the exchange up on every rank; all ranks agree on the outcome."""
+        import torch
+        import torch.distributed as dist
+        g, ok = None, 1
+        try:
+            g = PeerGather(device)
+        except Exception:                                         # no symmetric memory on this system / torch build
+            ok = 0
+        t = torch.tensor([ok], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return g if int(t.item()) == 1 else None
+
+    class Pending:
+        def __init__(self, g, frames, slot, step, src, nbytes):
+            self.g, self.local, self.slot, self.step, self.src, self.nbytes = g, frames, slot, step, src, nbytes
+            self.launched, self._counts = False, None
+
+        def launch(self):
+            g = self.g
+            if self.launched:
+                return self
+            self.launched = True
+            t = g.torch
+            with t.cuda.stream(g.stream):
+                for p in range(g.world):                                   # [header | records] into slot (me, step) of every rank
+                    g.views[p][g.rank, self.slot, : self.nbytes].copy_(self.src[: self.nbytes], non_blocking=True)
+                for p in range(g.world):
+                    if p != g.rank:
+                        g.hdl.put_signal(p)                                # my block of this step has landed at p
+                for p in range(g.world):
+                    if p != g.rank:
+                        g.hdl.wait_signal(p)                               # p's block of this step has landed here
+                g.hdr_host[self.slot].copy_(g.views[g.rank][:, self.slot, :16], non_blocking=True)
+                g.ev_done[self.slot].record(g.stream)
+            return self
+
+        def counts(self):
+            self.launch()
+            if self._counts is None:
+                g = self.g
+                g.ev_done[self.slot].synchronize()
+                h = g.hdr_host[self.slot].numpy().view(np.uint64).reshape(g.world, 2)
+                self._counts = [int(c) for c in h[:, 0]]
+            return self._counts
+
+        def frames(self):
+            g = self.g
+            c = self.counts()
+            if max(c) > g.cap:                                             # a rank overflowed its slot: exact two-phase gather
+                g.fallbacks += 1
+                return allgather_frames(self.local, g.device)
+            own = g.views[g.rank]
+            out = [own[r, self.slot, g.rec: g.rec * (1 + c[r])].cpu().numpy().view(FRAME_DTYPE) for r in range(g.world)]
+            return np.concatenate(out) if out else self.local[:0]
+
+    def start(self, frames: np.ndarray, device_ptr: int = 0, device_records: int = 0, defer: bool = False) -> "PeerGather.Pending":
+        """`device_ptr` / `device_records`: RxEngine.polled_frames_device() -- the engine's HBM list, whose header record
+        sits 160 bytes in front of it.  Collect a Pending before SLOTS - 1 further steps have been started."""
+        t = self.torch
+        if not device_ptr:
+            raise ValueError("PeerGather sends the engine's device frame list: pass RxEngine.polled_frames_device()")
+        n = len(frames)
+        m = min(n, self.cap)
+        key = (device_ptr, device_records)
+        src = self.src_cache.get(key)
+        if src is None:
+            src = t.as_tensor(_DevView(device_ptr - self.rec, (device_records + 1) * self.rec), device=self.device)
+            self.src_cache[key] = src
+        slot, step = self.step % self.SLOTS, self.step
+        self.step += 1
+        p = PeerGather.Pending(self, frames, slot, step, src, (m + 1) * self.rec)
+        if not defer:
+            p.launch()
+        return p
+
+
 def sort_reference_order(frames: np.ndarray) -> np.ndarray:
     order = np.lexsort((frames["sample_index"], frames["window"], frames["channel"],
                         255 - frames["proto"].astype(np.int32), frames["capture_id"]))

@@ -40,6 +40,23 @@ def main():
         counts = pend.counts()
         assert len(counts) == world and sum(counts) == len(want)
 
+        # the same exchange as peer-to-peer pushes on the copy engines (when symmetric memory is available here)
+        pg = sdist.PeerGather.available(dev)
+        peer_note = "PeerGather unavailable (NCCL path only)"
+        if pg is not None:
+            pend, got = None, []
+            for step in range(5):
+                fr = eng.process(x).poll(copy=True)
+                h = pg.start(fr, *eng.polled_frames_device()[:2], defer=(step % 2 == 1)).launch()
+                if pend is not None:
+                    got.append(pend.frames())
+                pend = h
+            got.append(pend.frames())
+            for k, f in enumerate(got):
+                assert f.tobytes() == want.tobytes(), ("peer", rank, k, len(f), len(want))
+            assert pend.counts() == counts
+            peer_note = f"PeerGather == exact gather over {len(got)} steps"
+
         # time-sharded job over two captures
         caps = [synth.wideband_capture(seconds=0.03, kind="ble", seed=7100 + c, esn0_db=25.0, gap=(300, 3000)).iq for c in range(2)]
     with RxEngine("ble_wb40", max_samples=24 * (8192 * 3 + 128 + 2048), device=local) as eng:
@@ -52,7 +69,7 @@ def main():
         if rank == 0:
             alone = sdist.run_job(eng, lambda c: caps[c], units, 0, 1, gather=False)
             assert alone.tobytes() == job.tobytes(), (len(alone), len(job))
-            print(f"multi-gpu check ok: world {world}, gather steps {len(got)} (fallbacks {g.fallbacks}), "
+            print(f"multi-gpu check ok: world {world}, {peer_note}; gather steps {len(got)} (fallbacks {g.fallbacks}), "
                   f"job frames {len(job)} identical on every rank and to world 1")
     dist.barrier()
     dist.destroy_process_group()
