@@ -181,3 +181,26 @@ def test_zigbee_rx_wideband_channel_select(Engine, tmp_path):
     tb.wait()
     assert tb.error is None and tb.frames_sent == len(sel) > 2
     assert got == [formats.rftap_datagram(f) for f in sel]
+
+
+def test_device_frame_list_and_header(Engine):
+    """snrx_polled_frames_device: the HBM list equals the host records, the record in front of it carries {count, batch number},
+    and a polled list survives two further process() calls (each lane alternates two lists)."""
+    import torch
+    from snout_b200.dist import _DevView
+    cap = synth.ble_capture(n=400_000, channel=37, seed=1001, esn0_db=25)
+    other = synth.ble_capture(n=400_000, channel=37, seed=1002, esn0_db=25)
+    with Engine("ble_nb", channel=37, max_samples=400_000) as e:
+        for batch in range(3):
+            fr = e.process(cap.iq).poll()
+            ptr, records, n = e.polled_frames_device()
+            assert n == len(fr) > 10 and records >= n
+            view = torch.as_tensor(_DevView(ptr - 160, (n + 1) * 160), device="cuda")
+            hdr = view[:16].cpu().numpy().view(np.uint64)
+            assert (int(hdr[0]), int(hdr[1])) == (n, 3 * batch)          # three process() calls per round of this loop
+            e.process(other.iq)                                   # two further batches (both lanes) ...
+            e.poll()
+            e.process(other.iq)
+            dev = view[160:].cpu().numpy().view(_abi.FRAME_DTYPE)  # ... and the polled list is still intact
+            assert dev.tobytes() == fr.tobytes()
+            e.poll()
