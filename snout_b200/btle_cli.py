@@ -225,11 +225,11 @@ def run(o: Options, out=sys.stdout, engine_factory=None, blocks=None) -> int:
         def emit(frames: np.ndarray):
             if o.wideband and not o.all_channels:
                 frames = frames[frames["channel"] == o.chan]
+            if fh_pcap:
+                fh_pcap.write(formats.ble_pcap_block(frames))          # the batch's records in one piece (same bytes)
             for f in frames:
                 ch = int(f["channel"])
                 pkt_count[ch] = pkt_count.get(ch, 0) + 1               # pkt_count++, btle_rx.c:2126
-                if fh_pcap:
-                    fh_pcap.write(formats.ble_pcap_record(f))
                 out.write(formats.btle_rx_line(f, pkt_count[ch]))
             out.flush()                                                # fflush(stdout), btle_rx.c:2383
 
