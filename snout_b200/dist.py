@@ -157,7 +157,8 @@ class FrameGather:
         g = FrameGather(device); h = g.start(frames, ptr, records)   ...next step...   all_frames = h.frames()
 
     A Pending must be collected before `depth` further steps have been started (the engine keeps a polled frame
-    list valid for two further process() calls, include/snoutrx.h)."""
+    list valid for two further process() calls, include/snoutrx.h).  The overflow fallback re-sends `frames` from host
+    memory: pass a copy (poll(copy=True)) if a step may exceed `cap` and the engine's pinned view will be reused."""
 
     def __init__(self, device=None, cap: int = 4096, depth: int = 2, record_bytes: int | None = None):
         """record_bytes: leading bytes of every 160-byte record that are exchanged (multiple of 16).  BLE records carry
