@@ -249,9 +249,16 @@ def oqpsk_modulate(ppdu: bytes) -> np.ndarray:
 
 
 def zb_baseband(n: int, channel: int, rng: np.random.Generator, gap=(2000, 40000), cfo_hz=40e3,
-                amp_db_spread: float = 0.0):
+                amp_db_spread: float = 0.0, psdus=None):
+    """`psdus`: PSDUs (FCS included) to transmit in turn instead of random MAC frames (cycled)."""
+    k = [0]
+
     def burst():
-        psdu = zb_psdu(rng)
+        if psdus:
+            psdu = bytes(psdus[k[0] % len(psdus)])
+            k[0] += 1
+        else:
+            psdu = zb_psdu(rng)
         ppdu = bytes([0, 0, 0, 0, 0xA7, len(psdu)]) + psdu
         return oqpsk_modulate(ppdu), psdu
 

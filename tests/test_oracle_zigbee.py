@@ -165,3 +165,31 @@ def test_segmented_receiver_equals_unsegmented_at_high_snr(oracle_mod):
     a = oracle_mod.zb_receive(cap.iq, 11)
     b = oracle_mod.zb_receive(cap.iq, 11, segment=1 << 40, prehalo=0)
     assert len(a) == len(b) > 100 and np.array_equal(a["bytes"], b["bytes"]) and a["crc_ok"].all()
+
+
+def _reference_psdus(oracle_mod):
+    """The 802.15.4 frames of the reference's own test captures (tests/golden/zb_ref_frames.json), FCS appended where the
+    capture has none (DLT 230)."""
+    g = json.load(open(os.path.join(GOLDEN, "zb_ref_frames.json")))
+    out = [bytes.fromhex(h) for h in g["with_fcs"]]
+    for h in g["without_fcs"]:
+        b = bytes.fromhex(h)
+        c = oracle_mod.zb_fcs16(b)
+        out.append(b + bytes([c & 0xFF, c >> 8]))
+    return g, out
+
+
+def test_reference_pcap_frames_fcs_and_air_round_trip(oracle_mod):
+    g, psdus = _reference_psdus(oracle_mod)
+    for h in g["with_fcs"]:                                               # captured with its FCS: a KAT of the FCS-16
+        b = bytes.fromhex(h)
+        assert oracle_mod.zb_fcs16(b[:-2]) == b[-2] | (b[-1] << 8)
+    assert len(psdus) == 55
+    # transmit every frame once (O-QPSK per transmitter_OQPSK.py, 20 dB), receive with the oracle
+    rng = np.random.default_rng(77)
+    sig, truth = synth.zb_baseband(1_000_000, 15, rng, gap=(1500, 6000), psdus=psdus)
+    x = (sig + synth._awgn(len(sig), rng, 2.0 / 10 ** 2.0)).astype(np.complex64)
+    sent = [bytes(t.data) for t in truth]
+    assert len(sent) >= 55 and sent[:55] == psdus
+    got = oracle_mod.zb_receive(x, 15)
+    assert [bytes(f["bytes"][: f["len"]]) for f in got] == sent and got["crc_ok"].all()
