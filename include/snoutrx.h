@@ -105,11 +105,16 @@ typedef struct snrx_frame {
     uint8_t  bytes[132];    /* BLE: header|payload|crc (de-whitened); Zigbee: PSDU incl. FCS */
 } snrx_frame_t;
 
-/* Default Zigbee chain geometry: one clock-recovery + packet-sink chain per 8192 channel-rate samples
- * (2 ms, the BLE window length), started 4096 samples early.  Part of the parity contract: the oracle
- * runs the same segments. */
-#define SNRX_ZB_SEGMENT_DEFAULT 8192
-#define SNRX_ZB_PREHALO_DEFAULT 4096
+/* Default Zigbee chain geometry: one clock-recovery + packet-sink chain per 4096 channel-rate samples
+ * (1 ms), started 2048 samples early.  Part of the parity contract: the oracle runs the same segments.
+ * (Measured on the oracle, tests/test_oracle_zigbee.py: how long the warm-up is does not change how close the
+ * segmented receiver is to one unsegmented chain -- 2048 .. 131072 samples give the same frame agreement.) */
+#define SNRX_ZB_SEGMENT_DEFAULT 4096
+#define SNRX_ZB_PREHALO_DEFAULT 2048
+/* Blocked DC tracker (a11): block length and memory in blocks; a time shard needs
+ * (SNRX_ZB_IIR_MEMORY_BLOCKS + 1) * SNRX_ZB_IIR_BLOCK + zb_prehalo channel samples of pre halo. */
+#define SNRX_ZB_IIR_BLOCK 2048
+#define SNRX_ZB_IIR_MEMORY_BLOCKS 48
 /* Span rule (also part of the contract): a CRC-failed 802.15.4 record whose sample_index lies inside the span of an
  * earlier CRC-ok record of the same (capture, channel) -- (2 + 2 * len) * 64 samples after its sample_index -- is not
  * reported: the reference's sequential packet sink is busy with that frame (packet_sink_scapy_impl.cc:247-359) and only
@@ -177,10 +182,11 @@ void snrx_destroy(snrx_t* h);
  * the result of one call on the whole capture, bit for bit.  Requirements (channel rate):
  *   BLE    pre halo multiple of 128 (>= 128 unless the shard starts the capture), post halo
  *          >= 2048, body on the 8192-sample window grid;
- *   Zigbee pre halo multiple of 4096 and >= 36864 + zb_prehalo unless the shard starts the
- *          capture (the DC tracker remembers 8 blocks of 4096 and the first block of a buffer
+ *   Zigbee pre halo multiple of 2048 and >= 100352 + zb_prehalo unless the shard starts the
+ *          capture (the DC tracker remembers 48 blocks of 2048 and the first block of a buffer
  *          starts without discriminator / channelizer history), post halo >= 16448, body on
- *          the zb_segment grid, zb_segment a multiple of 8192. */
+ *          the zb_segment grid; zb_segment and zb_prehalo multiples of 2048, zb_segment a divisor
+ *          or a multiple of 8192. */
 typedef struct snrx_shard {
     uint64_t pre_samples;      /* input-rate samples of pre halo                                   */
     uint64_t body_samples;     /* input-rate samples of the body (0 = rest of the buffer)          */

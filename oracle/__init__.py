@@ -232,8 +232,29 @@ def zb_chain(z: np.ndarray, begin: int, end: int, body_lo: int, body_hi: int, ch
     return res + (int(stop.value),) if want_stop else res
 
 
-def zb_receive(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = 8192,
-               prehalo: int = 4096, cap: int = 1 << 16) -> np.ndarray:
+ZB_SEGMENT_DEFAULT, ZB_PREHALO_DEFAULT = 4096, 2048      # include/snoutrx.h
+
+
+def zb_dc_remove_serial(f: np.ndarray) -> np.ndarray:
+    """The published single-pole IIR + subtract, one serial recurrence."""
+    f = _f32(f)
+    z = np.empty_like(f)
+    _lib("port").zb_oracle_dc_remove_serial(_ptr(f), c_int64(f.shape[0]), _ptr(z))
+    return z
+
+
+def zb_receive_serial(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, cap: int = 1 << 16) -> np.ndarray:
+    """The reference flowgraph as it is: serial DC tracker and ONE unsegmented clock-recovery + sink chain."""
+    x = np.ascontiguousarray(iq_cf32, dtype=np.complex64)
+    out = _frames(cap)
+    n = _lib("port").zb_oracle_receive_serial(_ptr(x), c_int64(x.shape[0]), c_int(channel), c_int(threshold), _ptr(out), c_int(cap))
+    if n < 0 or n > cap:
+        raise RuntimeError(f"zb oracle returned {n}")
+    return out[:n].copy()
+
+
+def zb_receive(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = ZB_SEGMENT_DEFAULT,
+               prehalo: int = ZB_PREHALO_DEFAULT, cap: int = 1 << 16) -> np.ndarray:
     x = np.ascontiguousarray(iq_cf32, dtype=np.complex64)
     out = _frames(cap)
     n = _lib("port").zb_oracle_receive(_ptr(x), c_int64(x.shape[0]), c_int(channel), c_int(threshold),
@@ -243,8 +264,8 @@ def zb_receive(iq_cf32: np.ndarray, channel: int = 11, threshold: int = 10, segm
     return out[:n].copy()
 
 
-def zb_receive_z(z: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = 8192,
-                 prehalo: int = 4096, cap: int = 1 << 16) -> np.ndarray:
+def zb_receive_z(z: np.ndarray, channel: int = 11, threshold: int = 10, segment: int = ZB_SEGMENT_DEFAULT,
+                 prehalo: int = ZB_PREHALO_DEFAULT, cap: int = 1 << 16) -> np.ndarray:
     z = _f32(z)
     out = _frames(cap)
     n = _lib("port").zb_oracle_receive_z(_ptr(z), c_int64(z.shape[0]), c_int(channel), c_int(threshold),
@@ -252,7 +273,7 @@ def zb_receive_z(z: np.ndarray, channel: int = 11, threshold: int = 10, segment:
     return out[:n].copy()
 
 
-def zb_time(iq_cf32: np.ndarray, channel: int = 11, segment: int = 8192, prehalo: int = 4096, reps: int = 1):
+def zb_time(iq_cf32: np.ndarray, channel: int = 11, segment: int = ZB_SEGMENT_DEFAULT, prehalo: int = ZB_PREHALO_DEFAULT, reps: int = 1):
     x = np.ascontiguousarray(iq_cf32, dtype=np.complex64)
     nf = c_int(0)
     lib = _lib("port")

@@ -22,13 +22,19 @@
  * kernels perform the same operations with __fmul_rn/__fadd_rn, so GPU and
  * oracle agree bit for bit.
  *
- * Two deliberate restatement choices, part of the parity contract:
+ * Deliberate restatement choices, part of the parity contract:
  *  - the single-pole DC tracker y[n] = a f[n] + (1-a) y[n-1] (double state) is
- *    evaluated in blocks of SNRX_IIR_BLOCK samples: inside a block from a zero
- *    state, plus (1-a)^(i+1) times a carried state folded from the 8 preceding
- *    blocks (memory truncated after 32768..36864 samples = 5.2 time constants,
- *    residual weight e^-5.2 = 0.5 %).  Blocks run in parallel on the GPU, and the
- *    output no longer depends on where a time shard of a long capture starts.
+ *    evaluated in blocks of SNRX_IIR_BLOCK = 2048 samples, each started from a
+ *    carried state folded from the 48 preceding blocks (memory cut after 98304
+ *    samples = 15.7 time constants, residual weight e^-15.7 = 1.5e-7: the result
+ *    equals the serial recurrence zb_oracle_dc_remove_serial to within a float
+ *    ulp, bounded in tests/test_oracle_zigbee.py).  Blocks run in parallel on the
+ *    GPU, and the output does not depend on where a time shard of a capture starts.
+ *  - the clock recovery + packet sink run as independent chains, one per segment
+ *    of the stream (zb_chains below); zb_oracle_receive_serial is the one
+ *    unsegmented chain the reference flowgraph is, and the tests state how far
+ *    the two can differ (not at all at high SNR; at marginal SNR by as much as
+ *    the serial chain differs from itself when the capture starts one sample later).
  *  - the 8-tap interpolator dot product is summed as a balanced tree.
  */
 #include <math.h>
@@ -81,31 +87,58 @@ void zb_oracle_quad_demod(const float* iq, int64_t n, float* f) {
     }
 }
 
-/* z[n] = f[n] - (float) y[n], y the blocked single-pole tracker described above.
- * The state carried into block b is folded from the SNRX_IIR_MEMORY_BLOCKS preceding blocks only,
- * so z[n] depends on f[4096*(b-8) .. n] and nothing older: any buffer that starts on the
- * absolute 4096-sample grid reproduces it exactly once 8 blocks have gone by. */
+/* z = f - (float) y.  |z| <= pi + |DC| for any finite input; anything else (Inf / NaN samples in the capture) is replaced
+ * by 0 so that the clock recovery state stays finite (same guard in csrc/zb.cuh zb_dc_out). */
+static inline float dc_out(float f, double y) {
+    float z = f - (float)y;
+    return (fabsf(z) <= 16.0f) ? z : 0.0f;
+}
+
+/* The published block, stated serially (single_pole_iir<float,float,double>, then sub_ff):
+ *   y[n] = a f[n] + (1-a) y[n-1]  (double state, y[-1] = 0),  z[n] = f[n] - (float) y[n].
+ * This is what the reference flowgraph computes (top_block.py:52,70,84-89); the tests bound the blocked
+ * evaluation below against it. */
+void zb_oracle_dc_remove_serial(const float* f, int64_t n, float* z) {
+    const double a = SNRX_IIR_ALPHA, b = SNRX_IIR_BETA;
+    double y = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        double t1 = a * (double)f[i];
+        double t2 = b * y;
+        y = t1 + t2;
+        z[i] = dc_out(f[i], y);
+    }
+}
+
+/* The same recurrence evaluated in blocks of SNRX_IIR_BLOCK samples on the absolute grid (what the GPU runs):
+ *   e_b      = the recurrence over block b started from 0 (block-local end value),
+ *   carry_b  = fold of the SNRX_IIR_MEMORY_BLOCKS preceding e_j, oldest first: c = e_j + (1-a)^BLOCK c,
+ *   y        = the recurrence over block b started from carry_b,   z = f - (float) y.
+ * With unlimited memory carry_b would be the serial state at the block start (up to double rounding); the memory
+ * is cut after 48 blocks = 98304 samples = 15.7 time constants, where the forgotten part weighs e^-15.7 = 1.5e-7
+ * of the DC -- so z equals the serial z to within a float ulp (tests/test_oracle_zigbee.py states the bound), and
+ * z[n] depends on f[BLOCK*(b-48) .. n] only: any buffer that starts on the absolute block grid reproduces it
+ * exactly once 48 blocks have gone by (time shards, include/snoutrx.h). */
 void zb_oracle_dc_remove(const float* f, int64_t n, float* z) {
     const double a = SNRX_IIR_ALPHA, b = SNRX_IIR_BETA;
-    static double pw[SNRX_IIR_BLOCK];
-    double p = 1.0;
-    for (int i = 0; i < SNRX_IIR_BLOCK; i++) { p = p * b; pw[i] = p; }
+    double decay = 1.0;
+    for (int i = 0; i < SNRX_IIR_BLOCK; i++) decay = decay * b;
     double ends[SNRX_IIR_MEMORY_BLOCKS];      /* block-local end values of the preceding blocks, oldest first */
     int n_ends = 0;
     for (int64_t n0 = 0; n0 < n; n0 += SNRX_IIR_BLOCK) {
         int64_t len = (n - n0 < SNRX_IIR_BLOCK) ? n - n0 : SNRX_IIR_BLOCK;
         double carry = 0.0;
         for (int j = 0; j < n_ends; j++) {
-            double t = pw[SNRX_IIR_BLOCK - 1] * carry;
+            double t = decay * carry;
             carry = ends[j] + t;
         }
-        double l = 0.0;
+        double l = 0.0, y = carry;
         for (int64_t i = 0; i < len; i++) {
             double t1 = a * (double)f[n0 + i];
             double t2 = b * l;
             l = t1 + t2;
-            double y = l + pw[i] * carry;
-            z[n0 + i] = f[n0 + i] - (float)y;
+            double t3 = b * y;
+            y = t1 + t3;
+            z[n0 + i] = dc_out(f[n0 + i], y);
         }
         if (n_ends == SNRX_IIR_MEMORY_BLOCKS) {
             for (int j = 1; j < n_ends; j++) ends[j - 1] = ends[j];
@@ -291,7 +324,9 @@ static inline float mm_step(zb_mm_t* st, const float* z) {
     float m1 = st->mu + st->omega;
     float m2 = m1 + g;
     float fl = floorf(m2);
-    st->ii += (int64_t)fl;
+    /* the advance is 1, 2 or 3 samples for every finite input (m2 lies in (1.6, 3.4)); the clamp only guards the loop */
+    int adv = (int)fl;
+    st->ii += adv < 1 ? 1 : adv > 3 ? 3 : adv;
     st->mu = m2 - fl;
     return out;
 }
@@ -401,6 +436,20 @@ int zb_oracle_receive(const float* iq, int64_t n, int channel, int threshold,
     zb_oracle_quad_demod(iq, n, f);
     zb_oracle_dc_remove(f, n, z);
     int nf = zb_chains(z, n, channel, threshold, segment, prehalo, out, cap);
+    free(f); free(z);
+    return nf;
+}
+
+/* The reference flowgraph as it is: serial DC tracker, ONE clock-recovery + sink chain over the whole stream
+ * (fresh at sample 0), no span rule needed.  The yardstick the segmented receiver is measured against. */
+int zb_oracle_receive_serial(const float* iq, int64_t n, int channel, int threshold, snrx_frame_t* out, int cap) {
+    float* f = (float*)malloc(sizeof(float) * (size_t)(n + 8));
+    float* z = (float*)malloc(sizeof(float) * (size_t)(n + 8));
+    if (!f || !z) { free(f); free(z); return -1; }
+    zb_oracle_quad_demod(iq, n, f);
+    zb_oracle_dc_remove_serial(f, n, z);
+    int nf = 0;
+    zb_oracle_chain_hold(z, 0, n, 0, n, 0, threshold, channel, 0, out, cap, &nf, NULL, NULL, 0, NULL);
     free(f); free(z);
     return nf;
 }

@@ -18,8 +18,10 @@ ABI_VERSION = 2
 
 MODE_BLE_NB, MODE_ZB_NB, MODE_ZB_WB16, MODE_BLE_WB40, MODE_MIXED_WB56 = 0, 1, 2, 3, 4
 F_KEEP_STREAMS = 1
-ZB_SEGMENT_DEFAULT = 8192      # include/snoutrx.h SNRX_ZB_SEGMENT_DEFAULT / SNRX_ZB_PREHALO_DEFAULT
-ZB_PREHALO_DEFAULT = 4096
+ZB_SEGMENT_DEFAULT = 4096      # include/snoutrx.h SNRX_ZB_SEGMENT_DEFAULT / SNRX_ZB_PREHALO_DEFAULT
+ZB_PREHALO_DEFAULT = 2048
+ZB_IIR_BLOCK = 2048            # SNRX_ZB_IIR_BLOCK / SNRX_ZB_IIR_MEMORY_BLOCKS
+ZB_IIR_MEMORY_BLOCKS = 48
 STAGE_BLE_Q8, STAGE_BLE_BITS, STAGE_CHAN_CF32, STAGE_ZB_DISC, STAGE_ZB_CHIPS, STAGE_ZB_F, STAGE_ZB_NCHIPS = 1, 2, 3, 4, 5, 6, 7
 PROTO_ZIGBEE, PROTO_BLE = 2, 3
 

@@ -211,6 +211,11 @@ def run(o: Options, out=sys.stdout, engine_factory=None, blocks=None) -> int:
     decim = chanplan.WB_DECIM if o.wideband else 1
     windows = o.shard_windows or (64 if o.wideband else 512)          # 64 windows x 24 = 12.6 M input samples per shard
     max_samples = (windows * chanplan.BLE_WINDOW + 128 + 2048) * decim
+    if o.access_mask == 0:
+        # the reference's -m 0 lets EVERY sample position match (search_unique_bits compares nothing, btle_rx.c:1395-1401);
+        # in snrx_config_t access_mask 0 means "default 0xFFFFFFFF", so the two must not be confused: refuse, loudly
+        out.write("btle_rx (snout_b200): -m 0 (no access-address bit takes part in the match) is not supported\n")
+        return 1
     try:
         eng = engine_factory(mode, channel=o.chan, device=o.device, max_samples=max_samples, access_addr=o.access_addr,
                              crc_init=o.crc_init, quant_scale=o.scale, access_mask=o.access_mask)

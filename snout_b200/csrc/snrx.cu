@@ -562,16 +562,16 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
         first_capture = shard->first_capture_id;
         if ((uint64_t)pre_out + body_out > n_out) return fail(h, SNRX_EINVAL, "shard body exceeds the buffer");
         if (h->has_zb) {
-            // the DC tracker is defined on the absolute 4096-sample grid with a memory of 8 blocks, the chains on
-            // the absolute segment grid: a shard reproduces the whole-capture result only from there on
+            // the DC tracker is defined on the absolute SNRX_IIR_BLOCK grid with a memory of SNRX_IIR_MEMORY_BLOCKS blocks, the
+            // chains on the absolute segment grid: a shard reproduces the whole-capture result only from there on
             const uint32_t seg = h->cfg.zb_segment;
-            if (seg % kWindow) return fail(h, SNRX_EINVAL, "Zigbee shards need zb_segment to be a multiple of 8192");
-            if (pre_out % SNRX_IIR_BLOCK) return fail(h, SNRX_EINVAL, "Zigbee shards: pre_samples must be a multiple of 4096 channel samples");
+            if ((seg % kWindow) && (kWindow % seg)) return fail(h, SNRX_EINVAL, "Zigbee shards need zb_segment to divide 8192 or be a multiple of it");
+            if (pre_out % SNRX_IIR_BLOCK) return fail(h, SNRX_EINVAL, "Zigbee shards: pre_samples must be a multiple of 2048 channel samples");
             if (((uint64_t)first_window * kWindow) % seg) return fail(h, SNRX_EINVAL, "Zigbee shards: the body must start on the segment grid");
             const uint32_t need = (SNRX_IIR_MEMORY_BLOCKS + 1) * SNRX_IIR_BLOCK + h->cfg.zb_prehalo;   // +1: the first block of a
             // buffer holds a discriminator sample without history (and the channelizer start-up), so its end value is off
             // (a buffer that starts at capture sample 0 holds the whole history there is)
-            if (first_window != 0 && pre_out < need && (uint64_t)first_window * kWindow != pre_out) return fail(h, SNRX_EINVAL, "Zigbee shards: pre halo shorter than 36864 + zb_prehalo channel samples");
+            if (first_window != 0 && pre_out < need && (uint64_t)first_window * kWindow != pre_out) return fail(h, SNRX_EINVAL, "Zigbee shards: pre halo shorter than (48 + 1) * 2048 + zb_prehalo channel samples");
         }
     }
 
@@ -744,6 +744,7 @@ static int finish_oldest(snrx_handle* h, Lane** out_lane) {
         sl.n_frames = 0;
         if (n_cand > h->cand_cap) { sl.pending = false; h->seq_poll++; return fail(h, SNRX_EOVERFLOW, "access-address candidates exceed capacity (raise max_frames)"); }
         if ((uint64_t)n_ble + n_zb > h->frame_cap) { sl.pending = false; h->seq_poll++; return fail(h, SNRX_EOVERFLOW, "frames exceed max_frames"); }
+        if (sl.totals[3]) { sl.pending = false; h->seq_poll++; return fail(h, SNRX_EOVERFLOW, "a Zigbee chain found more frames than its segment has slots"); }
         sl.n_frames = n_ble + n_zb;
         float ms = 0.f, msf = 0.f;
         cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_done);
@@ -864,7 +865,10 @@ int snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_ou
     if (r != SNRX_OK) return r;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->adv_stream;
-    const uint32_t n = h->dev_count;
+    // one batch can add up to frame_cap senders, so the counter may run past what the export buffer holds: the table is
+    // then over its design load and the surplus senders are reported as an overflow, never read out of bounds
+    const bool over = h->dev_count > kDevSlots / 2;
+    const uint32_t n = over ? kDevSlots / 2 : h->dev_count;
     if (n_out) *n_out = n;
     if (out && n) {
         if (cap < n) return fail(h, SNRX_ERANGE, "device buffer smaller than the table");
@@ -874,7 +878,7 @@ int snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_ou
         CK(cudaMemcpyAsync(out, h->d_devout, sizeof(snrx_device_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
-    const bool dropped = h->dev_dropped != 0;
+    const bool dropped = h->dev_dropped != 0 || over;
     if (reset) {
         CK(cudaMemsetAsync(h->d_devtab, 0, sizeof(snrx::DevSlot) * (size_t)kDevSlots, st));
         CK(cudaMemsetAsync(h->d_adv_counters, 0, 4 * sizeof(uint32_t), st));

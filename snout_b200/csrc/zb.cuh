@@ -30,9 +30,12 @@
 namespace snrx {
 
 constexpr int kZbPostHalo = 16448;          // PHR + 127 bytes = 256 symbols * 64 samples, + 64
-constexpr int kZbMinFrameSamples = 896;     // 10 SHR + 2 PHR + 2 PSDU symbols of 64 samples
+constexpr int kZbMinSyncSpacing = 448;      // the sink can complete a sync every 7 symbols of 64 samples: one '0' symbol + SFD (2),
+                                            // PHR (2), one byte (2) -- packet_sink_scapy_impl.cc:204-241, 247-359
 constexpr int kZbSinkLead = 1024;           // the sink starts this many samples before the body: SHR (640) + alignment
                                             // slack; the clock recovery starts `prehalo` samples early (warm-up only)
+constexpr float kZbClamp = 16.0f;           // |z| <= pi + |DC| for any finite input; anything else (Inf / NaN samples in the
+                                            // capture) is replaced by 0 so that the clock recovery state stays finite
 
 SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) {
     const float ya = fabsf(y), xa = fabsf(x);
@@ -95,104 +98,44 @@ SNRX_HD int popc32(uint32_t x) {
 #endif
 }
 
-struct ZbSink {
-    int state;                 // 0 search, 1 have sync (PHR), 2 have header (PSDU)
-    uint32_t reg;
-    int preamble_cnt, chip_cnt;
-    int byte, nibble_idx;
-    int frame_len, got;
-    unsigned lqi_sum, lqi_n;
-    int32_t sync_pos;
-};
-
-SNRX_HD void zb_sink_search(ZbSink& s) { s.state = 0; s.reg = 0; s.preamble_cnt = 0; s.chip_cnt = 0; s.byte = 0; }
-SNRX_HD void zb_sink_init(ZbSink& s) { s.got = 0; s.frame_len = 0; s.nibble_idx = 0; s.lqi_sum = 0; s.lqi_n = 0; s.sync_pos = 0; zb_sink_search(s); }
-
 SNRX_HD int zb_dist(uint32_t reg, uint32_t word) { return popc32((reg & 0x7FFFFFFEu) ^ word); }
 
-SNRX_HD int zb_decode_symbol(ZbSink& s, const uint32_t* map, int threshold) {     // decode_chips :95-125
-    int best = 0xFF, best_d = 33;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int d = zb_dist(s.reg, map[i]);
-        if (d < best_d) { best = i; best_d = d; }
-    }
-    if (best_d < threshold) {
-        if (s.lqi_n < 8) { s.lqi_sum += 32 - best_d; s.lqi_n++; }
-        return best & 0xF;
-    }
-    return 0xFF;
+SNRX_HD uint32_t zb_fcs16_byte(uint32_t crc, uint32_t c) {        // Dot15d4FCS.compute_fcs, dot15d4.py:151-164, one byte
+    uint32_t q = (crc ^ c) & 15u;
+    crc = ((crc >> 4) ^ (q * 4225u)) & 0xFFFFu;
+    q = (crc ^ (c >> 4)) & 15u;
+    return ((crc >> 4) ^ (q * 4225u)) & 0xFFFFu;
 }
-
-// push one hard chip; returns 1 when a frame is complete (psdu[0..got))
-SNRX_HD int zb_sink_push(ZbSink& s, int chip, int32_t pos, const uint32_t* map, int threshold, uint8_t* psdu) {
-    s.reg = (s.reg << 1) | (uint32_t)(chip & 1);
-    if (s.state == 0) {                                           // STATE_SYNC_SEARCH :176-245
-        if (s.preamble_cnt > 0) s.chip_cnt++;
-        if (s.preamble_cnt == 0) {
-            if (zb_dist(s.reg, map[0]) < threshold) s.preamble_cnt = 1;
-        } else if (s.chip_cnt == 32) {
-            s.chip_cnt = 0;
-            if (s.byte == 0) {
-                if (zb_dist(s.reg, map[0]) <= threshold) s.preamble_cnt++;
-                else if (zb_dist(s.reg, map[7]) <= threshold) s.byte = 7 << 4;
-                else zb_sink_search(s);
-            } else {
-                if (zb_dist(s.reg, map[10]) <= threshold) {       // enter_have_sync :67-79
-                    s.state = 1; s.got = 0; s.byte = 0; s.nibble_idx = 0; s.lqi_sum = 0; s.lqi_n = 0;
-                    s.sync_pos = pos;
-                } else zb_sink_search(s);
-            }
-        }
-        return 0;
-    }
-    if (s.state == 1) {                                           // STATE_HAVE_SYNC :247-291
-        s.chip_cnt++;
-        if (s.chip_cnt != 32) return 0;
-        s.chip_cnt = 0;
-        const int c = zb_decode_symbol(s, map, threshold);
-        if (c == 0xFF) { zb_sink_search(s); return 0; }
-        if (s.nibble_idx == 0) s.byte = c; else s.byte |= c << 4;
-        s.nibble_idx++;
-        if (s.nibble_idx % 2 == 0) {
-            if (s.byte <= 127) { s.state = 2; s.frame_len = s.byte; s.got = 0; s.byte = 0; s.nibble_idx = 0; }   // :81-92
-            else zb_sink_search(s);
-        }
-        return 0;
-    }
-    s.chip_cnt = (s.chip_cnt + 1) % 32;                           // STATE_HAVE_HEADER :293-359
-    if (s.chip_cnt != 0) return 0;
-    const int c = zb_decode_symbol(s, map, threshold);
-    if (c == 0xFF) { zb_sink_search(s); return 0; }
-    if (s.nibble_idx == 0) s.byte = c; else s.byte |= c << 4;
-    s.nibble_idx++;
-    if (s.nibble_idx % 2 != 0) return 0;
-    psdu[s.got++] = (uint8_t)s.byte;
-    s.nibble_idx = 0;
-    if (s.got >= s.frame_len) { zb_sink_search(s); return 1; }
-    return 0;
-}
-
-SNRX_HD uint16_t zb_fcs16(const uint8_t* d, int n) {              // Dot15d4FCS.compute_fcs, dot15d4.py:151-164
+SNRX_HD uint16_t zb_fcs16(const uint8_t* d, int n) {
     uint32_t crc = 0;
-    for (int i = 0; i < n; i++) {
-        const uint32_t c = d[i];
-        uint32_t q = (crc ^ c) & 15u;
-        crc = ((crc >> 4) ^ (q * 4225u)) & 0xFFFFu;
-        q = (crc ^ (c >> 4)) & 15u;
-        crc = ((crc >> 4) ^ (q * 4225u)) & 0xFFFFu;
-    }
+    for (int i = 0; i < n; i++) crc = zb_fcs16_byte(crc, d[i]);
     return (uint16_t)crc;
 }
 
-// state carried into block b of the DC tracker: fold of the (at most) SNRX_IIR_MEMORY_BLOCKS preceding
-// block-local end values, oldest first; decay = (1-alpha)^4096
+// ---- DC tracker (a11: single_pole_iir_filter_ff(0.00016) and the subtraction, top_block.py:52,70,84-89) -----------------
+// y[n] = a f[n] + (1-a) y[n-1] in double, z[n] = f[n] - (float) y[n], evaluated per block of SNRX_IIR_BLOCK samples on the
+// absolute grid: a block starts from the carried state folded from the block-local end values of the
+// SNRX_IIR_MEMORY_BLOCKS preceding blocks (oracle/zb_oracle.c zb_oracle_dc_remove states the same and bounds it against the
+// serial recurrence).
+SNRX_HD double zb_iir_step(double y, float f) { return d_add(d_mul(SNRX_IIR_ALPHA, (double)f), d_mul(SNRX_IIR_BETA, y)); }
+SNRX_HD float zb_dc_out(float f, double y) {
+    const float z = f_sub(f, (float)y);
+    return (fabsf(z) <= kZbClamp) ? z : 0.0f;
+}
+// state carried into block b: fold of the (at most) SNRX_IIR_MEMORY_BLOCKS preceding block-local end values, oldest
+// first; decay = (1-alpha)^SNRX_IIR_BLOCK
 SNRX_HD double zb_iir_fold(const double* ends, int b, double decay) {
     double carry = 0.0;
     for (int j = (b > SNRX_IIR_MEMORY_BLOCKS ? b - SNRX_IIR_MEMORY_BLOCKS : 0); j < b; j++) carry = d_add(ends[j], d_mul(decay, carry));
     return carry;
 }
+inline double zb_iir_block_decay() {
+    volatile double p = 1.0; const double b = SNRX_IIR_BETA;
+    for (int i = 0; i < SNRX_IIR_BLOCK; i++) p = p * b;
+    return p;
+}
 
+// ---- clock recovery (a12: clock_recovery_mm_ff(2, 0.000225, 0.5, 0.03, 0.0002), top_block.py:69) ---------------------------
 struct ZbMm { float mu, omega, last; int32_t ii; };     // ii: position in the stream (n_out < 2^31)
 
 // row of the MMSE interpolator table for the fractional delay mu: rint(mu * 128).  mu * 128 lies in [0, 128],
@@ -201,7 +144,7 @@ struct ZbMm { float mu, omega, last; int32_t ii; };     // ii: position in the s
 SNRX_HD int zb_mm_row(float mu) {
     const float t = f_add(f_mul(mu, (float)SNRX_MMSE_NSTEPS), 12582912.0f);
 #ifdef __CUDA_ARCH__
-    return __float_as_int(t) & 0x1FF;
+    return __float_as_int(t) & 0x1FF;           // 0..128: mu stays in [0, 1) because every z is finite (kZbClamp)
 #else
     uint32_t u; memcpy(&u, &t, 4); return (int)(u & 0x1FFu);
 #endif
@@ -227,15 +170,164 @@ SNRX_HD float zb_mm_step(ZbMm& st, const float (&in)[8], const float (&t)[8]) {
     const float g = f_mul(gain_mu, mm);
     const float m2 = f_add(f_add(st.mu, st.omega), g);
     const float fl = floorf(m2);
-    st.ii += (int32_t)fl;
+    // the advance is 1, 2 or 3 samples for every finite input (m2 lies in (1.6, 3.4)); the clamp only guards the loop
+    const int adv = (int)fl;
+    st.ii += adv < 1 ? 1 : adv > 3 ? 3 : adv;
     st.mu = f_sub(m2, fl);
     return out;
 }
 
-// where a chain reads its samples from: straight from the stream (host stepping harness) ...
+// ---- packet sink (a13-a15), one 32-chip window at a time ------------------------------------------------------------------
+// packet_sink_scapy_impl.cc:158-374 pushes one chip at a time.  Here the clock recovery first produces 32 chips, then
+// zb_sink_window replays the state machine over them: while the sink is locked (d_preamble_cnt > 0, or past the SFD) it
+// only looks at its register every 32 chips, so a window holds exactly one such symbol boundary, always at the same offset
+// jb; while it is unlocked it compares every chip position against symbol 0 (:190-201), which is one funnel shift + popcount
+// per position with no dependence between positions.  A register cleared by enter_search() (:55-65) is modelled by zeroing
+// the chips it no longer holds.  Every lane of a warp does its symbol boundary at the same point of the program, which a
+// chip-by-chip state machine per lane cannot (each lane's boundary falls on a different chip).
+struct ZbSinkW {
+    int state;                 // 0 search (unlocked, or locked on the preamble / first SFD half), 1 have sync (PHR), 2 have header (PSDU)
+    int locked;                // state 0: d_preamble_cnt > 0
+    int jb;                    // offset of the next symbol boundary inside the coming window (valid while locked or state > 0)
+    int byte, nibble_idx;      // d_packet_byte, d_packet_byte_index
+    int frame_len, got;        // d_packetlen, d_payload_cnt
+    unsigned lqi_sum, lqi_n;
+    int32_t sync_pos;          // input position of the chip that completed the SFD
+    uint32_t prev;             // the previous window's chips (first chip in bit 31), cleared chips read 0
+    uint32_t crc, crc1, crc2;  // FCS-16 over the PSDU bytes so far / without the last / without the last two
+    uint32_t last2;            // the last two PSDU bytes, little endian
+};
+SNRX_HD void zb_sinkw_init(ZbSinkW& s) {
+    s.state = 0; s.locked = 0; s.jb = 0; s.byte = 0; s.nibble_idx = 0; s.frame_len = 0; s.got = 0; s.lqi_sum = 0; s.lqi_n = 0;
+    s.sync_pos = 0; s.prev = 0; s.crc = s.crc1 = s.crc2 = 0; s.last2 = 0;
+}
+
+// Where a chain's frames go: the chain's slots in the batch's slot array, and what identifies the chain
+struct ZbEmit {
+    snrx_frame_t* slots; uint32_t cap, nf;
+    int32_t lo, hi;            // body of the chain: only frames whose sync position lies in [lo, hi) are reported
+    int64_t index_base;        // sample_index = sync_pos + index_base
+    uint32_t capture_id, window; uint16_t channel;
+    int64_t good_end;          // end (whole-capture index) of the last CRC-ok frame reported
+};
+SNRX_HD int64_t zb_frame_end(int64_t sample_index, int len) { return sample_index + (int64_t)(2 + 2 * len) * 64; }
+
+// the register the reference sink holds right after the chip at offset j of the window C (previous window P)
+SNRX_HD uint32_t zb_reg_at(uint32_t C, uint32_t P, int j) { return funnel_r(C, P, 31 - j); }
+
+// One window.  C: its chips, first chip in bit 31 (absent chips 0); nvalid: chips it holds (< 32 only when the stream
+// ended); jstop: chips whose position lies before the end of the chain's body; pos_evt: input position of the chip at
+// offset s.jb.  Returns true when the chain ends inside this window, *consumed = the chips of it that were pushed.
+SNRX_HD bool zb_sink_window(ZbSinkW& s, uint32_t C, int nvalid, int jstop, int32_t pos_evt, const uint32_t* map, int thr,
+                            ZbEmit& em, int* consumed) {
+    // a sink in the search state stops at the first chip past the body (zb_run_chain's loop condition), any sink stops
+    // where the stream ends; 32 = not inside this window
+    const int stop_x = nvalid;
+    const int stop_0 = jstop < nvalid ? jstop : nvalid;
+    uint32_t P = s.prev;
+    int j0 = 0;                                      // the unlocked search resumes here
+    int pushed = 0;                                  // chips pushed so far
+    if (s.locked || s.state != 0) {
+        const int e = s.jb;
+        const int limit = s.state == 0 ? stop_0 : stop_x;
+        if (e >= limit) { *consumed = limit; return true; }
+        const uint32_t reg = zb_reg_at(C, P, e);
+        // decode_chips :95-125: distance to every symbol, first minimum wins (the symbol number sits below the distance)
+        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t v = ((uint32_t)zb_dist(reg, map[i]) << 4) | (uint32_t)i;
+            best = v < best ? v : best;
+        }
+        const int best_d = (int)(best >> 4), best_i = (int)(best & 15u);
+        bool reset = false;
+        if (s.state == 0) {                                            // STATE_SYNC_SEARCH, locked :204-241
+            if (s.byte == 0) {
+                if (zb_dist(reg, map[0]) <= thr) { /* one more preamble symbol */ }
+                else if (zb_dist(reg, map[7]) <= thr) s.byte = 7 << 4;
+                else reset = true;
+            } else if (zb_dist(reg, map[10]) <= thr) {                 // enter_have_sync :67-79
+                s.state = 1; s.got = 0; s.byte = 0; s.nibble_idx = 0; s.lqi_sum = 0; s.lqi_n = 0;
+                s.sync_pos = pos_evt; s.crc = s.crc1 = s.crc2 = 0; s.last2 = 0;
+            } else reset = true;
+        } else if (best_d >= thr) {
+            reset = true;                                              // a symbol nobody recognises aborts the frame
+        } else {
+            if (s.lqi_n < 8) { s.lqi_sum += 32 - best_d; s.lqi_n++; }
+            if (s.nibble_idx == 0) s.byte = best_i; else s.byte |= best_i << 4;
+            s.nibble_idx++;
+            if ((s.nibble_idx & 1) == 0) {
+                if (s.state == 1) {                                    // STATE_HAVE_SYNC :247-291
+                    if (s.byte <= 127) { s.state = 2; s.frame_len = s.byte; s.got = 0; s.byte = 0; s.nibble_idx = 0; }   // :81-92
+                    else reset = true;
+                } else {                                               // STATE_HAVE_HEADER :293-359
+                    const uint32_t b = (uint32_t)s.byte;
+                    if (em.nf < em.cap) em.slots[em.nf].bytes[s.got] = (uint8_t)b;
+                    s.got++;
+                    s.nibble_idx = 0;
+                    s.crc2 = s.crc1; s.crc1 = s.crc; s.crc = zb_fcs16_byte(s.crc, b);
+                    s.last2 = (s.last2 >> 8) | (b << 8);
+                    if (s.got >= s.frame_len) {                        // publish :333-355
+                        if (s.sync_pos >= em.lo && s.sync_pos < em.hi) {
+                            if (em.nf < em.cap) {
+                                snrx_frame_t& f = em.slots[em.nf];
+                                f.sample_index = (int64_t)s.sync_pos + em.index_base;
+                                f.capture_id = em.capture_id;
+                                f.window = em.window;
+                                f.channel = em.channel;
+                                f.proto = SNRX_PROTO_ZIGBEE;
+                                const unsigned scaled = (s.lqi_sum / 8) << 3;           // :334-335
+                                f.lqi = (uint8_t)(scaled >= 256 ? 255 : scaled);
+                                f.phase = 0;
+                                f.len = (uint16_t)s.got;
+                                f.access_addr = 0;
+                                f.crc_ok = (uint8_t)(s.got >= 2 && s.crc2 == s.last2);
+                                for (int i = s.got; i < 132; i++) f.bytes[i] = 0;
+                                if (f.crc_ok) { const int64_t end = zb_frame_end(f.sample_index, s.got); if (end > em.good_end) em.good_end = end; }
+                            }
+                            em.nf++;
+                        }
+                        reset = true;
+                    }
+                }
+            }
+        }
+        pushed = e + 1;
+        if (reset) {                                                   // enter_search :55-65: the register is cleared
+            s.state = 0; s.locked = 0; s.byte = 0;
+            C &= (e < 31) ? ((1u << (31 - e)) - 1u) : 0u;
+            P = 0;
+            j0 = e + 1;
+        }
+    }
+    if (s.state == 0 && !s.locked) {
+        // unlocked search :190-201 over the offsets [j0, stop_0): first position whose register is within thr of symbol 0
+        uint32_t hits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) hits |= (uint32_t)(zb_dist(zb_reg_at(C, P, j), map[0]) < thr) << j;
+        if (j0 > 0) hits &= j0 < 32 ? ~((1u << j0) - 1u) : 0u;
+        if (stop_0 < 32) hits &= (1u << stop_0) - 1u;
+        if (hits) {
+#ifdef __CUDA_ARCH__
+            s.jb = __ffs((int)hits) - 1;
+#else
+            s.jb = __builtin_ctz(hits);
+#endif
+            s.locked = 1;
+        }
+    }
+    s.prev = C;
+    const int limit = s.state == 0 ? stop_0 : stop_x;
+    if (limit < 32) { *consumed = limit > pushed ? limit : pushed; return true; }
+    *consumed = 32;
+    return false;
+}
+
+// where a chain reads its samples from: straight from the DC-removed stream (host stepping harness) ...
 struct ZbDirectSrc {
     const float* z;
     const float* taps;     // [129][8]
+    SNRX_HD void tick(int, int32_t) {}
     SNRX_HD void get8(int32_t ii, float (&in)[8]) const {
 #pragma unroll
         for (int k = 0; k < 8; k++) in[k] = z[ii + k];
@@ -246,34 +338,28 @@ struct ZbDirectSrc {
     }
 };
 
-// Samples a frame occupies after its SFD-completing chip: PHR (2 symbols) + len bytes (2 symbols each), 64 samples per symbol.
-// While the reference's sequential sink decodes such a frame it cannot lock onto anything else, so a CRC-failed record whose
-// sync lies inside the span of an earlier CRC-ok record of the same stream is an artefact of restarting the sink per segment
-// and is not reported (k_zb_span_filter here, zb_span_filter in oracle/zb_oracle.c, stream.zb_span_filter across shards).
-SNRX_HD int64_t zb_frame_end(int64_t sample_index, int len) { return sample_index + (int64_t)(2 + 2 * len) * 64; }
-
 struct ZbChainParams {
     int32_t n_out;            // channel-rate samples per capture in the buffer
     int32_t origin;           // local index where segment `first_segment` starts (pre halo length)
     int32_t body;             // body length (local samples from origin)
     int32_t segment, prehalo;
     int32_t n_segments;
+    int32_t n_blocks;         // DC-tracker blocks per stream
     uint32_t first_segment, first_capture;
     uint32_t n_captures, n_channels;
     int32_t threshold;
     uint32_t slots_per_chain;
-    size_t z_stride;          // floats between (capture, channel) streams
+    size_t f_stride;          // floats between (capture, channel) streams
 };
 
-// One chain.  src: samples of this (capture, channel) stream.  Frames are written to slots[0..), returns count.
-// The chain ends at the post halo, or as soon as it has passed its body with the sink back in the search
-// state: a sync found from there on completes at a position >= hi and belongs to the next segment, so
-// nothing this chain could still report is lost (oracle/zb_oracle.c zb_oracle_chain stops at the same step).
-template <class Src>
+// One chain: clock recovery fresh at `begin` = lo - prehalo, the sink from lo - kZbSinkLead on.  Frames are written to
+// slots[0..), returns their count.  The chain ends at the post halo, or as soon as it has passed its body with the sink in
+// the search state: a sync found from there on completes at a position >= hi and belongs to the next segment, so nothing
+// this chain could still report is lost (oracle/zb_oracle.c zb_oracle_chain_hold stops at the same chip).
+template <bool DEBUG, class Src>
 SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const uint32_t* map,
                               int channel_number, uint32_t capture_id, snrx_frame_t* slots, float* chips_dbg,
-                              int64_t chips_cap, int64_t* nchips_out, int64_t* good_end_out = nullptr) {
-    int64_t good_end = 0;            // end (whole-capture index) of the last CRC-ok frame this chain reports
+                              int64_t chips_cap, int64_t* nchips_out, int64_t* good_end_out) {
     // all positions are < n_out + segment + post halo < 2^31 (zb_create bounds max_out)
     const int32_t lo = p.origin + seg * p.segment;
     int32_t hi = lo + p.segment;
@@ -283,47 +369,53 @@ SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const u
     int32_t end = hi + kZbPostHalo; if (end > p.n_out) end = p.n_out;
     const int32_t sink_from = lo - kZbSinkLead;
     ZbMm mm; mm.mu = 0.5f; mm.omega = 2.0f; mm.last = 0.0f; mm.ii = begin;
-    ZbSink sink; zb_sink_init(sink);
-    uint8_t psdu[128];
-    uint32_t nf = 0;
+    ZbEmit em;
+    em.slots = slots; em.cap = p.slots_per_chain; em.nf = 0; em.lo = lo; em.hi = hi;
+    em.index_base = (int64_t)p.first_segment * p.segment - (int64_t)p.origin;
+    em.capture_id = capture_id; em.window = p.first_segment + (uint32_t)seg; em.channel = (uint16_t)channel_number;
+    em.good_end = 0;
     int32_t nchips = 0;
-    while (mm.ii + 8 <= end && !(mm.ii >= hi && sink.state == 0)) {
-        const int32_t pos = mm.ii;
+    // warm-up: clock recovery only, the sink has not started yet
+    for (int j = 0; mm.ii + 8 <= end && mm.ii < sink_from; j++) {
         float in[8], t[8];
+        src.tick(j, mm.ii);
         src.row(zb_mm_row(mm.mu), t);
-        src.get8(pos, in);
+        src.get8(mm.ii, in);
         const float soft = zb_mm_step(mm, in, t);
-        if (chips_dbg && nchips < chips_cap) chips_dbg[nchips] = soft;
+        if (DEBUG && chips_dbg && nchips < chips_cap) chips_dbg[nchips] = soft;
         nchips++;
-        if (pos >= sink_from && zb_sink_push(sink, soft > 0.0f, pos, map, p.threshold, psdu)) {
-            if (sink.sync_pos >= lo && sink.sync_pos < hi) {
-                if (nf < p.slots_per_chain) {
-                    snrx_frame_t& f = slots[nf];
-                    f.sample_index = (int64_t)(sink.sync_pos - p.origin) + (int64_t)p.first_segment * p.segment;
-                    f.capture_id = capture_id;
-                    f.window = p.first_segment + (uint32_t)seg;
-                    f.channel = (uint16_t)channel_number;
-                    f.proto = SNRX_PROTO_ZIGBEE;
-                    unsigned scaled = (sink.lqi_sum / 8) << 3;                  // :334-335
-                    f.lqi = (uint8_t)(scaled >= 256 ? 255 : scaled);
-                    f.phase = 0;
-                    f.len = (uint16_t)sink.got;
-                    f.access_addr = 0;
-                    f.crc_ok = 0;
-                    if (sink.got >= 2) {
-                        const uint16_t c = zb_fcs16(psdu, sink.got - 2);
-                        f.crc_ok = (uint8_t)(c == (uint16_t)(psdu[sink.got - 2] | (psdu[sink.got - 1] << 8)));
-                    }
-                    for (int i = 0; i < 132; i++) f.bytes[i] = (i < sink.got) ? psdu[i] : 0;
-                    if (f.crc_ok) { const int64_t e = zb_frame_end(f.sample_index, sink.got); if (e > good_end) good_end = e; }
-                }
-                nf++;
+    }
+    ZbSinkW sink; zb_sinkw_init(sink);
+    bool done = false;
+    while (!done) {
+        uint32_t C = 0;
+        int nvalid = 0, below = 0;
+        int32_t pos_evt = 0;
+        const int jb = sink.jb;
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            if (mm.ii + 8 <= end) {
+                const int32_t pos = mm.ii;
+                float in[8], t[8];
+                src.tick(j, pos);
+                src.row(zb_mm_row(mm.mu), t);
+                src.get8(pos, in);
+                const float soft = zb_mm_step(mm, in, t);
+                if (DEBUG && chips_dbg && nchips + j < chips_cap) chips_dbg[nchips + j] = soft;
+                C = (C << 1) | (soft > 0.0f ? 1u : 0u);
+                below += pos < hi ? 1 : 0;
+                pos_evt = (j == jb) ? pos : pos_evt;
+                nvalid++;
             }
         }
+        if (nvalid < 32) C = nvalid ? C << (32 - nvalid) : 0u;
+        int consumed = 0;
+        done = zb_sink_window(sink, C, nvalid, below, pos_evt, map, p.threshold, em, &consumed);
+        nchips += consumed;
     }
     if (nchips_out) *nchips_out = nchips;
-    if (good_end_out) *good_end_out = good_end;
-    return nf;
+    if (good_end_out) *good_end_out = em.good_end;
+    return em.nf;
 }
 
 // Filter of one chain's records given the ends of the CRC-ok frames of the `lookback` preceding chains of its stream.
@@ -340,6 +432,7 @@ SNRX_HD uint32_t zb_filter_chain(snrx_frame_t* slots, uint32_t n, int64_t good_e
     return w;
 }
 SNRX_HD int zb_filter_lookback(int segment) { return (16384 + segment - 1) / segment + 1; }
+SNRX_HD uint32_t zb_slots_per_chain(uint32_t segment) { return segment / kZbMinSyncSpacing + 2; }
 
 #if defined(__CUDACC__)
 // ------------------------------------------------------------------------------------ kernels
@@ -367,14 +460,14 @@ __global__ void __launch_bounds__(256) k_zb_quad(ZbQuadArgs a) {
 }
 
 struct ZbIirArgs {
-    const float* f; float* z; size_t stride;      // per (capture, channel) stream stride
+    const float* f; size_t stride;                // per (capture, channel) stream stride
     int32_t n; int32_t n_blocks; uint32_t n_streams;
     double* block_end;    // [stream][n_blocks]  block-local recurrence value at the block end
     double* carry_in;     // [stream][n_blocks]  carried state entering each block
-    const double* pw;     // [4096] (1-alpha)^(i+1)
+    double decay;         // (1-alpha)^SNRX_IIR_BLOCK
 };
 
-// A (stream, block) unit is one thread's 4096-sample serial recurrence.  Its samples are contiguous and
+// A (stream, block) unit is one thread's SNRX_IIR_BLOCK-sample serial recurrence from 0.  Its samples are contiguous and
 // 128-byte aligned, so the thread streams them as float4 with the next 32 samples (8 loads) already in
 // flight while the current 32 go through the dependent double-precision chain.
 constexpr int kIirPf = 8;             // float4 loads in flight per thread
@@ -383,7 +476,7 @@ __global__ void __launch_bounds__(64) k_zb_iir_sum(ZbIirArgs a) {
     const uint32_t total = a.n_streams * (uint32_t)a.n_blocks;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    // consecutive threads take different streams (DRAM page spread, as in k_zb_chain)
+    // consecutive threads take different streams (DRAM page spread, as in k_zb_rx)
     const uint32_t b = idx / a.n_streams, s = idx % a.n_streams;
     const float* f = a.f + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
     const int len = min(SNRX_IIR_BLOCK, a.n - (int)b * SNRX_IIR_BLOCK);
@@ -392,23 +485,23 @@ __global__ void __launch_bounds__(64) k_zb_iir_sum(ZbIirArgs a) {
     double l = 0.0;
     float4 cur[kIirPf], nxt[kIirPf];
 #pragma unroll
-    for (int k = 0; k < kIirPf; k++) nxt[k] = (k < n4) ? __ldcs(f4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < kIirPf; k++) nxt[k] = (k < n4) ? __ldg(f4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i4 = 0; i4 < n4; i4 += kIirPf) {
 #pragma unroll
         for (int k = 0; k < kIirPf; k++) cur[k] = nxt[k];
 #pragma unroll
-        for (int k = 0; k < kIirPf; k++) nxt[k] = (i4 + kIirPf + k < n4) ? __ldcs(f4 + i4 + kIirPf + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < kIirPf; k++) nxt[k] = (i4 + kIirPf + k < n4) ? __ldg(f4 + i4 + kIirPf + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < kIirPf; k++) {
             if (i4 + k < n4) {
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].x), d_mul(SNRX_IIR_BETA, l));
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].y), d_mul(SNRX_IIR_BETA, l));
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].z), d_mul(SNRX_IIR_BETA, l));
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].w), d_mul(SNRX_IIR_BETA, l));
+                l = zb_iir_step(l, cur[k].x);
+                l = zb_iir_step(l, cur[k].y);
+                l = zb_iir_step(l, cur[k].z);
+                l = zb_iir_step(l, cur[k].w);
             }
         }
     }
-    for (int i = n4 << 2; i < len; i++) l = d_add(d_mul(SNRX_IIR_ALPHA, (double)f[i]), d_mul(SNRX_IIR_BETA, l));
+    for (int i = n4 << 2; i < len; i++) l = zb_iir_step(l, f[i]);
     a.block_end[(size_t)s * a.n_blocks + b] = l;
 }
 
@@ -416,119 +509,96 @@ __global__ void __launch_bounds__(64) k_zb_iir_sum(ZbIirArgs a) {
 // length), oldest first -- one thread per (stream, block), no serial pass over the stream
 __global__ void __launch_bounds__(128) k_zb_iir_carry(ZbIirArgs a) {
     const uint32_t total = a.n_streams * (uint32_t)a.n_blocks;
-    const double decay = a.pw[SNRX_IIR_BLOCK - 1];
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const uint32_t s = idx / (uint32_t)a.n_blocks;
         const int b = (int)(idx % (uint32_t)a.n_blocks);
-        a.carry_in[idx] = zb_iir_fold(a.block_end + (size_t)s * a.n_blocks, b, decay);
+        a.carry_in[idx] = zb_iir_fold(a.block_end + (size_t)s * a.n_blocks, b, a.decay);
     }
 }
 
-__global__ void __launch_bounds__(64) k_zb_dc(ZbIirArgs a) {
-    __shared__ double pw_s[SNRX_IIR_BLOCK];                   // (1-alpha)^(i+1): same index for every thread -> broadcast
-    for (int i = threadIdx.x; i < SNRX_IIR_BLOCK; i += blockDim.x) pw_s[i] = a.pw[i];
-    __syncthreads();
-    const uint32_t total = a.n_streams * (uint32_t)a.n_blocks;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const uint32_t b = idx / a.n_streams, s = idx % a.n_streams;
-    const float* f = a.f + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
-    float* z = a.z + (size_t)s * a.stride + (size_t)b * SNRX_IIR_BLOCK;
-    const int len = min(SNRX_IIR_BLOCK, a.n - (int)b * SNRX_IIR_BLOCK);
-    const int n4 = len >> 2;
-    const float4* f4 = reinterpret_cast<const float4*>(f);
-    float4* z4 = reinterpret_cast<float4*>(z);
-    const double carry = a.carry_in[(size_t)s * a.n_blocks + b];
-    double l = 0.0;
-    float4 cur[kIirPf], nxt[kIirPf];
-#pragma unroll
-    for (int k = 0; k < kIirPf; k++) nxt[k] = (k < n4) ? __ldcs(f4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i4 = 0; i4 < n4; i4 += kIirPf) {
-#pragma unroll
-        for (int k = 0; k < kIirPf; k++) cur[k] = nxt[k];
-#pragma unroll
-        for (int k = 0; k < kIirPf; k++) nxt[k] = (i4 + kIirPf + k < n4) ? __ldcs(f4 + i4 + kIirPf + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < kIirPf; k++) {
-            if (i4 + k < n4) {
-                const int i = (i4 + k) << 2;
-                float4 o;
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].x), d_mul(SNRX_IIR_BETA, l));
-                o.x = f_sub(cur[k].x, (float)d_add(l, d_mul(pw_s[i], carry)));
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].y), d_mul(SNRX_IIR_BETA, l));
-                o.y = f_sub(cur[k].y, (float)d_add(l, d_mul(pw_s[i + 1], carry)));
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].z), d_mul(SNRX_IIR_BETA, l));
-                o.z = f_sub(cur[k].z, (float)d_add(l, d_mul(pw_s[i + 2], carry)));
-                l = d_add(d_mul(SNRX_IIR_ALPHA, (double)cur[k].w), d_mul(SNRX_IIR_BETA, l));
-                o.w = f_sub(cur[k].w, (float)d_add(l, d_mul(pw_s[i + 3], carry)));
-                z4[i4 + k] = o;
-            }
-        }
-    }
-    for (int i = n4 << 2; i < len; i++) {
-        const float fv = f[i];
-        l = d_add(d_mul(SNRX_IIR_ALPHA, (double)fv), d_mul(SNRX_IIR_BETA, l));
-        z[i] = f_sub(fv, (float)d_add(l, d_mul(pw_s[i], carry)));
-    }
-}
-
-// ... or, on the device, through a per-thread ring in shared memory that cp.async keeps kZbAhead samples
-// ahead of the chain.  The M&M loop is one long dependent chain per thread; with the samples already on
-// chip its step costs shared-memory latency instead of an L2 / HBM round trip every few steps.
-// Layout: ring row r of lane l at ring[r * 32 + l] -> every access of a warp is bank-conflict free whatever
-// the lanes' positions; rows 0..7 are mirrored at kZbRing.. so the 8 taps never wrap.
-constexpr int kZbRing = 128;          // samples held per chain (power of two)
-constexpr int kZbChunk = 16;          // samples per cp.async group
-constexpr int kZbAhead = 64;          // a group is waited for 3 groups (48 samples) after its issue
-constexpr int kZbChainThreads = 64;
-
-__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const float* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
+// ... or, on the device, from the raw discriminator stream through two per-thread rings in shared memory:
+//   raw ring   cp.async (16 bytes = 4 samples per request) keeps it ~64 samples ahead of the DC tracker; chunk c of lane l
+//              at raw[(c * 32 + l)] (float4): the copies and the tracker's 8-byte reads are bank-conflict free;
+//   z ring     the chain's own DC tracker (zb_iir_step from the carried state of each SNRX_IIR_BLOCK block) turns two raw
+//              samples per clock-recovery step into z = f - y and stores them at zr[r * 32 + l] (row r = sample mod 64,
+//              rows 0..7 mirrored at 64..71 so the 8 interpolator taps never wrap): every access of a warp is
+//              conflict free whatever the lanes' positions.
+// The DC-removed stream never exists in HBM (only with SNRX_F_KEEP_STREAMS, for the parity tests).  Fetch and tracker
+// are paced by the STEP COUNT (4 samples every other step, 2 samples every step), which is the same for all lanes of a
+// warp, not by each lane's position: no divergent refill branches inside the dependent clock-recovery loop.  The lanes'
+// positions wander around 2 samples per step by a few samples only; the guards below catch up (or pause) when a lane
+// drifts further, so correctness never depends on the pacing.
+constexpr int kZbRawChunks = 32;      // float4 chunks per lane in the raw ring (128 samples)
+constexpr int kZbZRows = 64;          // z samples per lane (power of two), + 8 mirrored rows
+constexpr int kZbLeadConv = 32;       // samples the tracker starts ahead of the clock recovery
+constexpr int kZbLeadFetch = 96;      // samples the copies start ahead of the clock recovery
+constexpr int kZbRxThreads = 32;      // one warp per CTA: 480 CTAs per capture-second spread over all SMs
 
 struct ZbRingSrc {
-    const float* z;        // stream
-    uint32_t ring;         // shared-memory byte address of this lane's column
-    uint32_t taps;         // shared-memory byte address of the interpolator table (kept in a register: the
-                           // compiler would otherwise rebuild it from SR_CgaCtaId inside the loop)
-    int32_t begin;         // stream index of ring position 0
-    int32_t fetched;       // samples requested so far (relative to begin, multiple of kZbChunk)
-    int32_t last;          // last readable stream index (requests beyond it are clamped; never consumed)
+    const float* f;        // raw discriminator stream of this (capture, channel)
+    const double* carry;   // carried tracker state of this stream's blocks
+    float* z_dbg;          // where to store z (SNRX_F_KEEP_STREAMS) or null
+    uint32_t raw, zr, taps;  // shared-memory byte addresses: this lane's column of the raw ring / of the z ring, the taps table
+    int32_t begin;         // stream index of ring position 0 (a multiple of SNRX_IIR_BLOCK)
+    int32_t fetched;       // samples requested so far, relative to begin (multiple of 4)
+    int32_t conv;          // samples the tracker has converted, relative to begin (even)
+    int32_t n;             // samples in the stream
+    int32_t z_lo, z_hi;    // debug: this chain stores z[z_lo, z_hi)
+    double y;              // tracker state
 
-    __device__ __forceinline__ void issue() {
-        const int r = fetched & (kZbRing - 1);
-        const uint32_t dst = ring + (uint32_t)r * 128u;
+    __device__ __forceinline__ void issue4() {
+        const uint32_t dst = raw + (uint32_t)((fetched >> 2) & (kZbRawChunks - 1)) * 512u;
         const int32_t g0 = begin + fetched;
-        if (g0 + kZbChunk - 1 <= last) {
-            const float* g = z + g0;
-#pragma unroll
-            for (int k = 0; k < kZbChunk; k++) cp_async4(dst + 128u * k, g + k);
-            if (r == 0) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) cp_async4(dst + 128u * (kZbRing + k), g + k);
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kZbChunk; k++) cp_async4(dst + 128u * k, z + min(g0 + k, last));
-            if (r == 0) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) cp_async4(dst + 128u * (kZbRing + k), z + min(g0 + k, last));
-            }
-        }
+        const int left = n - g0;                                   // samples of the stream from g0 on
+        const int bytes = left >= 4 ? 16 : left > 0 ? 4 * left : 0;   // the rest of the 16 bytes is zero-filled
+        const float* g = f + (left > 0 ? g0 : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(g), "r"(bytes) : "memory");
         asm volatile("cp.async.commit_group;\n" ::: "memory");
-        fetched += kZbChunk;
+        fetched += 4;
+    }
+    __device__ __forceinline__ void convert2() {
+        const uint32_t src = raw + (uint32_t)((conv >> 2) & (kZbRawChunks - 1)) * 512u + (uint32_t)(conv & 2) * 4u;
+        float f0, f1;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f0), "=f"(f1) : "r"(src));
+        const int32_t g = begin + conv;
+        if ((g & (SNRX_IIR_BLOCK - 1)) == 0) y = carry[g / SNRX_IIR_BLOCK];
+        y = zb_iir_step(y, f0);
+        const float z0 = zb_dc_out(f0, y);
+        y = zb_iir_step(y, f1);
+        const float z1 = zb_dc_out(f1, y);
+        const int r = conv & (kZbZRows - 1);
+        const uint32_t dst = zr + (uint32_t)r * 128u;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(z0) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 128u), "f"(z1) : "memory");
+        if (r < 8) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 128u * kZbZRows), "f"(z0) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 128u * (kZbZRows + 1)), "f"(z1) : "memory");
+        }
+        if (z_dbg) {
+            if (g >= z_lo && g < z_hi) z_dbg[g] = z0;
+            if (g + 1 >= z_lo && g + 1 < z_hi) z_dbg[g + 1] = z1;
+        }
+        conv += 2;
     }
     __device__ __forceinline__ void prime() {
-        while (fetched < 8 + kZbAhead) issue();
+        while (fetched < kZbLeadFetch) issue4();
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        while (conv < kZbLeadConv) convert2();
     }
-    // the chain advances by at most 3 samples per step and one group brings 16, so one issue per step
-    // keeps `fetched >= rel + 8 + kZbAhead`; everything but the 3 newest groups has landed after the wait
-    __device__ __forceinline__ void get8(int32_t ii, float (&in)[8]) {
+    // once per clock-recovery step, before get8(ii): j = step number inside the window (warp uniform)
+    __device__ __forceinline__ void tick(int j, int32_t ii) {
         const int rel = ii - begin;
-        if (fetched < rel + 8 + kZbAhead) issue();
-        asm volatile("cp.async.wait_group 3;\n" ::: "memory");
-        const uint32_t p = ring + (uint32_t)(rel & (kZbRing - 1)) * 128u;
+        if ((j & 1) == 0 && fetched - conv < kZbRawChunks * 4 - 8) issue4();
+        asm volatile("cp.async.wait_group 6;\n" ::: "memory");      // all but the 6 newest requests (24 samples) have landed
+        if (conv - rel < kZbZRows - 16 && fetched - conv >= 32) convert2();
+        while (conv - rel < 11) {                                     // this lane ran ahead of the pacing: catch up (rare)
+            while (fetched - conv < 8) issue4();
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            convert2();
+        }
+    }
+    __device__ __forceinline__ void get8(int32_t ii, float (&in)[8]) {
+        const uint32_t p = zr + (uint32_t)((ii - begin) & (kZbZRows - 1)) * 128u;
 #pragma unroll
         for (int k = 0; k < 8; k++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(in[k]) : "r"(p + 128u * k));
     }
@@ -539,45 +609,62 @@ struct ZbRingSrc {
     }
 };
 
-__global__ void __launch_bounds__(kZbChainThreads) k_zb_chain(const float* __restrict__ z, ZbChainParams p,
-                                                 const float* __restrict__ taps_g, ChipMap map_arg,
-                                                 const int32_t* __restrict__ channel_numbers,
-                                                 snrx_frame_t* __restrict__ slots, uint32_t* __restrict__ counts,
-                                                 int64_t* __restrict__ good_end,
-                                                 float* chips_dbg, int64_t chips_cap_per_chain, int64_t* nchips_dbg) {
+struct ZbRxArgs {
+    const float* f;              // [stream][f_stride] raw discriminator streams
+    const double* carry;         // [stream][n_blocks]
+    const float* taps;           // [129][8]
+    const int32_t* channel_numbers;
+    snrx_frame_t* slots; uint32_t* counts; int64_t* good_end;
+    uint32_t* overflow;          // set to 1 when a chain found more frames than it has slots
+    float* z_dbg;                // [stream][f_stride] or null
+    float* chips_dbg; int64_t chips_cap; int64_t* nchips_dbg;
+    ChipMap map;                 // kernel parameter: the chip words are constant-bank operands
+    ZbChainParams p;
+};
+
+// thread per (capture, channel, segment) chain: DC tracker, clock recovery, packet sink, FCS
+template <bool DEBUG>
+__global__ void __launch_bounds__(kZbRxThreads) k_zb_rx(const __grid_constant__ ZbRxArgs a) {
     __shared__ __align__(16) float taps[(SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS];
-    __shared__ float ring[(kZbChainThreads / 32) * (kZbRing + 8) * 32];
-    for (int i = threadIdx.x; i < (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS; i += blockDim.x) taps[i] = taps_g[i];
+    __shared__ __align__(16) float4 raw[kZbRawChunks * kZbRxThreads];
+    __shared__ float zring[(kZbZRows + 8) * kZbRxThreads];
+    for (int i = threadIdx.x; i < (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS; i += blockDim.x) taps[i] = a.taps[i];
     __syncthreads();
-    const uint32_t total = p.n_captures * p.n_channels * (uint32_t)p.n_segments;
+    const ZbChainParams& p = a.p;
+    const uint32_t n_streams = p.n_captures * p.n_channels;
+    const uint32_t total = n_streams * (uint32_t)p.n_segments;
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
-    const uint32_t* map = map_arg.w;            // kernel parameter: the chip words are constant-bank operands
     // consecutive threads take different streams so that a warp touches many DRAM pages at once
-    const uint32_t seg = idx / (p.n_captures * p.n_channels);
-    const uint32_t sc = idx % (p.n_captures * p.n_channels);
+    const uint32_t seg = idx / n_streams, sc = idx % n_streams;
     const uint32_t cap = sc / p.n_channels, ch = sc % p.n_channels;
-    const uint32_t chain = (cap * p.n_channels + ch) * (uint32_t)p.n_segments + seg;    // output order
+    const uint32_t chain = sc * (uint32_t)p.n_segments + seg;          // output order
     ZbRingSrc src;
-    src.z = z + (size_t)sc * p.z_stride;
-    src.ring = (uint32_t)__cvta_generic_to_shared(ring + (threadIdx.x >> 5) * ((kZbRing + 8) * 32) + (threadIdx.x & 31));
+    src.f = a.f + (size_t)sc * p.f_stride;
+    src.carry = a.carry + (size_t)sc * p.n_blocks;
+    src.z_dbg = (DEBUG && a.z_dbg) ? a.z_dbg + (size_t)sc * p.f_stride : nullptr;
+    src.raw = (uint32_t)__cvta_generic_to_shared(raw + threadIdx.x);
+    src.zr = (uint32_t)__cvta_generic_to_shared(zring + threadIdx.x);
     src.taps = (uint32_t)__cvta_generic_to_shared(taps);
-    asm volatile("" : "+r"(src.ring), "+r"(src.taps));          // opaque: stay in registers
+    asm volatile("" : "+r"(src.raw), "+r"(src.zr), "+r"(src.taps));   // opaque: stay in registers
     {
         const int32_t lo = p.origin + (int32_t)seg * p.segment;
-        src.begin = lo - p.prehalo > 0 ? lo - p.prehalo : 0;                  // = the chain's first sample
+        src.begin = lo - p.prehalo > 0 ? lo - p.prehalo : 0;          // = the chain's first sample, on the tracker's block grid
+        int32_t hi = lo + p.segment; if (hi > p.origin + p.body) hi = p.origin + p.body;
+        src.z_lo = seg == 0 ? 0 : lo; src.z_hi = (int)seg == p.n_segments - 1 ? p.n_out : hi;
     }
-    src.fetched = 0;
-    src.last = p.n_out > 0 ? p.n_out - 1 : 0;
+    src.fetched = 0; src.conv = 0; src.n = p.n_out; src.y = 0.0;
     src.prime();
-    int64_t nchips = 0;
-    const uint32_t nf = zb_run_chain(src, p, (int)seg, map, channel_numbers[ch], p.first_capture + cap,
-                                     slots + (size_t)chain * p.slots_per_chain,
-                                     chips_dbg ? chips_dbg + (size_t)chain * chips_cap_per_chain : nullptr,
-                                     chips_cap_per_chain, &nchips, good_end + chain);
+    int64_t nchips = 0, good_end = 0;
+    const uint32_t nf = zb_run_chain<DEBUG>(src, p, (int)seg, a.map.w, a.channel_numbers[ch], p.first_capture + cap,
+                                            a.slots + (size_t)chain * p.slots_per_chain,
+                                            (DEBUG && a.chips_dbg) ? a.chips_dbg + (size_t)chain * a.chips_cap : nullptr,
+                                            a.chips_cap, &nchips, &good_end);
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    counts[chain] = nf < p.slots_per_chain ? nf : p.slots_per_chain;
-    if (nchips_dbg) nchips_dbg[chain] = nchips;
+    a.good_end[chain] = good_end;
+    a.counts[chain] = nf < p.slots_per_chain ? nf : p.slots_per_chain;
+    if (nf > p.slots_per_chain) *a.overflow = 1u;
+    if (DEBUG && a.nchips_dbg) a.nchips_dbg[chain] = nchips;
 }
 
 // one thread per chain: drop the CRC-failed records that lie inside a CRC-ok frame of this or a preceding chain
@@ -621,7 +708,8 @@ struct ZbState {
     uint32_t n_ch = 0, max_caps = 0, max_out = 0;
     size_t stride = 0;                 // floats per (capture, channel) stream
     float *d_f = nullptr, *d_z = nullptr;
-    double *d_block_end = nullptr, *d_carry = nullptr, *d_pw = nullptr;
+    double *d_block_end = nullptr, *d_carry = nullptr;
+    double decay = 0.0;
     float *d_atan = nullptr, *d_mmse = nullptr;
     int32_t* d_channels = nullptr;
     snrx_frame_t* d_slots = nullptr; size_t slots_bytes = 0;
@@ -636,7 +724,7 @@ struct ZbState {
 };
 
 inline void zb_free(ZbState& s) {
-    void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_pw, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
+    void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
                     s.d_counts, s.d_offsets, s.d_scratch, s.d_good_end, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     s = ZbState();
@@ -656,19 +744,21 @@ inline void zb_free(ZbState& s) {
 inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32_t n_ch, uint32_t max_caps,
                      uint32_t max_out, int sm_count, std::string& err) {
     (void)sm_count;
+    static_assert(SNRX_IIR_BLOCK == SNRX_ZB_IIR_BLOCK && SNRX_IIR_MEMORY_BLOCKS == SNRX_ZB_IIR_MEMORY_BLOCKS, "include/snoutrx.h and zb_tables.h disagree");
     s.n_ch = n_ch; s.max_caps = max_caps; s.max_out = max_out;
+    if (cfg.zb_segment % SNRX_IIR_BLOCK || cfg.zb_prehalo % SNRX_IIR_BLOCK) {
+        err = "zigbee: zb_segment and zb_prehalo must be multiples of 2048 (the DC tracker's block grid)"; return SNRX_EINVAL;
+    }
     if ((uint64_t)max_out + cfg.zb_segment + kZbPostHalo >= (1ull << 31)) { err = "zigbee: capture too long for 32-bit chain positions"; return SNRX_ERANGE; }
     s.stride = ((size_t)max_out + 8 + 31) & ~(size_t)31;
     const size_t streams = (size_t)max_caps * n_ch;
+    const bool keep = (cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
     ZCK(cudaMalloc((void**)&s.d_f, streams * s.stride * sizeof(float)));
-    ZCK(cudaMalloc((void**)&s.d_z, streams * s.stride * sizeof(float)));
+    if (keep) ZCK(cudaMalloc((void**)&s.d_z, streams * s.stride * sizeof(float)));
     const size_t nblk = (max_out + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK;
     ZCK(cudaMalloc((void**)&s.d_block_end, streams * nblk * sizeof(double)));
     ZCK(cudaMalloc((void**)&s.d_carry, streams * nblk * sizeof(double)));
-    std::vector<double> pw(SNRX_IIR_BLOCK);
-    { volatile double p = 1.0; const double b = SNRX_IIR_BETA; for (int i = 0; i < SNRX_IIR_BLOCK; i++) { p = p * b; pw[i] = p; } }
-    ZCK(cudaMalloc((void**)&s.d_pw, sizeof(double) * SNRX_IIR_BLOCK));
-    ZCK(cudaMemcpy(s.d_pw, pw.data(), sizeof(double) * SNRX_IIR_BLOCK, cudaMemcpyHostToDevice));
+    s.decay = zb_iir_block_decay();
     ZCK(cudaMalloc((void**)&s.d_atan, sizeof(SNRX_ATAN_TAB)));
     ZCK(cudaMemcpy(s.d_atan, SNRX_ATAN_TAB, sizeof(SNRX_ATAN_TAB), cudaMemcpyHostToDevice));
     ZCK(cudaMalloc((void**)&s.d_mmse, sizeof(SNRX_MMSE_TAPS)));
@@ -679,14 +769,14 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     ZCK(cudaMemcpy(s.d_channels, chans, sizeof chans, cudaMemcpyHostToDevice));
     const uint32_t max_segs = (max_out + cfg.zb_segment - 1) / cfg.zb_segment;
     s.max_chains = (uint32_t)(streams * max_segs);
-    s.slots_per_chain = cfg.zb_segment / kZbMinFrameSamples + 2;
+    s.slots_per_chain = zb_slots_per_chain(cfg.zb_segment);
     s.slots_bytes = (size_t)s.max_chains * s.slots_per_chain * sizeof(snrx_frame_t);
     ZCK(cudaMalloc((void**)&s.d_slots, s.slots_bytes));
     ZCK(cudaMalloc((void**)&s.d_counts, sizeof(uint32_t) * ((size_t)s.max_chains + 1)));
     ZCK(cudaMalloc((void**)&s.d_offsets, sizeof(uint32_t) * ((size_t)s.max_chains + 1)));
     ZCK(cudaMalloc((void**)&s.d_scratch, sizeof(uint32_t) * scan_scratch_items(s.max_chains)));
     ZCK(cudaMalloc((void**)&s.d_good_end, sizeof(int64_t) * ((size_t)s.max_chains + 1)));
-    if (cfg.flags & SNRX_F_KEEP_STREAMS) {
+    if (keep) {
         s.chips_cap = ((int64_t)cfg.zb_segment + cfg.zb_prehalo + kZbPostHalo) / 2 + 64;
         ZCK(cudaMalloc((void**)&s.d_chips, sizeof(float) * (size_t)s.max_chains * (size_t)s.chips_cap));
         ZCK(cudaMalloc((void**)&s.d_nchips, sizeof(int64_t) * (size_t)s.max_chains));
@@ -700,11 +790,13 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
 inline int zb_wideband_front(ZbState& s, const snrx_config_t& cfg, const float2* x, uint32_t n_captures, uint64_t n_samples,
                       uint64_t stride, uint32_t n_out, cudaStream_t st, int& launches, std::string& err);
 
+// totals: [2] receives the Zigbee frame count, [3] is set when a chain ran out of frame slots
 inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uint32_t n_captures, uint64_t n_samples,
                       uint64_t stride, uint32_t n_out, uint32_t pre_out, uint32_t body_out, uint32_t first_segment,
                       uint32_t first_capture, snrx_frame_t* frames, uint32_t frame_cap, uint32_t* totals, bool after_ble,
                       cudaStream_t st, int sm_count, int& launches, std::string& err, cudaEvent_t ev_front_done = nullptr) {
     const bool wideband = (cfg.mode != SNRX_MODE_ZB_NB);
+    const bool keep = (cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
     const uint32_t streams = n_captures * s.n_ch;
     if (wideband) {
         int r = zb_wideband_front(s, cfg, x, n_captures, n_samples, stride, n_out, st, launches, err);
@@ -720,26 +812,32 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     }
     if (ev_front_done) ZCK(cudaEventRecord(ev_front_done, st));      // front end = channelizer + discriminator (stats.gpu_ms_frontend)
     ZbIirArgs ia;
-    ia.f = s.d_f; ia.z = s.d_z; ia.stride = s.stride; ia.n = (int32_t)n_out;
+    ia.f = s.d_f; ia.stride = s.stride; ia.n = (int32_t)n_out;
     ia.n_blocks = (int32_t)((n_out + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK); ia.n_streams = streams;
-    ia.block_end = s.d_block_end; ia.carry_in = s.d_carry; ia.pw = s.d_pw;
+    ia.block_end = s.d_block_end; ia.carry_in = s.d_carry; ia.decay = s.decay;
     const uint32_t nb_total = streams * (uint32_t)ia.n_blocks;
     k_zb_iir_sum<<<(nb_total + 63) / 64, 64, 0, st>>>(ia);
-    k_zb_iir_carry<<<(nb_total + 127) / 128, 128, 0, st>>>(ia);
-    k_zb_dc<<<(nb_total + 63) / 64, 64, 0, st>>>(ia);
-    launches += 3;
+    k_zb_iir_carry<<<std::min<uint32_t>((nb_total + 127) / 128, (uint32_t)sm_count * 8), 128, 0, st>>>(ia);
+    launches += 2;
 
-    ZbChainParams p{};
+    ZbRxArgs a{};
+    ZbChainParams& p = a.p;
     p.n_out = (int32_t)n_out; p.origin = (int32_t)pre_out; p.body = (int32_t)body_out;
     p.segment = (int32_t)cfg.zb_segment; p.prehalo = (int32_t)cfg.zb_prehalo;
     p.n_segments = (int32_t)((body_out + cfg.zb_segment - 1) / cfg.zb_segment);
+    p.n_blocks = ia.n_blocks;
     p.first_segment = first_segment; p.first_capture = first_capture;
     p.n_captures = n_captures; p.n_channels = s.n_ch; p.threshold = cfg.zb_threshold;
-    p.slots_per_chain = s.slots_per_chain; p.z_stride = s.stride;
+    p.slots_per_chain = s.slots_per_chain; p.f_stride = s.stride;
     const uint32_t n_chains = streams * (uint32_t)p.n_segments;
     if (n_chains > s.max_chains) { err = "zigbee: more chains than capacity"; return SNRX_ERANGE; }
-    k_zb_chain<<<(n_chains + kZbChainThreads - 1) / kZbChainThreads, kZbChainThreads, 0, st>>>(s.d_z, p, s.d_mmse, s.map, s.d_channels, s.d_slots, s.d_counts,
-                                                  s.d_good_end, s.d_chips, s.chips_cap, s.d_nchips);
+    a.f = s.d_f; a.carry = s.d_carry; a.taps = s.d_mmse; a.channel_numbers = s.d_channels;
+    a.slots = s.d_slots; a.counts = s.d_counts; a.good_end = s.d_good_end; a.overflow = totals + 3;
+    a.z_dbg = s.d_z; a.chips_dbg = s.d_chips; a.chips_cap = s.chips_cap; a.nchips_dbg = s.d_nchips; a.map = s.map;
+    const uint32_t grid = (n_chains + kZbRxThreads - 1) / kZbRxThreads;
+    if (keep) ZCK(cudaMemsetAsync(s.d_z, 0, (size_t)streams * s.stride * sizeof(float), st));
+    if (keep) k_zb_rx<true><<<grid, kZbRxThreads, 0, st>>>(a);
+    else k_zb_rx<false><<<grid, kZbRxThreads, 0, st>>>(a);
     k_zb_span_filter<<<(n_chains + 127) / 128, 128, 0, st>>>(s.d_slots, s.slots_per_chain, s.d_counts, s.d_good_end, n_chains,
                                                              (uint32_t)p.n_segments, zb_filter_lookback(p.segment));
     launches += 2 + exclusive_scan(s.d_counts, n_chains, s.d_offsets, s.d_scratch, st);
@@ -754,7 +852,10 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
 inline int zb_debug_stage(ZbState& s, int stage, uint32_t caps, uint32_t n_out, const void** src, uint64_t* bytes) {
     (void)n_out;
     if (!s.ready) return SNRX_ESTATE;
-    if (stage == SNRX_STAGE_ZB_DISC) { *src = s.d_z; *bytes = (uint64_t)caps * s.n_ch * s.stride * sizeof(float); return SNRX_OK; }
+    if (stage == SNRX_STAGE_ZB_DISC) {
+        if (!s.d_z) return SNRX_ESTATE;
+        *src = s.d_z; *bytes = (uint64_t)caps * s.n_ch * s.stride * sizeof(float); return SNRX_OK;
+    }
     if (stage == SNRX_STAGE_ZB_CHIPS) {
         if (!s.d_chips) return SNRX_ESTATE;
         *src = s.d_chips; *bytes = (uint64_t)s.last_chains * (uint64_t)s.chips_cap * sizeof(float); return SNRX_OK;

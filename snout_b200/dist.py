@@ -63,7 +63,7 @@ def plan_job(n_captures: int, n_samples: int, engine=None, units_per_shard: int 
     so the union of the results is the same for any world size."""
     from . import stream
     if geometry is None:
-        geometry = stream.shard_geometry(engine.n_ble, engine.n_zb, engine.cfg.zb_segment or 8192, engine.cfg.zb_prehalo or 4096)
+        geometry = stream.shard_geometry(engine.n_ble, engine.n_zb, engine.cfg.zb_segment, engine.cfg.zb_prehalo)
     if decim is None:
         decim = engine.decim
     unit, pre, post = geometry

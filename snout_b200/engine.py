@@ -72,7 +72,7 @@ class RxEngine:
         self.decim = chanplan.WB_DECIM if self.wideband else 1
         self.n_ble = {MODE_BLE_NB: 1, MODE_BLE_WB40: 40, MODE_MIXED_WB56: 40}.get(self.mode, 0)
         self.n_zb = {MODE_ZB_NB: 1, MODE_ZB_WB16: 16, MODE_MIXED_WB56: 16}.get(self.mode, 0)
-        self._keepalive = None
+        self._keepalive = []             # inputs of the (up to two) batches in flight: released when their batch is polled
         self._last = None
 
     # ------------------------------------------------------------------ life cycle
@@ -113,7 +113,9 @@ class RxEngine:
         """Queue one batch.  `iq`: complex64 numpy array [n] or [captures, n] (host memory), a
         _abi.PinnedBuffer, or a torch CUDA tensor of complex64 [n] / [captures, n].  int8 arrays / tensors
         with a trailing axis of 2 ([n, 2] or [captures, n, 2]: interleaved I,Q as a HackRF delivers them,
-        btle_rx.c:489-498) take the sc8 entry point; their sample value is q / 128."""
+        btle_rx.c:489-498) take the sc8 entry point; their sample value is q / 128.  The engine reads the input
+        asynchronously (kernels on its own streams, chunked host->device copies): it keeps a reference until the batch has
+        been polled; callers that pass raw pointers (process_device_ptr) must keep the memory alive themselves."""
         sh = None
         if shard:
             sh = Shard(int(shard.get("pre_samples", 0)), int(shard.get("body_samples", 0)),
@@ -136,7 +138,7 @@ class RxEngine:
                 n = shape[-1] if n_samples is None else n_samples
                 st = stride or shape[-1]
                 self.set_stream(torch.cuda.current_stream(iq.device).cuda_stream)
-                self._keepalive = iq
+                self._keepalive.append(iq)
                 self._check(fn(self.handle, c_void_p(iq.data_ptr()), caps, n, st, byref(sh) if sh else None, 1))
                 self._last = (caps, n)
                 return self
@@ -153,7 +155,7 @@ class RxEngine:
         caps = 1 if len(shape) == 1 else shape[0]
         n = shape[-1] if n_samples is None else n_samples
         st = stride or shape[-1]
-        self._keepalive = a
+        self._keepalive.append(a)
         self._check(fn(self.handle, a.ctypes.data_as(c_void_p), caps, n, st, byref(sh) if sh else None, 0))
         self._last = (caps, n)
         return self
@@ -170,7 +172,11 @@ class RxEngine:
         pinned result buffer, valid until the second-next process()."""
         n = c_uint32(0)
         ptr = c_void_p()
-        self._check(self.lib.snrx_poll_view(self.handle, byref(ptr), byref(n)))
+        try:
+            self._check(self.lib.snrx_poll_view(self.handle, byref(ptr), byref(n)))
+        finally:
+            if self._keepalive:              # the oldest batch is done with its input (host copies and kernels have finished)
+                self._keepalive.pop(0)
         if n.value == 0:
             return np.zeros(0, dtype=FRAME_DTYPE)
         buf = (ctypes.c_char * (n.value * FRAME_DTYPE.itemsize)).from_address(ptr.value)

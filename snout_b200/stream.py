@@ -20,23 +20,25 @@ import numpy as np
 
 from . import _abi, chanplan
 
-ZB_IIR_MEMORY = (8 + 1) * 4096    # (SNRX_IIR_MEMORY_BLOCKS + 1) * SNRX_IIR_BLOCK: 8 remembered blocks + the buffer's first block
+ZB_IIR_MEMORY = (_abi.ZB_IIR_MEMORY_BLOCKS + 1) * _abi.ZB_IIR_BLOCK    # the remembered blocks + the buffer's first block (include/snoutrx.h)
 ZB_POST_HALO = 16448 + 64         # kZbPostHalo (csrc/zb.cuh) rounded up
 BLE_PRE_HALO = 128
 BLE_POST_HALO = 2048
 
 
-def shard_geometry(n_ble: int, n_zb: int, zb_segment: int = 8192, zb_prehalo: int = 4096) -> tuple[int, int, int]:
-    """(unit, pre, post) in channel-rate samples for an engine with n_ble / n_zb receivers."""
+def shard_geometry(n_ble: int, n_zb: int, zb_segment: int = 0, zb_prehalo: int = 0) -> tuple[int, int, int]:
+    """(unit, pre, post) in channel-rate samples for an engine with n_ble / n_zb receivers (0 = the library defaults)."""
+    zb_segment = zb_segment or _abi.ZB_SEGMENT_DEFAULT
+    zb_prehalo = zb_prehalo or _abi.ZB_PREHALO_DEFAULT
     unit, pre, post = chanplan.BLE_WINDOW, 0, 0
     if n_ble:
         pre, post = BLE_PRE_HALO, BLE_POST_HALO
     if n_zb:
-        if zb_segment % chanplan.BLE_WINDOW:
-            raise ValueError("zb_segment must be a multiple of 8192 for sharded operation")
-        unit = zb_segment
+        if zb_segment % chanplan.BLE_WINDOW and chanplan.BLE_WINDOW % zb_segment:
+            raise ValueError("zb_segment must divide 8192 or be a multiple of it for sharded operation")
+        unit = max(zb_segment, chanplan.BLE_WINDOW)      # shard bodies start on the 8192-sample window grid
         need = ZB_IIR_MEMORY + zb_prehalo
-        pre = max(pre, -(-need // 4096) * 4096)
+        pre = max(pre, -(-need // _abi.ZB_IIR_BLOCK) * _abi.ZB_IIR_BLOCK)
         post = max(post, ZB_POST_HALO)
     return unit, pre, post
 
@@ -53,7 +55,7 @@ def plan_shards(n_samples: int, decim: int, unit: int, pre: int, post: int, unit
         lo = max(0, b0 - pre)
         hi = min(n_ch, b1 + post)
         last = b0 + body + post >= n_ch            # the stream ends inside this shard's post halo: take the rest
-        out.append(dict(lo=lo * decim, hi=(n_samples if last else hi * decim), pre_samples=(b0 - lo) * decim,
+        out.append(dict(lo=lo * decim, hi=(n_ch if last else hi) * decim, pre_samples=(b0 - lo) * decim,
                         body_samples=0 if last else (b1 - b0) * decim, first_window=b0 // chanplan.BLE_WINDOW))
         if last:
             break
@@ -101,8 +103,7 @@ class ShardStreamer:
     def __init__(self, engine, units_per_shard: int | None = None):
         self.eng = engine
         self.decim = engine.decim
-        self.unit, self.pre, self.post = shard_geometry(engine.n_ble, engine.n_zb, engine.cfg.zb_segment or 8192,
-                                                        engine.cfg.zb_prehalo or 4096)
+        self.unit, self.pre, self.post = shard_geometry(engine.n_ble, engine.n_zb, engine.cfg.zb_segment, engine.cfg.zb_prehalo)
         cap_in = int(engine.cfg.max_samples) or (96_000_000 if engine.wideband else 10_000_000)   # snrx_create defaults
         cap_ch = cap_in // self.decim
         room = (cap_ch - self.pre - self.post) // self.unit

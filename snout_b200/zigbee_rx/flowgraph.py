@@ -34,7 +34,7 @@ from xmlrpc.server import SimpleXMLRPCServer
 
 import numpy as np
 
-from .. import chanplan, formats
+from .. import _abi, chanplan, formats
 
 XMLRPC_ADDR = ("localhost", 8080)           # top_block.py:47
 UDP_DEST = ("127.0.0.1", 52002)             # top_block.py:71
@@ -123,18 +123,19 @@ class top_block:
             self.frames_sent += 1
 
     def _run(self):
-        from ..stream import ShardStreamer, iq_blocks
+        from ..stream import ShardStreamer, iq_blocks, shard_geometry
         factory = self._engine_factory
         if factory is None:
             from ..engine import RxEngine
             factory = RxEngine
         mode = "zb_wb16" if self._wideband else "zb_nb"
         decim = chanplan.WB_DECIM if self._wideband else 1
-        seg = self._zb_segment or 8192
-        nseg = self._segments or (262144 if self._wideband else 1048576) // seg
+        seg = self._zb_segment or _abi.ZB_SEGMENT_DEFAULT
+        unit, pre, post = shard_geometry(0, 1, seg)                     # shard bodies: whole units of max(segment, 8192) samples
+        nseg = self._segments or (262144 if self._wideband else 1048576) // unit
         try:
             eng = factory(mode, channel=self.channel, device=self._device, zb_segment=seg,
-                          max_samples=(nseg * seg + 40960 + 16512) * decim)
+                          max_samples=(nseg * unit + pre + post) * decim)
         except Exception as e:                                         # no GPU / no library: there is no CPU path
             self.error = e
             sys.stderr.write(f"Zigbee_rx (snout_b200): cannot start the GPU receive engine: {e}\n")

@@ -265,44 +265,45 @@ void emu_zb_quad(const float* x, int64_t n, float* f) {
     }
 }
 void emu_zb_dc(const float* f, int64_t n, float* z) {
-    std::vector<double> pw(SNRX_IIR_BLOCK);
-    { volatile double p = 1.0; const double b = SNRX_IIR_BETA; for (int i = 0; i < SNRX_IIR_BLOCK; i++) { p = p * b; pw[i] = p; } }
+    const double decay = zb_iir_block_decay();
     const int nb = (int)((n + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK);
     std::vector<double> block_end(nb), carry_in(nb);
     for (int b = 0; b < nb; b++) {                      // k_zb_iir_sum
         const int len = (int)std::min<int64_t>(SNRX_IIR_BLOCK, n - (int64_t)b * SNRX_IIR_BLOCK);
         double l = 0.0;
-        for (int i = 0; i < len; i++) l = d_add(d_mul(SNRX_IIR_ALPHA, (double)f[(size_t)b * SNRX_IIR_BLOCK + i]), d_mul(SNRX_IIR_BETA, l));
+        for (int i = 0; i < len; i++) l = zb_iir_step(l, f[(size_t)b * SNRX_IIR_BLOCK + i]);
         block_end[b] = l;
     }
-    for (int b = 0; b < nb; b++) carry_in[b] = zb_iir_fold(block_end.data(), b, pw[SNRX_IIR_BLOCK - 1]);   // k_zb_iir_carry
-    for (int b = 0; b < nb; b++) {                      // k_zb_dc
+    for (int b = 0; b < nb; b++) carry_in[b] = zb_iir_fold(block_end.data(), b, decay);   // k_zb_iir_carry
+    for (int b = 0; b < nb; b++) {                      // the tracker inside k_zb_rx (ZbRingSrc::convert2)
         const int len = (int)std::min<int64_t>(SNRX_IIR_BLOCK, n - (int64_t)b * SNRX_IIR_BLOCK);
-        double l = 0.0;
+        double y = carry_in[b];
         for (int i = 0; i < len; i++) {
             const float fv = f[(size_t)b * SNRX_IIR_BLOCK + i];
-            l = d_add(d_mul(SNRX_IIR_ALPHA, (double)fv), d_mul(SNRX_IIR_BETA, l));
-            const double y = d_add(l, d_mul(pw[i], carry_in[b]));
-            z[(size_t)b * SNRX_IIR_BLOCK + i] = f_sub(fv, (float)y);
+            y = zb_iir_step(y, fv);
+            z[(size_t)b * SNRX_IIR_BLOCK + i] = zb_dc_out(fv, y);
         }
     }
 }
+// chains over a DC-removed stream: zb_run_chain (the per-thread code of k_zb_rx) with the samples read straight from z
 int emu_zb_chains(const float* z, int n_out, int origin, int body, int segment, int prehalo, uint32_t first_segment,
-                  int threshold, int channel, snrx_frame_t* out, int cap) {
+                  int threshold, int channel, snrx_frame_t* out, int cap, int64_t* nchips_out /* [n_segments] or null */) {
     ZbChainParams p{};
     p.n_out = n_out; p.origin = origin; p.body = body; p.segment = segment; p.prehalo = prehalo;
     p.n_segments = (body + segment - 1) / segment; p.first_segment = first_segment; p.first_capture = 0;
-    p.n_captures = 1; p.n_channels = 1; p.threshold = threshold; p.slots_per_chain = segment / kZbMinFrameSamples + 2;
-    p.z_stride = 0;
+    p.n_captures = 1; p.n_channels = 1; p.threshold = threshold; p.slots_per_chain = zb_slots_per_chain(segment);
+    p.f_stride = 0;
     ChipMap map = make_chip_map();
-    // k_zb_chain: every chain into its own slots + the end of its CRC-ok frames
+    // k_zb_rx: every chain into its own slots + the end of its CRC-ok frames
     std::vector<snrx_frame_t> slots((size_t)p.slots_per_chain * p.n_segments);
     std::vector<uint32_t> counts(p.n_segments);
     std::vector<int64_t> good_end(p.n_segments);
     for (int seg = 0; seg < p.n_segments; seg++) {
         ZbDirectSrc src{z, &SNRX_MMSE_TAPS[0][0]};
-        uint32_t nf = zb_run_chain(src, p, seg, map.w, channel, 0, slots.data() + (size_t)seg * p.slots_per_chain, nullptr, 0, nullptr,
-                                   &good_end[seg]);
+        int64_t nchips = 0;
+        uint32_t nf = zb_run_chain<false>(src, p, seg, map.w, channel, 0, slots.data() + (size_t)seg * p.slots_per_chain, nullptr, 0,
+                                          &nchips, &good_end[seg]);
+        if (nchips_out) nchips_out[seg] = nchips;
         counts[seg] = nf < p.slots_per_chain ? nf : p.slots_per_chain;
     }
     // k_zb_span_filter (one thread per chain), then k_zb_gather
@@ -315,6 +316,32 @@ int emu_zb_chains(const float* z, int n_out, int origin, int body, int segment, 
         for (uint32_t k = 0; k < w; k++) { if (n < cap) out[n] = slots[(size_t)seg * p.slots_per_chain + k]; n++; }
     }
     return n;
+}
+
+// the windowed sink alone on given hard chips (one bit per chip), against which the reference sink is compared:
+// returns the number of frames, lens[k] / bytes[k][128] / end_chip[k] (index of the chip that completed frame k)
+int emu_zb_sink_chips(const uint8_t* chips, int64_t n, int threshold, int32_t* lens, uint8_t* bytes, int64_t* end_chip, int cap) {
+    ChipMap map = make_chip_map();
+    ZbSinkW s; zb_sinkw_init(s);
+    snrx_frame_t slot;
+    ZbEmit em{};
+    em.slots = &slot; em.cap = 1; em.nf = 0; em.lo = 0; em.hi = 0x7FFFFFFF; em.index_base = 0; em.good_end = 0;
+    int k = 0;
+    for (int64_t w0 = 0; w0 < n; w0 += 32) {
+        const int nvalid = (int)std::min<int64_t>(32, n - w0);
+        uint32_t C = 0;
+        for (int j = 0; j < nvalid; j++) C = (C << 1) | (chips[w0 + j] & 1u);
+        if (nvalid < 32) C <<= (32 - nvalid);
+        int consumed = 0;
+        const int jb = s.jb;
+        const bool done = zb_sink_window(s, C, nvalid, nvalid, (int32_t)(w0 + jb), map.w, threshold, em, &consumed);
+        if (em.nf) {                                     // a frame completed at the boundary of this window
+            if (k < cap) { lens[k] = slot.len; memcpy(bytes + (size_t)k * 128, slot.bytes, 128); end_chip[k] = w0 + jb; }
+            k++; em.nf = 0;
+        }
+        if (done) break;
+    }
+    return k;
 }
 
 // one record through ble_adv_parse (k_ble_adv_summary's per-thread code)

@@ -94,10 +94,15 @@ def test_sort_reference_order():
 
 def test_plan_job_does_not_depend_on_world():
     from fake_engine import ContentEngine
-    eng = ContentEngine("mixed_wb56", max_samples=(2 * 65536 + 40960 + 16512) * 24, zb_segment=65536, zb_prehalo=4096)
+    from snout_b200 import stream
+    unit, pre, post = stream.shard_geometry(40, 16, 65536, 4096)
+    eng = ContentEngine("mixed_wb56", max_samples=(2 * unit + pre + post) * 24, zb_segment=65536, zb_prehalo=4096)
     units = sdist.plan_job(2, 24 * 65536 * 5 + 240, eng)
     assert [u["first_window"] for u in units if u["capture"] == 0] == [0, 16, 32]
-    assert all(u["pre_samples"] in (0, 40960 * 24) for u in units)
+    assert all(u["pre_samples"] in (0, pre * 24) for u in units)
+    # a capture whose length is not a multiple of the decimation: every shard still is
+    odd = sdist.plan_job(1, 24 * 65536 * 3 + 7, eng)
+    assert all((u["hi"] - u["lo"]) % 24 == 0 for u in odd) and odd[-1]["hi"] == 24 * 65536 * 3
     cover = sorted(i for w in (4,) for r in range(w) for i in sdist.assign_round_robin(len(units), r, w))
     assert cover == list(range(len(units)))
 

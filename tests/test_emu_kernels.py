@@ -165,10 +165,18 @@ def test_zigbee_cores(emu, oracle_mod):
     emu.emu_zb_dc(P(f), ctypes.c_int64(n), P(z))
     assert np.array_equal(z, oracle_mod.zb_dc_remove(f))
     out = np.zeros(1024, dtype=oracle_mod.FRAME_DTYPE)
-    k = emu.emu_zb_chains(P(z), n, 0, n, 65536, 4096, ctypes.c_uint32(0), 10, 11, P(out), 1024)
-    want = oracle_mod.zb_receive(cap.iq, 11, segment=65536, prehalo=4096)
-    assert len(want) > 5
-    assert_frames_equal(out[:k], want, what="zigbee chains")
+    for seg, pre in ((65536, 4096), (4096, 2048), (8192, 2048)):
+        nseg = -(-n // seg)
+        nch = np.zeros(nseg, dtype=np.int64)
+        k = emu.emu_zb_chains(P(z), n, 0, n, seg, pre, ctypes.c_uint32(0), 10, 11, P(out), 1024, P(nch))
+        want = oracle_mod.zb_receive(cap.iq, 11, segment=seg, prehalo=pre)
+        assert len(want) > 5
+        assert_frames_equal(out[:k], want, what=f"zigbee chains {seg}/{pre}")
+        # every chain stops at the very chip the oracle's chip-by-chip sink stops at
+        for c in range(nseg):
+            lo, hi = c * seg, min(n, (c + 1) * seg)
+            _, ck, _ = oracle_mod.zb_chain(z, max(0, lo - pre), min(n, hi + 16448), lo, hi, want_chips=True, hold=lo - 1024)
+            assert nch[c] == len(ck), (seg, c, nch[c], len(ck))
 
 
 @pytest.mark.parametrize("nt,name", [(16, "ZB_384"), (32, "ZB_768")])

@@ -60,8 +60,10 @@ def test_stream_equals_whole_zigbee(Engine):
     cap = synth.zigbee_capture(n=1_000_000, channel=15, seed=91, esn0_db=15.0, gap=(500, 9000))
     with Engine("zb_nb", channel=15, max_samples=len(cap.iq)) as e:
         whole = e.run(cap.iq)
-    with Engine("zb_nb", channel=15, max_samples=3 * 65536 + 40960 + 16512) as e:
-        got = _stream_all(e, cap.iq, units=3, block=77_777)
+    from snout_b200 import stream
+    unit, pre, post = stream.shard_geometry(0, 1)
+    with Engine("zb_nb", channel=15, max_samples=24 * unit + pre + post) as e:
+        got = _stream_all(e, cap.iq, units=24, block=77_777)
     assert len(whole) > 30
     assert_frames_equal(got, whole, what="Zigbee: streamed shards vs whole")
 
@@ -70,7 +72,9 @@ def test_stream_equals_whole_mixed(Engine):
     cap = synth.wideband_capture(seconds=0.045, kind="mixed", seed=5100, esn0_db=25.0, gap=(400, 5000))
     with Engine("mixed_wb56", max_samples=len(cap.iq), zb_segment=16384) as e:
         whole = e.run(cap.iq)
-    with Engine("mixed_wb56", max_samples=(3 * 16384 + 40960 + 16512) * 24, zb_segment=16384) as e:
+    from snout_b200 import stream
+    unit, pre, post = stream.shard_geometry(40, 16, 16384)
+    with Engine("mixed_wb56", max_samples=(3 * unit + pre + post) * 24, zb_segment=16384) as e:
         got = _stream_all(e, cap.iq, units=3, block=2_000_000)
     key = lambda f: np.lexsort((f["sample_index"], f["window"], f["channel"], 255 - f["proto"].astype(int)))   # noqa: E731
     assert len(whole) > 100 and (whole["proto"] == 2).sum() > 4

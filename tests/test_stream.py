@@ -25,7 +25,7 @@ def _check_cover(eng, x, decim, unit, pre, post):
         b0 = sh["first_window"] * 8192 * decim
         assert b0 == pos and (b0 // decim) % unit == 0
         lo = b0 - sh["pre_samples"]
-        assert sh["pre_samples"] == (0 if i == 0 else pre * decim)
+        assert sh["pre_samples"] == min(b0, pre * decim)          # a full pre halo, or everything back to the start of the stream
         body = sh["body_samples"] if sh["body_samples"] else len(buf) - sh["pre_samples"]
         assert (sh["body_samples"] == 0) == last
         n_expect = len(buf)
@@ -72,8 +72,11 @@ def test_streamer_covers_stream_exactly(mode, n, units):
 def test_shard_geometry_rules():
     assert stream.shard_geometry(1, 0) == (8192, 128, 2048)
     unit, pre, post = stream.shard_geometry(0, 1, 65536, 4096)
-    assert unit == 65536 and pre == 40960 and pre % 4096 == 0 and pre >= 36864 + 4096 and post >= 16448
-    assert stream.shard_geometry(40, 16, 65536, 4096) == (65536, 40960, post)
+    need = (_abi.ZB_IIR_MEMORY_BLOCKS + 1) * _abi.ZB_IIR_BLOCK + 4096       # tracker memory + the buffer's first block + chain warm-up
+    assert unit == 65536 and pre == need == 104448 and pre % _abi.ZB_IIR_BLOCK == 0 and post >= 16448
+    assert stream.shard_geometry(40, 16, 65536, 4096) == (65536, pre, post)
+    # library defaults (4096-sample segments, 2048 warm-up): bodies stay on the 8192-sample window grid
+    assert stream.shard_geometry(0, 1) == (8192, need - 2048, post) and stream.shard_geometry(40, 16)[0] == 8192
     with pytest.raises(ValueError):
         stream.shard_geometry(0, 1, 10000, 4096)
     with pytest.raises(ValueError):
