@@ -217,16 +217,18 @@ SNRX_HD uint32_t zb_reg_at(uint32_t C, uint32_t P, int j) { return funnel_r(C, P
 
 // One window.  C: its chips, first chip in bit 31 (absent chips 0); nvalid: chips it holds (< 32 only when the stream
 // ended); jstop: chips whose position lies before the end of the chain's body; pos_evt: input position of the chip at
-// offset s.jb.  Returns true when the chain ends inside this window, *consumed = the chips of it that were pushed.
+// offset s.jb; j_start: offset of the first chip the sink sees (> 0 only in the window in which the sink starts: the chips
+// before it must be 0 in C).  Returns true when the chain ends inside this window, *consumed = the chips of it that
+// count as processed.
 SNRX_HD bool zb_sink_window(ZbSinkW& s, uint32_t C, int nvalid, int jstop, int32_t pos_evt, const uint32_t* map, int thr,
-                            ZbEmit& em, int* consumed) {
+                            ZbEmit& em, int* consumed, int j_start = 0) {
     // a sink in the search state stops at the first chip past the body (zb_run_chain's loop condition), any sink stops
     // where the stream ends; 32 = not inside this window
     const int stop_x = nvalid;
     const int stop_0 = jstop < nvalid ? jstop : nvalid;
     uint32_t P = s.prev;
-    int j0 = 0;                                      // the unlocked search resumes here
-    int pushed = 0;                                  // chips pushed so far
+    int j0 = j_start;                                // the unlocked search resumes here
+    int pushed = j_start;                            // chips dealt with so far
     if (s.locked || s.state != 0) {
         const int e = s.jb;
         const int limit = s.state == 0 ? stop_0 : stop_x;
@@ -323,21 +325,6 @@ SNRX_HD bool zb_sink_window(ZbSinkW& s, uint32_t C, int nvalid, int jstop, int32
     return false;
 }
 
-// where a chain reads its samples from: straight from the DC-removed stream (host stepping harness) ...
-struct ZbDirectSrc {
-    const float* z;
-    const float* taps;     // [129][8]
-    SNRX_HD void tick(int, int32_t) {}
-    SNRX_HD void get8(int32_t ii, float (&in)[8]) const {
-#pragma unroll
-        for (int k = 0; k < 8; k++) in[k] = z[ii + k];
-    }
-    SNRX_HD void row(int r, float (&t)[8]) const {
-#pragma unroll
-        for (int k = 0; k < 8; k++) t[k] = taps[r * SNRX_MMSE_NTAPS + k];
-    }
-};
-
 struct ZbChainParams {
     int32_t n_out;            // channel-rate samples per capture in the buffer
     int32_t origin;           // local index where segment `first_segment` starts (pre halo length)
@@ -352,14 +339,17 @@ struct ZbChainParams {
     size_t f_stride;          // floats between (capture, channel) streams
 };
 
-// One chain: clock recovery fresh at `begin` = lo - prehalo, the sink from lo - kZbSinkLead on.  Frames are written to
-// slots[0..), returns their count.  The chain ends at the post halo, or as soon as it has passed its body with the sink in
-// the search state: a sync found from there on completes at a position >= hi and belongs to the next segment, so nothing
-// this chain could still report is lost (oracle/zb_oracle.c zb_oracle_chain_hold stops at the same chip).
-template <bool DEBUG, class Src>
-SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const uint32_t* map,
-                              int channel_number, uint32_t capture_id, snrx_frame_t* slots, float* chips_dbg,
-                              int64_t chips_cap, int64_t* nchips_out, int64_t* good_end_out) {
+// One chain = (capture, channel, segment): clock recovery fresh at `begin` = lo - prehalo, the sink from the first chip at
+// or after lo - kZbSinkLead.  The chain ends at the post halo, or as soon as it has passed its body with the sink in the
+// search state: a sync found from there on completes at a position >= hi and belongs to the next segment, so nothing this
+// chain could still report is lost (oracle/zb_oracle.c zb_oracle_chain_hold stops at the same chip).
+struct ZbChain {
+    ZbMm mm; ZbSinkW sink; ZbEmit em;
+    int32_t begin, hi, end, sink_from;
+    int32_t nchips;           // clock-recovery steps so far (= chips)
+    int sink_on;
+};
+SNRX_HD void zb_chain_init(ZbChain& c, const ZbChainParams& p, int seg, int channel_number, uint32_t capture_id, snrx_frame_t* slots) {
     // all positions are < n_out + segment + post halo < 2^31 (zb_create bounds max_out)
     const int32_t lo = p.origin + seg * p.segment;
     int32_t hi = lo + p.segment;
@@ -367,55 +357,114 @@ SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const u
     if (hi > body_end) hi = body_end;
     int32_t begin = lo - p.prehalo; if (begin < 0) begin = 0;
     int32_t end = hi + kZbPostHalo; if (end > p.n_out) end = p.n_out;
-    const int32_t sink_from = lo - kZbSinkLead;
-    ZbMm mm; mm.mu = 0.5f; mm.omega = 2.0f; mm.last = 0.0f; mm.ii = begin;
-    ZbEmit em;
-    em.slots = slots; em.cap = p.slots_per_chain; em.nf = 0; em.lo = lo; em.hi = hi;
-    em.index_base = (int64_t)p.first_segment * p.segment - (int64_t)p.origin;
-    em.capture_id = capture_id; em.window = p.first_segment + (uint32_t)seg; em.channel = (uint16_t)channel_number;
-    em.good_end = 0;
-    int32_t nchips = 0;
-    // warm-up: clock recovery only, the sink has not started yet
-    for (int j = 0; mm.ii + 8 <= end && mm.ii < sink_from; j++) {
-        float in[8], t[8];
-        src.tick(j, mm.ii);
-        src.row(zb_mm_row(mm.mu), t);
-        src.get8(mm.ii, in);
-        const float soft = zb_mm_step(mm, in, t);
-        if (DEBUG && chips_dbg && nchips < chips_cap) chips_dbg[nchips] = soft;
-        nchips++;
+    c.begin = begin; c.hi = hi; c.end = end; c.sink_from = lo - kZbSinkLead;
+    c.mm.mu = 0.5f; c.mm.omega = 2.0f; c.mm.last = 0.0f; c.mm.ii = begin;
+    zb_sinkw_init(c.sink);
+    c.em.slots = slots; c.em.cap = p.slots_per_chain; c.em.nf = 0; c.em.lo = lo; c.em.hi = hi;
+    c.em.index_base = (int64_t)p.first_segment * p.segment - (int64_t)p.origin;
+    c.em.capture_id = capture_id; c.em.window = p.first_segment + (uint32_t)seg; c.em.channel = (uint16_t)channel_number;
+    c.em.good_end = 0;
+    c.nchips = 0; c.sink_on = 0;
+}
+
+// what 32 clock-recovery steps leave behind for the sink
+struct ZbWin {
+    uint32_t C;               // hard chips, first chip in bit 31 (absent chips 0)
+    int nvalid;               // chips produced (< 32 only when the stream ended)
+    int below;                // chips whose position lies before the end of the body
+    int before;               // chips whose position lies before the point where the sink starts
+    int32_t pos_evt;          // position of the chip at the sink's boundary offset
+};
+
+// where a chain reads its samples from: straight from the DC-removed stream (host stepping harness) ...
+struct ZbDirectSrc {
+    const float* z;
+    const float* taps;     // [129][8]
+    template <int K, bool FAST> SNRX_HD void tick() {}
+    SNRX_HD void get8(int32_t ii, float (&in)[8]) const {
+#pragma unroll
+        for (int k = 0; k < 8; k++) in[k] = z[ii + k];
     }
-    ZbSinkW sink; zb_sinkw_init(sink);
+    SNRX_HD void row(float mu, float (&t)[8]) const {
+        const int r = zb_mm_row(mu);
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = taps[r * SNRX_MMSE_NTAPS + k];
+    }
+};
+
+template <int K, bool FAST, bool DEBUG, class Src>
+SNRX_HD void zb_chain_step(ZbChain& c, Src& src, ZbWin& w, int j, int jb, float* chips_dbg, int64_t chips_cap) {
+    if (FAST || c.mm.ii + 8 <= c.end) {
+        const int32_t pos = c.mm.ii;
+        float in[8], t[8];
+        src.template tick<K, FAST>();
+        src.row(c.mm.mu, t);
+        src.get8(pos, in);
+        const float soft = zb_mm_step(c.mm, in, t);
+        if (DEBUG && chips_dbg && c.nchips + j < chips_cap) chips_dbg[c.nchips + j] = soft;
+        w.C = (w.C << 1) | (soft > 0.0f ? 1u : 0u);
+        w.below += pos < c.hi ? 1 : 0;
+        w.before += pos < c.sink_from ? 1 : 0;
+        w.pos_evt = (j == jb) ? pos : w.pos_evt;
+        w.nvalid++;
+    }
+}
+
+// 32 clock-recovery steps.  FAST: the caller guarantees that none of them can reach the end of the stream (every step
+// advances by at most 3 samples), so the per-step end test is dropped.
+template <bool FAST, bool DEBUG, class Src>
+SNRX_HD void zb_chain_steps(ZbChain& c, Src& src, ZbWin& w, float* chips_dbg, int64_t chips_cap) {
+    w.C = 0; w.nvalid = 0; w.below = 0; w.before = 0; w.pos_evt = 0;
+    const int jb = c.sink.jb;
+    for (int j8 = 0; j8 < 32; j8 += 8) {
+        zb_chain_step<0, FAST, DEBUG>(c, src, w, j8 + 0, jb, chips_dbg, chips_cap);
+        zb_chain_step<1, FAST, DEBUG>(c, src, w, j8 + 1, jb, chips_dbg, chips_cap);
+        zb_chain_step<2, FAST, DEBUG>(c, src, w, j8 + 2, jb, chips_dbg, chips_cap);
+        zb_chain_step<3, FAST, DEBUG>(c, src, w, j8 + 3, jb, chips_dbg, chips_cap);
+        zb_chain_step<4, FAST, DEBUG>(c, src, w, j8 + 4, jb, chips_dbg, chips_cap);
+        zb_chain_step<5, FAST, DEBUG>(c, src, w, j8 + 5, jb, chips_dbg, chips_cap);
+        zb_chain_step<6, FAST, DEBUG>(c, src, w, j8 + 6, jb, chips_dbg, chips_cap);
+        zb_chain_step<7, FAST, DEBUG>(c, src, w, j8 + 7, jb, chips_dbg, chips_cap);
+    }
+    if (w.nvalid < 32) w.C = w.nvalid ? w.C << (32 - w.nvalid) : 0u;
+}
+
+// the sink's part of a window; returns true when the chain has ended
+SNRX_HD bool zb_chain_sink(ZbChain& c, const ZbWin& w, const uint32_t* map, int thr) {
+    uint32_t C = w.C;
+    int j_start = 0;
+    if (!c.sink_on) {
+        if (w.before >= w.nvalid) {                   // still warming up (or the stream ended before the sink started)
+            c.nchips += w.nvalid;
+            return w.nvalid < 32;
+        }
+        c.sink_on = 1;                                // the sink starts inside this window: it never saw the chips before
+        j_start = w.before;
+        if (j_start > 0) C &= (1u << (32 - j_start)) - 1u;
+    }
+    int consumed = 0;
+    const bool done = zb_sink_window(c.sink, C, w.nvalid, w.below, w.pos_evt, map, thr, c.em, &consumed, j_start);
+    c.nchips += consumed;
+    return done;
+}
+
+// a whole chain on one thread (host stepping harness; the device kernel k_zb_rx drives the same functions)
+template <bool DEBUG, class Src>
+SNRX_HD uint32_t zb_run_chain(Src& src, const ZbChainParams& p, int seg, const uint32_t* map,
+                              int channel_number, uint32_t capture_id, snrx_frame_t* slots, float* chips_dbg,
+                              int64_t chips_cap, int64_t* nchips_out, int64_t* good_end_out) {
+    ZbChain c;
+    zb_chain_init(c, p, seg, channel_number, capture_id, slots);
     bool done = false;
     while (!done) {
-        uint32_t C = 0;
-        int nvalid = 0, below = 0;
-        int32_t pos_evt = 0;
-        const int jb = sink.jb;
-#pragma unroll 4
-        for (int j = 0; j < 32; j++) {
-            if (mm.ii + 8 <= end) {
-                const int32_t pos = mm.ii;
-                float in[8], t[8];
-                src.tick(j, pos);
-                src.row(zb_mm_row(mm.mu), t);
-                src.get8(pos, in);
-                const float soft = zb_mm_step(mm, in, t);
-                if (DEBUG && chips_dbg && nchips + j < chips_cap) chips_dbg[nchips + j] = soft;
-                C = (C << 1) | (soft > 0.0f ? 1u : 0u);
-                below += pos < hi ? 1 : 0;
-                pos_evt = (j == jb) ? pos : pos_evt;
-                nvalid++;
-            }
-        }
-        if (nvalid < 32) C = nvalid ? C << (32 - nvalid) : 0u;
-        int consumed = 0;
-        done = zb_sink_window(sink, C, nvalid, below, pos_evt, map, p.threshold, em, &consumed);
-        nchips += consumed;
+        ZbWin w;
+        if (c.mm.ii + 8 + 3 * 32 <= c.end) zb_chain_steps<true, DEBUG>(c, src, w, chips_dbg, chips_cap);
+        else zb_chain_steps<false, DEBUG>(c, src, w, chips_dbg, chips_cap);
+        done = zb_chain_sink(c, w, map, p.threshold);
     }
-    if (nchips_out) *nchips_out = nchips;
-    if (good_end_out) *good_end_out = em.good_end;
-    return em.nf;
+    if (nchips_out) *nchips_out = c.nchips;
+    if (good_end_out) *good_end_out = c.em.good_end;
+    return c.em.nf;
 }
 
 // Filter of one chain's records given the ends of the CRC-ok frames of the `lookback` preceding chains of its stream.
@@ -516,94 +565,92 @@ __global__ void __launch_bounds__(128) k_zb_iir_carry(ZbIirArgs a) {
     }
 }
 
-// ... or, on the device, from the raw discriminator stream through two per-thread rings in shared memory:
-//   raw ring   cp.async (16 bytes = 4 samples per request) keeps it ~64 samples ahead of the DC tracker; chunk c of lane l
-//              at raw[(c * 32 + l)] (float4): the copies and the tracker's 8-byte reads are bank-conflict free;
-//   z ring     the chain's own DC tracker (zb_iir_step from the carried state of each SNRX_IIR_BLOCK block) turns two raw
-//              samples per clock-recovery step into z = f - y and stores them at zr[r * 32 + l] (row r = sample mod 64,
-//              rows 0..7 mirrored at 64..71 so the 8 interpolator taps never wrap): every access of a warp is
-//              conflict free whatever the lanes' positions.
-// The DC-removed stream never exists in HBM (only with SNRX_F_KEEP_STREAMS, for the parity tests).  Fetch and tracker
-// are paced by the STEP COUNT (4 samples every other step, 2 samples every step), which is the same for all lanes of a
-// warp, not by each lane's position: no divergent refill branches inside the dependent clock-recovery loop.  The lanes'
-// positions wander around 2 samples per step by a few samples only; the guards below catch up (or pause) when a lane
-// drifts further, so correctness never depends on the pacing.
-constexpr int kZbRawChunks = 32;      // float4 chunks per lane in the raw ring (128 samples)
-constexpr int kZbZRows = 64;          // z samples per lane (power of two), + 8 mirrored rows
-constexpr int kZbLeadConv = 32;       // samples the tracker starts ahead of the clock recovery
-constexpr int kZbLeadFetch = 96;      // samples the copies start ahead of the clock recovery
-constexpr int kZbRxThreads = 32;      // one warp per CTA: 480 CTAs per capture-second spread over all SMs
+// ... or, on the device, from the raw discriminator stream f in HBM:
+//   * every step the lane loads the raw pair it will need kZbQueue steps later (one 8-byte load into a register queue:
+//     HBM / L2 latency is covered without shared-memory staging), runs its own DC tracker over the pair that has arrived
+//     (zb_iir_step from the carried state of each SNRX_IIR_BLOCK block) and stores z = f - y into
+//   * the z ring in shared memory: zr[r * 32 + lane], row r = sample mod 128, rows 0..7 mirrored at 128..135 so that the
+//     8 interpolator taps never wrap; every access of a warp is bank-conflict free whatever the lanes' positions.
+// The DC-removed stream never exists in HBM (only with SNRX_F_KEEP_STREAMS, for the parity tests).  The tracker is
+// paced by the STEP COUNT -- two samples per clock-recovery step, the nominal advance -- not by each lane's position, so
+// the loop body has no refill branches.  A lane's position wanders around 2 samples per step by about one sample per
+// window (measured on the oracle: <= 1 per 32 steps, < 100 over 2 M steps); k_zb_rx re-centres the lead between
+// windows, so correctness never depends on the pacing.
+constexpr int kZbQueue = 8;           // raw pairs in flight per lane
+constexpr int kZbZRows = 128;         // z samples per lane (power of two), + 8 mirrored rows
+constexpr int kZbLead = 48;           // samples the tracker starts ahead of the clock recovery
+constexpr int kZbLeadMin = 44;        // a window may start with this much lead: 32 steps of 3 samples eat at most 32 of it, 8 are read
+constexpr int kZbLeadMax = 80;        // beyond it the tracker pauses for a window (the ring holds 128)
+constexpr int kZbRxWarps = 4;         // warps per CTA (they only share the interpolator table)
+constexpr int kZbRxCtasPerSm = 3;
+constexpr int kZbRxSmem = (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS * 4 + kZbRxWarps * (kZbZRows + 8) * 32 * 4;
 
-struct ZbRingSrc {
-    const float* f;        // raw discriminator stream of this (capture, channel)
-    const double* carry;   // carried tracker state of this stream's blocks
-    float* z_dbg;          // where to store z (SNRX_F_KEEP_STREAMS) or null
-    uint32_t raw, zr, taps;  // shared-memory byte addresses: this lane's column of the raw ring / of the z ring, the taps table
-    int32_t begin;         // stream index of ring position 0 (a multiple of SNRX_IIR_BLOCK)
-    int32_t fetched;       // samples requested so far, relative to begin (multiple of 4)
-    int32_t conv;          // samples the tracker has converted, relative to begin (even)
-    int32_t n;             // samples in the stream
-    int32_t z_lo, z_hi;    // debug: this chain stores z[z_lo, z_hi)
+template <bool DEBUG>
+struct ZbRegSrc {
+    const float2* nxt;     // next raw pair to load
+    const double* cptr;    // carried tracker state of the next block
+    float2 q[kZbQueue];    // raw pairs in flight / waiting for the tracker
     double y;              // tracker state
+    int32_t to_boundary;   // samples until the tracker reaches the next block boundary
+    uint32_t zr;           // shared-memory byte address of this lane's column of the z ring
+    uint32_t zw;           // byte offset of the row the tracker writes next (row * 128)
+    uint32_t taps_adj;     // shared-memory byte address of the interpolator table - 0x68000000 (see row())
+    int32_t begin;         // stream index of ring position 0 (a multiple of SNRX_IIR_BLOCK)
+    int32_t conv;          // samples the tracker has converted, relative to begin
+    bool enabled;          // slow windows only: the tracker runs
+    float* z_dbg; int32_t z_lo, z_hi;    // debug: this chain stores z[z_lo, z_hi) of its stream
 
-    __device__ __forceinline__ void issue4() {
-        const uint32_t dst = raw + (uint32_t)((fetched >> 2) & (kZbRawChunks - 1)) * 512u;
-        const int32_t g0 = begin + fetched;
-        const int left = n - g0;                                   // samples of the stream from g0 on
-        const int bytes = left >= 4 ? 16 : left > 0 ? 4 * left : 0;   // the rest of the 16 bytes is zero-filled
-        const float* g = f + (left > 0 ? g0 : 0);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(g), "r"(bytes) : "memory");
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
-        fetched += 4;
-    }
-    __device__ __forceinline__ void convert2() {
-        const uint32_t src = raw + (uint32_t)((conv >> 2) & (kZbRawChunks - 1)) * 512u + (uint32_t)(conv & 2) * 4u;
-        float f0, f1;
-        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f0), "=f"(f1) : "r"(src));
-        const int32_t g = begin + conv;
-        if ((g & (SNRX_IIR_BLOCK - 1)) == 0) y = carry[g / SNRX_IIR_BLOCK];
+    template <int K>
+    __device__ __forceinline__ void convert() {
+        const float f0 = q[K].x, f1 = q[K].y;
+        q[K] = __ldg(nxt);                                   // the pair kZbQueue steps ahead
+        nxt++;
+        if (to_boundary == 0) { y = __ldg(cptr); cptr++; to_boundary = SNRX_IIR_BLOCK; }
+        to_boundary -= 2;
         y = zb_iir_step(y, f0);
         const float z0 = zb_dc_out(f0, y);
         y = zb_iir_step(y, f1);
         const float z1 = zb_dc_out(f1, y);
-        const int r = conv & (kZbZRows - 1);
-        const uint32_t dst = zr + (uint32_t)r * 128u;
+        const uint32_t dst = zr + zw;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(z0) : "memory");
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 128u), "f"(z1) : "memory");
-        if (r < 8) {
+        if (zw < 8u * 128u) {
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 128u * kZbZRows), "f"(z0) : "memory");
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst + 128u * (kZbZRows + 1)), "f"(z1) : "memory");
         }
-        if (z_dbg) {
+        if (DEBUG && z_dbg) {
+            const int32_t g = begin + conv;
             if (g >= z_lo && g < z_hi) z_dbg[g] = z0;
             if (g + 1 >= z_lo && g + 1 < z_hi) z_dbg[g + 1] = z1;
         }
+        zw = (zw + 256u) & (128u * kZbZRows - 1u);
         conv += 2;
     }
-    __device__ __forceinline__ void prime() {
-        while (fetched < kZbLeadFetch) issue4();
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-        while (conv < kZbLeadConv) convert2();
+    __device__ __forceinline__ void burst() {                // 16 samples
+        convert<0>(); convert<1>(); convert<2>(); convert<3>(); convert<4>(); convert<5>(); convert<6>(); convert<7>();
     }
-    // once per clock-recovery step, before get8(ii): j = step number inside the window (warp uniform)
-    __device__ __forceinline__ void tick(int j, int32_t ii) {
-        const int rel = ii - begin;
-        if ((j & 1) == 0 && fetched - conv < kZbRawChunks * 4 - 8) issue4();
-        asm volatile("cp.async.wait_group 6;\n" ::: "memory");      // all but the 6 newest requests (24 samples) have landed
-        if (conv - rel < kZbZRows - 16 && fetched - conv >= 32) convert2();
-        while (conv - rel < 11) {                                     // this lane ran ahead of the pacing: catch up (rare)
-            while (fetched - conv < 8) issue4();
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-            convert2();
-        }
+    __device__ __forceinline__ void start(const float* f, const double* carry, int32_t begin_) {
+        begin = begin_; conv = 0; zw = 0; y = 0.0; to_boundary = 0; enabled = true;
+        cptr = carry + begin_ / SNRX_IIR_BLOCK;
+        nxt = reinterpret_cast<const float2*>(f + begin_);
+#pragma unroll
+        for (int k = 0; k < kZbQueue; k++) q[k] = __ldg(nxt + k);
+        nxt += kZbQueue;
+        while (conv < kZbLead) burst();
+    }
+    template <int K, bool FAST>
+    __device__ __forceinline__ void tick() {
+        if (FAST || enabled) convert<K>();
     }
     __device__ __forceinline__ void get8(int32_t ii, float (&in)[8]) {
-        const uint32_t p = zr + (uint32_t)((ii - begin) & (kZbZRows - 1)) * 128u;
+        const uint32_t p = zr + ((uint32_t)((ii - begin) & (kZbZRows - 1)) << 7);
 #pragma unroll
         for (int k = 0; k < 8; k++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(in[k]) : "r"(p + 128u * k));
     }
-    __device__ __forceinline__ void row(int r, float (&t)[8]) const {
-        const uint32_t a = taps + (uint32_t)r * (SNRX_MMSE_NTAPS * 4);
+    // interpolator row rint(mu * 128): mu * 128 is exact, so one FFMA with the magic number 1.5 * 2^23 gives the bits
+    // 0x4B400000 + row; (bits << 5) = 0x68000000 + 32 * row (mod 2^32), hence the adjusted base: one IMAD for the address
+    __device__ __forceinline__ void row(float mu, float (&t)[8]) const {
+        const uint32_t a = taps_adj + (__float_as_uint(__fmaf_rn(mu, (float)SNRX_MMSE_NSTEPS, 12582912.0f)) << 5);
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]) : "r"(a));
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7]) : "r"(a + 16u));
     }
@@ -615,6 +662,7 @@ struct ZbRxArgs {
     const float* taps;           // [129][8]
     const int32_t* channel_numbers;
     snrx_frame_t* slots; uint32_t* counts; int64_t* good_end;
+    uint32_t* queue;             // next chain to hand out (zeroed before the launch)
     uint32_t* overflow;          // set to 1 when a chain found more frames than it has slots
     float* z_dbg;                // [stream][f_stride] or null
     float* chips_dbg; int64_t chips_cap; int64_t* nchips_dbg;
@@ -622,49 +670,52 @@ struct ZbRxArgs {
     ZbChainParams p;
 };
 
-// thread per (capture, channel, segment) chain: DC tracker, clock recovery, packet sink, FCS
+// DC tracker, clock recovery, packet sink and FCS of the chains (capture, channel, segment).  A lane runs one chain at a
+// time and takes the next one from a queue when it is done: chains differ in length by a factor of four (a chain that
+// holds a frame follows it through the post halo), and the warp is busy as long as any of its lanes is.
 template <bool DEBUG>
-__global__ void __launch_bounds__(kZbRxThreads) k_zb_rx(const __grid_constant__ ZbRxArgs a) {
-    __shared__ __align__(16) float taps[(SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS];
-    __shared__ __align__(16) float4 raw[kZbRawChunks * kZbRxThreads];
-    __shared__ float zring[(kZbZRows + 8) * kZbRxThreads];
+__global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxCtasPerSm) k_zb_rx(const __grid_constant__ ZbRxArgs a) {
+    extern __shared__ __align__(16) unsigned char zb_smem[];
+    float* taps = reinterpret_cast<float*>(zb_smem);
+    float* zring = taps + (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS;
     for (int i = threadIdx.x; i < (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS; i += blockDim.x) taps[i] = a.taps[i];
     __syncthreads();
     const ZbChainParams& p = a.p;
     const uint32_t n_streams = p.n_captures * p.n_channels;
     const uint32_t total = n_streams * (uint32_t)p.n_segments;
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    // consecutive threads take different streams so that a warp touches many DRAM pages at once
-    const uint32_t seg = idx / n_streams, sc = idx % n_streams;
-    const uint32_t cap = sc / p.n_channels, ch = sc % p.n_channels;
-    const uint32_t chain = sc * (uint32_t)p.n_segments + seg;          // output order
-    ZbRingSrc src;
-    src.f = a.f + (size_t)sc * p.f_stride;
-    src.carry = a.carry + (size_t)sc * p.n_blocks;
-    src.z_dbg = (DEBUG && a.z_dbg) ? a.z_dbg + (size_t)sc * p.f_stride : nullptr;
-    src.raw = (uint32_t)__cvta_generic_to_shared(raw + threadIdx.x);
-    src.zr = (uint32_t)__cvta_generic_to_shared(zring + threadIdx.x);
-    src.taps = (uint32_t)__cvta_generic_to_shared(taps);
-    asm volatile("" : "+r"(src.raw), "+r"(src.zr), "+r"(src.taps));   // opaque: stay in registers
-    {
-        const int32_t lo = p.origin + (int32_t)seg * p.segment;
-        src.begin = lo - p.prehalo > 0 ? lo - p.prehalo : 0;          // = the chain's first sample, on the tracker's block grid
-        int32_t hi = lo + p.segment; if (hi > p.origin + p.body) hi = p.origin + p.body;
-        src.z_lo = seg == 0 ? 0 : lo; src.z_hi = (int)seg == p.n_segments - 1 ? p.n_out : hi;
+    ZbRegSrc<DEBUG> src;
+    src.zr = (uint32_t)__cvta_generic_to_shared(zring + (threadIdx.x >> 5) * ((kZbZRows + 8) * 32) + (threadIdx.x & 31));
+    src.taps_adj = (uint32_t)__cvta_generic_to_shared(taps) - 0x68000000u;
+    asm volatile("" : "+r"(src.zr), "+r"(src.taps_adj));               // opaque: stay in registers
+    for (;;) {
+        // consecutive chains belong to different streams, so that a warp touches many DRAM pages at once
+        const uint32_t idx = atomicAdd(a.queue, 1u);
+        if (idx >= total) break;
+        const uint32_t seg = idx / n_streams, sc = idx % n_streams;
+        const uint32_t cap = sc / p.n_channels, ch = sc % p.n_channels;
+        const uint32_t chain = sc * (uint32_t)p.n_segments + seg;      // output order
+        ZbChain c;
+        zb_chain_init(c, p, (int)seg, a.channel_numbers[ch], p.first_capture + cap, a.slots + (size_t)chain * p.slots_per_chain);
+        src.z_dbg = (DEBUG && a.z_dbg) ? a.z_dbg + (size_t)sc * p.f_stride : nullptr;
+        src.z_lo = seg == 0 ? 0 : c.em.lo; src.z_hi = (int)seg == p.n_segments - 1 ? p.n_out : c.hi;
+        src.start(a.f + (size_t)sc * p.f_stride, a.carry + (size_t)sc * p.n_blocks, c.begin);
+        float* chips_dbg = (DEBUG && a.chips_dbg) ? a.chips_dbg + (size_t)chain * a.chips_cap : nullptr;
+        bool done = false;
+        while (!done) {
+            // re-centre the tracker's lead (rare: a lane drifts by about one sample per window)
+            int lead = src.conv - (c.mm.ii - src.begin);
+            while (lead < kZbLeadMin) { src.burst(); lead += 2 * kZbQueue; }
+            src.enabled = lead <= kZbLeadMax;
+            ZbWin w;
+            if (src.enabled && c.mm.ii + 8 + 3 * 32 <= c.end) zb_chain_steps<true, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
+            else zb_chain_steps<false, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
+            done = zb_chain_sink(c, w, a.map.w, p.threshold);
+        }
+        a.good_end[chain] = c.em.good_end;
+        a.counts[chain] = c.em.nf < p.slots_per_chain ? c.em.nf : p.slots_per_chain;
+        if (c.em.nf > p.slots_per_chain) *a.overflow = 1u;
+        if (DEBUG && a.nchips_dbg) a.nchips_dbg[chain] = c.nchips;
     }
-    src.fetched = 0; src.conv = 0; src.n = p.n_out; src.y = 0.0;
-    src.prime();
-    int64_t nchips = 0, good_end = 0;
-    const uint32_t nf = zb_run_chain<DEBUG>(src, p, (int)seg, a.map.w, a.channel_numbers[ch], p.first_capture + cap,
-                                            a.slots + (size_t)chain * p.slots_per_chain,
-                                            (DEBUG && a.chips_dbg) ? a.chips_dbg + (size_t)chain * a.chips_cap : nullptr,
-                                            a.chips_cap, &nchips, &good_end);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    a.good_end[chain] = good_end;
-    a.counts[chain] = nf < p.slots_per_chain ? nf : p.slots_per_chain;
-    if (nf > p.slots_per_chain) *a.overflow = 1u;
-    if (DEBUG && a.nchips_dbg) a.nchips_dbg[chain] = nchips;
 }
 
 // one thread per chain: drop the CRC-failed records that lie inside a CRC-ok frame of this or a preceding chain
@@ -713,7 +764,7 @@ struct ZbState {
     float *d_atan = nullptr, *d_mmse = nullptr;
     int32_t* d_channels = nullptr;
     snrx_frame_t* d_slots = nullptr; size_t slots_bytes = 0;
-    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr;
+    uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr, *d_queue = nullptr;
     int64_t* d_good_end = nullptr;
     uint32_t max_chains = 0, slots_per_chain = 0;
     float* d_chips = nullptr; int64_t* d_nchips = nullptr; int64_t chips_cap = 0;
@@ -725,7 +776,7 @@ struct ZbState {
 
 inline void zb_free(ZbState& s) {
     void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
-                    s.d_counts, s.d_offsets, s.d_scratch, s.d_good_end, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
+                    s.d_counts, s.d_offsets, s.d_scratch, s.d_queue, s.d_good_end, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     s = ZbState();
 }
@@ -753,7 +804,10 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     s.stride = ((size_t)max_out + 8 + 31) & ~(size_t)31;
     const size_t streams = (size_t)max_caps * n_ch;
     const bool keep = (cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
-    ZCK(cudaMalloc((void**)&s.d_f, streams * s.stride * sizeof(float)));
+    // + slack: a chain's tracker runs up to kZbLeadMax + 32 + 2 * kZbQueue samples ahead of its clock recovery, i.e. past
+    // the end of its stream (those values are computed and never used)
+    ZCK(cudaMalloc((void**)&s.d_f, (streams * s.stride + 512) * sizeof(float)));
+    ZCK(cudaMemset(s.d_f, 0, (streams * s.stride + 512) * sizeof(float)));
     if (keep) ZCK(cudaMalloc((void**)&s.d_z, streams * s.stride * sizeof(float)));
     const size_t nblk = (max_out + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK;
     ZCK(cudaMalloc((void**)&s.d_block_end, streams * nblk * sizeof(double)));
@@ -776,6 +830,9 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     ZCK(cudaMalloc((void**)&s.d_offsets, sizeof(uint32_t) * ((size_t)s.max_chains + 1)));
     ZCK(cudaMalloc((void**)&s.d_scratch, sizeof(uint32_t) * scan_scratch_items(s.max_chains)));
     ZCK(cudaMalloc((void**)&s.d_good_end, sizeof(int64_t) * ((size_t)s.max_chains + 1)));
+    ZCK(cudaMalloc((void**)&s.d_queue, sizeof(uint32_t)));
+    ZCK(cudaFuncSetAttribute(k_zb_rx<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kZbRxSmem));
+    ZCK(cudaFuncSetAttribute(k_zb_rx<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kZbRxSmem));
     if (keep) {
         s.chips_cap = ((int64_t)cfg.zb_segment + cfg.zb_prehalo + kZbPostHalo) / 2 + 64;
         ZCK(cudaMalloc((void**)&s.d_chips, sizeof(float) * (size_t)s.max_chains * (size_t)s.chips_cap));
@@ -834,10 +891,13 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     a.f = s.d_f; a.carry = s.d_carry; a.taps = s.d_mmse; a.channel_numbers = s.d_channels;
     a.slots = s.d_slots; a.counts = s.d_counts; a.good_end = s.d_good_end; a.overflow = totals + 3;
     a.z_dbg = s.d_z; a.chips_dbg = s.d_chips; a.chips_cap = s.chips_cap; a.nchips_dbg = s.d_nchips; a.map = s.map;
-    const uint32_t grid = (n_chains + kZbRxThreads - 1) / kZbRxThreads;
+    a.queue = s.d_queue;
+    ZCK(cudaMemsetAsync(s.d_queue, 0, sizeof(uint32_t), st));
+    const uint32_t per_cta = kZbRxWarps * 32;
+    const uint32_t grid = std::min<uint32_t>((n_chains + per_cta - 1) / per_cta, (uint32_t)sm_count * kZbRxCtasPerSm);
     if (keep) ZCK(cudaMemsetAsync(s.d_z, 0, (size_t)streams * s.stride * sizeof(float), st));
-    if (keep) k_zb_rx<true><<<grid, kZbRxThreads, 0, st>>>(a);
-    else k_zb_rx<false><<<grid, kZbRxThreads, 0, st>>>(a);
+    if (keep) k_zb_rx<true><<<grid, per_cta, kZbRxSmem, st>>>(a);
+    else k_zb_rx<false><<<grid, per_cta, kZbRxSmem, st>>>(a);
     k_zb_span_filter<<<(n_chains + 127) / 128, 128, 0, st>>>(s.d_slots, s.slots_per_chain, s.d_counts, s.d_good_end, n_chains,
                                                              (uint32_t)p.n_segments, zb_filter_lookback(p.segment));
     launches += 2 + exclusive_scan(s.d_counts, n_chains, s.d_offsets, s.d_scratch, st);

@@ -436,7 +436,9 @@ def _tile_frames(fr, k, tile_ch, lo_guard=0, hi_guard=0):
     s = fr["sample_index"]
     sel = fr[(s >= k * tile_ch + lo_guard) & (s < (k + 1) * tile_ch - hi_guard)].copy()
     sel["sample_index"] -= k * tile_ch
-    sel["window"] -= (k * tile_ch) // 8192
+    # `window` counts 8192-sample BLE windows / Zigbee chain segments (include/snoutrx.h)
+    per = np.where(sel["proto"] == _abi.PROTO_ZIGBEE, _abi.ZB_SEGMENT_DEFAULT, 8192)
+    sel["window"] -= ((k * tile_ch) // per).astype(sel["window"].dtype)
     return sel
 
 
@@ -450,7 +452,7 @@ def test_wideband_full_size_time_invariance(Engine, mode, kind):
     past the capture end)."""
     base = synth.wideband_capture(seconds=0.1, kind=kind, seed=4000, esn0_db=25.0).iq
     tile_ch = len(base) // 24
-    assert tile_ch % 8192 == 0
+    assert tile_ch % 8192 == 0 and tile_ch % _abi.ZB_IIR_BLOCK == 0
     with Engine(mode, max_samples=10 * len(base), max_frames=1 << 18) as e:
         small = e.run(np.tile(base, 3))
         ref = _tile_frames(small, 1, tile_ch)
