@@ -114,10 +114,11 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SNRX_LIB", LIB_PATH)          # SNRX_LIB: another build of the same library (kernel A/B runs)
+    if not os.path.exists(path):
         raise SnrxError(-2, "libsnoutrx.so is not built",
-                        f"{LIB_PATH} missing -- run `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = ctypes.CDLL(LIB_PATH)
+                        f"{path} missing -- run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(path)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)          # AttributeError here = ABI symbol missing
         fn.restype = res

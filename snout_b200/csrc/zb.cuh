@@ -578,20 +578,25 @@ __global__ void __launch_bounds__(128) k_zb_iir_carry(ZbIirArgs a) {
 // windows, so correctness never depends on the pacing.
 constexpr int kZbQueue = 8;           // raw pairs in flight per lane
 constexpr int kZbZRows = 128;         // z samples per lane (power of two), + 8 mirrored rows
-constexpr int kZbLead = 48;           // samples the tracker starts ahead of the clock recovery
+constexpr int kZbLead = 64;           // samples the tracker starts ahead of the clock recovery: two windows' worth, so that the
+                                      // tracker's position stays a multiple of 64 at every window start and a block boundary
+                                      // of the tracker (2048) can only fall on a window start
 constexpr int kZbLeadMin = 44;        // a window may start with this much lead: 32 steps of 3 samples eat at most 32 of it, 8 are read
-constexpr int kZbLeadMax = 80;        // beyond it the tracker pauses for a window (the ring holds 128)
+constexpr int kZbLeadMax = 84;        // beyond it the tracker pauses for a window (the ring holds 128 >= 84 + 32 + 8)
 constexpr int kZbRxWarps = 4;         // warps per CTA (they only share the interpolator table)
-constexpr int kZbRxCtasPerSm = 3;
+#ifndef SNRX_ZB_RX_MINCTAS
+#define SNRX_ZB_RX_MINCTAS 4
+#endif
+constexpr int kZbRxCtasPerSm = 3;          // what shared memory allows (74 KB per CTA)
+constexpr int kZbRxMinCtas = SNRX_ZB_RX_MINCTAS;   // register budget of the kernel: 65536 / (128 * this)
 constexpr int kZbRxSmem = (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS * 4 + kZbRxWarps * (kZbZRows + 8) * 32 * 4;
 
 template <bool DEBUG>
 struct ZbRegSrc {
     const float2* nxt;     // next raw pair to load
-    const double* cptr;    // carried tracker state of the next block
+    const double* carry;   // carried tracker state of this stream's blocks
     float2 q[kZbQueue];    // raw pairs in flight / waiting for the tracker
     double y;              // tracker state
-    int32_t to_boundary;   // samples until the tracker reaches the next block boundary
     uint32_t zr;           // shared-memory byte address of this lane's column of the z ring
     uint32_t zw;           // byte offset of the row the tracker writes next (row * 128)
     uint32_t taps_adj;     // shared-memory byte address of the interpolator table - 0x68000000 (see row())
@@ -600,13 +605,19 @@ struct ZbRegSrc {
     bool enabled;          // slow windows only: the tracker runs
     float* z_dbg; int32_t z_lo, z_hi;    // debug: this chain stores z[z_lo, z_hi) of its stream
 
-    template <int K>
+    // a block of the tracker starts here: its state is the carried one
+    __device__ __forceinline__ void boundary() {
+        const int32_t g = begin + conv;
+        if ((g & (SNRX_IIR_BLOCK - 1)) == 0) y = __ldg(carry + (g >> 11));
+    }
+    // BOUNDARY = false: the caller knows that no block boundary falls on this pair (fast windows call boundary() once)
+    template <int K, bool BOUNDARY>
     __device__ __forceinline__ void convert() {
+        static_assert(SNRX_IIR_BLOCK == 2048, "boundary() shifts by 11");
         const float f0 = q[K].x, f1 = q[K].y;
         q[K] = __ldg(nxt);                                   // the pair kZbQueue steps ahead
         nxt++;
-        if (to_boundary == 0) { y = __ldg(cptr); cptr++; to_boundary = SNRX_IIR_BLOCK; }
-        to_boundary -= 2;
+        if (BOUNDARY) boundary();
         y = zb_iir_step(y, f0);
         const float z0 = zb_dc_out(f0, y);
         y = zb_iir_step(y, f1);
@@ -627,11 +638,12 @@ struct ZbRegSrc {
         conv += 2;
     }
     __device__ __forceinline__ void burst() {                // 16 samples
-        convert<0>(); convert<1>(); convert<2>(); convert<3>(); convert<4>(); convert<5>(); convert<6>(); convert<7>();
+        convert<0, true>(); convert<1, true>(); convert<2, true>(); convert<3, true>();
+        convert<4, true>(); convert<5, true>(); convert<6, true>(); convert<7, true>();
     }
-    __device__ __forceinline__ void start(const float* f, const double* carry, int32_t begin_) {
-        begin = begin_; conv = 0; zw = 0; y = 0.0; to_boundary = 0; enabled = true;
-        cptr = carry + begin_ / SNRX_IIR_BLOCK;
+    __device__ __forceinline__ void start(const float* f, const double* carry_, int32_t begin_) {
+        begin = begin_; conv = 0; zw = 0; y = 0.0; enabled = true;
+        carry = carry_;
         nxt = reinterpret_cast<const float2*>(f + begin_);
 #pragma unroll
         for (int k = 0; k < kZbQueue; k++) q[k] = __ldg(nxt + k);
@@ -640,8 +652,11 @@ struct ZbRegSrc {
     }
     template <int K, bool FAST>
     __device__ __forceinline__ void tick() {
-        if (FAST || enabled) convert<K>();
+        if (FAST) convert<K, false>();
+        else if (enabled) convert<K, true>();
     }
+    // a fast window converts the 64 samples from conv on; conv is a multiple of 64 there
+    __device__ __forceinline__ bool aligned() const { return ((begin + conv) & 63) == 0; }
     __device__ __forceinline__ void get8(int32_t ii, float (&in)[8]) {
         const uint32_t p = zr + ((uint32_t)((ii - begin) & (kZbZRows - 1)) << 7);
 #pragma unroll
@@ -674,7 +689,7 @@ struct ZbRxArgs {
 // time and takes the next one from a queue when it is done: chains differ in length by a factor of four (a chain that
 // holds a frame follows it through the post halo), and the warp is busy as long as any of its lanes is.
 template <bool DEBUG>
-__global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxCtasPerSm) k_zb_rx(const __grid_constant__ ZbRxArgs a) {
+__global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxMinCtas) k_zb_rx(const __grid_constant__ ZbRxArgs a) {
     extern __shared__ __align__(16) unsigned char zb_smem[];
     float* taps = reinterpret_cast<float*>(zb_smem);
     float* zring = taps + (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS;
@@ -704,11 +719,15 @@ __global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxCtasPerSm) k_zb_rx(const
         while (!done) {
             // re-centre the tracker's lead (rare: a lane drifts by about one sample per window)
             int lead = src.conv - (c.mm.ii - src.begin);
-            while (lead < kZbLeadMin) { src.burst(); lead += 2 * kZbQueue; }
+            while (lead < kZbLeadMin) { src.burst(); src.burst(); src.burst(); src.burst(); lead += 8 * kZbQueue; }
             src.enabled = lead <= kZbLeadMax;
             ZbWin w;
-            if (src.enabled && c.mm.ii + 8 + 3 * 32 <= c.end) zb_chain_steps<true, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
-            else zb_chain_steps<false, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
+            if (src.enabled && src.aligned() && c.mm.ii + 8 + 3 * 32 <= c.end) {
+                src.boundary();
+                zb_chain_steps<true, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
+            } else {
+                zb_chain_steps<false, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
+            }
             done = zb_chain_sink(c, w, a.map.w, p.threshold);
         }
         a.good_end[chain] = c.em.good_end;
