@@ -100,48 +100,77 @@ def make_capture(workload, seconds_base, seed):
     return c.iq, len(c.truth)
 
 
+def _oracle_taps(name):
+    """Prototype filters for the CPU arm, from the generator the kernels' tables come from (tools/gen_tables.py) -- the
+    reference arm must not load the product library."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from gen_tables import PFB_DESIGNS, kaiser_lowpass
+    return kaiser_lowpass(*PFB_DESIGNS[name])
+
+
+_POOL = None
+
+
+def _ref_decode_one(args):
+    """One BLE channel through the UNMODIFIED btle_rx.c (oracle/_ref): the reference keeps its state in globals, so every
+    worker is a process of its own."""
+    import oracle
+    q, ch = args
+    return len(oracle.ble_decode(q, ch, impl="reference"))
+
+
 def cpu_path(workload, sample, min_seconds=0.0):
     """CPU statement of the path on `sample` using every host core, repeated until at least `min_seconds`
     of CPU work have been timed; returns (seconds, samples processed, frames of one pass, cores, kind)."""
-    import oracle
-    from concurrent.futures import ThreadPoolExecutor
-    from snout_b200 import _abi, chanplan
-    oracle.build(native=True)
+    global _POOL
     cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)            # torchrun exports 1 to its workers; set before libgomp loads
+    import oracle
+    from concurrent.futures import ProcessPoolExecutor, ThreadPoolExecutor
+    from snout_b200 import chanplan
+    oracle.build(native=True)
+    oracle.set_threads(cores)
     kind = "port"
-    h = _abi.pfb_prototype(_abi.MODE_BLE_WB40, 384) if workload in ("ble_wb40", "mixed_wb56") else None
-    hz = _abi.pfb_prototype(_abi.MODE_ZB_WB16, 384) if workload in ("zb_wb16", "mixed_wb56") else None
+    h = _oracle_taps("BLE_384") if workload in ("ble_wb40", "mixed_wb56") else None
+    hz = _oracle_taps("ZB_384") if workload in ("zb_wb16", "mixed_wb56") else None
     bins = [chanplan.ble_channel_bin(c) for c in range(40)]
     zbins = [chanplan.zigbee_channel_bin(c) for c in range(11, 27)]
+    use_ref = oracle.have_ref("btle_ref")
+    if use_ref and workload in ("ble_wb40", "mixed_wb56") and _POOL is None:
+        _POOL = ProcessPoolExecutor(cores)
+        list(_POOL.map(_ref_decode_one, [(np.zeros((64, 2), np.int8), 37)] * cores))     # start the workers outside the timed region
     t0 = time.perf_counter()
     frames, done = 0, 0
     while True:
         if workload in ("zb_wb16", "mixed_wb56"):
             # CPU statement of the wideband Zigbee path: float channelizer (OpenMP) + the restated GNU Radio chain
             # and the packet sink, one channel per thread
-            y = oracle.pfb(sample, hz, zbins, fast=True)
+            y = oracle.pfb(sample, hz, zbins, fast=True, native=True)
             def zone(c):
                 return len(oracle.zb_receive(y[c], 11 + c))
             with ThreadPoolExecutor(cores) as ex:
                 frames = sum(ex.map(zone, range(16)))
         if workload in ("ble_wb40", "mixed_wb56"):
             # channelizer: no reference counterpart (the reference retunes one 4 Msps channel at a time), CPU
-            # statement = oracle/pfb_oracle.c with OpenMP over all cores; per-channel decode = the port of
-            # btle_rx.c's receiver(), one channel per thread
-            y = oracle.pfb(sample, h, bins, fast=True)
-            def one(c):
-                return len(oracle.ble_decode(oracle.ble_quantize(y[c], 100.0), c, impl="port"))
-            with ThreadPoolExecutor(cores) as ex:
-                frames = (frames if workload == "mixed_wb56" else 0) + sum(ex.map(one, range(40)))
+            # statement = oracle/pfb_oracle.c (vectorised, OpenMP over all cores); per-channel decode = the reference's own
+            # receiver() (oracle/_ref, one process per core) where it was compiled, else its port (one thread per core)
+            y = oracle.pfb(sample, h, bins, fast=True, native=True)
+            if use_ref:
+                n_ble = sum(_POOL.map(_ref_decode_one, [(oracle.ble_quantize(y[c], 100.0), c) for c in range(40)]))
+            else:
+                with ThreadPoolExecutor(cores) as ex:
+                    n_ble = sum(ex.map(lambda c: len(oracle.ble_decode(oracle.ble_quantize(y[c], 100.0), c, impl="port")), range(40)))
+            frames = (frames if workload == "mixed_wb56" else 0) + n_ble
+            kind = "port"                                  # the channelizer, where the time goes, is our own CPU statement
         elif workload == "zb_wb16":
             pass
         elif workload == "ble_nb":
-            kind = "reference" if oracle.have_ref("btle_ref") else "port"
+            kind = "reference" if use_ref else "port"
             q = oracle.ble_quantize(sample, 128.0)
             frames = len(oracle.ble_decode(q, 37, impl=kind))
             cores = 1
         else:
-            frames = len(oracle.zb_receive(sample, 11))
+            frames = len(oracle.zb_receive_serial(sample, 11))
             cores = 1
         done += len(sample)
         if time.perf_counter() - t0 >= min_seconds:
@@ -175,9 +204,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ble_wb40", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="ble_wb40", choices=sorted(WORKLOADS) + ["c5"])
     ap.add_argument("--base-seconds", type=float, default=0.1, help="length of the generated capture that is tiled")
-    ap.add_argument("--tiles", type=int, default=10, help="copies of the generated capture per step (wideband)")
+    ap.add_argument("--tiles", type=int, default=0, help="copies of the generated capture per step (wideband); 0 = 10 (0.98 s) for "
+                    "ble_wb40, 100 (9.8 s, the capture length of BASELINE configs[4]) for zb_wb16 / mixed_wb56")
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4]-shaped run (time-sharded mixed captures) reported under \"c5\"")
+    ap.add_argument("--c5-seconds", type=float, default=9.83, help="length of the resident mixed capture of the c5 run")
     ap.add_argument("--taps", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work timed for cpu_baseline (bounded sample)")
@@ -187,6 +219,11 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    c5_only = args.workload == "c5"
+    if c5_only:
+        args.workload = "mixed_wb56"
+    if not args.tiles:
+        args.tiles = 10 if args.workload == "ble_wb40" else 100
     mode, cfg_name, desc = WORKLOADS[args.workload]
     unit = "Msamples/s"
     metric = "input IQ Msamples/s channelized+decoded (whole job)"
@@ -208,8 +245,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "sample_samples": int(per_step),
-                       "note": "CPU statement of the same path on the host cores; the reference itself has no channelizer "
-                               "(it retunes one 4 Msps channel at a time)"},
+                       "note": "CPU statement of the same path on all host cores: vectorised OpenMP channelizer (oracle/pfb_oracle.c, "
+                               "-O3 -march=native; the reference has no channelizer, it retunes one 4 Msps channel at a time) + per channel "
+                               "the reference's own receiver() (unmodified btle_rx.c, oracle/_ref, one process per core) / the restated "
+                               "GNU Radio chain + packet sink for Zigbee"},
             "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": kind,
                              "sample": f"{per_step} samples per step = a {len(base)}-sample slice of the workload repeated for >= {args.ref_step_seconds} s, {frames} frames per pass"},
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -243,13 +282,22 @@ def main():
     # two gathers in flight.  (FrameGather(record_bytes=80) would exchange only the 80 bytes a BLE record uses; measured at
     # N=4 it does not change the step time, nor do three gathers in flight: the exchange is not bandwidth bound.)
     gather_depth = 2
-    gather, gather_kind = None, None
-    if world > 1:
-        # preferred: peer-to-peer pushes on the copy engines (no collective kernel beside the channelizer); NCCL otherwise
-        gather = None if os.environ.get("SNRX_GATHER", "peer") == "nccl" else sdist.PeerGather.available(dev)
-        gather_kind = "peer-to-peer copies over NVLink (dist.PeerGather)" if gather is not None else "NCCL all-gather (dist.FrameGather)"
-        if gather is None:
-            gather = sdist.FrameGather(dev, cap=1 << 15, depth=gather_depth)
+
+    def make_gather(engine):
+        """The frame exchange for `engine`: the C ABI's own (stores into every peer's HBM from the export kernel,
+        include/snoutrx.h snrx_exchange_*), else copy-engine pushes through torch symmetric memory, else NCCL."""
+        if world == 1:
+            return None, None
+        want = os.environ.get("SNRX_GATHER", "abi")
+        g = sdist.AbiGather.available(engine, dev) if want == "abi" else None
+        if g is not None:
+            return g, "stores into the peers' HBM over NVLink from k_export_frames (snrx_exchange_* / snrx_allgather)"
+        g = sdist.PeerGather.available(dev) if want in ("abi", "peer") else None
+        if g is not None:
+            return g, "peer-to-peer copies over NVLink (dist.PeerGather)"
+        return sdist.FrameGather(dev, cap=1 << 15, depth=gather_depth), "NCCL all-gather (dist.FrameGather)"
+
+    gather, gather_kind = make_gather(eng)
 
     def barrier():
         if world > 1:
@@ -386,6 +434,88 @@ def main():
         analytics = {"records_per_batch": int(len(fr)), "ms_per_batch": dt * 1e3, "records_per_s": len(fr) / dt, "senders": int(n_dev),
                      "note": "snrx_ble_adv_summary (k_ble_adv_summary + k_ble_adv_devices + counter read-back), not part of value/e2e"}
 
+
+    # ---- BASELINE configs[4]: long mixed BLE+Zigbee captures sharded by time segment WITH HALO, frames exchanged.  Every rank
+    #      holds one resident 10-s capture standing for its 1024/N captures (1024 x 7.7 GB cannot be materialised) and
+    #      processes it as dist.plan_job cuts it -- ~1-s bodies with the BLE / Zigbee halos of snrx_shard_t, i.e. exactly the
+    #      units a multi-GPU job hands out -- two shards in flight, every shard's records exchanged with all ranks.
+    def run_c5():
+        from snout_b200 import stream
+        cbase, _ = make_capture("mixed_wb56", args.base_seconds, 5000 + 37 * rank)
+        ctiles = max(1, int(round(args.c5_seconds / args.base_seconds)))
+        xc = torch.from_numpy(cbase).to(dev).repeat(ctiles)
+        unit, pre, post = stream.shard_geometry(40, 16)
+        body_units = 480                                        # 480 x 8192 channel samples = 0.983 s per shard body
+        ceng = RxEngine("mixed_wb56", max_samples=(body_units * unit + pre + post) * 24, pfb_taps=args.taps, device=local,
+                        max_frames=1 << 18)
+        cgather, ckind = make_gather(ceng)
+        units = sdist.plan_job(1, len(xc), ceng, units_per_shard=body_units)
+        halo = sum(u["hi"] - u["lo"] for u in units) / len(xc) - 1.0
+
+        def one_capture(cid, pend, stats):
+            for u in units:
+                if stats["queued"] == 2:
+                    fr = ceng.poll(copy=False)
+                    stats["queued"] -= 1
+                    stats["frames"] += len(fr)
+                    stats["launches"] += ceng.stats()["kernel_launches"]
+                    if world > 1:
+                        pend.append(cgather.start(fr, *ceng.polled_frames_device()[:2]))
+                        if len(pend) >= gather_depth:
+                            stats["gathered"] += sum(pend.pop(0).counts())
+                ceng.process(xc[u["lo"]: u["hi"]], shard=dict(pre_samples=u["pre_samples"], body_samples=u["body_samples"],
+                                                               first_window=u["first_window"], first_capture_id=cid))
+                stats["queued"] += 1
+
+        def drain(pend, stats):
+            while stats["queued"]:
+                fr = ceng.poll(copy=False)
+                stats["queued"] -= 1
+                stats["frames"] += len(fr)
+                stats["launches"] += ceng.stats()["kernel_launches"]
+                if world > 1:
+                    pend.append(cgather.start(fr, *ceng.polled_frames_device()[:2]))
+            while pend:
+                stats["gathered"] += sum(pend.pop(0).counts())
+
+        def run(k):
+            pend, stats = [], dict(queued=0, frames=0, gathered=0, launches=0)
+            for cid in range(k):
+                one_capture(cid, pend, stats)
+            drain(pend, stats)
+            return stats
+
+        run(max(1, min(args.warmup, 2)))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = run(args.steps)
+        e1.record()
+        barrier()
+        cms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as d
+            t = torch.tensor([cms], device=dev)
+            d.all_reduce(t, op=d.ReduceOp.MAX)
+            cms = float(t.item())
+        ceng.close()
+        return {"value": world * len(xc) * args.steps / (cms * 1e-3) / 1e6, "unit": unit_name, "ms_per_step": cms / args.steps,
+                "steps": args.steps, "scaling": "weak",
+                "config": {"workload": "c5 (configs[4]): 10-s 96 Msps mixed BLE+Zigbee captures sharded by time segment with halo, "
+                                       "frames exchanged over NVLink; one resident capture per GPU stands for its 1024/N captures",
+                           "samples_per_step_per_gpu": int(len(xc)), "shards_per_capture": len(units),
+                           "shard_body_samples": int(body_units * unit * 24), "halo_overhead": round(halo, 4),
+                           "frames_per_step": int(st["frames"] / args.steps), "frame_exchange": ckind,
+                           "frames_received_per_step_all_ranks": int(st["gathered"] / args.steps) if world > 1 else None},
+                "gpu_launches": int(st["launches"]),
+                "note": "a step = one capture = shards_per_capture snrx_process calls (snrx_shard_t halos: BLE 128 / 2048, Zigbee "
+                        "102400 / 16512 channel samples), two in flight; H2D excluded (resident data), as SURVEY 8d specifies for C5"}
+
+    unit_name = unit
+    c5 = None
+    if c5_only or (not args.no_c5 and args.workload == "ble_wb40"):
+        c5 = run_c5()
+
     e2e, d2h, _ = time_e2e(pinned)
     # the same capture as an 8-bit digitiser delivers it (interleaved int8 I,Q = the HackRF transfer format the
     # reference consumes, btle_rx.c:204,489-498) through snrx_process_sc8: a quarter of the PCIe bytes
@@ -400,6 +530,7 @@ def main():
             eng.close()
             eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps, device=local, max_frames=1 << 18,
                            quant_scale=100.0 * 1.28 * peak_amp)
+            gather, _ = make_gather(eng)
         v8, d2h8, nfr8 = time_e2e(pinned8)
         e2e_sc8 = {"value": v8, "unit": unit, "h2d_bytes_per_step": int(n * 2), "d2h_bytes_per_step": int(d2h8 / args.steps),
                    "frames_per_step": int(nfr8),
@@ -431,8 +562,21 @@ def main():
                                 "mixed_wb56": "k_pfb_ble (channelizer+slicer; the Zigbee front end runs after it on the tail stream)",
                                 "ble_nb": "k_ble_slice_nb", "zb_nb": "k_zb_quad"}[mode],
                      "algorithmic_bytes_per_launch": int(n * 8), "kernel_ms": fms,
-                     "note": "8 B per input sample (one cf32 read); the fused channelizer is FP32-pipe limited, see DESIGN.md"},
+                     "step_frac": n * 8 / (ms / args.steps * 1e-3) / 1e9 / peak,
+                     "binding_unit": "fp32 FMA pipe / issue slots" if args.workload in WIDEBAND else "hbm",
+                     "note": "frac = 8 B per input sample (one cf32 read) / the dominant kernel's launch time vs the measured HBM copy "
+                             "bandwidth; step_frac = the same bytes / the whole step.  The wideband kernels are bound by the FP32 pipe "
+                             "and issue slots, not by bytes (DESIGN.md 3, 6): the HBM fraction is reported because the contract asks "
+                             "for it, the binding unit is named beside it"},
+        "c5": c5,
     }
+    if c5_only:                    # --workload c5: the sharded run is the headline, the single-capture mixed run is context
+        single = {k: line[k] for k in ("value", "ms_per_step", "frames_per_s", "gpu_launches")}
+        single["config"] = line["config"]
+        line.update(value=c5["value"], ms_per_step=c5["ms_per_step"], gpu_launches=c5["gpu_launches"], config=c5["config"],
+                    frames_per_s=c5["config"]["frames_per_step"] * args.steps / (c5["ms_per_step"] * args.steps * 1e-3))
+        line["mixed_wb56_single_capture"] = single
+        line["c5"] = {"note": c5["note"]}
     tr = ncu_traffic(n) if mode == "ble_wb40" else None
     if tr:
         line["roofline"]["traffic"] = tr[0]

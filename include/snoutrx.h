@@ -288,6 +288,32 @@ int  snrx_ble_adv_summary(snrx_t* h, snrx_adv_t* out, uint32_t cap, uint32_t* n_
  * SNRX_EOVERFLOW if more than 2^18 distinct senders were seen (the extra ones were not recorded). */
 int  snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_out, int reset);
 
+/* ---- the one exchange of the path -- every engine of a node gets every engine's frame records.
+ * No reference counterpart (the reference runs on one host CPU); north_star: "NCCL over NVLink is used only to allgather
+ * the decoded-frame records".  Here the gather needs no collective kernel at all: once the engines are connected, the
+ * kernel that exports a batch's frame list (k_export_frames) also stores the records -- only the 16-byte pieces a record
+ * uses -- and then a {count, batch} header straight into a receive slot in every peer's HBM over NVLink / NVSwitch
+ * (peer pointers obtained through CUDA IPC).  Nothing is launched or waited for per batch on the host, and no SM-resident
+ * collective waits for the slowest rank beside the channelizer.
+ *
+ *   snrx_exchange_create   allocates this engine's receive area (8 slots x world x (1 + cap_records) records) and returns
+ *                          its 64-byte CUDA IPC handle; the caller passes the handles around (MPI, torch.distributed,
+ *                          a file: 64 bytes per rank) ...
+ *   snrx_exchange_connect  ... and hands all of them in, in rank order; every later batch is pushed to every rank.
+ *   snrx_allgather         waits until batch `batch_no` (0, 1, ... = the order of snrx_process calls on every engine) of
+ *                          all ranks has arrived here; counts[r] = records of rank r; with out != NULL the records are
+ *                          copied out in rank order (*n_out = their number).  Collective discipline: every rank calls it
+ *                          for every batch, in order, and before it queues batch_no + 4 (a slot is reused after 8 batches).
+ *                          SNRX_EOVERFLOW if some rank had more than cap_records records in that batch (the caller falls back
+ *                          to its own two-phase gather for that batch), SNRX_ESTATE after timeout_ms without the batch. */
+#define SNRX_XCHG_HANDLE_BYTES 64
+#define SNRX_XCHG_SLOTS 8
+#define SNRX_XCHG_MAX_WORLD 16
+int  snrx_exchange_create(snrx_t* h, uint32_t rank, uint32_t world, uint32_t cap_records, void* handle_out);
+int  snrx_exchange_connect(snrx_t* h, const void* handles);
+int  snrx_allgather(snrx_t* h, uint64_t batch_no, snrx_frame_t* out, uint32_t cap, uint32_t* counts, uint32_t* n_out,
+                    uint32_t timeout_ms);
+
 int  snrx_set_channel(snrx_t* h, int channel);           /* NB modes */
 int  snrx_set_stream(snrx_t* h, void* cuda_stream);       /* run on a caller stream */
 int  snrx_sync(snrx_t* h);

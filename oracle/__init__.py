@@ -38,13 +38,16 @@ def reference_available() -> bool:
 
 
 def build(ref: bool | None = None, native: bool = False, quiet: bool = True) -> None:
-    """Compile the port oracle, and the reference oracle when /root/reference is present."""
+    """Compile the port oracle, and the reference oracle when /root/reference is present.  native=True also builds
+    _build/liboracle_native.so (-O3 -march=native on THIS host): the library the CPU baseline legs of bench.py time."""
     args = ["make", "-C", HERE]
-    if native:
-        args.append("MARCH=-march=native -O3")
     out = subprocess.run(args + ["all"], capture_output=True, text=True)
     if out.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if native:
+        out = subprocess.run(args + ["native"], capture_output=True, text=True)
+        if out.returncode != 0:
+            raise RuntimeError("native oracle build failed:\n" + out.stdout + out.stderr)
     if ref is None:
         ref = reference_available()
     if ref:
@@ -61,11 +64,14 @@ def _lib(name: str) -> ctypes.CDLL:
     if name in _libs:
         return _libs[name]
     path = {"port": os.path.join(HERE, "_build", "liboracle.so"),
+            "native": os.path.join(HERE, "_build", "liboracle_native.so"),
             "btle_ref": os.path.join(HERE, "_ref", "libbtle_ref.so"),
             "zb_ref": os.path.join(HERE, "_ref", "libzbsink_ref.so")}[name]
     if not os.path.exists(path):
         if name == "port":
             build(ref=False)
+        elif name == "native":
+            build(ref=False, native=True)
         else:
             raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
     lib = ctypes.CDLL(path)
@@ -317,14 +323,20 @@ def zb_sink_reference(chips: np.ndarray, threshold: int = 10, cap: int = 4096):
 
 # ------------------------------------------------------------------------ PFB
 
-def pfb(iq_cf32: np.ndarray, taps: np.ndarray, bins, m0: int = 0, m1: int | None = None, fast: bool = False) -> np.ndarray:
-    """Channel streams [len(bins), m1-m0] complex64 of a 96 Msps capture."""
+def set_threads(n: int) -> None:
+    """OpenMP threads of the native library (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    _lib("native").pfb_oracle_set_threads(c_int(n))
+
+
+def pfb(iq_cf32: np.ndarray, taps: np.ndarray, bins, m0: int = 0, m1: int | None = None, fast: bool = False,
+        native: bool = False) -> np.ndarray:
+    """Channel streams [len(bins), m1-m0] complex64 of a 96 Msps capture.  native=True: the -march=native build."""
     x = np.ascontiguousarray(iq_cf32, dtype=np.complex64)
     if m1 is None:
         m1 = x.shape[0] // 24
     b = np.ascontiguousarray(bins, dtype=np.int32)
     out = np.zeros((b.shape[0], m1 - m0), dtype=np.complex64)
-    lib = _lib("port")
+    lib = _lib("native" if native else "port")
     if fast:
         h = np.ascontiguousarray(taps, dtype=np.float32)
         lib.pfb_oracle_fast(_ptr(x), c_int64(x.shape[0]), _ptr(h), c_int(h.shape[0]), _ptr(b), c_int(b.shape[0]),

@@ -24,6 +24,7 @@ ZB_IIR_BLOCK = 2048            # SNRX_ZB_IIR_BLOCK / SNRX_ZB_IIR_MEMORY_BLOCKS
 ZB_IIR_MEMORY_BLOCKS = 48
 STAGE_BLE_Q8, STAGE_BLE_BITS, STAGE_CHAN_CF32, STAGE_ZB_DISC, STAGE_ZB_CHIPS, STAGE_ZB_F, STAGE_ZB_NCHIPS = 1, 2, 3, 4, 5, 6, 7
 PROTO_ZIGBEE, PROTO_BLE = 2, 3
+XCHG_HANDLE_BYTES, XCHG_SLOTS, XCHG_MAX_WORLD = 64, 8, 16
 
 FRAME_DTYPE = np.dtype([
     ("sample_index", "<i8"), ("capture_id", "<u4"), ("window", "<u4"), ("channel", "<u2"),
@@ -91,6 +92,9 @@ SYMBOLS = [
     ("snrx_polled_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
     ("snrx_ble_adv_summary", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_ble_devices", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32), c_int]),
+    ("snrx_exchange_create", c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_void_p]),
+    ("snrx_exchange_connect", c_int, [c_void_p, c_void_p]),
+    ("snrx_allgather", c_int, [c_void_p, c_uint64, c_void_p, c_uint32, POINTER(c_uint32), POINTER(c_uint32), c_uint32]),
     ("snrx_set_channel", c_int, [c_void_p, c_int]),
     ("snrx_set_stream", c_int, [c_void_p, c_void_p]),
     ("snrx_sync", c_int, [c_void_p]),

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,7 +45,7 @@ struct Lane {
     snrx_frame_t* d_frames_buf[2] = {nullptr, nullptr};   // so a polled batch's list stays valid for two further snrx_process calls
     uint32_t uses = 0;
     uint32_t* totals = nullptr;         // pinned: [0] BLE frames [1] candidates [2] Zigbee frames
-    uint32_t* d_totals = nullptr;       // device: same layout
+    uint32_t* d_totals = nullptr;       // device: same layout; [5] CRC-ok frames, [6] arrival counter of k_export_frames' CTAs
     cudaEvent_t ev_start = nullptr, ev_front0 = nullptr, ev_front = nullptr, ev_done = nullptr, ev_in = nullptr;
     cudaEvent_t ev_handoff = nullptr;
     bool pending = false, done = false;
@@ -77,6 +79,15 @@ struct snrx_handle {
     uint32_t dev_count = 0, dev_dropped = 0;
     Lane lane[2];
     uint64_t seq_process = 0, seq_poll = 0;
+    // frame exchange (snrx_exchange_*): receive area of this engine and the peers' areas mapped through CUDA IPC
+    struct {
+        bool connected = false;
+        uint32_t rank = 0, world = 1, cap = 0;
+        unsigned char* d_recv = nullptr;                       // [world][SNRX_XCHG_SLOTS][1 + cap] records
+        unsigned char* peer[SNRX_XCHG_MAX_WORLD] = {nullptr};  // peer[r] = rank r's receive area (peer[rank] = d_recv)
+        uint64_t* h_hdr = nullptr;                             // pinned: world x {count, batch}
+        cudaStream_t stream = nullptr;
+    } xchg;
     int sm_count = 148;
     std::string err;
 
@@ -218,21 +229,63 @@ static int pfb_ble_dispatch(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st
 }
 static int ble_tile_stride(const snrx_handle* h) { return h->wideband ? PfbBleGeom<16>::kStride : kTileT; }
 
-// device frame list -> host-mapped pinned memory, fully coalesced 16-byte stores; also publishes the totals
-__global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __restrict__ src, const uint32_t* __restrict__ totals_dev,
+// where k_export_frames pushes a batch for the other engines of the node (snrx_exchange_*)
+struct ExportXchg {
+    unsigned char* peer[SNRX_XCHG_MAX_WORLD];   // receive areas, [src rank][slot][1 + cap] records each
+    uint32_t world, rank, cap, slot;
+};
+__device__ __forceinline__ uint4* xchg_slot(const ExportXchg& x, uint32_t p) {
+    return reinterpret_cast<uint4*>(x.peer[p] + ((size_t)x.rank * SNRX_XCHG_SLOTS + x.slot) * ((size_t)x.cap + 1) * sizeof(snrx_frame_t));
+}
+
+// device frame list -> host-mapped pinned memory, fully coalesced 16-byte stores; publishes the totals; and, when the
+// engine is connected to its peers, stores the records (only the 16-byte pieces a record uses: 28 bytes of fields + len
+// bytes of payload) and then the {count, batch} header into this rank's slot in every rank's receive area -- the frame
+// all-gather of the path as plain stores over NVLink, ordered by a system-scope fence before the header goes out.
+__global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __restrict__ src, uint32_t* __restrict__ totals_dev,
                                                        snrx_frame_t* __restrict__ dst_host, uint32_t* __restrict__ totals_host,
-                                                       uint32_t frame_cap, unsigned long long batch_no) {
+                                                       uint32_t frame_cap, unsigned long long batch_no, const ExportXchg x) {
     uint32_t n = totals_dev[0] + totals_dev[2];
     if (n > frame_cap) n = frame_cap;                      // few CTAs: this kernel is PCIe bound and must leave the SMs to the other lane
     if (blockIdx.x == 0 && threadIdx.x == 0) {             // header in front of the device list (see the allocation)
         unsigned long long* hdr = reinterpret_cast<unsigned long long*>(const_cast<snrx_frame_t*>(src) - 1);
         hdr[0] = n; hdr[1] = batch_no;
     }
-    const size_t n16 = (size_t)n * (sizeof(snrx_frame_t) / 16);
+    constexpr uint32_t kPieces = sizeof(snrx_frame_t) / 16;
+    const size_t n16 = (size_t)n * kPieces;
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst_host);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d4[i] = s4[i];
-    if (blockIdx.x == 0 && threadIdx.x < 8) totals_host[threadIdx.x] = totals_dev[threadIdx.x];
+    uint32_t ok = 0;
+    const uint32_t m = x.world > 1 ? min(n, x.cap) : 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = s4[i];
+        d4[i] = v;
+        const uint32_t rec = (uint32_t)(i / kPieces), k = (uint32_t)(i - (size_t)rec * kPieces);
+        if (k == 1) ok += (v.x >> 24) & 1u;                // piece 1 = bytes 16..31: channel, proto, crc_ok, lqi, phase, len, access_addr, bytes[0..3]
+        if (rec < m) {
+            const uint4 h1 = k == 1 ? v : s4[(size_t)rec * kPieces + 1];
+            const uint32_t used = (28u + (h1.y >> 16) + 15u) >> 4;
+            if (k < used) {
+                for (uint32_t p = 0; p < x.world; p++) xchg_slot(x, p)[(size_t)(rec + 1) * kPieces + k] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    if ((threadIdx.x & 31) == 0 && ok) atomicAdd(totals_dev + 5, ok);
+    // the last CTA to arrive publishes: every store above is ordered before it by the fences
+    __shared__ uint32_t ticket;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(totals_dev + 6, 1u);
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;
+    __threadfence_system();
+    if (threadIdx.x < 8) totals_host[threadIdx.x] = ((volatile uint32_t*)totals_dev)[threadIdx.x];
+    if (x.world > 1 && threadIdx.x < x.world) {
+        const uint4 hdr = make_uint4(n, 0u, (uint32_t)batch_no, (uint32_t)(batch_no >> 32));
+        *xchg_slot(x, threadIdx.x) = hdr;                  // {uint64 count, uint64 batch}: 16 bytes, one store
+    }
 }
 
 // Interleaved signed 8-bit I,Q (the HackRF transfer format the reference consumes: IQ_TYPE int8_t, btle_rx.c:204,
@@ -318,6 +371,11 @@ void snrx_destroy(snrx_t* h) {
         if (ln.tail) cudaStreamDestroy(ln.tail);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->xchg.stream) { cudaStreamSynchronize(h->xchg.stream); cudaStreamDestroy(h->xchg.stream); }
+    for (uint32_t r = 0; r < h->xchg.world && r < SNRX_XCHG_MAX_WORLD; r++)
+        if (h->xchg.peer[r] && h->xchg.peer[r] != h->xchg.d_recv) cudaIpcCloseMemHandle(h->xchg.peer[r]);
+    if (h->xchg.d_recv) cudaFree(h->xchg.d_recv);
+    if (h->xchg.h_hdr) cudaFreeHost(h->xchg.h_hdr);
     if (h->adv_stream) { cudaStreamSynchronize(h->adv_stream); cudaStreamDestroy(h->adv_stream); }
     { void* ab[] = {h->d_adv, h->d_devtab, h->d_devout, h->d_adv_counters}; for (void* b : ab) if (b) cudaFree(b); }
     delete h;
@@ -718,7 +776,14 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
         if (r != SNRX_OK) return r;
     }
     // export: device frame list -> pinned host memory; on this lane's stream, so it overlaps the other lane's front end
-    k_export_frames<<<32, 256, 0, st>>>(ln.d_frames, ln.d_totals, ln.frames, ln.totals, h->frame_cap, (unsigned long long)h->seq_process);
+    ExportXchg xa{};
+    if (h->xchg.connected) {
+        for (uint32_t r = 0; r < h->xchg.world; r++) xa.peer[r] = h->xchg.peer[r];
+        xa.world = h->xchg.world; xa.rank = h->xchg.rank; xa.cap = h->xchg.cap; xa.slot = (uint32_t)(h->seq_process % SNRX_XCHG_SLOTS);
+    } else {
+        xa.world = 1;
+    }
+    k_export_frames<<<32, 256, 0, st>>>(ln.d_frames, ln.d_totals, ln.frames, ln.totals, h->frame_cap, (unsigned long long)h->seq_process, xa);
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ln.ev_done, st));
@@ -749,8 +814,7 @@ static int finish_oldest(snrx_handle* h, Lane** out_lane) {
         float ms = 0.f, msf = 0.f;
         cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_done);
         cudaEventElapsedTime(&msf, sl.ev_front0, sl.ev_front);
-        uint32_t ok = 0;
-        for (uint32_t i = 0; i < sl.n_frames; i++) ok += sl.frames[i].crc_ok;
+        const uint32_t ok = sl.totals[5];               // counted by k_export_frames
         h->stats.samples_in = (uint64_t)sl.caps * sl.n_in;
         h->stats.channel_samples = (uint64_t)sl.caps * sl.n_out * (h->n_ble_ch + h->n_zb_ch);
         h->stats.frames = sl.n_frames;
@@ -886,6 +950,92 @@ int snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_ou
         h->dev_count = h->dev_dropped = 0;
     }
     if (dropped) return fail(h, SNRX_EOVERFLOW, "more than 2^18 distinct senders: some were not recorded");
+    return SNRX_OK;
+}
+
+// ---- frame exchange between the engines of a node ----------------------------------------------------------------------
+static size_t xchg_slot_bytes(const snrx_handle* h) { return ((size_t)h->xchg.cap + 1) * sizeof(snrx_frame_t); }
+
+int snrx_exchange_create(snrx_t* h, uint32_t rank, uint32_t world, uint32_t cap_records, void* handle_out) {
+    if (!h || !handle_out) return SNRX_EINVAL;
+    if (world < 1 || world > SNRX_XCHG_MAX_WORLD || rank >= world || cap_records == 0) return fail(h, SNRX_EINVAL, "exchange: rank / world / capacity out of range");
+    if (h->xchg.d_recv) return fail(h, SNRX_ESTATE, "exchange already created");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SNRX_XCHG_HANDLE_BYTES, "CUDA IPC handle size");
+    CK(cudaSetDevice(h->device));
+    h->xchg.rank = rank; h->xchg.world = world; h->xchg.cap = cap_records;
+    const size_t bytes = (size_t)world * SNRX_XCHG_SLOTS * xchg_slot_bytes(h);
+    CK(cudaMalloc((void**)&h->xchg.d_recv, bytes));
+    CK(cudaMemset(h->xchg.d_recv, 0xFF, bytes));                         // batch numbers of all ones: nothing has arrived
+    CK(cudaHostAlloc((void**)&h->xchg.h_hdr, sizeof(uint64_t) * 2 * SNRX_XCHG_MAX_WORLD, cudaHostAllocDefault));
+    CK(cudaStreamCreateWithFlags(&h->xchg.stream, cudaStreamNonBlocking));
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->xchg.d_recv));
+    memcpy(handle_out, &ipc, sizeof ipc);
+    CK(cudaDeviceSynchronize());
+    return SNRX_OK;
+}
+
+int snrx_exchange_connect(snrx_t* h, const void* handles) {
+    if (!h || !handles) return SNRX_EINVAL;
+    if (!h->xchg.d_recv) return fail(h, SNRX_ESTATE, "snrx_exchange_create first");
+    if (h->xchg.connected) return fail(h, SNRX_ESTATE, "exchange already connected");
+    CK(cudaSetDevice(h->device));
+    for (auto& ln : h->lane) { CK(cudaStreamSynchronize(ln.stream)); CK(cudaStreamSynchronize(ln.tail)); }
+    for (uint32_t r = 0; r < h->xchg.world; r++) {
+        if (r == h->xchg.rank) { h->xchg.peer[r] = h->xchg.d_recv; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const unsigned char*)handles + (size_t)r * SNRX_XCHG_HANDLE_BYTES, sizeof ipc);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->xchg.peer[r] = (unsigned char*)p;
+    }
+    h->xchg.connected = true;
+    return SNRX_OK;
+}
+
+int snrx_allgather(snrx_t* h, uint64_t batch_no, snrx_frame_t* out, uint32_t cap, uint32_t* counts, uint32_t* n_out,
+                   uint32_t timeout_ms) {
+    if (!h) return SNRX_EINVAL;
+    if (!h->xchg.connected) return fail(h, SNRX_ESTATE, "snrx_allgather: the engines are not connected (snrx_exchange_connect)");
+    CK(cudaSetDevice(h->device));
+    const uint32_t world = h->xchg.world, slot = (uint32_t)(batch_no % SNRX_XCHG_SLOTS);
+    const size_t sb = xchg_slot_bytes(h);
+    const unsigned char* base = h->xchg.d_recv + (size_t)slot * sb;          // slot of rank 0; ranks are SLOTS * sb apart
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        // the headers of all ranks in one strided copy
+        CK(cudaMemcpy2DAsync(h->xchg.h_hdr, 16, base, SNRX_XCHG_SLOTS * sb, 16, world, cudaMemcpyDeviceToHost, h->xchg.stream));
+        CK(cudaStreamSynchronize(h->xchg.stream));
+        bool all = true;
+        for (uint32_t r = 0; r < world; r++) all = all && h->xchg.h_hdr[2 * r + 1] == batch_no;
+        if (all) break;
+        const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        if ((uint64_t)ms >= timeout_ms) return fail(h, SNRX_ESTATE, "snrx_allgather: batch did not arrive from every rank in time");
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    uint64_t total = 0; bool over = false;
+    for (uint32_t r = 0; r < world; r++) {
+        const uint64_t c = h->xchg.h_hdr[2 * r];
+        if (counts) counts[r] = (uint32_t)c;
+        over = over || c > h->xchg.cap;
+        total += c;
+    }
+    if (n_out) *n_out = (uint32_t)total;
+    if (over) return fail(h, SNRX_EOVERFLOW, "snrx_allgather: a rank had more records than the exchange capacity");
+    if (out) {
+        if (total > cap) return fail(h, SNRX_ERANGE, "snrx_allgather: output buffer too small");
+        size_t off = 0;
+        for (uint32_t r = 0; r < world; r++) {
+            const size_t c = (size_t)h->xchg.h_hdr[2 * r];
+            if (c) CK(cudaMemcpyAsync(out + off, base + (size_t)r * SNRX_XCHG_SLOTS * sb + sizeof(snrx_frame_t), c * sizeof(snrx_frame_t),
+                                      cudaMemcpyDeviceToHost, h->xchg.stream));
+            off += c;
+        }
+        CK(cudaStreamSynchronize(h->xchg.stream));
+        // only the pieces a record uses travelled: what lies behind its payload is whatever the slot held before
+        for (size_t i = 0; i < off; i++)
+            if (out[i].len < sizeof out[i].bytes) memset(out[i].bytes + out[i].len, 0, sizeof out[i].bytes - out[i].len);
+    }
     return SNRX_OK;
 }
 

@@ -426,6 +426,64 @@ class PeerGather:
         return p
 
 
+class AbiGather:
+    """The frame exchange of the C ABI (include/snoutrx.h snrx_exchange_create / _connect / snrx_allgather): once the
+    engines of the node are connected, the kernel that exports a batch also stores its records and a {count, batch} header
+    into every rank's HBM over NVLink -- no collective kernel, nothing launched per step on the host.  torch.distributed is
+    only used once, to pass the 64-byte CUDA IPC handles around.  Same interface as FrameGather / PeerGather: start() after
+    a poll() -> Pending with counts() / frames().  Every rank must start() every batch, in order, and collect a Pending
+    before it queues four further batches."""
+
+    def __init__(self, engine, device, cap: int = 1 << 15):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.eng, self.device = torch, dist, engine, device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.cap, self.fallbacks = int(cap), 0
+        mine = engine.exchange_create(self.rank, self.world, self.cap)
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
+        allh = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(allh, t)
+        engine.exchange_connect(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+        dist.barrier()
+
+    @staticmethod
+    def available(engine, device) -> "AbiGather | None":
+        """Try to connect the engines of all ranks; every rank agrees on the outcome (CUDA IPC may be unavailable)."""
+        import torch
+        import torch.distributed as dist
+        g, ok = None, 1
+        try:
+            g = AbiGather(engine, device)
+        except Exception:
+            ok = 0
+        t = torch.tensor([ok], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return g if int(t.item()) == 1 else None
+
+    class Pending:
+        def __init__(self, g, frames, batch_no):
+            self.g, self.local, self.batch_no, self._counts = g, frames, batch_no, None
+
+        def launch(self):
+            return self
+
+        def counts(self):
+            if self._counts is None:
+                self._counts, _ = self.g.eng.allgather(self.batch_no)
+            return self._counts
+
+        def frames(self):
+            self._counts, fr = self.g.eng.allgather(self.batch_no, want_frames=True)
+            if fr is None:                                         # a rank exceeded the slot capacity (all ranks see it)
+                self.g.fallbacks += 1
+                fr = allgather_frames(self.local, self.g.device)
+            return fr
+
+    def start(self, frames: np.ndarray, device_ptr: int = 0, device_records: int = 0, defer: bool = False) -> "AbiGather.Pending":
+        return AbiGather.Pending(self, frames, self.eng.polled_batch_no)
+
+
 def sort_reference_order(frames: np.ndarray) -> np.ndarray:
     order = np.lexsort((frames["sample_index"], frames["window"], frames["channel"],
                         255 - frames["proto"].astype(np.int32), frames["capture_id"]))

@@ -74,6 +74,8 @@ class RxEngine:
         self.n_zb = {MODE_ZB_NB: 1, MODE_ZB_WB16: 16, MODE_MIXED_WB56: 16}.get(self.mode, 0)
         self._keepalive = []             # inputs of the (up to two) batches in flight: released when their batch is polled
         self._last = None
+        self.batches_queued = 0          # snrx_process calls so far = the number the library gives the next batch
+        self.polled_batch_no = -1        # number of the batch most recently returned by poll()
 
     # ------------------------------------------------------------------ life cycle
     def close(self):
@@ -141,6 +143,7 @@ class RxEngine:
                 self._keepalive.append(iq)
                 self._check(fn(self.handle, c_void_p(iq.data_ptr()), caps, n, st, byref(sh) if sh else None, 1))
                 self._last = (caps, n)
+                self.batches_queued += 1
                 return self
         a = np.asarray(iq)
         if a.dtype == np.int8:
@@ -158,12 +161,14 @@ class RxEngine:
         self._keepalive.append(a)
         self._check(fn(self.handle, a.ctypes.data_as(c_void_p), caps, n, st, byref(sh) if sh else None, 0))
         self._last = (caps, n)
+        self.batches_queued += 1
         return self
 
     def process_device_ptr(self, ptr: int, n_captures: int, n_samples: int, stride: int = 0, shard: Shard | None = None):
         self._check(self.lib.snrx_process(self.handle, c_void_p(ptr), n_captures, n_samples, stride,
                                           byref(shard) if shard else None, 1))
         self._last = (n_captures, n_samples)
+        self.batches_queued += 1
         return self
 
     def poll(self, copy: bool = True) -> np.ndarray:
@@ -177,6 +182,7 @@ class RxEngine:
         finally:
             if self._keepalive:              # the oldest batch is done with its input (host copies and kernels have finished)
                 self._keepalive.pop(0)
+            self.polled_batch_no += 1
         if n.value == 0:
             return np.zeros(0, dtype=FRAME_DTYPE)
         buf = (ctypes.c_char * (n.value * FRAME_DTYPE.itemsize)).from_address(ptr.value)
@@ -205,6 +211,37 @@ class RxEngine:
         f, n = c_void_p(), c_uint32(0)
         self._check(self.lib.snrx_polled_frames_device(self.handle, byref(f), byref(n)))
         return int(f.value or 0), int(self.cfg.max_frames) or (1 << 17), int(n.value)   # 1 << 17: the library default
+
+    # ------------------------------------------------------------------ frame exchange between engines
+    def exchange_create(self, rank: int, world: int, cap_records: int = 1 << 15) -> bytes:
+        """Allocate this engine's receive area; returns its 64-byte CUDA IPC handle (include/snoutrx.h snrx_exchange_create)."""
+        buf = ctypes.create_string_buffer(_abi.XCHG_HANDLE_BYTES)
+        self._check(self.lib.snrx_exchange_create(self.handle, rank, world, cap_records, buf))
+        self._xchg_world = world
+        return buf.raw
+
+    def exchange_connect(self, handles: bytes):
+        """`handles`: the handles of all ranks, concatenated in rank order.  Every batch queued afterwards is pushed to every
+        rank by the kernel that exports it."""
+        assert len(handles) == _abi.XCHG_HANDLE_BYTES * self._xchg_world
+        self._check(self.lib.snrx_exchange_connect(self.handle, ctypes.c_char_p(handles)))
+
+    def allgather(self, batch_no: int, want_frames: bool = False, timeout_ms: int = 30000):
+        """Wait for batch `batch_no` of every rank; returns (counts per rank, frames in rank order or None).  If a rank had
+        more records than the exchange capacity the frames are None even when asked for (counts are still exact): the
+        caller gathers that batch some other way (dist.allgather_frames)."""
+        counts = (c_uint32 * self._xchg_world)()
+        n = c_uint32(0)
+        out, ptr, cap = None, None, 0
+        if want_frames:
+            cap = (int(self.cfg.max_frames) or (1 << 17)) * self._xchg_world
+            out = np.zeros(cap, dtype=FRAME_DTYPE)
+            ptr = out.ctypes.data_as(c_void_p)
+        rc = self.lib.snrx_allgather(self.handle, batch_no, ptr, cap, counts, byref(n), timeout_ms)
+        if rc == -6:                                           # SNRX_EOVERFLOW
+            return list(counts), None
+        self._check(rc)
+        return list(counts), (out[: n.value].copy() if want_frames else None)
 
     # ------------------------------------------------------------------ SURVEY 8(f) N1: advertising analytics
     def adv_summary(self, want: bool = True) -> np.ndarray:
