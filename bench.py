@@ -115,8 +115,8 @@ def _ref_decode_one(args):
     """One BLE channel through the UNMODIFIED btle_rx.c (oracle/_ref): the reference keeps its state in globals, so every
     worker is a process of its own."""
     import oracle
-    q, ch = args
-    return len(oracle.ble_decode(q, ch, impl="reference"))
+    y, ch = args
+    return len(oracle.ble_decode(oracle.ble_quantize(y, 100.0), ch, impl="reference"))
 
 
 def cpu_path(workload, sample, min_seconds=0.0):
@@ -138,7 +138,7 @@ def cpu_path(workload, sample, min_seconds=0.0):
     use_ref = oracle.have_ref("btle_ref")
     if use_ref and workload in ("ble_wb40", "mixed_wb56") and _POOL is None:
         _POOL = ProcessPoolExecutor(cores)
-        list(_POOL.map(_ref_decode_one, [(np.zeros((64, 2), np.int8), 37)] * cores))     # start the workers outside the timed region
+        list(_POOL.map(_ref_decode_one, [(np.zeros(64, np.complex64), 37)] * cores))     # start the workers outside the timed region
     t0 = time.perf_counter()
     frames, done = 0, 0
     while True:
@@ -156,7 +156,7 @@ def cpu_path(workload, sample, min_seconds=0.0):
             # receiver() (oracle/_ref, one process per core) where it was compiled, else its port (one thread per core)
             y = oracle.pfb(sample, h, bins, fast=True, native=True)
             if use_ref:
-                n_ble = sum(_POOL.map(_ref_decode_one, [(oracle.ble_quantize(y[c], 100.0), c) for c in range(40)]))
+                n_ble = sum(_POOL.map(_ref_decode_one, [(y[c], c) for c in range(40)]))
             else:
                 with ThreadPoolExecutor(cores) as ex:
                     n_ble = sum(ex.map(lambda c: len(oracle.ble_decode(oracle.ble_quantize(y[c], 100.0), c, impl="port")), range(40)))
@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--base-seconds", type=float, default=0.1, help="length of the generated capture that is tiled")
     ap.add_argument("--tiles", type=int, default=0, help="copies of the generated capture per step (wideband); 0 = 10 (0.98 s) for "
                     "ble_wb40, 100 (9.8 s, the capture length of BASELINE configs[4]) for zb_wb16 / mixed_wb56")
+    ap.add_argument("--captures", type=int, default=0, help="narrow-band workloads: captures per step (one snrx_process batch); 0 = 256, "
+                    "the batch SURVEY 8d prescribes for the roofline run of configs[0] / [1] (one 80-MB capture alone is launch-latency bound)")
     ap.add_argument("--no-c5", action="store_true", help="skip the configs[4]-shaped run (time-sharded mixed captures) reported under \"c5\"")
     ap.add_argument("--c5-seconds", type=float, default=9.83, help="length of the resident mixed capture of the c5 run")
     ap.add_argument("--taps", type=int, default=384)
@@ -270,13 +272,21 @@ def main():
 
     base, n_truth = make_capture(args.workload, args.base_seconds, 4000 + 37 * rank)
     tiles = args.tiles if args.workload in WIDEBAND else 1
-    n = len(base) * tiles
-    pinned = _abi.PinnedBuffer(n, np.complex64)
-    for i in range(tiles):
+    caps = 1 if args.workload in WIDEBAND else (args.captures or 256)
+    caps_e2e = min(caps, 8)                                          # the host leg pins at most 8 captures (640 MB)
+    n_cap = len(base) * tiles                                        # samples per capture
+    n = n_cap * caps                                                 # samples per step
+    pinned = _abi.PinnedBuffer(n_cap * caps_e2e, np.complex64)
+    for i in range(tiles * caps_e2e):
         pinned.array[i * len(base):(i + 1) * len(base)] = base
-    x_dev = torch.from_numpy(pinned.array).to(dev)                   # resident input, larger than L2 for the wideband run
-    eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps if args.workload in WIDEBAND else 0, device=local,
-                   channel=None, max_frames=1 << 18)
+    if caps > 1:
+        x_dev = torch.from_numpy(base).to(dev).repeat(caps, 1)       # [captures, samples]: one snrx_process batch
+        pinned_in = pinned.array.reshape(caps_e2e, n_cap)
+    else:
+        x_dev = torch.from_numpy(pinned.array).to(dev)               # resident input, larger than L2 for the wideband run
+        pinned_in = pinned
+    eng = RxEngine(mode, max_samples=n_cap, max_captures=caps, pfb_taps=args.taps if args.workload in WIDEBAND else 0, device=local,
+                   channel=None, max_frames=(1 << 18) if caps == 1 else (1 << 20))
 
     # whole records go zero-copy from the engine's HBM frame list, which stays valid for two further process() calls ->
     # two gathers in flight.  (FrameGather(record_bytes=80) would exchange only the 80 bytes a BLE record uses; measured at
@@ -418,7 +428,7 @@ def main():
             t = torch.tensor([dt], device=dev)
             d.all_reduce(t, op=d.ReduceOp.MAX)
             dt = float(t.item())
-        return world * n * args.steps / dt / 1e6, d2h, nfr
+        return world * n_e2e * args.steps / dt / 1e6, d2h, nfr
 
     # SURVEY 8(f) N1 (outside the timed region): advertising summaries + sender table of one polled batch, on the GPU
     analytics = None
@@ -516,23 +526,34 @@ def main():
     if c5_only or (not args.no_c5 and args.workload == "ble_wb40"):
         c5 = run_c5()
 
-    e2e, d2h, _ = time_e2e(pinned)
+    n_e2e = n_cap * caps_e2e
+    e2e, d2h, _ = time_e2e(pinned_in)
+    # narrow band: the latency of ONE capture (what a single `snout scan` sees), beside the batched throughput
+    single = None
+    if caps > 1:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            eng.process(x_dev[0]).poll(copy=False)
+        single = {"ms_per_capture": (time.perf_counter() - t0) / 10 * 1e3, "value": n_cap * 10 / (time.perf_counter() - t0) / 1e6, "unit": unit,
+                  "note": "one capture per snrx_process, resident, not pipelined: launch latency bound"}
     # the same capture as an 8-bit digitiser delivers it (interleaved int8 I,Q = the HackRF transfer format the
     # reference consumes, btle_rx.c:204,489-498) through snrx_process_sc8: a quarter of the PCIe bytes
     e2e_sc8 = None
     if args.workload in WIDEBAND or args.workload == "ble_nb":
         peak_amp = float(np.abs(pinned.array[: len(base)]).max())
-        pinned8 = _abi.PinnedBuffer((n, 2), np.int8)
+        pinned8 = _abi.PinnedBuffer((n_e2e, 2), np.int8)
         q = np.clip(np.rint(base.view(np.float32).reshape(-1, 2) * (100.0 / peak_amp)), -128, 127).astype(np.int8)
-        for i in range(tiles):
+        for i in range(tiles * caps_e2e):
             pinned8.array[i * len(base):(i + 1) * len(base)] = q
+        pinned8_in = pinned8.array.reshape(caps_e2e, n_cap, 2) if caps > 1 else pinned8
         if args.workload in WIDEBAND:                      # keep the per-channel int8 amplitude of the cf32 run
             eng.close()
-            eng = RxEngine(mode, max_samples=n, pfb_taps=args.taps, device=local, max_frames=1 << 18,
+            eng = RxEngine(mode, max_samples=n_cap, pfb_taps=args.taps, device=local, max_frames=1 << 18,
                            quant_scale=100.0 * 1.28 * peak_amp)
             gather, _ = make_gather(eng)
-        v8, d2h8, nfr8 = time_e2e(pinned8)
-        e2e_sc8 = {"value": v8, "unit": unit, "h2d_bytes_per_step": int(n * 2), "d2h_bytes_per_step": int(d2h8 / args.steps),
+        v8, d2h8, nfr8 = time_e2e(pinned8_in)
+        e2e_sc8 = {"value": v8, "unit": unit, "h2d_bytes_per_step": int(n_e2e * 2), "d2h_bytes_per_step": int(d2h8 / args.steps),
                    "frames_per_step": int(nfr8),
                    "note": "same capture quantised to interleaved int8 I,Q (full scale = 1.28 x peak), RxEngine.run via snrx_process_sc8"}
 
@@ -545,14 +566,15 @@ def main():
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": f"synthetic: {args.base_seconds}s seeded GFSK capture with AWGN, tiled x{tiles}; random frames on every channel",
-        "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "samples_per_step_per_gpu": int(n),
+        "config": {"workload": f"{args.workload} ({cfg_name}): {desc}", "samples_per_step_per_gpu": int(n), "captures_per_step": int(caps),
+                   "single_capture": single,
                    "input_bytes_per_step_per_gpu": int(n * 8), "pfb_taps": args.taps if args.workload in WIDEBAND else None,
                    "l2": "input (%.0f MB) larger than L2; no flush needed" % (n * 8 / 1e6),
                    "frames_per_step": int(frames_per_step), "frame_exchange": gather_kind, "timed": "K x (process + poll), two batches in flight, frames land in pinned host memory; CUDA events on the engine stream"},
         "frames_per_s": frames_per_step * args.steps / (ms * 1e-3),
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(n * 8), "d2h_bytes_per_step": int(d2h / args.steps),
+        "e2e": {"value": e2e, "unit": unit, "h2d_bytes_per_step": int(n_e2e * 8), "d2h_bytes_per_step": int(d2h / args.steps),
                 "note": "RxEngine.process/poll on a pinned host cf32 buffer, two batches in flight: chunked H2D overlapped with the channelizer, frames copied out"},
         "e2e_sc8": e2e_sc8,
         "analytics": analytics,
@@ -586,7 +608,7 @@ def main():
             line["roofline"]["note"] = ("8 B per input sample (one cf32 read). The binding unit is the FP32 FMA pipe: ncu "
                                         "sm__pipe_fma_cycles_active of the same launch, committed in profiles/; see DESIGN.md 3, 6")
     if world == 1 and not args.no_cpu_baseline:
-        sample = base[: min(len(base), 4_800_000)] if args.workload in WIDEBAND else base
+        sample = base                                  # the whole generated capture (0.1 s wideband / 1e7 samples narrow band)
         dt, done, frames, cores, kind = cpu_path(args.workload, sample, min_seconds=args.cpu_seconds)
         line["cpu_baseline"] = {"value": done / dt / 1e6, "unit": unit, "cores": cores, "kind": kind,
                                 "sample": f"{done} samples = a {len(sample)}-sample slice of the same capture repeated for "

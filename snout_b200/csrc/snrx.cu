@@ -232,7 +232,7 @@ static int ble_tile_stride(const snrx_handle* h) { return h->wideband ? PfbBleGe
 // where k_export_frames pushes a batch for the other engines of the node (snrx_exchange_*)
 struct ExportXchg {
     unsigned char* peer[SNRX_XCHG_MAX_WORLD];   // receive areas, [src rank][slot][1 + cap] records each
-    uint32_t world, rank, cap, slot;
+    uint32_t world, rank, cap, slot;            // world = 0: not connected
 };
 __device__ __forceinline__ uint4* xchg_slot(const ExportXchg& x, uint32_t p) {
     return reinterpret_cast<uint4*>(x.peer[p] + ((size_t)x.rank * SNRX_XCHG_SLOTS + x.slot) * ((size_t)x.cap + 1) * sizeof(snrx_frame_t));
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __res
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst_host);
     uint32_t ok = 0;
-    const uint32_t m = x.world > 1 ? min(n, x.cap) : 0u;
+    const uint32_t m = x.world ? min(n, x.cap) : 0u;       // world = 0: the engine is not connected to any peer
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
         const uint4 v = s4[i];
         d4[i] = v;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) k_export_frames(const snrx_frame_t* __res
     if (ticket != gridDim.x - 1) return;
     __threadfence_system();
     if (threadIdx.x < 8) totals_host[threadIdx.x] = ((volatile uint32_t*)totals_dev)[threadIdx.x];
-    if (x.world > 1 && threadIdx.x < x.world) {
+    if (threadIdx.x < x.world) {
         const uint4 hdr = make_uint4(n, 0u, (uint32_t)batch_no, (uint32_t)(batch_no >> 32));
         *xchg_slot(x, threadIdx.x) = hdr;                  // {uint64 count, uint64 batch}: 16 bytes, one store
     }
@@ -780,8 +780,6 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
     if (h->xchg.connected) {
         for (uint32_t r = 0; r < h->xchg.world; r++) xa.peer[r] = h->xchg.peer[r];
         xa.world = h->xchg.world; xa.rank = h->xchg.rank; xa.cap = h->xchg.cap; xa.slot = (uint32_t)(h->seq_process % SNRX_XCHG_SLOTS);
-    } else {
-        xa.world = 1;
     }
     k_export_frames<<<32, 256, 0, st>>>(ln.d_frames, ln.d_totals, ln.frames, ln.totals, h->frame_cap, (unsigned long long)h->seq_process, xa);
     h->launches++;

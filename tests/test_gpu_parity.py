@@ -487,3 +487,29 @@ def test_zb_reference_pcap_frames_round_trip(Engine, oracle_mod):
     assert_frames_equal(got, oracle_mod.zb_receive(x, 15), what="reference pcap frames")
     assert [bytes(f["bytes"][: f["len"]]) for f in got] == [bytes(t.data) for t in truth] and got["crc_ok"].all()
     assert [bytes(f["bytes"][: f["len"]]) for f in got[:55]] == psdus
+
+
+# ------------------------------------------------------------------------------------ frame exchange (C ABI), one engine
+def test_exchange_loopback_world1(Engine):
+    """snrx_exchange_* / snrx_allgather with a world of one: the export kernel stores the batch's records (only the
+    16-byte pieces in use) and the {count, batch} header into the engine's own receive area; snrx_allgather returns them
+    with zeroed tails.  (The multi-rank path over CUDA IPC is exercised by tools/check_multi_gpu.py under torchrun.)"""
+    caps = [synth.ble_capture(n=200_000, channel=37, seed=900 + i, esn0_db=30, gap=(100, 1500 + 700 * i)).iq for i in range(3)]
+    with Engine("ble_nb", channel=37, max_samples=200_000) as e:
+        with pytest.raises(_abi.SnrxError):
+            e._xchg_world = 1
+            e.allgather(0)                                    # not connected: refused
+        e.exchange_connect(e.exchange_create(0, 1, cap_records=1 << 12))
+        for k, c in enumerate(caps * 4):                      # 12 batches: the 8 slots are reused
+            fr = e.run(c)
+            counts, got = e.allgather(e.polled_batch_no, want_frames=True)
+            assert counts == [len(fr)] and len(fr) > 20
+            assert_frames_equal(got, fr, what=f"loopback batch {k}")
+            assert got.tobytes() == fr.tobytes()
+        with pytest.raises(_abi.SnrxError):
+            e.allgather(e.polled_batch_no + 1, timeout_ms=50)  # a batch nobody has produced: times out
+    with Engine("ble_nb", channel=37, max_samples=200_000) as e:
+        e.exchange_connect(e.exchange_create(0, 1, cap_records=8))
+        fr = e.run(caps[0])
+        counts, got = e.allgather(0, want_frames=True)
+        assert counts == [len(fr)] and got is None            # more records than the slot holds: counts exact, caller falls back

@@ -57,6 +57,26 @@ def main():
             assert pend.counts() == counts
             peer_note = f"PeerGather == exact gather over {len(got)} steps"
 
+        # the exchange of the C ABI: records stored into every rank's HBM by the export kernel (snrx_exchange_* / snrx_allgather)
+        ag = sdist.AbiGather.available(eng, dev)
+        abi_note = "AbiGather unavailable (CUDA IPC)"
+        if ag is not None:
+            pend, got = None, []
+            for step in range(6):
+                xs = x if step % 2 == 0 else x[: len(x) - 24 * 4000]         # the record count changes from step to step
+                fr = eng.process(xs).poll(copy=True)
+                h = ag.start(fr)
+                w = sdist.allgather_frames(fr, dev)
+                if pend is not None:
+                    got.append((pend[0].frames(), pend[1]))
+                pend = (h, w)
+            got.append((pend[0].frames(), pend[1]))
+            for k, (f, w) in enumerate(got):
+                assert f.tobytes() == w.tobytes(), ("abi", rank, k, len(f), len(w))
+            assert sum(pend[0].counts()) == len(pend[1])
+            abi_note = f"AbiGather == exact gather over {len(got)} steps"
+        peer_note = peer_note + "; " + abi_note
+
         # time-sharded job over two captures
         caps = [synth.wideband_capture(seconds=0.03, kind="ble", seed=7100 + c, esn0_db=25.0, gap=(300, 3000)).iq for c in range(2)]
     with RxEngine("ble_wb40", max_samples=24 * (8192 * 3 + 128 + 2048), device=local) as eng:

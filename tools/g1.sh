@@ -1,10 +1,24 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "zb or mixed" 2>&1 | tail -5
-for v in a b; do
-  if [ $v = b ]; then export SNRX_LIB=$PWD/snout_b200/lib/libsnoutrx_b.so; fi
-  for t in 10 100; do
-    timeout 300 python bench.py --workload zb_wb16 --tiles $t --steps 6 --warmup 3 --no-cpu-baseline 2>&1 | grep '^{' | tail -1 | tee gpurun_out/bench_zb_wb16_${v}_t$t.json | python -c "import json,sys; j=json.loads(sys.stdin.read()); print('$v', $t, round(j['value']), j['ms_per_step'])"
-  done
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "exchange or zb_nb_parity" 2>&1 | tail -5
+for w in ble_nb zb_nb; do
+  timeout 400 python bench.py --workload $w --steps 10 --warmup 3 --cpu-seconds 4 2>&1 | grep '^{' | tail -1 | tee gpurun_out/bench_$w.json | python -c "import json,sys; j=json.loads(sys.stdin.read()); print('$w', round(j['value']), j['ms_per_step'], 'frac', round(j['roofline']['frac'],3), 'step_frac', round(j['roofline']['step_frac'],3), 'e2e', round(j['e2e']['value']), 'single', j['config']['single_capture'], 'cpu', j.get('cpu_baseline',{}).get('value'))"
 done
-unset SNRX_LIB
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_zb_wb16_t100.csv python bench.py --workload zb_wb16 --tiles 100 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo rc=$?
+timeout 400 python bench.py --taps 768 --steps 10 --warmup 3 --no-cpu-baseline --no-c5 2>&1 | grep '^{' | tail -1 | tee gpurun_out/bench_ble_wb40_768.json | python -c "import json,sys; j=json.loads(sys.stdin.read()); print('768 taps', round(j['value']), j['ms_per_step'], 'frac', round(j['roofline']['frac'],3))"
+python - <<'PY'
+import sys, time, os
+sys.path.insert(0,'.'); sys.path.insert(0,'tools')
+import numpy as np, oracle
+from gen_tables import PFB_DESIGNS, kaiser_lowpass
+from snout_b200 import chanplan
+oracle.build(native=True)
+h = kaiser_lowpass(*PFB_DESIGNS["BLE_384"])
+rng = np.random.default_rng(0)
+x = (rng.standard_normal(4_800_000) + 1j*rng.standard_normal(4_800_000)).astype(np.complex64)
+bins = [chanplan.ble_channel_bin(c) for c in range(40)]
+for thr in (1, 4, 8, 16, os.cpu_count()):
+    oracle.set_threads(thr)
+    best = 1e9
+    for rep in range(3):
+        t0=time.perf_counter(); y = oracle.pfb(x, h, bins, fast=True, native=True); best=min(best,time.perf_counter()-t0)
+    print('cpu channelizer threads',thr, f'{len(x)/best/1e6:.1f} Msamples/s')
+PY
