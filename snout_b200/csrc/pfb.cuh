@@ -37,6 +37,10 @@
 namespace snrx {
 
 constexpr int kPfbD = 24;
+#ifndef SNRX_PFB_TILES_PER_CTA
+#define SNRX_PFB_TILES_PER_CTA 1
+#endif
+constexpr int kPfbTilesPerCta = SNRX_PFB_TILES_PER_CTA;   // consecutive tiles per one-warp CTA of the wideband kernels
 constexpr int kTileT = 128;                    // channel-rate samples computed per tile
 constexpr int kTileStride = 127;               // samples whose slicer bit the tile emits (needs y[m+1])
 constexpr int kChunkT = 8;                     // output times per FIR lane and pass
@@ -72,7 +76,10 @@ template <int NT> struct PfbBleGeom {
     static constexpr int kXsBytes = ((G::kXsLen * 8 + 15) / 16) * 16;
     static constexpr int kVBytes = 8 * 32 * 16;                        // V[8][32] float4 = (branch r2 = rl, r2 = rl + 8) of one pass
     static constexpr int kSmemBytes = kXsBytes + kVBytes + 16;         // + the staging mbarrier
-    static constexpr int kCtasPerSm = (228 * 1024) / (kSmemBytes + 1024) < 16 ? (228 * 1024) / (kSmemBytes + 1024) : 16;
+#ifndef SNRX_PFB_CTAS
+#define SNRX_PFB_CTAS 16
+#endif
+    static constexpr int kCtasPerSm = (228 * 1024) / (kSmemBytes + 1024) < SNRX_PFB_CTAS ? (228 * 1024) / (kSmemBytes + 1024) : SNRX_PFB_CTAS;
 };
 
 // FIR of one thread.  xb = &xs[xs_pos-base of this thread], see fir_base().  acc[a][e] accumulates
@@ -231,10 +238,8 @@ template <class G, int TT>
 __device__ __forceinline__ void pfb_stage_tile_bulk(float2* xs, const float2* xtile /* sample i' = 0 */, uint64_t* bar, int lane) {
     constexpr int kPer = 24 * TT;
     static_assert(G::kPieces <= 32 && G::kTileIn % 2 == 0, "one lane per piece");
-    if (lane == 0) {
-        mbar_init(bar, 1);
-        mbar_expect_tx(bar, (uint32_t)(G::kTileIn * sizeof(float2)));
-    }
+    // the barrier was initialised once per warp (count 1); every tile is one phase of it
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(G::kTileIn * sizeof(float2)));
     __syncwarp();
     if (lane < G::kPieces) {
         const int lo = lane == 0 ? 0 : kPer * lane - 12;
@@ -298,8 +303,9 @@ struct PfbBleArgs {
     uint64_t stride;          // samples between captures
     int64_t n_in;             // samples per capture
     int32_t n_out;            // channel-rate samples per capture (n_in / 24)
-    int32_t n_tiles;          // tiles of this launch
+    int32_t n_tiles;          // tiles per capture in this launch
     int32_t tile0;            // first tile of this launch
+    int32_t n_caps;           // captures in this launch
     const float4* taps_pass;  // [3][NT/4][8] float4: element (gi, d4, rl) = h[rho + 24 (4 d4 + 0..3)], rho = gi + 3 rl --
                               // the 8 FIR rows of a pass read 128 contiguous bytes per load
     float scale;              // quantiser scale
@@ -309,6 +315,19 @@ struct PfbBleArgs {
     float2* dbg_cf;           // [cap][40][n_out] or null
 };
 
+// whether the tile is staged by bulk copies (it lies entirely inside the capture) or by the zero-filling generic path
+template <class G>
+__device__ __forceinline__ bool pfb_tile_interior(int64_t x0, int64_t n_in) { return x0 >= 0 && x0 + G::kTileIn <= n_in; }
+
+// A one-warp CTA computes kPfbTilesPerCta consecutive tiles; with more than one, the bulk copy of the NEXT tile is issued
+// as soon as the last FIR pass has read the current one (no second tile buffer).  MEASURED (round 2, B200, ble_wb40,
+// kernel time per 94.4 M samples): 1 tile per CTA 0.365-0.393 ms | 2 tiles 0.438 | 4 tiles 0.441 | 8 tiles 0.422 (0.443
+// without the prefetch) | 32 tiles 0.504 | fully persistent grid (16 CTAs per SM walking over all tiles) 0.454.  More
+// than one tile per CTA LOSES: ptxas emits the 27 KB tile body twice inside the loop (1240 FFMA2 instead of 684, WARPSYNC /
+// ENDCOLLECTIVE around every shuffle group because it no longer assumes a converged warp, 92 bytes of spills at 128
+// registers), which no longer fits the 32 KB instruction cache level, and a persistent grid also keeps the other lane's
+// small high-priority kernels from slipping in between tiles.  So the default stays ONE tile per CTA (the loop then
+// compiles away and the code is the single-tile kernel); the switch is kept for A/B runs (-DSNRX_PFB_TILES_PER_CTA=n).
 template <int NT, bool DEBUG>
 __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbBleArgs a) {
     using B = PfbBleGeom<NT>;
@@ -319,22 +338,34 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
 
     const int lane = threadIdx.x;
-    const int tile = a.tile0 + (int)(blockIdx.x % a.n_tiles);
-    const int cap = blockIdx.x / a.n_tiles;
+    const int total = a.n_tiles * a.n_caps;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    uint32_t parity = 0;
+    int staged = 0;                                                        // this tile's bulk copy is already in flight
+    asm volatile("" : "+r"(staged));                                       // opaque: keeps the compiler from peeling the first tile (a second copy
+                                                                           // of the 27 KB loop body does not fit the instruction cache)
+    const int t_begin = blockIdx.x * kPfbTilesPerCta, t_end = min(total, t_begin + kPfbTilesPerCta);
+#pragma unroll 1
+  for (int t = t_begin; t < t_end; t++) {
+    const int tile = a.tile0 + t % a.n_tiles;
+    const int cap = t / a.n_tiles;
     const float2* xcap = a.x + (size_t)cap * a.stride;
     const int g_first = B::kStride * tile;                                 // first channel sample of the tile
 
     // ---- phase 0: stage the input tile (bulk copies for interior tiles, zero-filling cp.async at the capture ends)
     {
         const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
-        if (x0 >= 0 && x0 + G::kTileIn <= a.n_in) {
-            pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
-            mbar_wait(bar, 0);
+        if (pfb_tile_interior<G>(x0, a.n_in)) {
+            if (!staged) pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
+            mbar_wait(bar, parity);
+            parity ^= 1u;
         } else {
             pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, x0, a.n_in, lane);
             cp_async_commit_wait_all();
             __syncwarp();
         }
+        staged = 0;
     }
 
     // ---- phase 1: three passes of FIR (branches r = gi mod 3) -> transpose -> 16-point inverse DFT
@@ -357,6 +388,22 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
             for (int e = 0; e < kChunkT; e++)
                 V[v_pos(rl, 8 * c + e)] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
             __syncwarp();
+            if (gi == 2) {
+                // every lane has read the tile for the last time: bring in this warp's next tile
+                const int tn = t + 1;
+#ifdef SNRX_PFB_NO_PREFETCH
+                if (false) {
+#else
+                if (tn < t_end) {
+#endif
+                    const int64_t xn = (int64_t)kPfbD * (B::kStride * (a.tile0 + tn % a.n_tiles)) - G::kHist;
+                    if (pfb_tile_interior<G>(xn, a.n_in)) {
+                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic reads before the async-proxy writes
+                        pfb_stage_tile_bulk<G, kChunkT>(xs, a.x + (size_t)(tn / a.n_tiles) * a.stride + xn, bar, lane);
+                        staged = 1;
+                    }
+                }
+            }
             cf v16[16];
             pfb_load_col16(V, lane, v16);
             __syncwarp();                                                  // V is rewritten by the next pass
@@ -428,6 +475,8 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
             }
         }
     }
+    __syncwarp();                                            // V and the quantised values of this tile are done with
+  }
 }
 #endif  // __CUDACC__
 

@@ -215,9 +215,12 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
         CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         return SNRX_OK;
     }
-    const dim3 grid((unsigned)(a->n_tiles) * caps);
-    if (h->cfg.flags & SNRX_F_KEEP_STREAMS) k_pfb_ble<NT, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
-    else k_pfb_ble<NT, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(*a);
+    PfbBleArgs args = *a;
+    args.n_caps = (int32_t)caps;
+    const unsigned total = (unsigned)(a->n_tiles) * caps;
+    const dim3 grid((total + kPfbTilesPerCta - 1) / kPfbTilesPerCta);
+    if (h->cfg.flags & SNRX_F_KEEP_STREAMS) k_pfb_ble<NT, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(args);
+    else k_pfb_ble<NT, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(args);
     return SNRX_OK;
 }
 static int pfb_ble_dispatch(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint32_t caps) {
