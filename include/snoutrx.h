@@ -288,6 +288,45 @@ int  snrx_ble_adv_summary(snrx_t* h, snrx_adv_t* out, uint32_t cap, uint32_t* n_
  * SNRX_EOVERFLOW if more than 2^18 distinct senders were seen (the extra ones were not recorded). */
 int  snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_out, int reset);
 
+/* ---- the Zigbee consumer path on the decoded 802.15.4 records (what Snout does per datagram:
+ * RFtap(pkt) -> Dot15d4FCS dissection, snout/util/zigbee.py:194-202; ZigbeeMessage.fromraw, snout/core/message.py:258-304;
+ * the touchlink scan's haslayer(ZLLScanResponse), zigbee.py:176-192) ---- */
+#define SNRX_ZBMAC_SECURITY           0x0001  /* FCF security enabled                                        */
+#define SNRX_ZBMAC_PENDING            0x0002  /* FCF frame pending                                           */
+#define SNRX_ZBMAC_ACKREQ             0x0004  /* FCF acknowledgement request                                 */
+#define SNRX_ZBMAC_PANID_COMPRESS     0x0008  /* FCF PAN id compression                                      */
+#define SNRX_ZBMAC_DEST_PANID         0x0010  /* dest_panid holds a value                                    */
+#define SNRX_ZBMAC_DEST_ADDR          0x0020  /* dest_addr holds a value (dest_mode 2: 16 bit, 3: 64 bit)    */
+#define SNRX_ZBMAC_SRC_PANID          0x0040
+#define SNRX_ZBMAC_SRC_ADDR           0x0080
+#define SNRX_ZBMAC_INTERPAN           0x0100  /* data frame whose payload is a ZigBee inter-PAN stub NWK frame */
+#define SNRX_ZBMAC_ZLL                0x0200  /* ... carrying a ZLL commissioning cluster command (zll_command) */
+#define SNRX_ZBMAC_ZLL_SCAN_RESPONSE  0x0400  /* ... which is a scan response (what the touchlink scan collects) */
+#define SNRX_ZBMAC_NO_ADDRESSING      0x0800  /* an address mode without a length (none / reserved): the reference dissector
+                                                 raises (dot15d4.py:60-63) and yields no addressing fields               */
+#define SNRX_ZBMAC_MALFORMED          0x4000  /* the record ends inside a field the header announces          */
+#define SNRX_ZBMAC_NOT_ZIGBEE         0x8000  /* the record is not an 802.15.4 record                         */
+
+typedef struct snrx_zbmac {         /* one per record of the batch, 40 bytes */
+    uint64_t dest_addr, src_addr;   /* short addresses in the low 16 bits                                      */
+    uint16_t dest_panid, src_panid;
+    uint16_t fcf;                   /* frame control field as transmitted (little endian)                      */
+    uint16_t present;               /* SNRX_ZBMAC_*                                                            */
+    uint8_t  seqnum;
+    uint8_t  frame_type;            /* 0 beacon, 1 data, 2 ack, 3 command (0xff: record too short)             */
+    uint8_t  dest_mode, src_mode;   /* addressing modes 0 none, 2 short, 3 long                                */
+    uint8_t  cmd_id;                /* MAC command id (command frames), else 0xff                              */
+    uint8_t  payload_off;           /* offset of the MAC payload inside the PSDU                               */
+    uint8_t  zll_command;           /* ZLL commissioning command id, 0xff none                                 */
+    uint8_t  reserved;
+    uint16_t cluster, profile;      /* inter-PAN APS stub cluster / profile                                    */
+    uint32_t frame;                 /* index of the record in the batch                                        */
+} snrx_zbmac_t;
+
+/* Summaries of the batch most recently retired by snrx_poll / snrx_poll_view, computed on the GPU from the device frame
+ * list (call before the second-next snrx_process).  *n_out = records of the batch (BLE records get SNRX_ZBMAC_NOT_ZIGBEE). */
+int  snrx_zb_mac_summary(snrx_t* h, snrx_zbmac_t* out, uint32_t cap, uint32_t* n_out);
+
 /* ---- the one exchange of the path -- every engine of a node gets every engine's frame records.
  * No reference counterpart (the reference runs on one host CPU); north_star: "NCCL over NVLink is used only to allgather
  * the decoded-frame records".  Here the gather needs no collective kernel at all: once the engines are connected, the

@@ -25,6 +25,16 @@ ZB_IIR_MEMORY_BLOCKS = 48
 STAGE_BLE_Q8, STAGE_BLE_BITS, STAGE_CHAN_CF32, STAGE_ZB_DISC, STAGE_ZB_CHIPS, STAGE_ZB_F, STAGE_ZB_NCHIPS = 1, 2, 3, 4, 5, 6, 7
 PROTO_ZIGBEE, PROTO_BLE = 2, 3
 XCHG_HANDLE_BYTES, XCHG_SLOTS, XCHG_MAX_WORLD = 64, 8, 16
+# SURVEY 8(f) N2 record (include/snoutrx.h snrx_zbmac_t)
+(ZBMAC_SECURITY, ZBMAC_PENDING, ZBMAC_ACKREQ, ZBMAC_PANID_COMPRESS, ZBMAC_DEST_PANID, ZBMAC_DEST_ADDR, ZBMAC_SRC_PANID,
+ ZBMAC_SRC_ADDR, ZBMAC_INTERPAN, ZBMAC_ZLL, ZBMAC_ZLL_SCAN_RESPONSE, ZBMAC_NO_ADDRESSING) = (1 << i for i in range(12))
+ZBMAC_MALFORMED, ZBMAC_NOT_ZIGBEE = 0x4000, 0x8000
+ZBMAC_DTYPE = np.dtype([
+    ("dest_addr", "<u8"), ("src_addr", "<u8"), ("dest_panid", "<u2"), ("src_panid", "<u2"), ("fcf", "<u2"), ("present", "<u2"),
+    ("seqnum", "u1"), ("frame_type", "u1"), ("dest_mode", "u1"), ("src_mode", "u1"), ("cmd_id", "u1"), ("payload_off", "u1"),
+    ("zll_command", "u1"), ("reserved", "u1"), ("cluster", "<u2"), ("profile", "<u2"), ("frame", "<u4"),
+], align=True)
+assert ZBMAC_DTYPE.itemsize == 40
 
 FRAME_DTYPE = np.dtype([
     ("sample_index", "<i8"), ("capture_id", "<u4"), ("window", "<u4"), ("channel", "<u2"),
@@ -92,6 +102,7 @@ SYMBOLS = [
     ("snrx_polled_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
     ("snrx_ble_adv_summary", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_ble_devices", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32), c_int]),
+    ("snrx_zb_mac_summary", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_exchange_create", c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_void_p]),
     ("snrx_exchange_connect", c_int, [c_void_p, c_void_p]),
     ("snrx_allgather", c_int, [c_void_p, c_uint64, c_void_p, c_uint32, POINTER(c_uint32), POINTER(c_uint32), c_uint32]),

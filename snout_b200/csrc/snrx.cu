@@ -22,6 +22,7 @@
 #include "scan.cuh"
 #include "zb.cuh"
 #include "pfb_zb.cuh"
+#include "zb_mac.cuh"
 
 using namespace snrx;
 
@@ -73,6 +74,7 @@ struct snrx_handle {
     // advertising analytics, allocated by the first snrx_ble_adv_summary
     cudaStream_t adv_stream = nullptr;
     snrx_adv_t* d_adv = nullptr;
+    snrx_zbmac_t* d_zbmac = nullptr;
     snrx::DevSlot* d_devtab = nullptr;
     snrx_device_t* d_devout = nullptr;
     uint32_t* d_adv_counters = nullptr;   // [0] records summarised (BLE), [1] new devices, [2] dropped (table full), [3] export count
@@ -380,7 +382,7 @@ void snrx_destroy(snrx_t* h) {
     if (h->xchg.d_recv) cudaFree(h->xchg.d_recv);
     if (h->xchg.h_hdr) cudaFreeHost(h->xchg.h_hdr);
     if (h->adv_stream) { cudaStreamSynchronize(h->adv_stream); cudaStreamDestroy(h->adv_stream); }
-    { void* ab[] = {h->d_adv, h->d_devtab, h->d_devout, h->d_adv_counters}; for (void* b : ab) if (b) cudaFree(b); }
+    { void* ab[] = {h->d_adv, h->d_zbmac, h->d_devtab, h->d_devout, h->d_adv_counters}; for (void* b : ab) if (b) cudaFree(b); }
     delete h;
 }
 
@@ -921,6 +923,25 @@ int snrx_ble_adv_summary(snrx_t* h, snrx_adv_t* out, uint32_t cap, uint32_t* n_o
     CK(cudaStreamSynchronize(st));
     h->dev_count = c[1];
     h->dev_dropped = c[2];
+    return SNRX_OK;
+}
+
+int snrx_zb_mac_summary(snrx_t* h, snrx_zbmac_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h) return SNRX_EINVAL;
+    if (h->polled_lane < 0) return fail(h, SNRX_ESTATE, "snrx_zb_mac_summary needs a polled batch");
+    int r = adv_init(h);                                       // shares the analytics stream
+    if (r != SNRX_OK) return r;
+    CK(cudaSetDevice(h->device));
+    if (!h->d_zbmac) CK(cudaMalloc((void**)&h->d_zbmac, sizeof(snrx_zbmac_t) * (size_t)h->frame_cap));
+    const uint32_t n = h->lane[h->polled_lane].n_frames;
+    if (n_out) *n_out = n;
+    if (n == 0) return SNRX_OK;
+    if (out && cap < n) return fail(h, SNRX_ERANGE, "summary buffer smaller than the batch");
+    cudaStream_t st = h->adv_stream;
+    k_zb_mac_summary<<<(n + 255) / 256, 256, 0, st>>>(h->polled_frames_dev, n, h->d_zbmac);
+    CK(cudaGetLastError());
+    if (out) CK(cudaMemcpyAsync(out, h->d_zbmac, sizeof(snrx_zbmac_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return SNRX_OK;
 }
 

@@ -270,6 +270,17 @@ class RxEngine:
         key = out["adv_a"].astype(np.uint64) @ (np.uint64(256) ** np.arange(6, dtype=np.uint64)) + (out["tx_add"].astype(np.uint64) << np.uint64(48))
         return out[np.argsort(key, kind="stable")]
 
+    # ------------------------------------------------------------------ Zigbee consumer path
+    def zb_mac_summary(self) -> np.ndarray:
+        """Per-record MAC summaries (_abi.ZBMAC_DTYPE: frame type, sequence number, PAN ids, addresses, inter-PAN / ZLL
+        scan-response flags) of the batch most recently returned by poll(), computed on the GPU from the HBM frame list:
+        what Snout reads off a scapy Dot15d4FCS tree per packet (zigbee.py:194-202, message.py:258-304)."""
+        n = c_uint32(0)
+        cap = int(self.cfg.max_frames) or (1 << 17)
+        out = np.zeros(cap, dtype=_abi.ZBMAC_DTYPE)
+        self._check(self.lib.snrx_zb_mac_summary(self.handle, out.ctypes.data_as(c_void_p), cap, byref(n)))
+        return out[: n.value].copy()
+
     def frames_device(self) -> tuple[int, int]:
         f, c = c_void_p(), c_void_p()
         self._check(self.lib.snrx_frames_device(self.handle, byref(f), byref(c)))

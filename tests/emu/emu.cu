@@ -13,6 +13,7 @@
 #include "../../snout_b200/csrc/ble_adv.cuh"
 #include "../../snout_b200/csrc/zb.cuh"
 #include "../../snout_b200/csrc/pfb_zb.cuh"
+#include "../../snout_b200/csrc/zb_mac.cuh"
 
 using namespace snrx;
 
@@ -343,6 +344,9 @@ int emu_zb_sink_chips(const uint8_t* chips, int64_t n, int threshold, int32_t* l
     }
     return k;
 }
+
+// one record through zb_mac_parse (k_zb_mac_summary's per-thread code)
+void emu_zb_mac_parse(const uint8_t* psdu, int len, snrx_zbmac_t* out) { zb_mac_parse(psdu, len, *out); out->frame = 0; }
 
 // one record through ble_adv_parse (k_ble_adv_summary's per-thread code)
 void emu_ble_adv_parse(const uint8_t* pdu, int len, snrx_adv_t* out) { ble_adv_parse(pdu, len, *out); out->frame = 0; }
