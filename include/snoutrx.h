@@ -353,6 +353,33 @@ int  snrx_exchange_connect(snrx_t* h, const void* handles);
 int  snrx_allgather(snrx_t* h, uint64_t batch_no, snrx_frame_t* out, uint32_t cap, uint32_t* counts, uint32_t* n_out,
                     uint32_t timeout_ms);
 
+/* ---- the transmit side on the GPU -- synthetic / replay captures generated where they are consumed.
+ * Waveforms as the reference's transmitters state them: GFSK per vendor/BTLE/host/btle-tools/src/btle_tx.c:1111-1149
+ * (gen_sample_from_phy_bit, float version; h = 0.5, 4 samples per symbol, 16 Gaussian taps :103-128), half-sine O-QPSK per
+ * snout/grc-blocks/transmitter_OQPSK.py:96-111 with the SHR / PHR of gr-zigbee preamble_prefixer_scapy_impl.cc:48-52,67-88.
+ * Every burst is one frame: the caller provides its bits / bytes and where it goes (the schedule is a few bytes per frame
+ * and is drawn on the host, snout_b200/synth.py); the GPU modulates, places the bursts in their 4 Msps channel streams,
+ * lifts the streams to 96 Msps through a 96-bin synthesis filterbank (x24 polyphase interpolation, 384 taps, and the
+ * rotation to the bin centre) and adds white Gaussian noise from a counter-based generator (a function of seed and
+ * sample index only: the same call gives the same capture). */
+typedef struct snrx_tx_burst {
+    int64_t  start;        /* channel-rate (4 Msps) sample index of the burst's first sample                              */
+    uint32_t data_offset;  /* offset of the burst's data in `data`                                                       */
+    uint32_t n_units;      /* BLE: PHY bits (preamble | access address | whitened PDU + CRC, LSB first, 8 per data byte);
+                              802.15.4: PPDU bytes (SHR | PHR | PSDU)                                                     */
+    uint16_t bin_slot;     /* index into `bins`: the filterbank bin (snrx_*_channel_bin) the burst is sent on             */
+    uint8_t  proto;        /* SNRX_PROTO_BLE (GFSK) or SNRX_PROTO_ZIGBEE (O-QPSK)                                         */
+    uint8_t  reserved;
+    float    cfo_hz, phase0, amp;   /* carrier offset, initial phase (rad), amplitude                                     */
+} snrx_tx_burst_t;                  /* 32 bytes */
+
+/* Writes n_steps * 24 cf32 samples of a 96 Msps capture (centre 2440 MHz) to iq_out (device pointer if out_is_device,
+ * else host).  bins[n_bins]: filterbank bins in use (n_bins <= 48); taps[384]: the synthesis prototype (gain 24);
+ * gauss[16]: Gaussian taps of the GFSK modulator; sigma: noise standard deviation per I / Q component (0 = none). */
+int  snrx_synth_wideband(int device, const snrx_tx_burst_t* bursts, uint32_t n_bursts, const uint8_t* data, uint64_t n_data,
+                         const int32_t* bins, uint32_t n_bins, const float* taps, const double* gauss, uint64_t n_steps,
+                         float sigma, uint64_t seed, float* iq_out, int out_is_device);
+
 int  snrx_set_channel(snrx_t* h, int channel);           /* NB modes */
 int  snrx_set_stream(snrx_t* h, void* cuda_stream);       /* run on a caller stream */
 int  snrx_sync(snrx_t* h);

@@ -25,6 +25,10 @@ ZB_IIR_MEMORY_BLOCKS = 48
 STAGE_BLE_Q8, STAGE_BLE_BITS, STAGE_CHAN_CF32, STAGE_ZB_DISC, STAGE_ZB_CHIPS, STAGE_ZB_F, STAGE_ZB_NCHIPS = 1, 2, 3, 4, 5, 6, 7
 PROTO_ZIGBEE, PROTO_BLE = 2, 3
 XCHG_HANDLE_BYTES, XCHG_SLOTS, XCHG_MAX_WORLD = 64, 8, 16
+# SURVEY 8(f) N4 burst descriptor (include/snoutrx.h snrx_tx_burst_t)
+TX_BURST_DTYPE = np.dtype([("start", "<i8"), ("data_offset", "<u4"), ("n_units", "<u4"), ("bin_slot", "<u2"), ("proto", "u1"),
+                           ("reserved", "u1"), ("cfo_hz", "<f4"), ("phase0", "<f4"), ("amp", "<f4")], align=True)
+assert TX_BURST_DTYPE.itemsize == 32
 # SURVEY 8(f) N2 record (include/snoutrx.h snrx_zbmac_t)
 (ZBMAC_SECURITY, ZBMAC_PENDING, ZBMAC_ACKREQ, ZBMAC_PANID_COMPRESS, ZBMAC_DEST_PANID, ZBMAC_DEST_ADDR, ZBMAC_SRC_PANID,
  ZBMAC_SRC_ADDR, ZBMAC_INTERPAN, ZBMAC_ZLL, ZBMAC_ZLL_SCAN_RESPONSE, ZBMAC_NO_ADDRESSING) = (1 << i for i in range(12))
@@ -106,6 +110,8 @@ SYMBOLS = [
     ("snrx_exchange_create", c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_void_p]),
     ("snrx_exchange_connect", c_int, [c_void_p, c_void_p]),
     ("snrx_allgather", c_int, [c_void_p, c_uint64, c_void_p, c_uint32, POINTER(c_uint32), POINTER(c_uint32), c_uint32]),
+    ("snrx_synth_wideband", c_int, [c_int, c_void_p, c_uint32, c_void_p, c_uint64, c_void_p, c_uint32, c_void_p, c_void_p, c_uint64,
+                             c_float, c_uint64, c_void_p, c_int]),
     ("snrx_set_channel", c_int, [c_void_p, c_int]),
     ("snrx_set_stream", c_int, [c_void_p, c_void_p]),
     ("snrx_sync", c_int, [c_void_p]),

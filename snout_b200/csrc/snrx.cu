@@ -23,6 +23,7 @@
 #include "zb.cuh"
 #include "pfb_zb.cuh"
 #include "zb_mac.cuh"
+#include "synth.cuh"
 
 using namespace snrx;
 
@@ -1058,6 +1059,82 @@ int snrx_allgather(snrx_t* h, uint64_t batch_no, snrx_frame_t* out, uint32_t cap
         for (size_t i = 0; i < off; i++)
             if (out[i].len < sizeof out[i].bytes) memset(out[i].bytes + out[i].len, 0, sizeof out[i].bytes - out[i].len);
     }
+    return SNRX_OK;
+}
+
+// ---- N4: synthetic captures on the GPU ---------------------------------------------------------------------------------
+int snrx_synth_wideband(int device, const snrx_tx_burst_t* bursts, uint32_t n_bursts, const uint8_t* data, uint64_t n_data,
+                        const int32_t* bins, uint32_t n_bins, const float* taps, const double* gauss, uint64_t n_steps,
+                        float sigma, uint64_t seed, float* iq_out, int out_is_device) {
+    snrx_handle* h = nullptr;
+    if (!bins || !taps || !gauss || !iq_out || n_bins == 0 || n_bins > (uint32_t)kTxMaxBins || n_steps == 0) return fail(nullptr, SNRX_EINVAL, "synth: bad argument");
+    if (n_bursts && (!bursts || !data)) return fail(nullptr, SNRX_EINVAL, "synth: bursts without data");
+    CK(cudaSetDevice(device));
+    // bursts in start order, so that every time chunk only launches the bursts that reach into it
+    std::vector<snrx_tx_burst_t> sorted(bursts, bursts + n_bursts);
+    std::stable_sort(sorted.begin(), sorted.end(), [](const snrx_tx_burst_t& a, const snrx_tx_burst_t& b) { return a.start < b.start; });
+    int64_t longest = 0;
+    for (const auto& b : sorted) {
+        if (b.bin_slot >= n_bins || (uint64_t)b.data_offset + (b.proto == SNRX_PROTO_BLE ? (b.n_units + 7) / 8 : b.n_units) > n_data)
+            return fail(nullptr, SNRX_EINVAL, "synth: burst outside its data / bins");
+        longest = std::max<int64_t>(longest, tx_burst_samples(b));
+    }
+    const int64_t hist = kTxTapsPerPhase - 1;
+    const int64_t chunk = std::min<int64_t>((int64_t)n_steps, 1 << 20);
+    const int64_t slen = chunk + hist;
+    snrx_tx_burst_t* d_bursts = nullptr; uint8_t* d_data = nullptr; float2* d_streams = nullptr; float* d_taps = nullptr;
+    double* d_gauss = nullptr; float2* d_out = nullptr;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() {
+        for (void* p : {(void*)d_bursts, (void*)d_data, (void*)d_streams, (void*)d_taps, (void*)d_gauss}) if (p) cudaFree(p);
+        if (d_out && !out_is_device) cudaFree(d_out);
+        if (st) cudaStreamDestroy(st);
+    };
+#define SCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_err = std::string(#call) + " -> " + cudaGetErrorString(e__); cleanup(); return e__ == cudaErrorMemoryAllocation ? SNRX_ENOMEM : SNRX_ECUDA; } } while (0)
+    SCK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    SCK(cudaFuncSetAttribute(k_tx_synthesis, cudaFuncAttributeMaxDynamicSharedMemorySize, kTxSynSmem));
+    if (n_bursts) {
+        SCK(cudaMalloc((void**)&d_bursts, sizeof(snrx_tx_burst_t) * n_bursts));
+        SCK(cudaMemcpyAsync(d_bursts, sorted.data(), sizeof(snrx_tx_burst_t) * n_bursts, cudaMemcpyHostToDevice, st));
+        SCK(cudaMalloc((void**)&d_data, n_data));
+        SCK(cudaMemcpyAsync(d_data, data, n_data, cudaMemcpyHostToDevice, st));
+    }
+    SCK(cudaMalloc((void**)&d_streams, sizeof(float2) * (size_t)n_bins * (size_t)slen));
+    SCK(cudaMalloc((void**)&d_taps, sizeof(float) * kTxTapsPerPhase * 24));
+    SCK(cudaMemcpyAsync(d_taps, taps, sizeof(float) * kTxTapsPerPhase * 24, cudaMemcpyHostToDevice, st));
+    SCK(cudaMalloc((void**)&d_gauss, sizeof(double) * 16));
+    SCK(cudaMemcpyAsync(d_gauss, gauss, sizeof(double) * 16, cudaMemcpyHostToDevice, st));
+    if (out_is_device) d_out = reinterpret_cast<float2*>(iq_out);
+    else SCK(cudaMalloc((void**)&d_out, sizeof(float2) * 24 * (size_t)chunk));
+    size_t first = 0;                                            // bursts before `first` end before the current chunk
+    for (int64_t p0 = 0; p0 < (int64_t)n_steps; p0 += chunk) {
+        const int64_t steps = std::min<int64_t>(chunk, (int64_t)n_steps - p0);
+        const int64_t c0 = p0 - hist, c1 = p0 + steps;           // channel-rate samples [c0, c1) live in the streams
+        SCK(cudaMemsetAsync(d_streams, 0, sizeof(float2) * (size_t)n_bins * (size_t)slen, st));
+        while (first < sorted.size() && sorted[first].start + longest <= c0) first++;
+        size_t last = first;
+        while (last < sorted.size() && sorted[last].start < c1) last++;
+        if (last > first) {
+            TxModArgs m{};
+            m.bursts = d_bursts + first; m.n_bursts = (uint32_t)(last - first); m.data = d_data; m.streams = d_streams;
+            m.stream_len = slen; m.chunk_start = c0; m.gauss = d_gauss;
+            k_tx_modulate<<<(unsigned)(last - first), 256, 0, st>>>(m);
+        }
+        TxSynArgs sa{};
+        sa.streams = d_streams; sa.stream_len = slen; sa.n_bins = (int32_t)n_bins;
+        for (uint32_t k = 0; k < n_bins; k++) sa.bins[k] = ((bins[k] % 96) + 96) % 96;
+        sa.g = d_taps; sa.n_steps = steps; sa.sample0 = p0 * 24; sa.sigma = sigma; sa.seed = seed;
+        sa.out = out_is_device ? d_out + (size_t)p0 * 24 : d_out;
+        k_tx_synthesis<<<(unsigned)((steps + kTxTileP - 1) / kTxTileP), 256, kTxSynSmem, st>>>(sa);
+        SCK(cudaGetLastError());
+        if (!out_is_device) {
+            SCK(cudaMemcpyAsync(iq_out + (size_t)p0 * 24 * 2, d_out, sizeof(float2) * 24 * (size_t)steps, cudaMemcpyDeviceToHost, st));
+            SCK(cudaStreamSynchronize(st));
+        }
+    }
+    SCK(cudaStreamSynchronize(st));
+#undef SCK
+    cleanup();
     return SNRX_OK;
 }
 

@@ -342,3 +342,113 @@ def wideband_capture(seconds: float = 0.02, kind: str = "ble", seed: int = 4000,
     x = x + _awgn(len(x), rng, sigma2).astype(np.complex64)
     return Capture(x.astype(np.complex64), chanplan.WB_RATE, truth,
                    dict(kind="wb_" + kind, seed=seed, esn0_db=esn0_db, seconds=seconds))
+
+
+# ------------------------------------------------------------- GPU transmit side
+# The frame SCHEDULE -- which bytes, where, which carrier offset, phase and amplitude -- is a few bytes per frame and is
+# drawn here with exactly the random draws of ble_baseband / zb_baseband above (same generator, same order), so that
+# wideband_capture() (numpy) and wideband_capture_gpu() place the same frames.  The waveform work -- GFSK / O-QPSK
+# modulation, x24 synthesis filterbank, noise -- runs in libsnoutrx (csrc/synth.cuh, snrx_synth_wideband).
+
+def _schedule(n: int, rng: np.random.Generator, make_frame, gap_lo: int, gap_hi: int, cfo_hz: float, amp_db_spread: float = 0.0):
+    """_place_bursts without the waveform: [(start, length, cfo, phase0, amp, proto, units, data bytes, extra)]."""
+    out = []
+    pos = int(rng.integers(gap_lo, gap_hi + 1))
+    while True:
+        length, proto, units, data, extra = make_frame()
+        if pos + length >= n:
+            break
+        cfo = float(rng.uniform(-cfo_hz, cfo_hz))
+        ph0 = float(rng.uniform(0, 2 * math.pi))
+        amp = 10.0 ** (float(rng.uniform(-amp_db_spread, 0.0)) / 20.0) if amp_db_spread else 1.0
+        out.append((pos, length, cfo, ph0, amp, proto, units, data, extra))
+        pos += length + int(rng.integers(gap_lo, gap_hi + 1))
+    return out
+
+
+def ble_schedule(n: int, channel: int, rng: np.random.Generator, gap=(200, 9000), cfo_hz=50e3,
+                 access_addr=chanplan.BLE_ADV_AA, crc_init=chanplan.BLE_ADV_CRC_INIT, amp_db_spread: float = 0.0):
+    adv = channel in chanplan.BLE_ADV_CHANNELS
+
+    def frame():
+        pdu = ble_adv_pdu(rng) if adv else ble_data_pdu(rng)
+        bits = ble_phy_bits(pdu, channel, access_addr, crc_init)
+        return len(bits) * 4 + len(_GAUSS4) - 1, 3, len(bits), np.packbits(bits, bitorder="little").tobytes(), pdu + ble_crc24(pdu, crc_init)
+
+    return _schedule(n, rng, frame, gap[0], gap[1], cfo_hz, amp_db_spread)
+
+
+def zb_schedule(n: int, channel: int, rng: np.random.Generator, gap=(2000, 40000), cfo_hz=40e3, amp_db_spread: float = 0.0, psdus=None):
+    k = [0]
+
+    def frame():
+        if psdus:
+            psdu = bytes(psdus[k[0] % len(psdus)])
+            k[0] += 1
+        else:
+            psdu = zb_psdu(rng)
+        ppdu = bytes([0, 0, 0, 0, 0xA7, len(psdu)]) + psdu
+        return len(ppdu) * 128 + 2, 2, len(ppdu), ppdu, psdu
+
+    return _schedule(n, rng, frame, gap[0], gap[1], cfo_hz, amp_db_spread)
+
+
+def wideband_schedule(seconds: float = 0.02, kind: str = "ble", seed: int = 4000, channels=None, amp_db_spread: float = 0.0, gap=None):
+    """The frames of wideband_capture(seconds, kind, seed, ...) as burst descriptors for snrx_synth_wideband:
+    (bursts [_abi.TX_BURST_DTYPE], data bytes, bins, truth, n_ch)."""
+    from . import _abi
+    n_ch = int(round(seconds * chanplan.NB_RATE))
+    n_ch -= n_ch % chanplan.BLE_WINDOW if n_ch >= chanplan.BLE_WINDOW else 0
+    plan = []
+    if kind in ("ble", "mixed"):
+        plan += [("ble", c) for c in (channels if channels is not None and kind == "ble" else chanplan.BLE_CHANNELS)]
+    if kind in ("zigbee", "mixed"):
+        plan += [("zb", c) for c in (channels if channels is not None and kind == "zigbee" else chanplan.ZIGBEE_CHANNELS)]
+    bins, rows, blob, truth = [], [], bytearray(), []
+    for proto, c in plan:
+        if proto == "ble":
+            rng = np.random.default_rng(seed + c)
+            sched = ble_schedule(n_ch, c, rng, amp_db_spread=amp_db_spread, **({"gap": gap} if gap else {}))
+            b = chanplan.ble_channel_bin(c)
+        else:
+            rng = np.random.default_rng(seed - 1000 + c)
+            sched = zb_schedule(n_ch, c, rng, amp_db_spread=amp_db_spread, **({"gap": gap} if gap else {}))
+            b = chanplan.zigbee_channel_bin(c)
+        if b not in bins:
+            bins.append(b)
+        slot = bins.index(b)
+        for pos, length, cfo, ph0, amp, pr, units, data, extra in sched:
+            rows.append((pos, len(blob), units, slot, pr, 0, cfo, ph0, amp))
+            blob += data
+            truth.append(Truth(c, pos, pos + (8 * 4 + 8 if pr == 3 else 10 * 64), extra, pr))
+    bursts = np.array(rows, dtype=_abi.TX_BURST_DTYPE) if rows else np.zeros(0, dtype=_abi.TX_BURST_DTYPE)
+    return bursts, bytes(blob), np.array(bins, dtype=np.int32), truth, n_ch
+
+
+def wideband_capture_gpu(seconds: float = 0.02, kind: str = "ble", seed: int = 4000, esn0_db: float | None = 25.0, device: int = 0,
+                         channels=None, amp_db_spread: float = 0.0, gap=None, to_host: bool = False):
+    """wideband_capture() generated on the GPU: same frames at the same places, modulated, lifted to 96 Msps
+    and noised by libsnoutrx.  Returns (iq, truth): iq a torch CUDA complex64 tensor (or a numpy array with to_host=True).
+    esn0_db=None: no noise (then the samples equal the numpy statement within float32 rounding).  The noise is the GPU's own
+    counter-based generator: same statistics as wideband_capture's, different values."""
+    import ctypes
+    from . import _abi
+    lib = _abi.load()
+    bursts, blob, bins, truth, n_ch = wideband_schedule(seconds, kind, seed, channels, amp_db_spread, gap)
+    taps = np.ascontiguousarray(interp_taps(), dtype=np.float32)
+    gauss = np.ascontiguousarray(_GAUSS4, dtype=np.float64)
+    sps = 4.0 if kind == "ble" else 2.0
+    sigma = 0.0 if esn0_db is None else math.sqrt(sps * chanplan.WB_DECIM / (10.0 ** (esn0_db / 10.0)) / 2.0)
+    data = np.frombuffer(blob if blob else b"\0", dtype=np.uint8)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    if to_host:
+        out = np.zeros(n_ch * chanplan.WB_DECIM, dtype=np.complex64)
+        dst, on_dev, ret = P(out), 0, out
+    else:
+        import torch
+        out = torch.empty(n_ch * chanplan.WB_DECIM, dtype=torch.complex64, device=torch.device("cuda", device))
+        torch.cuda.synchronize(device)
+        dst, on_dev, ret = ctypes.c_void_p(out.data_ptr()), 1, out
+    _abi.check(lib.snrx_synth_wideband(device, P(bursts), len(bursts), P(data), len(blob), P(bins), len(bins), P(taps), P(gauss),
+                                       n_ch, ctypes.c_float(sigma), seed & 0xFFFFFFFFFFFFFFFF, dst, on_dev))
+    return ret, truth
