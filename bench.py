@@ -451,9 +451,11 @@ def main():
     #      units a multi-GPU job hands out -- two shards in flight, every shard's records exchanged with all ranks.
     def run_c5():
         from snout_b200 import stream
-        cbase, _ = make_capture("mixed_wb56", args.base_seconds, 5000 + 37 * rank)
-        ctiles = max(1, int(round(args.c5_seconds / args.base_seconds)))
-        xc = torch.from_numpy(cbase).to(dev).repeat(ctiles)
+        # the capture is MADE on the GPU (snrx_synth_wideband): a 0.98-s schedule of random BLE + 802.15.4 frames on
+        # all 56 receivers, sent c5_seconds times over with fresh noise -- nothing crosses PCIe
+        from snout_b200 import synth
+        xc, ctruth = synth.wideband_capture_gpu(seconds=0.983, kind="mixed", seed=5000 + 37 * rank, esn0_db=25.0, device=local,
+                                                repeat=max(1, int(round(args.c5_seconds / 0.983))))
         unit, pre, post = stream.shard_geometry(40, 16)
         body_units = 480                                        # 480 x 8192 channel samples = 0.983 s per shard body
         ceng = RxEngine("mixed_wb56", max_samples=(body_units * unit + pre + post) * 24, pfb_taps=args.taps, device=local,
@@ -513,7 +515,8 @@ def main():
                 "steps": args.steps, "scaling": "weak",
                 "config": {"workload": "c5 (configs[4]): 10-s 96 Msps mixed BLE+Zigbee captures sharded by time segment with halo, "
                                        "frames exchanged over NVLink; one resident capture per GPU stands for its 1024/N captures",
-                           "samples_per_step_per_gpu": int(len(xc)), "shards_per_capture": len(units),
+                           "samples_per_step_per_gpu": int(len(xc)), "shards_per_capture": len(units), "frames_sent_per_capture": len(ctruth),
+                           "data": "generated on the GPU by snrx_synth_wideband (GFSK / O-QPSK bursts, x24 synthesis filterbank, AWGN 25 dB)",
                            "shard_body_samples": int(body_units * unit * 24), "halo_overhead": round(halo, 4),
                            "frames_per_step": int(st["frames"] / args.steps), "frame_exchange": ckind,
                            "frames_received_per_step_all_ranks": int(st["gathered"] / args.steps) if world > 1 else None},

@@ -288,6 +288,35 @@ int  snrx_ble_adv_summary(snrx_t* h, snrx_adv_t* out, uint32_t cap, uint32_t* n_
  * SNRX_EOVERFLOW if more than 2^18 distinct senders were seen (the extra ones were not recorded). */
 int  snrx_ble_devices(snrx_t* h, snrx_device_t* out, uint32_t cap, uint32_t* n_out, int reset);
 
+/* ---- BLE connections.  btle_rx -o follows ONE connection by retuning its single channel on a wall-clock
+ * schedule (receiver_controller, btle_rx.c:2167-2282: on a CRC-ok CONNECT_REQ it takes AA, CRCInit, ChM, Hop, Interval from
+ * the fields parsed at btle_rx.c:1476-1557, hops hop_chan = (hop_chan + hop) % 37 and receives with the new access address
+ * and crc_init_reorder(CRCInit)).  With all 40 channels channelized at once nothing has to be retuned or timed: the
+ * CONNECT_REQs are picked out of the decoded records, and the data channels of the batch -- whose slicer bit streams are
+ * still in HBM -- are searched and decoded AGAIN with the learned access address and CRC init. ---- */
+typedef struct snrx_conn {          /* one per CRC-ok CONNECT_REQ (ADV PDU type 5, payload 34 bytes), 56 bytes */
+    int64_t  sample_index;  /* of the CONNECT_REQ record                                                       */
+    uint32_t capture_id;
+    uint32_t frame;         /* index of the record in the batch                                                */
+    uint32_t access_addr;   /* AA of the connection (payload bytes 12..15, little endian; btle_rx.c:1543-1546)  */
+    uint32_t crc_init;      /* CRCInit as btle_rx.c:1505-1507 assembles it (byte 16 is the most significant):
+                               the value to pass as crc_init (`-k`) for this connection                         */
+    uint8_t  init_a[6], adv_a[6];   /* as transmitted (the reference stores them reversed for printing)          */
+    uint16_t win_offset, interval, latency, timeout;
+    uint8_t  chm[5];        /* channel map as transmitted (payload bytes 28..32)                               */
+    uint8_t  win_size, hop, sca;
+    uint8_t  channel;       /* advertising channel the request was heard on                                    */
+    uint8_t  chm_full;      /* all 37 data channels used (the only maps btle_rx -o follows, btle_rx.c:2158-2163) */
+    uint8_t  reserved[2];
+} snrx_conn_t;
+
+/* CONNECT_REQs (CRC ok) among the records of the batch most recently retired by snrx_poll / snrx_poll_view, in record order. */
+int  snrx_ble_connections(snrx_t* h, snrx_conn_t* out, uint32_t cap, uint32_t* n_out);
+/* Searches and decodes the BLE channels of that same batch again with another access address / CRC init (`-a` / `-k` of a
+ * connection learned from snrx_ble_connections): *n_out frames in reference order, copied to out (up to cap).  The batch's
+ * slicer bit streams are reused: nothing is channelized twice.  Call before the second-next snrx_process. */
+int  snrx_ble_follow(snrx_t* h, uint32_t access_addr, uint32_t crc_init, snrx_frame_t* out, uint32_t cap, uint32_t* n_out);
+
 /* ---- the Zigbee consumer path on the decoded 802.15.4 records (what Snout does per datagram:
  * RFtap(pkt) -> Dot15d4FCS dissection, snout/util/zigbee.py:194-202; ZigbeeMessage.fromraw, snout/core/message.py:258-304;
  * the touchlink scan's haslayer(ZLLScanResponse), zigbee.py:176-192) ---- */

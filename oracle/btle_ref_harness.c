@@ -165,3 +165,19 @@ uint32_t btle_ref_crc_table(int i) { return (uint32_t)crc_table[i & 255]; }
 uint32_t btle_ref_crc_init_reorder(uint32_t x) { return crc_init_reorder(x); }
 uint32_t btle_ref_crc24(const uint8_t* b, int n, uint32_t init_internal) { return (uint32_t)crc24_byte((uint8_t*)b, n, init_internal); }
 uint64_t btle_ref_freq(int channel) { return get_freq_by_channel_number(channel); }
+
+/* the reference's own CONNECT_REQ field extraction (parse_adv_pdu_payload_byte, btle_rx.c:1476-1557) and
+ * what receiver_controller would start tracking (receiver_status).  payload: the 34 payload bytes.  out[0..11] = AA (as the
+ * receiver uses it), CRCInit, WinSize, WinOffset, Interval, Latency, Timeout, Hop, SCA, chm_is_full_map, receiver_status.hop,
+ * receiver_status.interval; init_a / adv_a / chm: the byte arrays as the reference stores them (reversed). Returns its return code. */
+int btle_ref_parse_connect_req(const uint8_t* payload, int n, uint32_t* out, uint8_t* init_a, uint8_t* adv_a, uint8_t* chm) {
+    ADV_PDU_PAYLOAD_TYPE_5 p;
+    memset(&p, 0, sizeof p);
+    int rc = parse_adv_pdu_payload_byte((uint8_t*)payload, n, CONNECT_REQ, (void*)&p);
+    if (rc != 0) return rc;
+    out[0] = receiver_status.access_addr; out[1] = p.CRCInit; out[2] = p.WinSize; out[3] = p.WinOffset; out[4] = p.Interval;
+    out[5] = p.Latency; out[6] = p.Timeout; out[7] = p.Hop; out[8] = p.SCA; out[9] = chm_is_full_map(receiver_status.chm) ? 1u : 0u;
+    out[10] = (uint32_t)receiver_status.hop; out[11] = (uint32_t)receiver_status.interval;
+    memcpy(init_a, p.InitA, 6); memcpy(adv_a, p.AdvA, 6); memcpy(chm, p.ChM, 5);
+    return 0;
+}

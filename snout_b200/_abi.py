@@ -25,6 +25,12 @@ ZB_IIR_MEMORY_BLOCKS = 48
 STAGE_BLE_Q8, STAGE_BLE_BITS, STAGE_CHAN_CF32, STAGE_ZB_DISC, STAGE_ZB_CHIPS, STAGE_ZB_F, STAGE_ZB_NCHIPS = 1, 2, 3, 4, 5, 6, 7
 PROTO_ZIGBEE, PROTO_BLE = 2, 3
 XCHG_HANDLE_BYTES, XCHG_SLOTS, XCHG_MAX_WORLD = 64, 8, 16
+# SURVEY 8(f) N3 record (include/snoutrx.h snrx_conn_t)
+CONN_DTYPE = np.dtype([("sample_index", "<i8"), ("capture_id", "<u4"), ("frame", "<u4"), ("access_addr", "<u4"), ("crc_init", "<u4"),
+                       ("init_a", "u1", (6,)), ("adv_a", "u1", (6,)), ("win_offset", "<u2"), ("interval", "<u2"), ("latency", "<u2"),
+                       ("timeout", "<u2"), ("chm", "u1", (5,)), ("win_size", "u1"), ("hop", "u1"), ("sca", "u1"), ("channel", "u1"),
+                       ("chm_full", "u1"), ("reserved", "u1", (2,))], align=True)
+assert CONN_DTYPE.itemsize == 56
 # SURVEY 8(f) N4 burst descriptor (include/snoutrx.h snrx_tx_burst_t)
 TX_BURST_DTYPE = np.dtype([("start", "<i8"), ("data_offset", "<u4"), ("n_units", "<u4"), ("bin_slot", "<u2"), ("proto", "u1"),
                            ("reserved", "u1"), ("cfo_hz", "<f4"), ("phase0", "<f4"), ("amp", "<f4")], align=True)
@@ -106,6 +112,8 @@ SYMBOLS = [
     ("snrx_polled_frames_device", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_uint32)]),
     ("snrx_ble_adv_summary", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_ble_devices", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32), c_int]),
+    ("snrx_ble_connections", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
+    ("snrx_ble_follow", c_int, [c_void_p, c_uint32, c_uint32, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_zb_mac_summary", c_int, [c_void_p, c_void_p, c_uint32, POINTER(c_uint32)]),
     ("snrx_exchange_create", c_int, [c_void_p, c_uint32, c_uint32, c_uint32, c_void_p]),
     ("snrx_exchange_connect", c_int, [c_void_p, c_void_p]),

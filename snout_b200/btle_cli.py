@@ -16,9 +16,16 @@ sc8 = the HackRF's int8 stream), at 4 Msps for one channel or, with `--wideband`
 centred on 2440 MHz, in which case all 40 channels are decoded at once and `-c` only selects
 which channel is printed (`--all-channels` prints every channel; Pkt numbers then count per
 channel as they do with one btle_rx process per channel).  `-g` and `-f` configure the radio in
-the reference; here they are accepted, echoed and otherwise unused.  `-o` (hop following,
-btle_rx.c:2167-2282) and `-r` (raw mode) are outside the receive path that Snout uses and are
-refused with a message.
+the reference; here they are accepted, echoed and otherwise unused.  `-r` (raw mode) is outside
+the receive path that Snout uses and is refused with a message.
+
+`-o` (data channel tracking, receiver_controller btle_rx.c:2167-2282) works with `--wideband`: the
+reference retunes its one channel on a wall-clock schedule after a CRC-ok CONNECT_REQ with a full
+channel map; here every data channel is already channelized, so from the CONNECT_REQ on the batch's
+bit streams are searched again with the connection's access address / CRC init (RxEngine.follow)
+and every LL PDU of the connection is printed with the channel it was heard on -- no retuning, no
+missed events.  The `Hop:` status lines of the reference are printed where it prints them.  With
+one 4 Msps channel there is nothing to hop to and `-o` is refused.
 
 There is no CPU path: without a usable GPU / libsnoutrx.so the program exits with an error.
 """
@@ -53,7 +60,7 @@ USAGE = """Usage:
     -m --access_mask
       If a bit is 1 in this mask, corresponding bit in access address will be taken into packet existing decision
     -o --hop
-      Data channel tracking (not supported by this engine)
+      This will turn on data channel tracking (only with --wideband: all data channels are received at once)
     -s --filename
       Store packets to this pcap file (LINKTYPE_BLUETOOTH_LE_LL_WITH_PHDR)
     --iq FILE|-
@@ -190,8 +197,11 @@ def run(o: Options, out=sys.stdout, engine_factory=None, blocks=None) -> int:
     freq_hz = o.freq_hz if o.freq_hz != 123 else chanplan.ble_channel_mhz(o.chan) * 1_000_000
     out.write(f"Cmd line input: chan {o.chan}, freq {freq_hz // 1000000}MHz, access addr {o.access_addr:08x}, "
               f"crc init {o.crc_init:06x} raw {o.raw} verbose {o.verbose} rx {o.gain}dB (B200) file={o.filename_pcap or '(null)'}\n")
-    if o.hop or o.raw:
-        out.write("btle_rx (snout_b200): -o/--hop and -r/--raw are not supported by the GPU receive engine\n")
+    if o.raw:
+        out.write("btle_rx (snout_b200): -r/--raw is not supported by the GPU receive engine\n")
+        return 1
+    if o.hop and not o.wideband:
+        out.write("btle_rx (snout_b200): -o/--hop needs --wideband (a 4 Msps single-channel capture holds no data channel to hop to)\n")
         return 1
     if o.iq is None and blocks is None:
         out.write("btle_rx (snout_b200): no IQ source; pass --iq FILE (or - for stdin)\n")
@@ -224,19 +234,62 @@ def run(o: Options, out=sys.stdout, engine_factory=None, blocks=None) -> int:
         return 1
     pkt_count = {}
     rc = 0
+    track = {"conn": None, "first": False}                             # -o: the connection being followed
+
+    def lines(frames: np.ndarray, key=None):
+        if fh_pcap:
+            fh_pcap.write(formats.ble_pcap_block(frames))              # the batch's records in one piece (same bytes)
+        for f in frames:
+            ch = int(f["channel"]) if key is None else key
+            pkt_count[ch] = pkt_count.get(ch, 0) + 1                   # pkt_count++, btle_rx.c:2126
+            out.write(formats.btle_rx_line(f, pkt_count[ch]))
+
     try:
         st = ShardStreamer(eng, units_per_shard=windows)
 
         def emit(frames: np.ndarray):
             if o.wideband and not o.all_channels:
                 frames = frames[frames["channel"] == o.chan]
-            if fh_pcap:
-                fh_pcap.write(formats.ble_pcap_block(frames))          # the batch's records in one piece (same bytes)
-            for f in frames:
-                ch = int(f["channel"])
-                pkt_count[ch] = pkt_count.get(ch, 0) + 1               # pkt_count++, btle_rx.c:2126
-                out.write(formats.btle_rx_line(f, pkt_count[ch]))
+            if o.hop:
+                follow(frames)
+            else:
+                lines(frames)
             out.flush()                                                # fflush(stdout), btle_rx.c:2383
+
+        def follow(frames: np.ndarray):
+            """receiver_controller (btle_rx.c:2167-2282) without a radio to retune.  State 0: advertising frames are printed
+            until a CRC-ok CONNECT_REQ with a full channel map is heard on the listened channel (others: the reference's
+            'Not full ChnMap' line, keep listening).  From there on the reference leaves the advertising channel, so only
+            the connection's LL PDUs are printed: all of them, on whatever data channel they were sent."""
+            c = track["conn"]
+            if c is None:
+                conns = eng.connections()
+                if not o.all_channels:
+                    conns = conns[conns["channel"] == o.chan]
+                started = [k for k in conns if k["chm_full"]][:1]
+                upto = int(started[0]["sample_index"]) if started else None
+                heard = {(int(k["sample_index"]), int(k["channel"])): k for k in conns}
+                for f in (frames if upto is None else frames[frames["sample_index"] <= upto]):
+                    lines(np.asarray([f]))
+                    k = heard.get((int(f["sample_index"]), int(f["channel"])))
+                    if k is not None and not k["chm_full"]:            # btle_rx.c:2180-2184: stay on the advertising channel
+                        out.write("Hop: Not full ChnMap 1FFFFFFFFF! (%s) Stay in ADV Chn\n" % bytes(k["chm"][::-1]).hex())
+                if not started:
+                    return
+                c = track["conn"] = started[0].copy()
+                ch0 = int(c["hop"]) % 37                               # hop_chan = (0 + hop) % 37, btle_rx.c:2194
+                out.write("Hop: track start ...\n")
+                out.write(f"Hop: next ch {ch0} freq {chanplan.ble_channel_mhz(ch0)}MHz access {int(c['access_addr']):08x} "
+                          f"crcInit {int(c['crc_init']):06x}\n")
+                out.write("Hop: next state 1\n")
+            data = eng.follow(int(c["access_addr"]), int(c["crc_init"]))
+            data = data[(data["channel"] < 37) & (data["sample_index"] > int(c["sample_index"]))]
+            data = data[np.argsort(data["sample_index"], kind="stable")]    # records come channel by channel; print in air order
+            for f in data:
+                lines(np.asarray([f]), key=None if o.all_channels else o.chan)
+                if not track["first"] and int(f["crc_ok"]):            # state 1 -> 2, btle_rx.c:2212-2217
+                    track["first"] = True
+                    out.write("Hop: 1st data pdu\nHop: next state 2\n")
 
         src = blocks if blocks is not None else iq_blocks(o.iq, o.fmt, scale=None)
         for block in src:

@@ -49,3 +49,13 @@ def ble_channel_bin(ch: int) -> int:
 
 def zigbee_channel_bin(ch: int) -> int:
     return (zigbee_channel_mhz(ch) - WB_CENTER_MHZ) % WB_BINS
+
+
+def ble_hop_channels(hop: int, n_events: int, last: int = 0) -> list[int]:
+    """Data channel of each of the next connection events as btle_rx -o steps through them with a full channel map:
+    hop_chan = (hop_chan + hop) % 37 (btle_rx.c:2194, 2227, 2254)."""
+    out = []
+    for _ in range(n_events):
+        last = (last + hop) % 37
+        out.append(last)
+    return out

@@ -15,6 +15,7 @@
 
 #include "ble_adv.cuh"
 #include "ble_back.cuh"
+#include "ble_conn.cuh"
 #include "ble_front.cuh"
 #include "common.cuh"
 #include "pfb.cuh"
@@ -65,6 +66,8 @@ struct Lane {
     float2* d_cf = nullptr; size_t d_cf_bytes = 0;
     ZbState zb;
     std::vector<cudaEvent_t> ev_chunks;
+    // the BLE back-end parameters of the lane's last batch (snrx_ble_follow searches its bit streams again)
+    BleParams last_p{}; BitsLayout last_lay{}; uint32_t last_chunks = 0; bool last_ble = false;
 };
 
 struct snrx_handle {
@@ -76,6 +79,8 @@ struct snrx_handle {
     cudaStream_t adv_stream = nullptr;
     snrx_adv_t* d_adv = nullptr;
     snrx_zbmac_t* d_zbmac = nullptr;
+    snrx_conn_t* d_conn = nullptr; uint32_t *d_conn_flags = nullptr, *d_conn_offsets = nullptr, *d_conn_scratch = nullptr;
+    snrx_frame_t* d_follow = nullptr;    // frames of snrx_ble_follow
     snrx::DevSlot* d_devtab = nullptr;
     snrx_device_t* d_devout = nullptr;
     uint32_t* d_adv_counters = nullptr;   // [0] records summarised (BLE), [1] new devices, [2] dropped (table full), [3] export count
@@ -383,7 +388,7 @@ void snrx_destroy(snrx_t* h) {
     if (h->xchg.d_recv) cudaFree(h->xchg.d_recv);
     if (h->xchg.h_hdr) cudaFreeHost(h->xchg.h_hdr);
     if (h->adv_stream) { cudaStreamSynchronize(h->adv_stream); cudaStreamDestroy(h->adv_stream); }
-    { void* ab[] = {h->d_adv, h->d_zbmac, h->d_devtab, h->d_devout, h->d_adv_counters}; for (void* b : ab) if (b) cudaFree(b); }
+    { void* ab[] = {h->d_adv, h->d_zbmac, h->d_conn, h->d_conn_flags, h->d_conn_offsets, h->d_conn_scratch, h->d_follow, h->d_devtab, h->d_devout, h->d_adv_counters}; for (void* b : ab) if (b) cudaFree(b); }
     delete h;
 }
 
@@ -748,6 +753,7 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
         p.n_captures = n_captures;
         p.n_channels = h->n_ble_ch;
         const uint32_t n_chunks = div_up(lay.words_per_stream, 32);
+        ln.last_p = p; ln.last_lay = lay; ln.last_chunks = n_chunks; ln.last_ble = true;
         const uint32_t aa_items = n_captures * h->n_ble_ch * n_chunks;
         const uint32_t w_items = n_captures * h->n_ble_ch * (uint32_t)p.n_windows;
 
@@ -924,6 +930,81 @@ int snrx_ble_adv_summary(snrx_t* h, snrx_adv_t* out, uint32_t cap, uint32_t* n_o
     CK(cudaStreamSynchronize(st));
     h->dev_count = c[1];
     h->dev_dropped = c[2];
+    return SNRX_OK;
+}
+
+int snrx_ble_connections(snrx_t* h, snrx_conn_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h) return SNRX_EINVAL;
+    if (h->polled_lane < 0) return fail(h, SNRX_ESTATE, "snrx_ble_connections needs a polled batch");
+    int r = adv_init(h);
+    if (r != SNRX_OK) return r;
+    CK(cudaSetDevice(h->device));
+    if (!h->d_conn) {
+        CK(cudaMalloc((void**)&h->d_conn, sizeof(snrx_conn_t) * (size_t)h->frame_cap));
+        CK(cudaMalloc((void**)&h->d_conn_flags, sizeof(uint32_t) * ((size_t)h->frame_cap + 1)));
+        CK(cudaMalloc((void**)&h->d_conn_offsets, sizeof(uint32_t) * ((size_t)h->frame_cap + 1)));
+        CK(cudaMalloc((void**)&h->d_conn_scratch, sizeof(uint32_t) * scan_scratch_items(h->frame_cap)));
+    }
+    const uint32_t n = h->lane[h->polled_lane].n_frames;
+    if (n_out) *n_out = 0;
+    if (n == 0) return SNRX_OK;
+    cudaStream_t st = h->adv_stream;
+    k_ble_conn_flag<<<(n + 255) / 256, 256, 0, st>>>(h->polled_frames_dev, n, h->d_conn_flags);
+    exclusive_scan(h->d_conn_flags, n, h->d_conn_offsets, h->d_conn_scratch, st);
+    k_ble_conn_fill<<<(n + 255) / 256, 256, 0, st>>>(h->polled_frames_dev, n, h->d_conn_flags, h->d_conn_offsets, h->d_conn, h->frame_cap);
+    CK(cudaGetLastError());
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, h->d_conn_offsets + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_out) *n_out = total;
+    if (out && total) {
+        if (cap < total) return fail(h, SNRX_ERANGE, "connection buffer smaller than the number of CONNECT_REQs");
+        CK(cudaMemcpy(out, h->d_conn, sizeof(snrx_conn_t) * (size_t)total, cudaMemcpyDeviceToHost));
+    }
+    return SNRX_OK;
+}
+
+int snrx_ble_follow(snrx_t* h, uint32_t access_addr, uint32_t crc_init, snrx_frame_t* out, uint32_t cap, uint32_t* n_out) {
+    if (!h) return SNRX_EINVAL;
+    if (h->polled_lane < 0) return fail(h, SNRX_ESTATE, "snrx_ble_follow needs a polled batch");
+    Lane& ln = h->lane[h->polled_lane];
+    if (!h->has_ble || !ln.last_ble) return fail(h, SNRX_ESTATE, "snrx_ble_follow: the polled batch has no BLE bit streams");
+    if (ln.pending) return fail(h, SNRX_ESTATE, "snrx_ble_follow: the batch's bit streams have been overwritten (call before the second-next snrx_process)");
+    CK(cudaSetDevice(h->device));
+    if (!h->d_follow) CK(cudaMalloc((void**)&h->d_follow, sizeof(snrx_frame_t) * (size_t)h->frame_cap));
+    cudaStream_t st = ln.tail;                                   // the lane is idle: its working set and streams are free
+    BleParams p = ln.last_p;
+    p.aa = access_addr;
+    p.aa_mask = 0xFFFFFFFFu;
+    p.crc_init_internal = crc_init_internal(crc_init);
+    const BitsLayout lay = ln.last_lay;
+    const uint32_t n_chunks = ln.last_chunks;
+    const uint32_t aa_items = p.n_captures * h->n_ble_ch * n_chunks;
+    const uint32_t w_items = p.n_captures * h->n_ble_ch * (uint32_t)p.n_windows;
+    const int g_aa = grid_for(h, aa_items, 8, 8);
+    k_aa_search<<<g_aa, 256, 0, st>>>(ln.d_bits, lay, p, n_chunks, ln.d_counts, ln.d_hits);
+    exclusive_scan(ln.d_counts, aa_items, ln.d_offsets, ln.d_scratch, st);
+    k_aa_fill<<<g_aa, 256, 0, st>>>(ln.d_bits, ln.d_hits, lay, p, n_chunks, ln.d_counts, ln.d_offsets, ln.d_cands, h->cand_cap);
+    k_ble_decode<<<h->sm_count * 16, 128, 0, st>>>(ln.d_bits, lay, p, ln.d_offsets + aa_items, h->cand_cap, ln.d_cands,
+                                               ln.d_decs, h->d_crc_tab, h->d_whiten, h->d_ble_channels);
+    const int g_w = grid_for(h, w_items, 256, 8);
+    k_ble_resolve<false><<<g_w, 256, 0, st>>>(ln.d_cands, ln.d_decs, ln.d_offsets, n_chunks, p, ln.d_wcounts, nullptr,
+                                             nullptr, 0, h->d_ble_channels, h->cand_cap);
+    exclusive_scan(ln.d_wcounts, w_items, ln.d_woffsets, ln.d_scratch, st);
+    k_ble_resolve<true><<<g_w, 256, 0, st>>>(ln.d_cands, ln.d_decs, ln.d_offsets, n_chunks, p, ln.d_wcounts, ln.d_woffsets,
+                                            h->d_follow, h->frame_cap, h->d_ble_channels, h->cand_cap);
+    CK(cudaGetLastError());
+    uint32_t tot[2] = {0, 0};
+    CK(cudaMemcpyAsync(&tot[0], ln.d_woffsets + w_items, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&tot[1], ln.d_offsets + aa_items, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (tot[1] > h->cand_cap) return fail(h, SNRX_EOVERFLOW, "access-address candidates exceed capacity (raise max_frames)");
+    if (tot[0] > h->frame_cap) return fail(h, SNRX_EOVERFLOW, "frames exceed max_frames");
+    if (n_out) *n_out = tot[0];
+    if (out && tot[0]) {
+        if (cap < tot[0]) return fail(h, SNRX_ERANGE, "frame buffer smaller than the number of frames");
+        CK(cudaMemcpy(out, h->d_follow, sizeof(snrx_frame_t) * (size_t)tot[0], cudaMemcpyDeviceToHost));
+    }
     return SNRX_OK;
 }
 

@@ -270,6 +270,25 @@ class RxEngine:
         key = out["adv_a"].astype(np.uint64) @ (np.uint64(256) ** np.arange(6, dtype=np.uint64)) + (out["tx_add"].astype(np.uint64) << np.uint64(48))
         return out[np.argsort(key, kind="stable")]
 
+    # ------------------------------------------------------------------ BLE connections
+    def connections(self) -> np.ndarray:
+        """The CRC-ok CONNECT_REQs (_abi.CONN_DTYPE: AA, CRCInit, ChM, Hop, Interval, ...) among the records of the batch most
+        recently returned by poll(): what btle_rx -o starts tracking (btle_rx.c:1476-1557, 2167-2282)."""
+        n = c_uint32(0)
+        cap = int(self.cfg.max_frames) or (1 << 17)
+        out = np.zeros(cap, dtype=_abi.CONN_DTYPE)
+        self._check(self.lib.snrx_ble_connections(self.handle, out.ctypes.data_as(c_void_p), cap, byref(n)))
+        return out[: n.value].copy()
+
+    def follow(self, access_addr: int, crc_init: int) -> np.ndarray:
+        """Search and decode the BLE channels of that batch again with a connection's access address and CRC init: the
+        data-channel PDUs of the connection, from the slicer bit streams already in HBM (nothing is channelized twice)."""
+        n = c_uint32(0)
+        cap = int(self.cfg.max_frames) or (1 << 17)
+        out = np.zeros(cap, dtype=FRAME_DTYPE)
+        self._check(self.lib.snrx_ble_follow(self.handle, access_addr & 0xFFFFFFFF, crc_init & 0xFFFFFF, out.ctypes.data_as(c_void_p), cap, byref(n)))
+        return out[: n.value].copy()
+
     # ------------------------------------------------------------------ SURVEY 8(f) N2: Zigbee consumer path
     def zb_mac_summary(self) -> np.ndarray:
         """Per-record MAC summaries (_abi.ZBMAC_DTYPE: frame type, sequence number, PAN ids, addresses, inter-PAN / ZLL

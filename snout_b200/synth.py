@@ -27,10 +27,20 @@ from . import chanplan
 # --------------------------------------------------------------------------- BLE
 
 
+_WHITEN_CACHE: dict = {}
+
+
 def ble_whitening(channel: int, nbytes: int) -> np.ndarray:
     """Whitening sequence of a BLE channel index, packed LSB first.
     LFSR x^7+x^4+1, position 0 = 1, positions 1..6 = channel index MSB first
     (Bluetooth Core 4.0 Vol 6 Part B 3.2; equals scramble_table.h of the reference)."""
+    full = _WHITEN_CACHE.get(channel)
+    if full is None or len(full) < nbytes:
+        full = _WHITEN_CACHE[channel] = _ble_whitening(channel, max(nbytes, 64))
+    return full[:nbytes]
+
+
+def _ble_whitening(channel: int, nbytes: int) -> np.ndarray:
     reg = [1] + [(channel >> (5 - k)) & 1 for k in range(6)]
     out = np.zeros(nbytes, dtype=np.uint8)
     for i in range(nbytes):
@@ -45,15 +55,25 @@ def ble_whitening(channel: int, nbytes: int) -> np.ndarray:
 
 
 def ble_crc24(data: bytes, init: int = chanplan.BLE_ADV_CRC_INIT) -> bytes:
-    """CRC-24 of the BLE link layer, returned in transmit order (3 bytes)."""
+    """CRC-24 of the BLE link layer, returned in transmit order (3 bytes).  init: the 24-bit seed as a number (CRCInit of the
+    specification, least significant byte transmitted first) -- btle_rx's `-k` is its byte-swapped form (same for 0x555555)."""
     crc = int(f"{init & 0xFFFFFF:024b}"[::-1], 2)
     for byte in data:
-        for b in range(8):
-            if (crc ^ (byte >> b)) & 1:
-                crc = (crc >> 1) ^ 0xDA6000
-            else:
-                crc >>= 1
+        crc = _CRC24_TABLE[(crc ^ byte) & 0xFF] ^ (crc >> 8)
     return bytes((crc & 0xFF, (crc >> 8) & 0xFF, (crc >> 16) & 0xFF))
+
+
+def _crc24_table():
+    t = []
+    for i in range(256):
+        r = i
+        for _ in range(8):
+            r = (r >> 1) ^ 0xDA6000 if r & 1 else r >> 1
+        t.append(r)
+    return t
+
+
+_CRC24_TABLE = _crc24_table()
 
 
 def gaussian_taps(sps: int = 4, bt: float = 0.5, span: int = 4) -> np.ndarray:
@@ -344,6 +364,71 @@ def wideband_capture(seconds: float = 0.02, kind: str = "ble", seed: int = 4000,
                    dict(kind="wb_" + kind, seed=seed, esn0_db=esn0_db, seconds=seconds))
 
 
+# ------------------------------------------------------------- a BLE connection (SURVEY 8(f) N3 test input)
+
+def ble_connect_req(init_a: bytes, adv_a: bytes, access_addr: int, crc_init: int, hop: int, interval: int = 6, chm: bytes = b"\xff\xff\xff\xff\x1f",
+                    win_size: int = 2, win_offset: int = 1, latency: int = 0, timeout: int = 100, sca: int = 1, tx_add: int = 0, rx_add: int = 0) -> bytes:
+    """CONNECT_REQ PDU (type 5, 34-byte payload) in the field order btle_rx.c:1482-1557 reads."""
+    ll = (access_addr.to_bytes(4, "little") + bytes([(crc_init >> 16) & 0xFF, (crc_init >> 8) & 0xFF, crc_init & 0xFF, win_size])
+          + win_offset.to_bytes(2, "little") + interval.to_bytes(2, "little") + latency.to_bytes(2, "little") + timeout.to_bytes(2, "little")
+          + bytes(chm) + bytes([(hop & 0x1F) | ((sca & 7) << 5)]))
+    return bytes([5 | (tx_add << 6) | (rx_add << 7), 34]) + bytes(init_a) + bytes(adv_a) + ll
+
+
+def connection_capture(seconds: float = 0.06, seed: int = 7000, esn0_db: float = 25.0, hop: int = 7, interval: int = 6,
+                       access_addr: int = 0x50655A3B, crc_init: int = 0x1A2B3C, partial_first: bool = True) -> Capture:
+    """96 Msps capture of a connection being opened: advertising on 37/38/39, (optionally) a CONNECT_REQ with a partial channel
+    map, then a CONNECT_REQ with the full map on channel 37, then one master and one slave LL PDU per connection event on the
+    data channel (last + hop) % 37 (the sequence receiver_controller steps through, btle_rx.c:2194,2227), every
+    interval * 1.25 ms, with the connection's access address and CRC init.  truth holds every frame in time order; meta the
+    connection parameters and the index of the full-map request."""
+    rng = np.random.default_rng(seed)
+    n_ch = int(round(seconds * chanplan.NB_RATE))
+    n_ch -= n_ch % chanplan.BLE_WINDOW
+    streams: dict[int, np.ndarray] = {}
+    truth: list[Truth] = []
+    # crc_init is the value btle_rx prints and takes as -k: the three CRCInit bytes in transmit order, first byte most
+    # significant (btle_rx.c:1505-1507); the CRC register is seeded with them least significant byte first (crc_init_reorder)
+    crc_seed = int.from_bytes(crc_init.to_bytes(3, "big"), "little")
+
+    def put(channel: int, pos: int, pdu: bytes, aa=chanplan.BLE_ADV_AA, ci=chanplan.BLE_ADV_CRC_INIT):
+        wave = gfsk_modulate(ble_phy_bits(pdu, channel, aa, ci))
+        cfo, ph0 = float(rng.uniform(-50e3, 50e3)), float(rng.uniform(0, 2 * math.pi))
+        b = chanplan.ble_channel_bin(channel)
+        if b not in streams:
+            streams[b] = np.zeros(n_ch, dtype=np.complex128)
+        k = np.arange(len(wave))
+        streams[b][pos:pos + len(wave)] += wave * np.exp(1j * (ph0 + 2 * math.pi * cfo * k / chanplan.NB_RATE))
+        truth.append(Truth(channel, pos, pos + 8 * 4 + 8, pdu + ble_crc24(pdu, ci), 3))
+        return pos + len(wave)
+
+    init_a, adv_a = bytes(rng.integers(0, 256, 6, dtype=np.uint8)), bytes(rng.integers(0, 256, 6, dtype=np.uint8))
+    pos = 3000
+    for ch in (37, 38, 39, 37):                                            # advertising events before the request
+        pos = put(ch, pos, bytes([0x00, 6 + 9]) + adv_a + bytes(rng.integers(0, 256, 9, dtype=np.uint8))) + 1500
+    if partial_first:                                                     # the reference refuses to follow this one
+        pos = put(37, pos, ble_connect_req(init_a, adv_a, 0x12345679, 0x00BEEF, 5, chm=b"\xff\xff\x0f\xff\x1f")) + 6000
+        pos = put(37, pos, bytes([0x00, 6 + 3]) + adv_a + b"\x02\x01\x06") + 1500
+    req_at = len(truth)
+    pos = put(37, pos, ble_connect_req(init_a, adv_a, access_addr, crc_init, hop, interval)) + 5000
+    put(38, pos, bytes([0x02, 6 + 4]) + bytes(rng.integers(0, 256, 10, dtype=np.uint8)))     # someone else keeps advertising
+    ev, ch, events = pos + 1200, 0, []
+    step = int(interval * 1.25e-3 * chanplan.NB_RATE)
+    while ev + 4000 < n_ch - 2048:
+        ch = (ch + hop) % 37
+        end = put(ch, ev, ble_data_pdu(rng), access_addr, crc_seed)
+        put(ch, end + 600 - 16, ble_data_pdu(rng), access_addr, crc_seed)   # T_IFS = 150 us after the master's last bit
+        events.append(ch)
+        ev += step
+    x = wideband_mix(streams)
+    sigma2 = 4.0 * chanplan.WB_DECIM / (10.0 ** (esn0_db / 10.0))
+    x = x + _awgn(len(x), np.random.default_rng(seed + 999), sigma2).astype(np.complex64)
+    truth.sort(key=lambda t: t.anchor)
+    return Capture(x.astype(np.complex64), chanplan.WB_RATE, truth,
+                   dict(kind="wb_ble_conn", seed=seed, esn0_db=esn0_db, access_addr=access_addr, crc_init=crc_init, hop=hop,
+                        interval=interval, init_a=init_a, adv_a=adv_a, request_index=req_at, event_channels=events))
+
+
 # ------------------------------------------------------------- GPU transmit side (SURVEY 8(f) N4)
 # The frame SCHEDULE -- which bytes, where, which carrier offset, phase and amplitude -- is a few bytes per frame and is
 # drawn here with exactly the random draws of ble_baseband / zb_baseband above (same generator, same order), so that
@@ -426,15 +511,22 @@ def wideband_schedule(seconds: float = 0.02, kind: str = "ble", seed: int = 4000
 
 
 def wideband_capture_gpu(seconds: float = 0.02, kind: str = "ble", seed: int = 4000, esn0_db: float | None = 25.0, device: int = 0,
-                         channels=None, amp_db_spread: float = 0.0, gap=None, to_host: bool = False):
+                         channels=None, amp_db_spread: float = 0.0, gap=None, to_host: bool = False, repeat: int = 1):
     """wideband_capture() generated on the GPU: same frames at the same places, modulated, lifted to 96 Msps
     and noised by libsnoutrx.  Returns (iq, truth): iq a torch CUDA complex64 tensor (or a numpy array with to_host=True).
     esn0_db=None: no noise (then the samples equal the numpy statement within float32 rounding).  The noise is the GPU's own
-    counter-based generator: same statistics as wideband_capture's, different values."""
+    counter-based generator: same statistics as wideband_capture's, different values.  repeat > 1: the schedule of `seconds`
+    is sent `repeat` times back to back (long captures without a long host-side schedule; the noise does not repeat)."""
     import ctypes
     from . import _abi
     lib = _abi.load()
     bursts, blob, bins, truth, n_ch = wideband_schedule(seconds, kind, seed, channels, amp_db_spread, gap)
+    if repeat > 1:
+        one, n_one = bursts, n_ch
+        bursts = np.concatenate([one] * repeat)
+        bursts["start"] += np.repeat(np.arange(repeat, dtype=np.int64) * n_one, len(one))
+        truth = [Truth(t.channel, t.start + k * n_one, t.anchor + k * n_one, t.data, t.proto) for k in range(repeat) for t in truth]
+        n_ch = n_one * repeat
     taps = np.ascontiguousarray(interp_taps(), dtype=np.float32)
     gauss = np.ascontiguousarray(_GAUSS4, dtype=np.float64)
     sps = 4.0 if kind == "ble" else 2.0

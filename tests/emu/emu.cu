@@ -11,6 +11,7 @@
 #include "../../snout_b200/csrc/fft.cuh"
 #include "../../snout_b200/csrc/pfb.cuh"
 #include "../../snout_b200/csrc/ble_adv.cuh"
+#include "../../snout_b200/csrc/ble_conn.cuh"
 #include "../../snout_b200/csrc/zb.cuh"
 #include "../../snout_b200/csrc/pfb_zb.cuh"
 #include "../../snout_b200/csrc/zb_mac.cuh"
@@ -350,5 +351,8 @@ void emu_zb_mac_parse(const uint8_t* psdu, int len, snrx_zbmac_t* out) { zb_mac_
 
 // one record through ble_adv_parse (k_ble_adv_summary's per-thread code)
 void emu_ble_adv_parse(const uint8_t* pdu, int len, snrx_adv_t* out) { ble_adv_parse(pdu, len, *out); out->frame = 0; }
+
+// one record through ble_conn_parse (k_ble_conn_fill's per-thread code); returns 1 for a CONNECT_REQ
+int emu_ble_conn_parse(const uint8_t* pdu, int len, snrx_conn_t* out) { memset(out, 0, sizeof *out); return ble_conn_parse(pdu, len, *out) ? 1 : 0; }
 
 }  // extern "C"
