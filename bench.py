@@ -430,6 +430,14 @@ def main():
             dt = float(t.item())
         return world * n_e2e * args.steps / dt / 1e6, d2h, nfr
 
+    # the dominant kernel with the GPU to itself: one batch at a time, so that no other lane's back-end kernels share the SMs
+    # (outside the timed region; reported beside the live figure as roofline.alone)
+    alone_ms = []
+    for _ in range(12):
+        eng.process(x_dev).poll(copy=False)
+        alone_ms.append(eng.stats()["gpu_ms_frontend"])
+    alone_ms = float(np.median(alone_ms[3:]))
+
     # SURVEY 8(f) N1 (outside the timed region): advertising summaries + sender table of one polled batch, on the GPU
     analytics = None
     if world == 1 and eng.n_ble:
@@ -587,6 +595,8 @@ def main():
                                 "mixed_wb56": "k_pfb_ble (channelizer+slicer; the Zigbee front end runs after it on the tail stream)",
                                 "ble_nb": "k_ble_slice_nb", "zb_nb": "k_zb_quad"}[mode],
                      "algorithmic_bytes_per_launch": int(n * 8), "kernel_ms": fms,
+                     "alone": {"kernel_ms": alone_ms, "achieved": n * 8 / (alone_ms * 1e-3) / 1e9, "frac": n * 8 / (alone_ms * 1e-3) / 1e9 / peak,
+                               "note": "same launch with one batch queued at a time (no other lane's kernels on the SMs); measured after the timed region"},
                      "step_frac": n * 8 / (ms / args.steps * 1e-3) / 1e9 / peak,
                      "binding_unit": "fp32 FMA pipe / issue slots" if args.workload in WIDEBAND else "hbm",
                      "note": "frac = 8 B per input sample (one cf32 read) / the dominant kernel's launch time vs the measured HBM copy "

@@ -246,6 +246,24 @@ int  snrx_polled_frames_device(snrx_t* h, const snrx_frame_t** frames_dev, uint3
 #define SNRX_ADV_MALFORMED     0x0040  /* truncated where the reference parser raises / never returns  */
 #define SNRX_ADV_SENDER        0x0080  /* adv_a holds the sender address                               */
 
+/* snrx_adv_t.hints.  Low nibble: the first Nearby TLV (Apple type 0x10) of the record's Apple data -- 0 none, 1 present
+ * without a version hint, 2 / 3 / 4 = the reference's 'iOS Version Hint' '10' / '11' / '12' (advertising.py:267-281). */
+#define SNRX_HINT_NEARBY_MASK  0x0f
+#define SNRX_HINT_FITBIT       0x10    /* the AD 0x06 field contains ba5689a6fabfa2bd01467d6e00fbabad (device.py:187-190)  */
+/* snrx_device_t.model / .os codes */
+#define SNRX_MODEL_NONE 0
+#define SNRX_MODEL_FITBIT_CHARGE 1     /* 'Charge / Charge HR' (device.py:210-213)                             */
+#define SNRX_MODEL_AIRPODS 2           /* Apple record of type 0x07 (device.py:214-219)                        */
+#define SNRX_OS_NONE 0
+#define SNRX_OS_UNDECIDED 1            /* a Nearby record without a version hint: the reference answers '-'    */
+#define SNRX_OS_IOS10 2
+#define SNRX_OS_IOS11 3
+#define SNRX_OS_IOS12 4
+#define SNRX_OS_WINDOWS10 5            /* company id 0x0006 (device.py:243-245)                                */
+#define SNRX_VENDOR_NONE    0
+#define SNRX_VENDOR_COMPANY 1          /* vendor_company holds the company id whose name Device.vendor returns */
+#define SNRX_VENDOR_FITBIT  2          /* no company id in the first deciding packet, but the FitBit UUID: "FitBit" */
+
 typedef struct snrx_adv {           /* one per record of the batch, 32 bytes */
     uint8_t  adv_a[6];      /* sender address as transmitted (btle_rx prints it reversed, btle_rx.c:1434-1441) */
     uint8_t  pdu_type;      /* header & 0x0f; 0xff: not a BLE record                                  */
@@ -259,7 +277,7 @@ typedef struct snrx_adv {           /* one per record of the batch, 32 bytes */
     uint8_t  unknown_type;
     uint8_t  apple_action;  /* Apple Nearby (type 0x10) action code, 0xff none                         */
     uint8_t  oob_flags;     /* AD 0x11 value                                                           */
-    uint8_t  reserved;
+    uint8_t  hints;         /* SNRX_HINT_*: what Device.vendor / .model / .os look at (device.py:171-265)      */
     uint32_t apple_types;   /* bit t: Apple Continuity TLV type t (< 32) present (last Apple AD wins)   */
     uint32_t frame;         /* index of the record in the batch                                        */
 } snrx_adv_t;
@@ -275,9 +293,13 @@ typedef struct snrx_device {        /* one per sender (AdvA, TxAdd), 64 bytes */
     uint16_t pdu_mask;      /* bit t: PDU type t seen                                                  */
     uint16_t present;       /* OR of SNRX_ADV_* over its packets                                       */
     uint16_t company_id;    /* of its latest packet with manufacturer data, 0xffff none                */
-    uint16_t reserved;
+    uint16_t vendor_company;/* Device.vendor (device.py:171-191): company id of its FIRST packet that carries one
+                               (valid when vendor_kind == SNRX_VENDOR_COMPANY)                              */
     uint32_t apple_types;   /* OR over its packets                                                     */
-    uint32_t pad;
+    uint8_t  model;         /* Device.model (device.py:193-220): SNRX_MODEL_* decided by its first deciding packet */
+    uint8_t  os;            /* Device.os (device.py:222-246): SNRX_OS_* decided by its first deciding packet   */
+    uint8_t  vendor_kind;   /* SNRX_VENDOR_*                                                           */
+    uint8_t  pad;
 } snrx_device_t;
 
 /* Summaries of the batch most recently retired by snrx_poll / snrx_poll_view (computed on the GPU from the device frame

@@ -88,14 +88,19 @@ ADV_FLAGS, ADV_UUID128, ADV_OOB, ADV_SERVICE_DATA, ADV_MANUFACTURER, ADV_UNKNOWN
 ADV_DTYPE = np.dtype([
     ("adv_a", "u1", (6,)), ("pdu_type", "u1"), ("tx_add", "u1"), ("rx_add", "u1"), ("adv_len", "u1"), ("n_ad", "u1"),
     ("ad_flags", "u1"), ("present", "<u2"), ("company_id", "<u2"), ("service_uuid", "<u2"), ("unknown_type", "u1"),
-    ("apple_action", "u1"), ("oob_flags", "u1"), ("reserved", "u1"), ("apple_types", "<u4"), ("frame", "<u4"),
+    ("apple_action", "u1"), ("oob_flags", "u1"), ("hints", "u1"), ("apple_types", "<u4"), ("frame", "<u4"),
 ], align=True)
 DEVICE_DTYPE = np.dtype([
     ("adv_a", "u1", (6,)), ("tx_add", "u1"), ("ad_flags", "u1"), ("packets", "<u4"), ("crc_ok", "<u4"), ("chan_mask", "<u8"),
     ("first_index", "<i8"), ("last_index", "<i8"), ("first_capture", "<u4"), ("last_capture", "<u4"), ("pdu_mask", "<u2"),
-    ("present", "<u2"), ("company_id", "<u2"), ("reserved", "<u2"), ("apple_types", "<u4"), ("pad", "<u4"),
+    ("present", "<u2"), ("company_id", "<u2"), ("vendor_company", "<u2"), ("apple_types", "<u4"), ("model", "u1"), ("os", "u1"),
+    ("vendor_kind", "u1"), ("pad", "u1"),
 ], align=True)
 assert ADV_DTYPE.itemsize == 32 and DEVICE_DTYPE.itemsize == 64
+HINT_NEARBY_MASK, HINT_FITBIT = 0x0F, 0x10                    # snrx_adv_t.hints
+MODEL_NONE, MODEL_FITBIT_CHARGE, MODEL_AIRPODS = 0, 1, 2       # snrx_device_t.model
+OS_NONE, OS_UNDECIDED, OS_IOS10, OS_IOS11, OS_IOS12, OS_WINDOWS10 = range(6)
+VENDOR_NONE, VENDOR_COMPANY, VENDOR_FITBIT = 0, 1, 2
 
 SYMBOLS = [
     ("snrx_abi_version", c_int, []),

@@ -25,6 +25,7 @@ SNRX_HD bool ble_pdu_has_adv_data(int pdu_type) { return pdu_type == 0 || pdu_ty
 SNRX_HD void ble_adv_apple(const uint8_t* d, int n, snrx_adv_t& o) {
     o.apple_types = 0;
     o.apple_action = 0xFF;
+    o.hints &= (uint8_t)~SNRX_HINT_NEARBY_MASK;                                   // the dict entry is replaced: last Apple AD wins
     int pos = 0;
     while (pos < n) {
         if (pos + 1 >= n) { o.present |= SNRX_ADV_MALFORMED; break; }           // the reference loops forever here
@@ -35,9 +36,57 @@ SNRX_HD void ble_adv_apple(const uint8_t* d, int n, snrx_adv_t& o) {
         if (t < 32) o.apple_types |= 1u << t;
         if (t == 0x10) {                                                          // Nearby: action code (:262-266)
             if (vl >= 1) o.apple_action = v[0] & 0x0F; else o.present |= SNRX_ADV_MALFORMED;
+            if (vl >= 1 && !(o.hints & SNRX_HINT_NEARBY_MASK)) {                  // Device.os stops at the FIRST Nearby record
+                int hint = 1;                                                     // nearby_data = apple_data[1:], :272-281
+                if (vl - 1 == 1 && v[1] == 0x00) hint = 2;
+                if (vl - 1 == 4) { if (v[1] == 0x10) hint = 3; if (v[1] == 0x18 || v[1] == 0x1C) hint = 4; }
+                o.hints |= (uint8_t)hint;
+            }
         }
         if (t == 0x0C && vl < 3) o.present |= SNRX_ADV_MALFORMED;                 // Handoff reads 3 bytes (:247-249): IndexError
     }
+}
+
+// `'ba5689a6fabfa2bd01467d6e00fbabad' in data.hex()` (device.py:187-190, 210-213): a substring test on the hex text, so the
+// 32 hex digits may start at either nibble of a byte
+SNRX_HD bool ble_adv_has_fitbit_uuid(const uint8_t* v, int n) {
+    const uint8_t pat[16] = {0xba, 0x56, 0x89, 0xa6, 0xfa, 0xbf, 0xa2, 0xbd, 0x01, 0x46, 0x7d, 0x6e, 0x00, 0xfb, 0xab, 0xad};
+    for (int s = 0; s + 32 <= 2 * n; s++) {                                       // s: first hex digit of the candidate match
+        bool ok = true;
+        for (int k = 0; k < 32 && ok; k++) {
+            const int i = s + k;
+            const int have = (i & 1) ? (v[i >> 1] & 0x0F) : (v[i >> 1] >> 4);
+            const int want = (k & 1) ? (pat[k >> 1] & 0x0F) : (pat[k >> 1] >> 4);
+            ok = have == want;
+        }
+        if (ok) return true;
+    }
+    return false;
+}
+
+// What one packet contributes to Device.vendor / .model / .os (device.py:171-246): 0 = the packet does not decide.
+// Packets the reference parser raises on never become messages (MALFORMED), and only the AdvA + AD-structure PDU types do.
+SNRX_HD uint32_t ble_adv_vendor_vote(const snrx_adv_t& a) {                       // 2^16 | company id, or 1 = FitBit
+    if (a.present & SNRX_ADV_MALFORMED) return 0;
+    if (a.present & SNRX_ADV_MANUFACTURER) return (1u << 16) | a.company_id;      // company_name is never empty ('??')
+    if (a.hints & SNRX_HINT_FITBIT) return 1u;
+    return 0;
+}
+// key of "first deciding packet": larger for earlier packets; vote < 2^17 (position at 2-sample resolution: 47 bits)
+SNRX_HD unsigned long long ble_dev_first_key(unsigned long long pos, uint32_t vote) {
+    return ((((1ull << 47) - 1ull) - (pos >> 1)) << 17) | vote;
+}
+SNRX_HD uint32_t ble_adv_model_vote(const snrx_adv_t& a) {
+    if (a.present & SNRX_ADV_MALFORMED) return 0;
+    if (a.hints & SNRX_HINT_FITBIT) return SNRX_MODEL_FITBIT_CHARGE;
+    if ((a.present & SNRX_ADV_MANUFACTURER) && a.company_id == 0x004C && (a.apple_types & (1u << 7))) return SNRX_MODEL_AIRPODS;
+    return 0;
+}
+SNRX_HD uint32_t ble_adv_os_vote(const snrx_adv_t& a) {
+    if ((a.present & SNRX_ADV_MALFORMED) || !(a.present & SNRX_ADV_MANUFACTURER)) return 0;
+    if (a.company_id == 0x004C && (a.hints & SNRX_HINT_NEARBY_MASK)) return (uint32_t)(a.hints & SNRX_HINT_NEARBY_MASK);   // 1..4 = SNRX_OS_UNDECIDED..IOS12
+    if (a.company_id == 0x0006) return SNRX_OS_WINDOWS10;
+    return 0;
 }
 
 // One BLE record -> summary.  pdu = header(2) | payload | crc(3) as in snrx_frame_t.bytes, len = valid bytes.
@@ -45,7 +94,7 @@ SNRX_HD void ble_adv_parse(const uint8_t* pdu, int len, snrx_adv_t& o) {
     for (int i = 0; i < 6; i++) o.adv_a[i] = 0;
     o.pdu_type = 0xFF; o.tx_add = 0; o.rx_add = 0; o.adv_len = 0; o.n_ad = 0; o.ad_flags = 0; o.present = 0;
     o.company_id = 0xFFFF; o.service_uuid = 0xFFFF; o.unknown_type = 0; o.apple_action = 0xFF; o.apple_types = 0;
-    o.oob_flags = 0; o.reserved = 0;
+    o.oob_flags = 0; o.hints = 0;
     if (len < 5) { o.present |= SNRX_ADV_MALFORMED; return; }
     o.pdu_type = pdu[0] & 0x0F;
     o.tx_add = (pdu[0] >> 6) & 1;
@@ -79,6 +128,8 @@ SNRX_HD void ble_adv_parse(const uint8_t* pdu, int len, snrx_adv_t& o) {
             if (vl >= 1) { o.ad_flags = v[0]; o.present |= SNRX_ADV_FLAGS; } else o.present |= SNRX_ADV_MALFORMED;
         } else if (t == 0x06) {
             o.present |= SNRX_ADV_UUID128;
+            o.hints &= (uint8_t)~SNRX_HINT_FITBIT;                                // last AD 0x06 wins
+            if (ble_adv_has_fitbit_uuid(v, vl)) o.hints |= SNRX_HINT_FITBIT;
         } else if (t == 0x11) {                                                   // security manager OOB flags :183-201
             if (vl >= 1) { o.oob_flags = v[0]; o.present |= SNRX_ADV_OOB; } else o.present |= SNRX_ADV_MALFORMED;
         } else if (t == 0x16) {                                                   // service data :203-210
@@ -118,8 +169,11 @@ struct DevSlot {
     unsigned int packets, crc_ok;
     unsigned int pdu_mask, apple_types;
     unsigned int present, ad_flags;   // OR over packets
+    // FIRST deciding packet of Device.vendor / .model / .os: max over deciding packets of ble_dev_first_key(pos, vote)
+    unsigned long long first_vendor, first_model, first_os;
+    unsigned long long pad[5];
 };
-static_assert(sizeof(DevSlot) == 64, "one slot per 64-byte line");
+static_assert(sizeof(DevSlot) == 128, "one slot per 128-byte line");
 
 // order of appearance inside a job: capture, then channel-rate position (sample_index >= -4)
 SNRX_HD unsigned long long ble_dev_pos(uint32_t capture_id, int64_t sample_index) {
@@ -138,7 +192,12 @@ SNRX_HD void ble_dev_export(const DevSlot& d, snrx_device_t& o) {
     o.pdu_mask = (uint16_t)d.pdu_mask;
     o.present = (uint16_t)d.present;
     o.company_id = d.last_company ? (uint16_t)(d.last_company & 0xFFFF) : 0xFFFF;
-    o.reserved = 0;
+    o.vendor_company = (uint16_t)(d.first_vendor & 0xFFFF);
+    o.vendor_kind = (uint8_t)(((d.first_vendor >> 16) & 1u) ? SNRX_VENDOR_COMPANY : d.first_vendor ? SNRX_VENDOR_FITBIT : SNRX_VENDOR_NONE);
+    if (o.vendor_kind != SNRX_VENDOR_COMPANY) o.vendor_company = 0xFFFF;
+    o.model = (uint8_t)(d.first_model & 0xFF);
+    o.os = (uint8_t)(d.first_os & 0xFF);
+    o.pad = 0;
     o.apple_types = d.apple_types;
 }
 
@@ -191,6 +250,11 @@ __global__ void __launch_bounds__(256) k_ble_adv_devices(const snrx_frame_t* __r
             atomicMax(&d.first_inv, (1ull << 63) - pos);
             atomicMax(&d.last_pos, pos);
             if (a.present & SNRX_ADV_MANUFACTURER) atomicMax(&d.last_company, (pos << 16) | a.company_id);
+            if (f.crc_ok) {                                       // only CRC0 lines become messages (message.py:225-226)
+                if (const uint32_t v = ble_adv_vendor_vote(a)) atomicMax(&d.first_vendor, ble_dev_first_key(pos, v));
+                if (const uint32_t v = ble_adv_model_vote(a)) atomicMax(&d.first_model, ble_dev_first_key(pos, v));
+                if (const uint32_t v = ble_adv_os_vote(a)) atomicMax(&d.first_os, ble_dev_first_key(pos, v));
+            }
             return;
         }
     }

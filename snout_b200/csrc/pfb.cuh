@@ -37,10 +37,6 @@
 namespace snrx {
 
 constexpr int kPfbD = 24;
-#ifndef SNRX_PFB_TILES_PER_CTA
-#define SNRX_PFB_TILES_PER_CTA 1
-#endif
-constexpr int kPfbTilesPerCta = SNRX_PFB_TILES_PER_CTA;   // consecutive tiles per one-warp CTA of the wideband kernels
 constexpr int kTileT = 128;                    // channel-rate samples computed per tile
 constexpr int kTileStride = 127;               // samples whose slicer bit the tile emits (needs y[m+1])
 constexpr int kChunkT = 8;                     // output times per FIR lane and pass
@@ -306,6 +302,8 @@ struct PfbBleArgs {
     int32_t n_tiles;          // tiles per capture in this launch
     int32_t tile0;            // first tile of this launch
     int32_t n_caps;           // captures in this launch
+    int32_t tiles_per_cta;    // k_pfb_ble_run only
+    int32_t tile_step;        // k_pfb_ble_run: 1 = a CTA's tiles are consecutive; gridDim.x = CTA b takes tiles b, b + grid, ...
     const float4* taps_pass;  // [3][NT/4][8] float4: element (gi, d4, rl) = h[rho + 24 (4 d4 + 0..3)], rho = gi + 3 rl --
                               // the 8 FIR rows of a pass read 128 contiguous bytes per load
     float scale;              // quantiser scale
@@ -317,57 +315,32 @@ struct PfbBleArgs {
 
 // whether the tile is staged by bulk copies (it lies entirely inside the capture) or by the zero-filling generic path
 template <class G>
-__device__ __forceinline__ bool pfb_tile_interior(int64_t x0, int64_t n_in) { return x0 >= 0 && x0 + G::kTileIn <= n_in; }
+SNRX_HD bool pfb_tile_interior(int64_t x0, int64_t n_in) { return x0 >= 0 && x0 + G::kTileIn <= n_in; }
 
-// A one-warp CTA computes kPfbTilesPerCta consecutive tiles; with more than one, the bulk copy of the NEXT tile is issued
-// as soon as the last FIR pass has read the current one (no second tile buffer).  MEASURED (round 2, B200, ble_wb40,
-// kernel time per 94.4 M samples): 1 tile per CTA 0.365-0.393 ms | 2 tiles 0.438 | 4 tiles 0.441 | 8 tiles 0.422 (0.443
-// without the prefetch) | 32 tiles 0.504 | fully persistent grid (16 CTAs per SM walking over all tiles) 0.454.  More
-// than one tile per CTA LOSES: ptxas emits the 27 KB tile body twice inside the loop (1240 FFMA2 instead of 684, WARPSYNC /
-// ENDCOLLECTIVE around every shuffle group because it no longer assumes a converged warp, 92 bytes of spills at 128
-// registers), which no longer fits the 32 KB instruction cache level, and a persistent grid also keeps the other lane's
-// small high-priority kernels from slipping in between tiles.  So the default stays ONE tile per CTA (the loop then
-// compiles away and the code is the single-tile kernel); the switch is kept for A/B runs (-DSNRX_PFB_TILES_PER_CTA=n).
-template <int NT, bool DEBUG>
-__global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbBleArgs a) {
+// The same bulk staging with every instruction PREDICATED instead of branched around (`on` = stage / do nothing): the
+// persistent kernel issues the next tile's copies from inside its tile loop, and a branch there makes ptxas duplicate the
+// rest of the loop body (see k_pfb_ble_run).  No __syncwarp between the expect_tx and the copies: complete_tx may run
+// ahead of expect_tx (the phase cannot complete before lane 0's arrival).
+template <class G, int TT>
+__device__ __forceinline__ void pfb_stage_tile_bulk_pred(float2* xs, const float2* xtile, uint64_t* bar, int lane, bool on) {
+    constexpr int kPer = 24 * TT;
+    const uint32_t p0 = (on && lane == 0) ? 1u : 0u;
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}\n" ::"r"(smem_u32(bar)),
+                 "r"((uint32_t)(G::kTileIn * sizeof(float2))), "r"(p0)
+                 : "memory");
+    const int lo = lane == 0 ? 0 : kPer * lane - 12;
+    const int hi = min(kPer * (lane + 1) - 12, G::kTileIn);
+    const uint32_t p1 = (on && lane < G::kPieces) ? 1u : 0u;
+    asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %4, 0;\n@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}\n" ::"r"(
+                     smem_u32(xs + lo + 8 * lane)),
+                 "l"(xtile + lo), "r"((uint32_t)((hi - lo) * sizeof(float2))), "r"(smem_u32(bar)), "r"(p1)
+                 : "memory");
+}
+
+// One tile, staged in xs, through phases 1-3.  after_fir() runs once every lane has read the tile for the last time.
+template <int NT, bool DEBUG, class AfterFir>
+__device__ __forceinline__ void pfb_ble_tile(const PfbBleArgs& a, const float2* xs, float4* V, int lane, int cap, int g_first, AfterFir after_fir) {
     using B = PfbBleGeom<NT>;
-    using G = typename B::G;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* xs = reinterpret_cast<float2*>(smem_raw);
-    float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [8][32], see v_pos()
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
-
-    const int lane = threadIdx.x;
-    const int total = a.n_tiles * a.n_caps;
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
-    uint32_t parity = 0;
-    int staged = 0;                                                        // this tile's bulk copy is already in flight
-    asm volatile("" : "+r"(staged));                                       // opaque: keeps the compiler from peeling the first tile (a second copy
-                                                                           // of the 27 KB loop body does not fit the instruction cache)
-    const int t_begin = blockIdx.x * kPfbTilesPerCta, t_end = min(total, t_begin + kPfbTilesPerCta);
-#pragma unroll 1
-  for (int t = t_begin; t < t_end; t++) {
-    const int tile = a.tile0 + t % a.n_tiles;
-    const int cap = t / a.n_tiles;
-    const float2* xcap = a.x + (size_t)cap * a.stride;
-    const int g_first = B::kStride * tile;                                 // first channel sample of the tile
-
-    // ---- phase 0: stage the input tile (bulk copies for interior tiles, zero-filling cp.async at the capture ends)
-    {
-        const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
-        if (pfb_tile_interior<G>(x0, a.n_in)) {
-            if (!staged) pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-        } else {
-            pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, x0, a.n_in, lane);
-            cp_async_commit_wait_all();
-            __syncwarp();
-        }
-        staged = 0;
-    }
-
     // ---- phase 1: three passes of FIR (branches r = gi mod 3) -> transpose -> 16-point inverse DFT
     cf f[3][16];
     {
@@ -388,22 +361,7 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
             for (int e = 0; e < kChunkT; e++)
                 V[v_pos(rl, 8 * c + e)] = make_float4(acc[0][e].x, acc[0][e].y, acc[1][e].x, acc[1][e].y);
             __syncwarp();
-            if (gi == 2) {
-                // every lane has read the tile for the last time: bring in this warp's next tile
-                const int tn = t + 1;
-#ifdef SNRX_PFB_NO_PREFETCH
-                if (false) {
-#else
-                if (tn < t_end) {
-#endif
-                    const int64_t xn = (int64_t)kPfbD * (B::kStride * (a.tile0 + tn % a.n_tiles)) - G::kHist;
-                    if (pfb_tile_interior<G>(xn, a.n_in)) {
-                        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");     // generic reads before the async-proxy writes
-                        pfb_stage_tile_bulk<G, kChunkT>(xs, a.x + (size_t)(tn / a.n_tiles) * a.stride + xn, bar, lane);
-                        staged = 1;
-                    }
-                }
-            }
+            if (gi == 2) after_fir();
             cf v16[16];
             pfb_load_col16(V, lane, v16);
             __syncwarp();                                                  // V is rewritten by the next pass
@@ -475,8 +433,89 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
             }
         }
     }
-    __syncwarp();                                            // V and the quantised values of this tile are done with
-  }
+}
+
+// One tile per one-warp CTA: any tile (interior tiles by bulk copies, tiles that touch either end of the capture through the
+// zero-filling generic path).
+template <int NT, bool DEBUG>
+__global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbBleArgs a) {
+    using B = PfbBleGeom<NT>;
+    using G = typename B::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* xs = reinterpret_cast<float2*>(smem_raw);
+    float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [8][32], see v_pos()
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
+
+    const int lane = threadIdx.x;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const int t = blockIdx.x;
+    const int tile = a.tile0 + t % a.n_tiles;
+    const int cap = t / a.n_tiles;
+    const float2* xcap = a.x + (size_t)cap * a.stride;
+    const int g_first = B::kStride * tile;                                 // first channel sample of the tile
+
+    // ---- phase 0: stage the input tile (bulk copies for interior tiles, zero-filling cp.async at the capture ends)
+    const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
+    if (pfb_tile_interior<G>(x0, a.n_in)) {
+        pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
+        mbar_wait(bar, 0);
+    } else {
+        pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, x0, a.n_in, lane);
+        cp_async_commit_wait_all();
+        __syncwarp();
+    }
+    pfb_ble_tile<NT, DEBUG>(a, xs, V, lane, cap, g_first, [] {});
+}
+
+// INTERIOR tiles only (a.tile0 .. a.tile0 + a.n_tiles - 1 of every capture lie entirely inside it), several tiles per one-warp
+// CTA: the bulk copy of the NEXT tile is issued as soon as the last FIR pass has read the current one (no second tile
+// buffer), so only a CTA's first tile waits for memory with nothing else to do.  The staging inside the loop is predicated,
+// not branched around (pfb_stage_tile_bulk_pred); ptxas still emits a second copy of the body behind a BRA.DIV for the
+// not-converged case (1240 FFMA2 in the listing), which is never executed.
+// MEASURED and REJECTED (round 2, B200, 94.4 M samples, profiles/r02_pfb_run_ncu.json): it stays off (SNRX_PFB_TILES=0).
+//   channelizer alone, one batch at a time:  one tile per CTA 0.328 ms | 2 tiles 0.388 | 8 tiles 0.390
+//   inside the two-lane pipeline (bench):    one tile per CTA 0.391 ms | 2 tiles 0.452 | 4 tiles 0.495-0.52 | 8 tiles 0.555
+//   consecutive tiles per CTA or grid-strided tiles (SNRX_PFB_ORDER=1) make no difference, so DRAM locality is not it.
+// ncu of the 8-tile launch vs the one-tile launch: same DRAM traffic (800 MB), L2 hit 47 % vs 33 %, long-scoreboard stall
+// 0.93 vs 0.60 per issue, FMA pipe 57 % vs 64 %: the tile's own copy (9 KB, issued ~40 % into the previous tile) is NOT
+// what a warp waits for any more, yet the loop-carried state costs 108 bytes of spills at the 128-register cap and the
+// long-lived CTAs interleave worse with the other lane's high-priority kernels than 126 844 seven-microsecond CTAs do.
+// The block scheduler starting a fresh one-warp CTA per tile IS the cheapest software pipeline here.
+template <int NT>
+__global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble_run(PfbBleArgs a) {
+    using B = PfbBleGeom<NT>;
+    using G = typename B::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* xs = reinterpret_cast<float2*>(smem_raw);
+    float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
+
+    const int lane = threadIdx.x;
+    const int total = a.n_tiles * a.n_caps;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    const int step = a.tile_step;
+    const int t_begin = step == 1 ? blockIdx.x * a.tiles_per_cta : (int)blockIdx.x;
+    const int t_end = step == 1 ? min(total, t_begin + a.tiles_per_cta) : total;
+    auto tile_src = [&](int t) {
+        const int tile = a.tile0 + t % a.n_tiles;
+        return a.x + (size_t)(t / a.n_tiles) * a.stride + ((int64_t)kPfbD * (B::kStride * tile) - G::kHist);
+    };
+    pfb_stage_tile_bulk_pred<G, kChunkT>(xs, tile_src(t_begin), bar, lane, true);
+    uint32_t parity = 0;
+#pragma unroll 1
+    for (int t = t_begin; t < t_end; t += step) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        const int tile = a.tile0 + t % a.n_tiles;
+        pfb_ble_tile<NT, false>(a, xs, V, lane, t / a.n_tiles, B::kStride * tile, [&] {
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic reads before the async-proxy writes
+            const int tn = min(t + step, total - 1);
+            pfb_stage_tile_bulk_pred<G, kChunkT>(xs, tile_src(tn), bar, lane, t + step < t_end);
+        });
+        __syncwarp();                                            // V and the quantised values of this tile are done with
+    }
 }
 #endif  // __CUDACC__
 

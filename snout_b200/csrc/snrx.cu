@@ -13,6 +13,15 @@
 #include <string>
 #include <vector>
 
+#ifndef SNRX_LANES
+#define SNRX_LANES 2
+#endif
+#ifndef SNRX_BACK_BPS_DEFAULT
+#define SNRX_BACK_BPS_DEFAULT 8
+#endif
+#ifndef SNRX_PFB_TILES_DEFAULT
+#define SNRX_PFB_TILES_DEFAULT 0
+#endif
 #include "ble_adv.cuh"
 #include "ble_back.cuh"
 #include "ble_conn.cuh"
@@ -39,6 +48,13 @@ struct DevBuf {
 
 // One "lane" per output slot: a complete working set with its own stream, so that the latency-bound tail of
 // batch i (search, decode, resolve, export) overlaps the FP32-bound front end of batch i+1.
+// Batches that can be queued at once (lanes).  MEASURED (round 2, B200, resident 0.98-s BLE capture, tools/ab_serial.py):
+// one batch at a time: channelizer 0.328 ms, whole batch 0.58 ms | two queued: 0.405 ms per step (channelizer 0.39 ms next
+// to the other lane's back end) | three queued (-DSNRX_LANES=3): 0.399 ms.  The step is not waiting for the host or for a
+// free lane: the back end's kernels (access-address search 39 us, fill 27 us, resolve 37 us, decode 13 us, scans) take
+// real SM time from the next channelizer, so a third working set buys 1.5 % and stays off.
+constexpr int kLanes = SNRX_LANES;
+
 struct Lane {
     cudaStream_t stream = nullptr;      // front end (channelizer / slicer): low priority, fills the machine
     cudaStream_t tail = nullptr;        // everything after it: high priority, so its small latency-bound kernels are
@@ -85,7 +101,7 @@ struct snrx_handle {
     snrx_device_t* d_devout = nullptr;
     uint32_t* d_adv_counters = nullptr;   // [0] records summarised (BLE), [1] new devices, [2] dropped (table full), [3] export count
     uint32_t dev_count = 0, dev_dropped = 0;
-    Lane lane[2];
+    Lane lane[kLanes];
     uint64_t seq_process = 0, seq_poll = 0;
     // frame exchange (snrx_exchange_*): receive area of this engine and the peers' areas mapped through CUDA IPC
     struct {
@@ -214,21 +230,64 @@ int grid_for(snrx_handle* h, uint64_t items, int per_block, int blocks_per_sm) {
 
 }  // namespace
 
+// blocks per SM of the BLE back-end kernels (see process_impl)
+static int back_bps() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SNRX_BACK_BPS"); v = e ? atoi(e) : SNRX_BACK_BPS_DEFAULT; if (v < 1) v = 1; if (v > 8) v = 8; }
+    return v;
+}
+
+// tiles per CTA of the persistent interior-tile kernel; 0 = every tile through the one-tile kernel (SNRX_PFB_TILES overrides, A/B runs)
+static int pfb_tiles_per_cta() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SNRX_PFB_TILES"); v = e ? atoi(e) : SNRX_PFB_TILES_DEFAULT; if (v < 0) v = 0; }
+    return v;
+}
+
 template <int NT>
 static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint32_t caps) {
     using B = PfbBleGeom<NT>;
+    using G = typename B::G;
     if (!a) {
         CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
         CK(cudaFuncSetAttribute(k_pfb_ble<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        CK(cudaFuncSetAttribute(k_pfb_ble_run<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
         CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(k_pfb_ble_run<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         return SNRX_OK;
     }
     PfbBleArgs args = *a;
     args.n_caps = (int32_t)caps;
-    const unsigned total = (unsigned)(a->n_tiles) * caps;
-    const dim3 grid((total + kPfbTilesPerCta - 1) / kPfbTilesPerCta);
-    if (h->cfg.flags & SNRX_F_KEEP_STREAMS) k_pfb_ble<NT, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(args);
-    else k_pfb_ble<NT, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(args);
+    args.tiles_per_cta = 1;
+    const bool dbg = (h->cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
+    auto one_tile = [&](int t0, int t1) {                       // tiles [t0, t1) of every capture, one per CTA, any position
+        if (t1 <= t0) return;
+        PfbBleArgs b = args;
+        b.tile0 = t0; b.n_tiles = t1 - t0;
+        const dim3 grid((unsigned)(t1 - t0) * caps);
+        if (dbg) k_pfb_ble<NT, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
+        else k_pfb_ble<NT, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
+        h->launches++;
+    };
+    const int t0 = a->tile0, t1 = a->tile0 + a->n_tiles, per = pfb_tiles_per_cta();
+    // interior tiles: 24 * 31 * tile - kHist >= 0 and ... + kTileIn <= n_in
+    const int64_t step = (int64_t)kPfbD * B::kStride;
+    int lo = (int)((G::kHist + step - 1) / step);
+    int hi = a->n_in >= G::kTileIn ? (int)((a->n_in - G::kTileIn + G::kHist) / step) + 1 : 0;          // first tile past the interior
+    lo = std::max(lo, t0); hi = std::min(hi, t1);
+    if (dbg || per == 0 || hi - lo < 4 * per) { one_tile(t0, t1); return SNRX_OK; }
+    one_tile(t0, lo);
+    {
+        PfbBleArgs b = args;
+        b.tile0 = lo; b.n_tiles = hi - lo; b.tiles_per_cta = per;
+        const unsigned total = (unsigned)(hi - lo) * caps;
+        static const int order = getenv("SNRX_PFB_ORDER") ? atoi(getenv("SNRX_PFB_ORDER")) : 0;
+        const unsigned grid = (total + per - 1) / per;
+        b.tile_step = order ? (int)grid : 1;
+        k_pfb_ble_run<NT><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
+        h->launches++;
+    }
+    one_tile(hi, t1);
     return SNRX_OK;
 }
 static int pfb_ble_dispatch(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint32_t caps) {
@@ -585,6 +644,8 @@ static int launch_ble_front(snrx_handle* h, Lane& ln, const float2* x, uint32_t 
         a.tile0 = tile_begin;
         int r = pfb_ble_dispatch(h, &a, ln.stream, caps);
         if (r != SNRX_OK) return r;
+        CK(cudaGetLastError());
+        return SNRX_OK;
     } else {
         NbArgs a;
         a.x = x; a.stride = stride; a.n = (int64_t)n_in;
@@ -614,9 +675,9 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
     if ((((uintptr_t)iq) & 15) || (n_captures > 1 && (stride_samples & 1))) return fail(h, SNRX_EINVAL, "captures must be 16-byte aligned (even stride)");
     if (h->wideband && (n_samples % kPfbD) != 0) return fail(h, SNRX_EINVAL, "wideband captures must hold a multiple of 24 samples");
     CK(cudaSetDevice(h->device));
-    const int li = (int)(h->seq_process & 1);
+    const int li = (int)(h->seq_process % kLanes);
     Lane& ln = h->lane[li];
-    if (ln.pending) return fail(h, SNRX_ESTATE, "two batches already queued: snrx_poll the oldest first");
+    if (ln.pending) return fail(h, SNRX_ESTATE, "every lane holds a queued batch: snrx_poll the oldest first");
     h->launches = 0;
     // this lane's previous batch (two batches ago) has been polled, hence finished: its buffers are free
     cudaStream_t st = ln.stream;
@@ -757,13 +818,17 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
         const uint32_t aa_items = n_captures * h->n_ble_ch * n_chunks;
         const uint32_t w_items = n_captures * h->n_ble_ch * (uint32_t)p.n_windows;
 
-        const int g_aa = grid_for(h, aa_items, 8, 8);
+        // Blocks per SM of the back-end kernels: SNRX_BACK_BPS.  MEASURED (tools/ab_serial.py, ms per step with two batches
+        // queued): 8 blocks 0.404 | 4 blocks 0.402 | 2 blocks 0.422 | 1 block 0.471 -- smaller grids do not give the next
+        // batch's channelizer more of the machine, they only stretch the latency-bound chain search -> scan -> fill ->
+        // decode -> resolve -> export until it no longer fits beside one channelizer launch.
+        const int g_aa = grid_for(h, aa_items, 8, back_bps());
         k_aa_search<<<g_aa, 256, 0, st>>>(ln.d_bits, lay, p, n_chunks, ln.d_counts, ln.d_hits);
         h->launches += 1 + exclusive_scan(ln.d_counts, aa_items, ln.d_offsets, ln.d_scratch, st);
         k_aa_fill<<<g_aa, 256, 0, st>>>(ln.d_bits, ln.d_hits, lay, p, n_chunks, ln.d_counts, ln.d_offsets, ln.d_cands, h->cand_cap);
-        k_ble_decode<<<h->sm_count * 16, 128, 0, st>>>(ln.d_bits, lay, p, ln.d_offsets + aa_items, h->cand_cap, ln.d_cands,
+        k_ble_decode<<<h->sm_count * 2 * back_bps(), 128, 0, st>>>(ln.d_bits, lay, p, ln.d_offsets + aa_items, h->cand_cap, ln.d_cands,
                                                    ln.d_decs, h->d_crc_tab, h->d_whiten, h->d_ble_channels);
-        const int g_w = grid_for(h, w_items, 256, 8);
+        const int g_w = grid_for(h, w_items, 256, back_bps());
         k_ble_resolve<false><<<g_w, 256, 0, st>>>(ln.d_cands, ln.d_decs, ln.d_offsets, n_chunks, p, ln.d_wcounts, nullptr,
                                                  nullptr, 0, h->d_ble_channels, h->cand_cap);
         h->launches += 3 + exclusive_scan(ln.d_wcounts, w_items, ln.d_woffsets, ln.d_scratch, st);
@@ -808,7 +873,7 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
 
 // wait for the oldest queued batch, fill its stats; does not consume it
 static int finish_oldest(snrx_handle* h, Lane** out_lane) {
-    Lane& sl = h->lane[h->seq_poll & 1];
+    Lane& sl = h->lane[h->seq_poll % kLanes];
     if (!sl.pending) return fail(h, SNRX_ESTATE, "snrx_poll without a queued batch");
     if (!sl.done) {
         CK(cudaSetDevice(h->device));

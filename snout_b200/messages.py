@@ -48,3 +48,27 @@ def zll_scan_responses(frames: np.ndarray, mac: np.ndarray) -> list[dict]:
     sel = (mac["present"] & _abi.ZBMAC_ZLL_SCAN_RESPONSE) != 0
     return [dict(pkt=bytes(f["bytes"][: int(f["len"])]), qual=float(f["lqi"]) / 255.0, channel=int(f["channel"]))
             for f in frames[mac["frame"][sel]]]
+
+
+# ----------------------------------------------------------------------------------------------------- SURVEY 8(f) N1
+# A few well-known Bluetooth SIG company identifiers; a Snout installation passes its own table
+# (snout.core.protocols.btle.assigned_numbers.company_ids) as `company_names`.
+COMPANY_NAMES = {0x0006: "Microsoft", 0x004C: "Apple, Inc.", 0x0075: "Samsung Electronics Co. Ltd.", 0x00E0: "Google", 0x0087: "Garmin International, Inc.",
+                 0x0059: "Nordic Semiconductor ASA"}
+_OS_TEXT = {_abi.OS_NONE: "-", _abi.OS_UNDECIDED: "-", _abi.OS_IOS10: "iOS 10", _abi.OS_IOS11: "iOS 11", _abi.OS_IOS12: "iOS 12",
+            _abi.OS_WINDOWS10: "Windows 10 >= v10.0.10240.0"}
+_MODEL_TEXT = {_abi.MODEL_NONE: "-", _abi.MODEL_FITBIT_CHARGE: "Charge / Charge HR", _abi.MODEL_AIRPODS: "AirPods"}
+
+
+def device_fingerprints(devices: np.ndarray, company_names: dict | None = None) -> list[dict]:
+    """Device.vendor / .model / .os (snout/core/device.py:171-246) of every row of the GPU sender table (RxEngine.devices()):
+    the three answers are decided on the GPU by each sender's FIRST deciding packet (csrc/ble_adv.cuh); this only renders the
+    text.  Unknown company ids read '??' as in the reference (advertising.py:225)."""
+    names = COMPANY_NAMES if company_names is None else company_names
+    out = []
+    for d in devices:
+        kind = int(d["vendor_kind"])
+        vendor = "-" if kind == _abi.VENDOR_NONE else "FitBit" if kind == _abi.VENDOR_FITBIT else names.get(int(d["vendor_company"]), "??")
+        out.append(dict(address=bytes(d["adv_a"])[::-1].hex(), tx_add=int(d["tx_add"]), vendor=vendor, model=_MODEL_TEXT[int(d["model"])],
+                        os=_OS_TEXT[int(d["os"])]))
+    return out

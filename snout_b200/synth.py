@@ -201,6 +201,24 @@ def ble_capture(n: int = 10_000_000, channel: int = 37, seed: int = 1001, esn0_d
                                                      quant_scale=128.0, kind="ble_nb"))
 
 
+def ble_capture_of(pdus: list[bytes], channel: int = 37, seed: int = 1, esn0_db: float = 30.0, gap: int = 600) -> Capture:
+    """4 Msps cf32 capture (int8 grid / 128, like ble_capture) that carries exactly these advertising PDUs, in order."""
+    rng = np.random.default_rng(seed)
+    waves = [gfsk_modulate(ble_phy_bits(p, channel)) for p in pdus]
+    n = 2000 + sum(len(w) + gap for w in waves) + 4096
+    n += -n % chanplan.BLE_WINDOW
+    sig = np.zeros(n, dtype=np.complex128)
+    truth, pos = [], 2000
+    for p, w in zip(pdus, waves):
+        cfo, ph0 = float(rng.uniform(-50e3, 50e3)), float(rng.uniform(0, 2 * math.pi))
+        sig[pos:pos + len(w)] += w * np.exp(1j * (ph0 + 2 * math.pi * cfo * np.arange(len(w)) / chanplan.NB_RATE))
+        truth.append(Truth(channel, pos, pos + 8 * 4 + 8, bytes(p) + ble_crc24(p), 3))
+        pos += len(w) + gap
+    x = (sig + _awgn(n, rng, 4.0 / (10.0 ** (esn0_db / 10.0)))) * 100.0
+    q = np.clip(np.rint(np.stack([x.real, x.imag], axis=-1)), -128, 127).astype(np.float32) / 128.0
+    return Capture(q.view(np.complex64).reshape(n), chanplan.NB_RATE, truth, dict(channel=channel, seed=seed, quant_scale=128.0, kind="ble_nb"))
+
+
 # ---------------------------------------------------------------------- 802.15.4
 
 _PN0 = "11011001110000110101001000101110"   # IEEE 802.15.4-2003 table 24, data symbol 0
