@@ -37,31 +37,37 @@ constexpr int kZbSinkLead = 1024;           // the sink starts this many samples
 constexpr float kZbClamp = 16.0f;           // |z| <= pi + |DC| for any finite input; anything else (Inf / NaN samples in the
                                             // capture) is replaced by 0 so that the clock recovery state stays finite
 
+// fast_atan2f as GNU Radio publishes it (256-entry arctan table of |min| / |max| with linear interpolation, octant fix-up;
+// restated with branches in oracle/zb_oracle.c zb_tab_atan2).  Here WITHOUT a branch: sixteen of these run per output time of
+// the wideband front end, and the branchy form cost that kernel ~200 BRA + 170 BSSY/BSYNC per tile and a "branch resolving"
+// stall of 0.77 per issue (profiles/r02_zb_wb16_ncu.json).  Every arithmetic result is the one the branchy statement
+// computes: the octant cases differ only by exact operations (negation, adding +0), e.g. base - pi == -(pi - base) and
+// -hpi + base == -(hpi - base) under round-to-nearest, so  ang = +-( C + (+-base) )  with C in {0, pi, pi/2}.
+SNRX_HD float f_flip(float v, bool neg) {          // exact: v or -v
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__float_as_uint(v) ^ (neg ? 0x80000000u : 0u));
+#else
+    return neg ? -v : v;
+#endif
+}
 SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) {
     const float ya = fabsf(y), xa = fabsf(x);
-    if (!(ya > 0.0f || xa > 0.0f)) return 0.0f;
-    const float z = (ya < xa) ? f_div(ya, xa) : f_div(xa, ya);
-    float base;
-    if (z < 0.003921569f) {
-        base = z;
-    } else {
-        float alpha = f_mul(z, 255.0f);
-        const int idx = ((int)alpha) & 0xFF;
-        alpha = f_sub(alpha, (float)idx);
-        const float lo = tab[idx];
-        const float d = f_sub(tab[idx + 1], lo);
-        base = f_add(lo, f_mul(d, alpha));
-    }
+    const bool x_major = xa > ya;                             // |x| > |y|: the angle is measured from the x axis
+    const bool y_lt = ya < xa;
+    const float z = f_div(y_lt ? ya : xa, y_lt ? xa : ya);    // (ya < xa) ? ya / xa : xa / ya
+    const bool small = z < 0.003921569f;
+    float alpha = f_mul(z, 255.0f);
+    const int idx = small ? 0 : (((int)alpha) & 0xFF);        // the table is read either way; its value is dropped when small
+    alpha = f_sub(alpha, (float)idx);
+    const float lo = tab[idx];
+    const float d = f_sub(tab[idx + 1], lo);
+    const float base = small ? z : f_add(lo, f_mul(d, alpha));
     const float pi = 3.14159265358979323846f, hpi = 1.57079632679489661923f;
-    float ang;
-    if (xa > ya) {
-        if (x >= 0.0f) ang = (y >= 0.0f) ? base : -base;
-        else ang = (y >= 0.0f) ? f_sub(pi, base) : f_sub(base, pi);
-    } else {
-        if (y >= 0.0f) ang = (x >= 0.0f) ? f_sub(hpi, base) : f_add(hpi, base);
-        else ang = (x >= 0.0f) ? f_add(-hpi, base) : f_sub(-hpi, base);
-    }
-    return ang;
+    const bool xpos = x >= 0.0f, ypos = y >= 0.0f;
+    const float c = x_major ? (xpos ? 0.0f : pi) : hpi;
+    const float r = f_add(c, f_flip(base, x_major != xpos));  // x-major: base | pi - base;  y-major: hpi - base | hpi + base
+    const float ang = f_flip(r, !ypos);
+    return (ya > 0.0f || xa > 0.0f) ? ang : 0.0f;
 }
 
 // f = arg(x * conj(p))

@@ -60,3 +60,13 @@ def assert_frames_equal(got, want, keys=FRAME_KEYS, what=""):
         if not np.array_equal(got[k], want[k]):
             bad = np.nonzero(np.any(np.atleast_2d(got[k] != want[k]).reshape(len(got), -1), axis=1))[0][:5]
             raise AssertionError(f"{what}: field {k} differs at frames {bad.tolist()}: {got[k][bad]} vs {want[k][bad]}")
+
+
+def ble_expected(oracle_mod, q8, channel, **kw):
+    """Expected BLE frames of one int8 channel stream: the restatement (oracle/ble_oracle.c), and -- wherever the UNMODIFIED
+    btle_rx.c was compiled (oracle/_ref/libbtle_ref.so travels to the GPU box as a prebuilt file) -- the reference itself,
+    which must say the same."""
+    want = oracle_mod.ble_decode(q8, channel, **kw)
+    if oracle_mod.have_ref("btle_ref") and not (set(kw) - {"aa", "crc_init", "aa_mask"}):
+        assert_frames_equal(oracle_mod.ble_decode(q8, channel, impl="reference", **kw), want, what=f"unmodified btle_rx.c vs its restatement, channel {channel}")
+    return want

@@ -11,7 +11,7 @@ import xmlrpc.client
 import numpy as np
 import pytest
 
-from conftest import ROOT, assert_frames_equal
+from conftest import ROOT, assert_frames_equal, ble_expected
 from snout_b200 import _abi, btle_cli, formats, stream, synth
 
 pytestmark = pytest.mark.gpu
@@ -42,7 +42,7 @@ def test_stream_equals_whole_ble_nb(Engine, oracle_mod):
         got = _stream_all(e, cap.iq, units=6, block=33_333)
     assert len(whole) > 150
     assert_frames_equal(got, whole, what="BLE narrow band: streamed shards vs whole")
-    assert_frames_equal(whole, oracle_mod.ble_decode(oracle_mod.ble_quantize(cap.iq, 128.0), 38), what="vs oracle")
+    assert_frames_equal(whole, ble_expected(oracle_mod, oracle_mod.ble_quantize(cap.iq, 128.0), 38), what="vs oracle")
 
 
 def test_stream_equals_whole_ble_wb40(Engine):
@@ -91,7 +91,7 @@ def test_ble_access_mask(Engine, oracle_mod, golden):
             got = e.run(cap.iq)
         assert len(got) > 10
         assert_frames_equal(got, g[f"frames_{mask:08x}"], what=f"mask {mask:08x} vs reference fixture")
-        assert_frames_equal(got, oracle_mod.ble_decode(q, 37, aa_mask=mask), what=f"mask {mask:08x} vs oracle")
+        assert_frames_equal(got, ble_expected(oracle_mod, q, 37, aa_mask=mask), what=f"mask {mask:08x} vs oracle")
 
 
 # ------------------------------------------------------------------------------------ btle_rx

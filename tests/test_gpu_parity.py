@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import assert_frames_equal
+from conftest import assert_frames_equal, ble_expected
 from snout_b200 import _abi, chanplan, synth
 
 pytestmark = pytest.mark.gpu
@@ -51,7 +51,7 @@ def test_ble_nb_synthetic_vs_reference_fixture(Engine, oracle_mod, golden, seed)
     with Engine("ble_nb", channel=int(ch), max_samples=int(n)) as e:
         got = e.run(cap.iq)
     assert_frames_equal(got, g[f"frames_{seed}"], what=f"seed {seed} vs reference fixture")
-    assert_frames_equal(got, oracle_mod.ble_decode(oracle_mod.ble_quantize(cap.iq, 128.0), int(ch)), what="vs oracle")
+    assert_frames_equal(got, ble_expected(oracle_mod, oracle_mod.ble_quantize(cap.iq, 128.0), int(ch)), what="vs oracle")
 
 
 def test_ble_nb_window_boundary_rule(Engine, golden):
@@ -74,7 +74,7 @@ def test_ble_nb_batch_ragged_and_edge_cases(Engine, oracle_mod):
         got = e.run(batch)
         want = []
         for i, c in enumerate(caps):
-            f = oracle_mod.ble_decode(oracle_mod.ble_quantize(c, 128.0), 12)
+            f = ble_expected(oracle_mod, oracle_mod.ble_quantize(c, 128.0), 12)
             f["capture_id"] = i
             want.append(f)
         want = np.concatenate(want)
@@ -87,7 +87,7 @@ def test_ble_nb_batch_ragged_and_edge_cases(Engine, oracle_mod):
         rng = np.random.default_rng(7)
         noise = (rng.integers(-128, 128, (n, 2)).astype(np.float32) / 128.0).view(np.complex64).reshape(-1)
         f = e.run(noise)
-        assert_frames_equal(f, oracle_mod.ble_decode(oracle_mod.ble_quantize(noise, 128.0), 12), what="noise")
+        assert_frames_equal(f, ble_expected(oracle_mod, oracle_mod.ble_quantize(noise, 128.0), 12), what="noise")
         with pytest.raises(_abi.SnrxError):
             e.run(np.zeros(n + 2, np.complex64))          # over capacity -> SNRX_ERANGE, loudly
 
@@ -159,7 +159,7 @@ def test_ble_nb_shard_equals_whole(Engine, oracle_mod):
             parts.append(e.run(cap.iq[lo:hi].copy(), shard=dict(pre_samples=w0 * 8192 - lo, body_samples=(w1 - w0) * 8192,
                                                                first_window=w0)))
         assert_frames_equal(np.concatenate(parts), whole, what="3 shards vs whole")
-    assert_frames_equal(whole, oracle_mod.ble_decode(q, 37), what="whole vs oracle")
+    assert_frames_equal(whole, ble_expected(oracle_mod, q, 37), what="whole vs oracle")
 
 
 def test_ble_nb_full_size_config1(Engine, oracle_mod):
@@ -167,7 +167,7 @@ def test_ble_nb_full_size_config1(Engine, oracle_mod):
     cap = synth.ble_capture(n=10_000_000, channel=37, seed=1001, esn0_db=30.0)
     with Engine("ble_nb", channel=37, max_samples=10_000_000) as e:
         got = e.run(cap.iq)
-    want = oracle_mod.ble_decode(oracle_mod.ble_quantize(cap.iq, 128.0), 37)
+    want = ble_expected(oracle_mod, oracle_mod.ble_quantize(cap.iq, 128.0), 37)
     assert len(want) > 1000
     assert_frames_equal(got, want, what="config 1")
     truth = {bytes(t.data) for t in cap.truth}
@@ -177,7 +177,7 @@ def test_ble_nb_full_size_config1(Engine, oracle_mod):
 
 # ------------------------------------------------------------------------------------ BLE wideband
 def _wb_oracle_frames(oracle_mod, q8):
-    return np.concatenate([oracle_mod.ble_decode(q8[c], c) for c in range(40)])
+    return np.concatenate([ble_expected(oracle_mod, q8[c], c) for c in range(40)])
 
 
 @pytest.mark.parametrize("taps", [384, 768])
