@@ -45,16 +45,26 @@ SNRX_HD int aa_virtual_bits(uint32_t aa, uint32_t mask) {
 // the four that follow: access-address bit p is compared with the stream shifted by 4p samples.  After
 // bit p has been applied a random position survives with probability 2^-(p+1); `keep_going` lets a warp
 // stop as soon as none of its lanes has a survivor.
+// The per-position constants of the correlation, computed once on the host and passed as a kernel parameter: in the kernel they
+// are constant-bank operands of ONE LOP3 per access-address position (computing them from aa / mask in the loop cost three
+// uniform-datapath instructions per position: 143 of the kernel's 560 instructions).
+struct AaTables {
+    uint32_t want0[32];      // all ones when AA bit p is 0
+    uint32_t dont_care[32];  // all ones when position p is not compared
+};
+inline AaTables make_aa_tables(uint32_t aa, uint32_t mask_hi /* mask & ~((1<<z)-1) */) {
+    AaTables t;
+    for (int p = 0; p < 32; p++) { t.want0[p] = ((aa >> p) & 1u) - 1u; t.dont_care[p] = ((mask_hi >> p) & 1u) - 1u; }
+    return t;
+}
+
 template <class KEEP>
-SNRX_HD uint32_t aa_word_hits(const uint32_t (&w)[5], uint32_t aa, uint32_t mask_hi /* mask & ~((1<<z)-1) */,
-                              KEEP keep_going) {
+SNRX_HD uint32_t aa_word_hits(const uint32_t (&w)[5], const AaTables& t, KEEP keep_going) {
     uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
     for (int p = 0; p < 32; p++) {
         const uint32_t s = (p & 7) ? funnel_r(w[p >> 3], w[(p >> 3) + 1], 4 * (p & 7)) : w[p >> 3];   // bit i = sample i + 4p
-        const uint32_t want0 = ((aa >> p) & 1u) - 1u;                 // all ones when AA bit p is 0
-        const uint32_t dont_care = ((mask_hi >> p) & 1u) - 1u;        // all ones when position p is not compared
-        m &= (s ^ want0) | dont_care;
+        m &= (s ^ t.want0[p]) | t.dont_care[p];
         if ((p & 3) == 3 && p >= 11 && p < 31) { if (!keep_going(m)) return 0u; }
     }
     return m;
@@ -165,12 +175,10 @@ SNRX_HD void ble_fill_frame(snrx_frame_t& f, const Cand& c, const Dec& d, const 
 // s, without atomics or a sort.
 __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ bits, BitsLayout lay, BleParams p,
                                                    uint32_t n_chunks, uint32_t* __restrict__ counts,
-                                                   uint32_t* __restrict__ hits_out) {
+                                                   uint32_t* __restrict__ hits_out, const __grid_constant__ AaTables tabs) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t n_items = p.n_captures * p.n_channels * n_chunks;
-    const int z = aa_virtual_bits(p.aa, p.aa_mask);
-    const uint32_t mask_hi = p.aa_mask & ~((1u << z) - 1u);
     const uint32_t nw = lay.words_per_stream;
     for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
          item += gridDim.x * warps_per_block) {
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(256) k_aa_search(const uint32_t* __restrict__ 
         uint32_t ww[5];
 #pragma unroll
         for (int d = 0; d < 5; d++) ww[d] = (w + d < nw) ? __ldg(pw + w + d) : 0u;
-        uint32_t h = aa_word_hits(ww, p.aa, mask_hi, [](uint32_t m) { return __any_sync(0xffffffffu, m != 0u) != 0; });
+        uint32_t h = aa_word_hits(ww, tabs, [](uint32_t m) { return __any_sync(0xffffffffu, m != 0u) != 0; });
         // start positions beyond the capture carry no data
         const int nvalid = p.n_out - 32 * ((int)w - kBitsLeadWords);
         if (nvalid <= 0 || w >= nw) h = 0u; else if (nvalid < 32) h &= (1u << nvalid) - 1u;
@@ -203,9 +211,14 @@ __global__ void __launch_bounds__(256) k_aa_fill(const uint32_t* __restrict__ bi
     const int lane = threadIdx.x & 31;
     const uint32_t warps_per_block = blockDim.x >> 5;
     const uint32_t n_items = p.n_captures * p.n_channels * n_chunks;
-    for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
-         item += gridDim.x * warps_per_block) {
-        if (counts[item] == 0u) continue;                           // warp-uniform
+    // a warp takes 32 consecutive items at a time and reads their counts in ONE coalesced load: most chunks hold no hit, and
+    // a dependent global load per item made this kernel a chain of L2 round trips
+    for (uint32_t base = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * 32u; base < n_items; base += gridDim.x * warps_per_block * 32u) {
+      const uint32_t mine = (base + lane < n_items) ? __ldg(counts + base + lane) : 0u;
+      uint32_t todo = __ballot_sync(0xffffffffu, mine != 0u);
+      while (todo) {
+        const uint32_t item = base + (uint32_t)(__ffs(todo) - 1);
+        todo &= todo - 1u;
         const uint32_t chunk = item % n_chunks;
         const uint32_t ch = (item / n_chunks) % p.n_channels;
         const uint32_t cap = item / (n_chunks * p.n_channels);
@@ -230,6 +243,7 @@ __global__ void __launch_bounds__(256) k_aa_fill(const uint32_t* __restrict__ bi
             }
             dst++;
         }
+      }
     }
 }
 

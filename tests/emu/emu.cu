@@ -227,7 +227,8 @@ int emu_ble_back(const uint32_t* bits, uint32_t nw, int n_out, int m_origin, int
     for (uint32_t w = 0; w < nw; w++) {                                // k_aa_search + k_aa_fill
         uint32_t ww[5];
         for (int d = 0; d < 5; d++) ww[d] = (w + d < nw) ? bits[w + d] : 0u;
-        uint32_t h = aa_word_hits(ww, aa, mask_hi, [](uint32_t m) { return m != 0u; });
+        const AaTables tabs = make_aa_tables(aa, mask_hi);
+        uint32_t h = aa_word_hits(ww, tabs, [](uint32_t m) { return m != 0u; });
         const int nvalid = n_out - 32 * ((int)w - kBitsLeadWords);
         if (nvalid <= 0) h = 0u; else if (nvalid < 32) h &= (1u << nvalid) - 1u;
         for (int i = 0; i < 32; i++)

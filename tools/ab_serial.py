@@ -25,5 +25,6 @@ def piped(n, depth=2):
         eng.poll(copy=False)
     torch.cuda.synchronize()
     return np.median(fe[3:]), (time.perf_counter() - t0) / n * 1e3
-a = serial(25); b = piped(40); c = piped(60, 3)
+a = serial(25); b = piped(40)
+c = piped(60, 3) if os.environ.get('AB_DEPTH3') else (float('nan'), float('nan'))
 print(f"tiles={os.environ.get('SNRX_PFB_TILES','-')} order={os.environ.get('SNRX_PFB_ORDER','-')} serial: frontend {a[0]:.4f} ms, batch {a[1]:.4f} ms | two in flight: frontend {b[0]:.4f} ms, wall/step {b[1]:.4f} ms | three in flight: frontend {c[0]:.4f} ms, wall/step {c[1]:.4f} ms")
