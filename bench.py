@@ -212,6 +212,7 @@ def main():
                     "the batch SURVEY 8d prescribes for the roofline run of configs[0] / [1] (one 80-MB capture alone is launch-latency bound)")
     ap.add_argument("--no-c5", action="store_true", help="skip the configs[4]-shaped run (time-sharded mixed captures) reported under \"c5\"")
     ap.add_argument("--c5-seconds", type=float, default=9.83, help="length of the resident mixed capture of the c5 run")
+    ap.add_argument("--c5-shard-units", type=int, default=960, help="c5 run: shard body in units of 8192 channel samples (960 = 1.97 s: 5 shards per 10-s capture; measured 480: 47.2, 960: 54.2, 2400: 58.3 Gsamples/s -- longer shards give k_zb_rx more chains per launch)")
     ap.add_argument("--taps", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work timed for cpu_baseline (bounded sample)")
@@ -465,7 +466,7 @@ def main():
         xc, ctruth = synth.wideband_capture_gpu(seconds=0.983, kind="mixed", seed=5000 + 37 * rank, esn0_db=25.0, device=local,
                                                 repeat=max(1, int(round(args.c5_seconds / 0.983))))
         unit, pre, post = stream.shard_geometry(40, 16)
-        body_units = 480                                        # 480 x 8192 channel samples = 0.983 s per shard body
+        body_units = args.c5_shard_units                        # x 8192 channel samples per shard body
         ceng = RxEngine("mixed_wb56", max_samples=(body_units * unit + pre + post) * 24, pfb_taps=args.taps, device=local,
                         max_frames=1 << 18)
         cgather, ckind = make_gather(ceng)
