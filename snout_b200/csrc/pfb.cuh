@@ -304,6 +304,7 @@ struct PfbBleArgs {
     int32_t n_caps;           // captures in this launch
     int32_t tiles_per_cta;    // k_pfb_ble_run only
     int32_t tile_step;        // k_pfb_ble_run: 1 = a CTA's tiles are consecutive; gridDim.x = CTA b takes tiles b, b + grid, ...
+    int32_t l2_ahead;         // k_pfb_ble: tiles ahead whose NEW input bytes this CTA asks L2 to fetch (0 = off)
     const float4* taps_pass;  // [3][NT/4][8] float4: element (gi, d4, rl) = h[rho + 24 (4 d4 + 0..3)], rho = gi + 3 rl --
                               // the 8 FIR rows of a pass read 128 contiguous bytes per load
     float scale;              // quantiser scale
@@ -466,6 +467,15 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
 
     // ---- phase 0: stage the input tile (bulk copies for interior tiles, zero-filling cp.async at the capture ends)
     const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
+    if (a.l2_ahead > 0 && lane == 0) {
+        // the tile that a CTA `l2_ahead` launches behind this one will stage: ask L2 for the 744 samples it adds to the stream now,
+        // so that its bulk copy finds them there instead of waiting for HBM.  MEASURED (SNRX_PFB_L2_AHEAD = 0 / 1184 / 2368 /
+        // 4736 / 9472 tiles): 0.333 / 0.334 / 0.336 / 0.336 / 0.338 ms -- no gain, off by default: what a fresh CTA waits for is
+        // not HBM-vs-L2 latency
+        const int64_t xp = x0 + (int64_t)a.l2_ahead * kPfbD * B::kStride + G::kTileIn - kPfbD * B::kStride;
+        if (xp >= 0 && xp + kPfbD * B::kStride <= a.n_in)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(xcap + xp), "r"((uint32_t)(kPfbD * B::kStride * sizeof(float2))) : "memory");
+    }
 #ifdef SNRX_PROBE_NO_STAGE                                   // measurement builds only: the tile is whatever shared memory holds
     if (pfb_tile_interior<G>(x0, a.n_in)) {
     } else

@@ -589,6 +589,7 @@ constexpr int kZbLead = 64;           // samples the tracker starts ahead of the
                                       // of the tracker (2048) can only fall on a window start
 constexpr int kZbLeadMin = 44;        // a window may start with this much lead: 32 steps of 3 samples eat at most 32 of it, 8 are read
 constexpr int kZbLeadMax = 84;        // beyond it the tracker pauses for a window (the ring holds 128 >= 84 + 32 + 8)
+constexpr int kZbTapsPlane = (SNRX_MMSE_NSTEPS + 1) * 16;   // bytes of one plane of the interpolator table in shared memory
 constexpr int kZbRxWarps = 4;         // warps per CTA (they only share the interpolator table)
 #ifndef SNRX_ZB_RX_MINCTAS
 #define SNRX_ZB_RX_MINCTAS 4
@@ -605,7 +606,7 @@ struct ZbRegSrc {
     double y;              // tracker state
     uint32_t zr;           // shared-memory byte address of this lane's column of the z ring
     uint32_t zw;           // byte offset of the row the tracker writes next (row * 128)
-    uint32_t taps_adj;     // shared-memory byte address of the interpolator table - 0x68000000 (see row())
+    uint32_t taps_adj;     // shared-memory byte address of the interpolator table - 0xB4000000 (see row())
     int32_t begin;         // stream index of ring position 0 (a multiple of SNRX_IIR_BLOCK)
     int32_t conv;          // samples the tracker has converted, relative to begin
     bool enabled;          // slow windows only: the tracker runs
@@ -669,11 +670,14 @@ struct ZbRegSrc {
         for (int k = 0; k < 8; k++) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(in[k]) : "r"(p + 128u * k));
     }
     // interpolator row rint(mu * 128): mu * 128 is exact, so one FFMA with the magic number 1.5 * 2^23 gives the bits
-    // 0x4B400000 + row; (bits << 5) = 0x68000000 + 32 * row (mod 2^32), hence the adjusted base: one IMAD for the address
+    // 0x4B400000 + row; (bits << 4) = 0xB4000000 + 16 * row (mod 2^32), hence the adjusted base: one shift for the address.
+    // The table lies in shared memory as TWO planes of 16-byte rows (taps 0..3 | taps 4..7, kZbTapsPlane bytes apart): the
+    // lanes of a warp sit at unrelated rows, and 16-byte rows spread a 16-byte load over 8 bank groups where the natural
+    // 32-byte rows allowed 4 (300 M bank conflicts per 10-s capture in round 2's first ncu capture of this kernel).
     __device__ __forceinline__ void row(float mu, float (&t)[8]) const {
-        const uint32_t a = taps_adj + (__float_as_uint(__fmaf_rn(mu, (float)SNRX_MMSE_NSTEPS, 12582912.0f)) << 5);
+        const uint32_t a = taps_adj + (__float_as_uint(__fmaf_rn(mu, (float)SNRX_MMSE_NSTEPS, 12582912.0f)) << 4);
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]) : "r"(a));
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7]) : "r"(a + 16u));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7]) : "r"(a + (uint32_t)kZbTapsPlane));
     }
 };
 
@@ -699,14 +703,15 @@ __global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxMinCtas) k_zb_rx(const _
     extern __shared__ __align__(16) unsigned char zb_smem[];
     float* taps = reinterpret_cast<float*>(zb_smem);
     float* zring = taps + (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS;
-    for (int i = threadIdx.x; i < (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS; i += blockDim.x) taps[i] = a.taps[i];
+    for (int i = threadIdx.x; i < (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS; i += blockDim.x)            // [row][8] -> two planes of [row][4]
+        taps[((i & 4) ? kZbTapsPlane / 4 : 0) + (i >> 3) * 4 + (i & 3)] = a.taps[i];
     __syncthreads();
     const ZbChainParams& p = a.p;
     const uint32_t n_streams = p.n_captures * p.n_channels;
     const uint32_t total = n_streams * (uint32_t)p.n_segments;
     ZbRegSrc<DEBUG> src;
     src.zr = (uint32_t)__cvta_generic_to_shared(zring + (threadIdx.x >> 5) * ((kZbZRows + 8) * 32) + (threadIdx.x & 31));
-    src.taps_adj = (uint32_t)__cvta_generic_to_shared(taps) - 0x68000000u;
+    src.taps_adj = (uint32_t)__cvta_generic_to_shared(taps) - 0xB4000000u;
     asm volatile("" : "+r"(src.zr), "+r"(src.taps_adj));               // opaque: stay in registers
     for (;;) {
         // consecutive chains belong to different streams, so that a warp touches many DRAM pages at once
