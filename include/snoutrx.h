@@ -288,7 +288,9 @@ typedef struct snrx_device {        /* one per sender (AdvA, TxAdd), 64 bytes */
     uint8_t  ad_flags;      /* OR over its packets                                                     */
     uint32_t packets, crc_ok;
     uint64_t chan_mask;     /* bit c: seen on BLE channel c                                            */
-    int64_t  first_index, last_index;     /* channel-rate position of its first / last packet ...      */
+    int64_t  first_index, last_index;     /* channel-rate position of its first / last packet (kept modulo 2^32 samples and
+                                             2^16 captures inside the table: a stream longer than 17.9 minutes at 4 Msps
+                                             should advance capture_id -- snrx_shard_t.first_capture_id -- per 2^32 samples) */
     uint32_t first_capture, last_capture; /* ... and their capture ids                                 */
     uint16_t pdu_mask;      /* bit t: PDU type t seen                                                  */
     uint16_t present;       /* OR of SNRX_ADV_* over its packets                                       */
