@@ -212,6 +212,7 @@ def main():
                     "the batch SURVEY 8d prescribes for the roofline run of configs[0] / [1] (one 80-MB capture alone is launch-latency bound)")
     ap.add_argument("--no-c5", action="store_true", help="skip the configs[4]-shaped run (time-sharded mixed captures) reported under \"c5\"")
     ap.add_argument("--c5-seconds", type=float, default=9.83, help="length of the resident mixed capture of the c5 run")
+    ap.add_argument("--c5-depth", type=int, default=2, help="c5 run: shards queued at once (the library holds SNRX_LANES of them)")
     ap.add_argument("--c5-shard-units", type=int, default=960, help="c5 run: shard body in units of 8192 channel samples (960 = 1.97 s: 5 shards per 10-s capture; measured 480: 47.2, 960: 54.2, 2400: 58.3 Gsamples/s -- longer shards give k_zb_rx more chains per launch)")
     ap.add_argument("--taps", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -475,7 +476,7 @@ def main():
 
         def one_capture(cid, pend, stats):
             for u in units:
-                if stats["queued"] == 2:
+                if stats["queued"] == args.c5_depth:
                     fr = ceng.poll(copy=False)
                     stats["queued"] -= 1
                     stats["frames"] += len(fr)

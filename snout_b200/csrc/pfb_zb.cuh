@@ -269,7 +269,8 @@ __global__ void __launch_bounds__(32, PfbZbWarpGeom<NT>::kCtasPerSm) k_pfb_zb_wa
     }
 
     const int mg = g_first + lane;
-    if (DEBUG && a.dbg_cf && lane < B::kStride && mg < a.n_out) {
+    // (lane 31's sample belongs to the next tile -- except in the capture's last tile, which has no successor)
+    if (DEBUG && a.dbg_cf && (lane < B::kStride || tile == a.n_tiles - 1) && mg < a.n_out) {
 #pragma unroll
         for (int c = 0; c < 16; c++) {
             const int rot = (zb_bin_of_slot(c) * (mg & 3)) & 3;

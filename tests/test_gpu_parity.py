@@ -572,3 +572,18 @@ def test_c5_full_size_time_shards_equal_whole_and_truth(Engine):
     # one 802.15.4 frame in seven get through with a good FCS (measured: 220 577 / 290 970 and 3 144 / 20 330); the Zigbee
     # receive chain by itself is checked against the oracle and the transmitted frames in test_zb_wb16_stagewise_parity
     assert hits[3] >= 0.70 * n_sent[3] and hits[2] >= 0.12 * n_sent[2], stats
+
+
+def test_zb_wb16_debug_stream_holds_the_last_sample(Engine, oracle_mod):
+    """Found by tools/fuzz_parity.py: when the capture's last channel sample is lane 31 of the last tile (n_out = 31 k + 1) the
+    SNRX_STAGE_CHAN_CF32 test stream missed it (the discriminator and the frames were right: they never read that stream)."""
+    cap = synth.wideband_capture(seconds=0.01, kind="zigbee", seed=3300, esn0_db=25.0, gap=(400, 4000))
+    n_out = (len(cap.iq) // 24 - 40) // 31 * 31 + 1
+    x = cap.iq[: n_out * 24]
+    with Engine("zb_wb16", max_samples=len(x), keep_streams=True) as e:
+        e.run(x)
+        y = e.debug_stage(_abi.STAGE_CHAN_CF32)[0]
+        f = e.debug_stage(_abi.STAGE_ZB_F)[0]
+    assert y.shape[1] == n_out and np.all(np.abs(y[:, -1]) > 0)
+    for c in range(16):
+        assert np.array_equal(f[c], oracle_mod.zb_quad_demod(y[c])), c
