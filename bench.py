@@ -183,9 +183,9 @@ def ncu_traffic(n_samples):
     summary (profiles/), valid when it was captured on this same workload size; else None."""
     best = None
     import re
-    def version(name):                   # r01_pfb_ncu_v10.json -> (1, 10): newest capture last
-        m = re.match(r"r(\d+)_pfb_ncu_v(\d+)\.json$", name)
-        return (int(m.group(1)), int(m.group(2))) if m else (-1, -1)
+    def version(name):                   # r01_pfb_ncu_v10.json -> (1, 10), r02_pfb_ncu.json -> (2, 0): newest capture last
+        m = re.match(r"r(\d+)_pfb_ncu(?:_v(\d+))?\.json$", name)
+        return (int(m.group(1)), int(m.group(2) or 0)) if m else (-1, -1)
     for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), key=version):
         if version(name)[0] >= 0:
             try:
