@@ -831,15 +831,15 @@ static int process_impl(snrx_t* h, const void* iq, int fmt, uint32_t n_captures,
         // queued): 8 blocks 0.404 | 4 blocks 0.402 | 2 blocks 0.422 | 1 block 0.471 -- smaller grids do not give the next
         // batch's channelizer more of the machine, they only stretch the latency-bound chain search -> scan -> fill ->
         // decode -> resolve -> export until it no longer fits beside one channelizer launch.
-        static const int skip_back = getenv("SNRX_DEBUG_SKIP_BACK") ? atoi(getenv("SNRX_DEBUG_SKIP_BACK")) : 0;   // measurement only
         const int g_aa = grid_for(h, aa_items, 8, back_bps());
-        if (skip_back < 1)
+#ifdef SNRX_PROBE_SKIP_BACK                                  // measurement builds only: no candidates, hence no back-end work (a step then
+        CK(cudaMemsetAsync(ln.d_counts, 0, sizeof(uint32_t) * aa_items, st));     // takes 0.345 ms instead of 0.397: DESIGN.md 6)
+#else
         k_aa_search<<<g_aa, 256, 0, st>>>(ln.d_bits, lay, p, n_chunks, ln.d_counts, ln.d_hits, aa_tables_of(p));
-        if (skip_back) CK(cudaMemsetAsync(ln.d_counts, 0, sizeof(uint32_t) * aa_items, st));
+#endif
         h->launches += 1 + exclusive_scan(ln.d_counts, aa_items, ln.d_offsets, ln.d_scratch, st);
         k_aa_fill<<<grid_for(h, aa_items, 256, back_bps()), 256, 0, st>>>(ln.d_bits, ln.d_hits, lay, p, n_chunks, ln.d_counts, ln.d_offsets, ln.d_cands, h->cand_cap);
-        static const int dec_bps = getenv("SNRX_DEC_BPS") ? atoi(getenv("SNRX_DEC_BPS")) : 16;
-        k_ble_decode<<<h->sm_count * dec_bps, 128, 0, st>>>(ln.d_bits, lay, p, ln.d_offsets + aa_items, h->cand_cap, ln.d_cands,
+        k_ble_decode<<<h->sm_count * 16, 128, 0, st>>>(ln.d_bits, lay, p, ln.d_offsets + aa_items, h->cand_cap, ln.d_cands,
                                                    ln.d_decs, h->d_crc_tab, h->d_whiten, h->d_ble_channels);
         const int g_w = grid_for(h, w_items, 256, back_bps());
         k_ble_resolve<false><<<g_w, 256, 0, st>>>(ln.d_cands, ln.d_decs, ln.d_offsets, n_chunks, p, ln.d_wcounts, nullptr,
