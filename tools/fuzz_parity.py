@@ -48,10 +48,26 @@ for seed in range(7100, 7100 + int(os.environ.get("FUZZ_ZB", 8))):
     with RxEngine("zb_wb16", max_samples=len(x), zb_segment=seg, zb_prehalo=pre) as e:
         assert_frames_equal(e.run(x), want, what=f"zb production kernel seed {seed}")
     n_zb += len(want)
+n_nb = 0
+for seed in range(7300, 7300 + int(os.environ.get("FUZZ_NB", 6))):
+    rng = np.random.default_rng(seed)
+    ch = int(rng.choice([37, 38, 39, 5, 22]))
+    n = int(rng.integers(60_000, 400_000))
+    cap = synth.ble_capture(n=n, channel=ch, seed=seed, esn0_db=float(rng.choice([8.0, 12.0, 20.0, 30.0])))
+    with RxEngine("ble_nb", channel=ch, max_samples=n) as e:
+        got = e.run(cap.iq)
+    want = ble_expected(oracle, oracle.ble_quantize(cap.iq, 128.0), ch)
+    assert_frames_equal(got, want, what=f"ble_nb seed {seed} ch {ch} n {n}")
+    zch = int(rng.integers(11, 27))
+    zc = synth.zigbee_capture(n=n, channel=zch, seed=seed, esn0_db=float(rng.choice([9.0, 12.0, 20.0, 30.0])))
+    with RxEngine("zb_nb", channel=zch, max_samples=n) as e:
+        gz = e.run(zc.iq)
+    assert_frames_equal(gz, oracle.zb_receive(zc.iq, zch), what=f"zb_nb seed {seed} ch {zch} n {n}")
+    n_nb += len(want) + len(gz)
 for seed in range(7200, 7204):
     cap = synth.wideband_capture(seconds=0.0125, kind="mixed", seed=seed, esn0_db=20.0, gap=(400, 5000))
     with RxEngine("ble_wb40", max_samples=len(cap.iq)) as e: a = e.run(cap.iq)
     with RxEngine("zb_wb16", max_samples=len(cap.iq)) as e: b = e.run(cap.iq)
     with RxEngine("mixed_wb56", max_samples=len(cap.iq)) as e: m = e.run(cap.iq)
     assert_frames_equal(m, np.concatenate([a, b]), what=f"mixed seed {seed}")
-print(f"fuzz ok: {n_ble} BLE frames over {os.environ.get('FUZZ_BLE', 12)} captures, {n_zb} 802.15.4 frames over {os.environ.get('FUZZ_ZB', 8)} captures, 4 mixed captures, {time.time() - t0:.0f} s")
+print(f"fuzz ok: {n_ble} BLE frames over {os.environ.get('FUZZ_BLE', 12)} captures, {n_zb} 802.15.4 frames over {os.environ.get('FUZZ_ZB', 8)} captures, 4 mixed captures, {n_nb} narrow-band frames over 2 x {os.environ.get('FUZZ_NB', 6)} captures, {time.time() - t0:.0f} s")
