@@ -202,6 +202,10 @@ struct PfbZbWarpArgs {
     float2* dbg_cf;            // [cap][16][n_out] rotated channel streams, or null
 };
 
+#ifndef SNRX_PFB_ZB_UNROLL
+#define SNRX_PFB_ZB_UNROLL 1          // 1 = the pass loop stays a loop; 3 = unrolled (round 2's first version)
+#endif
+constexpr int kZbPassUnroll = SNRX_PFB_ZB_UNROLL;
 template <int NT, bool DEBUG>
 __global__ void __launch_bounds__(32, PfbZbWarpGeom<NT>::kCtasPerSm) k_pfb_zb_warp(PfbZbWarpArgs a) {
     using B = PfbZbWarpGeom<NT>;
@@ -233,7 +237,11 @@ __global__ void __launch_bounds__(32, PfbZbWarpGeom<NT>::kCtasPerSm) k_pfb_zb_wa
     cf y[16];
     {
         const int rl = lane & 7, c = lane >> 3;
-#pragma unroll
+        // The three passes are ONE loop body (not unrolled): FIR and 32-point transform are the same code for every gi, only
+        // the 16 twiddles of the accumulation differ.  Unrolled, the kernel is 2656 instructions = 42 KB of straight-line code
+        // that every one-warp CTA runs through exactly once -- more than the 32 KB instruction cache of the SM, and ncu showed
+        // 11 % of the warp time as no_instruction; rolled it is a third of that.  Same operations in the same order.
+#pragma unroll kZbPassUnroll
         for (int gi = 0; gi < 3; gi++) {
             const int rho = gi + 3 * rl;
             float g[NT];

@@ -594,6 +594,9 @@ constexpr int kZbRxWarps = 4;         // warps per CTA (they only share the inte
 #ifndef SNRX_ZB_RX_MINCTAS
 #define SNRX_ZB_RX_MINCTAS 4
 #endif
+#ifndef SNRX_ZB_RX_REFILL
+#define SNRX_ZB_RX_REFILL 1             // 1 = lanes take their next chain inside the window loop; 0 = chain loop around a window loop
+#endif
 constexpr int kZbRxCtasPerSm = 3;          // what shared memory allows (74 KB per CTA)
 constexpr int kZbRxMinCtas = SNRX_ZB_RX_MINCTAS;   // register budget of the kernel: 65536 / (128 * this)
 constexpr int kZbRxSmem = (SNRX_MMSE_NSTEPS + 1) * SNRX_MMSE_NTAPS * 4 + kZbRxWarps * (kZbZRows + 8) * 32 * 4;
@@ -713,6 +716,58 @@ __global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxMinCtas) k_zb_rx(const _
     src.zr = (uint32_t)__cvta_generic_to_shared(zring + (threadIdx.x >> 5) * ((kZbZRows + 8) * 32) + (threadIdx.x & 31));
     src.taps_adj = (uint32_t)__cvta_generic_to_shared(taps) - 0xB4000000u;
     asm volatile("" : "+r"(src.zr), "+r"(src.taps_adj));               // opaque: stay in registers
+#if SNRX_ZB_RX_REFILL
+    // ONE loop over windows for the whole life of the warp: a lane whose chain has ended takes the next chain from the queue at
+    // the top of the next iteration while the other lanes of its warp carry on with theirs.  (Round 2's first version nested
+    // the window loop inside the chain loop; the warp reconverges behind the inner loop, so every lane waited for the longest
+    // of the warp's 32 chains -- a chain that holds a frame follows it through the post halo and runs up to 3.7x as long as an
+    // empty one: ncu counted 13.5 active lanes per instruction, profiles/r02_zb_wb16_ncu_v2.json.)  Which lane runs which chain
+    // has no influence on any result: a chain's state is private and its records go to the chain's own slots.
+    ZbChain c;
+    uint32_t chain = 0;
+    float* chips_dbg = nullptr;
+    bool have = false, more = true;
+    for (;;) {
+        if (!have && more) {
+            // consecutive chains belong to different streams, so that a warp touches many DRAM pages at once
+            const uint32_t idx = atomicAdd(a.queue, 1u);
+            if (idx >= total) {
+                more = false;
+            } else {
+                const uint32_t seg = idx / n_streams, sc = idx % n_streams;
+                const uint32_t cap = sc / p.n_channels, ch = sc % p.n_channels;
+                chain = sc * (uint32_t)p.n_segments + seg;                 // output order
+                zb_chain_init(c, p, (int)seg, a.channel_numbers[ch], p.first_capture + cap, a.slots + (size_t)chain * p.slots_per_chain);
+                src.z_dbg = (DEBUG && a.z_dbg) ? a.z_dbg + (size_t)sc * p.f_stride : nullptr;
+                src.z_lo = seg == 0 ? 0 : c.em.lo; src.z_hi = (int)seg == p.n_segments - 1 ? p.n_out : c.hi;
+                src.start(a.f + (size_t)sc * p.f_stride, a.carry + (size_t)sc * p.n_blocks, c.begin);
+                chips_dbg = (DEBUG && a.chips_dbg) ? a.chips_dbg + (size_t)chain * a.chips_cap : nullptr;
+                have = true;
+            }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;                         // the queue is empty and every lane's chain has ended
+        if (have) {
+            // re-centre the tracker's lead (rare: a lane drifts by about one sample per window)
+            int lead = src.conv - (c.mm.ii - src.begin);
+            while (lead < kZbLeadMin) { src.burst(); src.burst(); src.burst(); src.burst(); lead += 8 * kZbQueue; }
+            src.enabled = lead <= kZbLeadMax;
+            ZbWin w;
+            if (src.enabled && src.aligned() && c.mm.ii + 8 + 3 * 32 <= c.end) {
+                src.boundary();
+                zb_chain_steps<true, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
+            } else {
+                zb_chain_steps<false, DEBUG>(c, src, w, chips_dbg, a.chips_cap);
+            }
+            if (zb_chain_sink(c, w, a.map.w, p.threshold)) {
+                a.good_end[chain] = c.em.good_end;
+                a.counts[chain] = c.em.nf < p.slots_per_chain ? c.em.nf : p.slots_per_chain;
+                if (c.em.nf > p.slots_per_chain) *a.overflow = 1u;
+                if (DEBUG && a.nchips_dbg) a.nchips_dbg[chain] = c.nchips;
+                have = false;
+            }
+        }
+    }
+#else
     for (;;) {
         // consecutive chains belong to different streams, so that a warp touches many DRAM pages at once
         const uint32_t idx = atomicAdd(a.queue, 1u);
@@ -746,6 +801,7 @@ __global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxMinCtas) k_zb_rx(const _
         if (c.em.nf > p.slots_per_chain) *a.overflow = 1u;
         if (DEBUG && a.nchips_dbg) a.nchips_dbg[chain] = c.nchips;
     }
+#endif
 }
 
 // one thread per chain: drop the CRC-failed records that lie inside a CRC-ok frame of this or a preceding chain
