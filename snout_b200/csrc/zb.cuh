@@ -856,6 +856,7 @@ struct ZbState {
     float* d_chips = nullptr; int64_t* d_nchips = nullptr; int64_t chips_cap = 0;
     float *d_wb_taps_rho = nullptr, *d_wb_taps_flat = nullptr, *d_wb_taps_pass = nullptr; float2* d_wb_cf = nullptr; int wb_nt = 16;
     bool wb_cta_kernel = false;   // wideband front end
+    uint32_t rx_cta_cap = 0;      // SNRX_ZB_RX_CTAS: upper bound of k_zb_rx's grid (tests: few lanes, many chains per lane); 0 = none
     ChipMap map;
     uint32_t last_chains = 0;
 };
@@ -883,6 +884,7 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     (void)sm_count;
     static_assert(SNRX_IIR_BLOCK == SNRX_ZB_IIR_BLOCK && SNRX_IIR_MEMORY_BLOCKS == SNRX_ZB_IIR_MEMORY_BLOCKS, "include/snoutrx.h and zb_tables.h disagree");
     s.n_ch = n_ch; s.max_caps = max_caps; s.max_out = max_out;
+    { const char* e = getenv("SNRX_ZB_RX_CTAS"); const int v = e ? atoi(e) : 0; s.rx_cta_cap = v > 0 ? (uint32_t)v : 0u; }
     if (cfg.zb_segment % SNRX_IIR_BLOCK || cfg.zb_prehalo % SNRX_IIR_BLOCK) {
         err = "zigbee: zb_segment and zb_prehalo must be multiples of 2048 (the DC tracker's block grid)"; return SNRX_EINVAL;
     }
@@ -980,7 +982,8 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     a.queue = s.d_queue;
     ZCK(cudaMemsetAsync(s.d_queue, 0, sizeof(uint32_t), st));
     const uint32_t per_cta = kZbRxWarps * 32;
-    const uint32_t grid = std::min<uint32_t>((n_chains + per_cta - 1) / per_cta, (uint32_t)sm_count * kZbRxCtasPerSm);
+    uint32_t grid = std::min<uint32_t>((n_chains + per_cta - 1) / per_cta, (uint32_t)sm_count * kZbRxCtasPerSm);
+    if (s.rx_cta_cap) grid = std::min(grid, s.rx_cta_cap);
     if (keep) ZCK(cudaMemsetAsync(s.d_z, 0, (size_t)streams * s.stride * sizeof(float), st));
     if (keep) k_zb_rx<true><<<grid, per_cta, kZbRxSmem, st>>>(a);
     else k_zb_rx<false><<<grid, per_cta, kZbRxSmem, st>>>(a);

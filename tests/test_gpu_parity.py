@@ -275,6 +275,36 @@ def test_zb_nb_parity(Engine, oracle_mod, seed, esn0, segment):
         assert np.array_equal(chips[k, : len(ck)], ck), k
 
 
+def test_zb_nb_lanes_take_several_chains(Engine, oracle_mod, monkeypatch):
+    """k_zb_rx hands chains to LANES from a queue inside its window loop.  With the grid capped at one CTA (128 lanes) the 733
+    chains of this capture make every lane run five or six chains, restarting at different windows than its neighbours:
+    DC-removed stream, frames and the soft chips of every chain must still be the oracle's, bit for bit."""
+    monkeypatch.setenv("SNRX_ZB_RX_CTAS", "1")
+    cap = synth.zigbee_capture(n=3_000_000, channel=15, seed=2011, esn0_db=14.0)
+    with Engine("zb_nb", channel=15, max_samples=len(cap.iq), keep_streams=True) as e:
+        got = e.run(cap.iq)
+        z = e.debug_stage(_abi.STAGE_ZB_DISC)[0, 0]
+        nchips = e.debug_stage(_abi.STAGE_ZB_NCHIPS)
+        chips = e.debug_stage(_abi.STAGE_ZB_CHIPS)
+    monkeypatch.delenv("SNRX_ZB_RX_CTAS")
+    with Engine("zb_nb", channel=15, max_samples=len(cap.iq)) as e:
+        free = e.run(cap.iq)
+    seg, pre = _abi.ZB_SEGMENT_DEFAULT, _abi.ZB_PREHALO_DEFAULT
+    zo = oracle_mod.zb_dc_remove(oracle_mod.zb_quad_demod(cap.iq))
+    assert np.array_equal(z, zo)
+    want = oracle_mod.zb_receive(cap.iq, 15, segment=seg, prehalo=pre)
+    assert len(want) > 20
+    assert_frames_equal(got, want, what="one CTA, many chains per lane")
+    assert_frames_equal(free, want, what="default grid")
+    n_chains = -(-len(zo) // seg)
+    assert n_chains > 5 * 128 and len(nchips) == n_chains
+    for k in range(0, n_chains, 7):
+        lo, hi = k * seg, min(len(zo), (k + 1) * seg)
+        _, ck, _ = oracle_mod.zb_chain(zo, max(0, lo - pre), min(len(zo), hi + 16448), lo, hi, want_chips=True, hold=lo - 1024)
+        assert nchips[k] == len(ck), (k, nchips[k], len(ck))
+        assert np.array_equal(chips[k, : len(ck)], ck), k
+
+
 def test_zb_nb_batch_and_set_channel(Engine, oracle_mod):
     n = 300_000
     caps = [synth.zigbee_capture(n=n, channel=20, seed=600 + i, esn0_db=20.0, gap=(500, 6000)).iq for i in range(3)]
