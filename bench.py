@@ -213,7 +213,7 @@ def main():
     ap.add_argument("--no-c5", action="store_true", help="skip the configs[4]-shaped run (time-sharded mixed captures) reported under \"c5\"")
     ap.add_argument("--c5-seconds", type=float, default=9.83, help="length of the resident mixed capture of the c5 run")
     ap.add_argument("--c5-depth", type=int, default=2, help="c5 run: shards queued at once (the library holds SNRX_LANES of them)")
-    ap.add_argument("--c5-shard-units", type=int, default=960, help="c5 run: shard body in units of 8192 channel samples (960 = 1.97 s: 5 shards per 10-s capture; measured 480: 47.2, 960: 54.2, 2400: 58.3 Gsamples/s -- longer shards give k_zb_rx more chains per launch)")
+    ap.add_argument("--c5-shard-units", type=int, default=2400, help="c5 run: shard body in units of 8192 channel samples (2400 = 4.9 s: 2 shards per 10-s capture; measured 480: 47.2, 960: 51.3-54.2, 2400: 56.3-58.3 Gsamples/s -- longer shards give k_zb_rx more chains per launch)")
     ap.add_argument("--taps", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work timed for cpu_baseline (bounded sample)")

@@ -56,21 +56,22 @@ SNRX_HD void pfb_dft96_combine(const cf* f0, const cf* f1, const cf* f2, cf (&y)
 }
 
 // discriminator of slot C from un-rotated y[m] (cur) and y[m+1] (nxt)
-template <int C>
-SNRX_HD float zb_disc(const cf& cur, const cf& nxt, const float* tab) {
+template <int C, class Tab>
+SNRX_HD float zb_disc_g(const cf& cur, const cf& nxt, Tab tab) {
     // d = nxt * conj(cur), then times (-j)^k
     const float re = f_add(f_mul(nxt.r, cur.r), f_mul(nxt.i, cur.i));
     const float im = f_sub(f_mul(nxt.i, cur.r), f_mul(nxt.r, cur.i));
     constexpr int rot = zb_bin_of_slot(C) & 3;
     const float rr = rot == 0 ? re : rot == 1 ? im : rot == 2 ? -re : -im;
     const float ii = rot == 0 ? im : rot == 1 ? -re : rot == 2 ? -im : re;
-    return tab_atan2(ii, rr, tab);
+    return tab_atan2_g(ii, rr, tab);
 }
+template <int C>
+SNRX_HD float zb_disc(const cf& cur, const cf& nxt, const float* tab) { return zb_disc_g<C>(cur, nxt, AtanTab{tab}); }
 
 #if defined(__CUDACC__)
-template <int C>
-__device__ __forceinline__ void zb_disc_all(const cf (&y)[16], const float2* next_warp_first, int lane, const float* tab,
-                                            float (&out)[16]);
+template <int C, bool EDGE = true, class Tab = AtanTab>
+__device__ __forceinline__ void zb_disc_all(const cf (&y)[16], const float2* next_warp_first, int lane, Tab tab, float (&out)[16]);
 
 struct PfbZbArgs {
     const float2* x; uint64_t stride; int64_t n_in; int32_t n_out; int32_t n_tiles; int32_t tile0;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(kZbFirThreads, 1) k_pfb_zb(PfbZbArgs a) {
         }
         asm volatile("bar.sync 1, 128;\n" ::);
         float out[16];
-        zb_disc_all<0>(y, edge + ((wid + 1) & 3) * 16, lane, tab, out);
+        zb_disc_all<0>(y, edge + ((wid + 1) & 3) * 16, lane, AtanTab{tab}, out);
         const int n = mg + 1;                                           // f[n] pairs y[n] with y[n-1]
         if (m < kTileStride && n < a.n_out) {
 #pragma unroll
@@ -149,15 +150,25 @@ __global__ void __launch_bounds__(kZbFirThreads, 1) k_pfb_zb(PfbZbArgs a) {
     }
 }
 
-template <int C>
-__device__ __forceinline__ void zb_disc_all(const cf (&y)[16], const float2* next_warp_first, int lane, const float* tab,
-                                            float (&out)[16]) {
+// EDGE: lane 31's successor is the first sample of the next warp (k_pfb_zb); the one-warp tile never stores lane 31's value
+// (its successor belongs to the next tile), so there the fix-up -- a predicated address computation and shared-memory load
+// per channel -- is left out
+template <int C, bool EDGE, class Tab>
+__device__ __forceinline__ void zb_disc_all(const cf (&y)[16], const float2* next_warp_first, int lane, Tab tab, float (&out)[16]) {
     cf nxt;
-    nxt.r = __shfl_down_sync(0xffffffffu, y[C].r, 1);
-    nxt.i = __shfl_down_sync(0xffffffffu, y[C].i, 1);
-    if (lane == 31) { const float2 t = next_warp_first[C]; nxt.r = t.x; nxt.i = t.y; }
-    out[C] = zb_disc<C>(y[C], nxt, tab);
-    if constexpr (C + 1 < 16) zb_disc_all<C + 1>(y, next_warp_first, lane, tab, out);
+    if (EDGE) {
+        nxt.r = __shfl_down_sync(0xffffffffu, y[C].r, 1);
+        nxt.i = __shfl_down_sync(0xffffffffu, y[C].i, 1);
+        if (lane == 31) { const float2 t = next_warp_first[C]; nxt.r = t.x; nxt.i = t.y; }
+    } else {
+        // lane 31 pairs with lane 0 (any ordinary sample will do: its value is dropped).  With shfl_down it would pair with
+        // ITSELF: y conj(y) has a zero imaginary part, 0 / |y|^2 sends the IEEE division of tab_atan2 down its slow path, and the
+        // whole warp waits for one lane's subroutine call in every channel of every tile (measured: the front end 24 % slower)
+        nxt.r = __shfl_sync(0xffffffffu, y[C].r, (lane + 1) & 31);
+        nxt.i = __shfl_sync(0xffffffffu, y[C].i, (lane + 1) & 31);
+    }
+    out[C] = zb_disc_g<C>(y[C], nxt, tab);
+    if constexpr (C + 1 < 16) zb_disc_all<C + 1, EDGE, Tab>(y, next_warp_first, lane, tab, out);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -198,7 +209,7 @@ struct PfbZbWarpArgs {
     const float2* x; uint64_t stride; int64_t n_in; int32_t n_out; int32_t n_tiles;
     const float4* taps_pass;   // [3][NT/4][8] float4, as PfbBleArgs::taps_pass
     float* f; size_t f_stride; // [cap][16][f_stride]
-    const float* atan_tab;     // [257] global (L1 resident)
+    const float2* atan_pairs;  // [256] AtanTabPairs, global (L1 resident)
     float2* dbg_cf;            // [cap][16][n_out] rotated channel streams, or null
 };
 
@@ -288,8 +299,7 @@ __global__ void __launch_bounds__(32, PfbZbWarpGeom<NT>::kCtasPerSm) k_pfb_zb_wa
         }
     }
     float out[16];
-    zb_disc_all<0>(y, reinterpret_cast<const float2*>(xs) /* lane 31's successor is not in the tile: value unused */,
-                   lane, a.atan_tab, out);
+    zb_disc_all<0, false>(y, nullptr /* lane 31's successor is not in the tile: its value is never stored */, lane, AtanTabPairs{a.atan_pairs}, out);
     const int n = mg + 1;                                                   // f[n] pairs y[n] with y[n-1]
     if (lane < B::kStride && n < a.n_out) {
 #pragma unroll
@@ -342,7 +352,7 @@ inline int zb_wideband_front(ZbState& s, const snrx_config_t& cfg, const float2*
         a.x = x; a.stride = stride; a.n_in = (int64_t)n_samples; a.n_out = (int32_t)n_out;
         a.n_tiles = (int32_t)std::max<uint32_t>(1u, (n_out - 1 + 30) / 31);
         a.taps_pass = reinterpret_cast<const float4*>(s.d_wb_taps_pass);
-        a.f = s.d_f; a.f_stride = s.stride; a.atan_tab = s.d_atan; a.dbg_cf = s.d_wb_cf;
+        a.f = s.d_f; a.f_stride = s.stride; a.atan_pairs = s.d_atan_pairs; a.dbg_cf = s.d_wb_cf;
         const dim3 grid((unsigned)a.n_tiles * n_captures);
         if (s.wb_nt == 16) {
             if (dbg) k_pfb_zb_warp<16, true><<<grid, 32, PfbZbWarpGeom<16>::kSmemBytes, st>>>(a);

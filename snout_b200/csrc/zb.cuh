@@ -50,7 +50,24 @@ SNRX_HD float f_flip(float v, bool neg) {          // exact: v or -v
     return neg ? -v : v;
 #endif
 }
-SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) {
+// the table as the kernels read it: entry idx and the step to entry idx + 1
+struct AtanTab {                                   // the 257 values themselves
+    const float* t;
+    SNRX_HD void get(int idx, float& lo, float& d) const { lo = t[idx]; d = f_sub(t[idx + 1], lo); }
+};
+struct AtanTabPairs {                              // [256] {tab[i], tab[i+1] - tab[i]}: the same single-precision subtraction, done once on
+    const float2* t;                               // the host (zb_create) -- one 8-byte load per lookup instead of two loads and an FADD
+    SNRX_HD void get(int idx, float& lo, float& d) const {
+#ifdef __CUDA_ARCH__
+        const float2 e = __ldg(t + idx);
+#else
+        const float2 e = t[idx];
+#endif
+        lo = e.x; d = e.y;
+    }
+};
+template <class Tab>
+SNRX_HD float tab_atan2_g(float y, float x, Tab tab) {
     const float ya = fabsf(y), xa = fabsf(x);
     const bool x_major = xa > ya;                             // |x| > |y|: the angle is measured from the x axis
     const bool y_lt = ya < xa;
@@ -59,8 +76,8 @@ SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) {
     float alpha = f_mul(z, 255.0f);
     const int idx = small ? 0 : (((int)alpha) & 0xFF);        // the table is read either way; its value is dropped when small
     alpha = f_sub(alpha, (float)idx);
-    const float lo = tab[idx];
-    const float d = f_sub(tab[idx + 1], lo);
+    float lo, d;
+    tab.get(idx, lo, d);
     const float base = small ? z : f_add(lo, f_mul(d, alpha));
     const float pi = 3.14159265358979323846f, hpi = 1.57079632679489661923f;
     const bool xpos = x >= 0.0f, ypos = y >= 0.0f;
@@ -69,6 +86,7 @@ SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) {
     const float ang = f_flip(r, !ypos);
     return (ya > 0.0f || xa > 0.0f) ? ang : 0.0f;
 }
+SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) { return tab_atan2_g(y, x, AtanTab{tab}); }
 
 // f = arg(x * conj(p))
 SNRX_HD float quad_demod(float xr, float xi, float pr, float pi, const float* tab) {
@@ -848,6 +866,7 @@ struct ZbState {
     double *d_block_end = nullptr, *d_carry = nullptr;
     double decay = 0.0;
     float *d_atan = nullptr, *d_mmse = nullptr;
+    float2* d_atan_pairs = nullptr;   // AtanTabPairs
     int32_t* d_channels = nullptr;
     snrx_frame_t* d_slots = nullptr; size_t slots_bytes = 0;
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr, *d_queue = nullptr;
@@ -863,7 +882,7 @@ struct ZbState {
 
 inline void zb_free(ZbState& s) {
     void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
-                    s.d_counts, s.d_offsets, s.d_scratch, s.d_queue, s.d_good_end, s.d_chips, s.d_nchips, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
+                    s.d_counts, s.d_offsets, s.d_scratch, s.d_queue, s.d_good_end, s.d_chips, s.d_nchips, s.d_atan_pairs, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     s = ZbState();
 }
@@ -903,6 +922,12 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     s.decay = zb_iir_block_decay();
     ZCK(cudaMalloc((void**)&s.d_atan, sizeof(SNRX_ATAN_TAB)));
     ZCK(cudaMemcpy(s.d_atan, SNRX_ATAN_TAB, sizeof(SNRX_ATAN_TAB), cudaMemcpyHostToDevice));
+    {
+        std::vector<float2> pairs(256);
+        for (int i = 0; i < 256; i++) pairs[i] = make_float2(SNRX_ATAN_TAB[i], f_sub(SNRX_ATAN_TAB[i + 1], SNRX_ATAN_TAB[i]));
+        ZCK(cudaMalloc((void**)&s.d_atan_pairs, sizeof(float2) * 256));
+        ZCK(cudaMemcpy(s.d_atan_pairs, pairs.data(), sizeof(float2) * 256, cudaMemcpyHostToDevice));
+    }
     ZCK(cudaMalloc((void**)&s.d_mmse, sizeof(SNRX_MMSE_TAPS)));
     ZCK(cudaMemcpy(s.d_mmse, SNRX_MMSE_TAPS, sizeof(SNRX_MMSE_TAPS), cudaMemcpyHostToDevice));
     int32_t chans[16];
