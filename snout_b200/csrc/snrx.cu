@@ -257,8 +257,8 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
     using B = PfbBleGeom<NT>;
     using G = typename B::G;
     if (!a) {
-        CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
-        CK(cudaFuncSetAttribute(k_pfb_ble<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes * SNRX_PFB_WARPS));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes * SNRX_PFB_WARPS));
         CK(cudaFuncSetAttribute(k_pfb_ble_run<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
         CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaFuncSetAttribute(k_pfb_ble_run<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -273,9 +273,9 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
         if (t1 <= t0) return;
         PfbBleArgs b = args;
         b.tile0 = t0; b.n_tiles = t1 - t0;
-        const dim3 grid((unsigned)(t1 - t0) * caps);
-        if (dbg) k_pfb_ble<NT, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
-        else k_pfb_ble<NT, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
+        const dim3 grid(((unsigned)(t1 - t0) * caps + SNRX_PFB_WARPS - 1) / SNRX_PFB_WARPS);
+        if (dbg) k_pfb_ble<NT, true><<<grid, B::kThreads * SNRX_PFB_WARPS, B::kSmemBytes * SNRX_PFB_WARPS, st>>>(b);
+        else k_pfb_ble<NT, false><<<grid, B::kThreads * SNRX_PFB_WARPS, B::kSmemBytes * SNRX_PFB_WARPS, st>>>(b);
         h->launches++;
     };
     const int t0 = a->tile0, t1 = a->tile0 + a->n_tiles, per = pfb_tiles_per_cta();

@@ -538,7 +538,15 @@ struct ZbIirArgs {
     double* block_end;    // [stream][n_blocks]  block-local recurrence value at the block end
     double* carry_in;     // [stream][n_blocks]  carried state entering each block
     double decay;         // (1-alpha)^SNRX_IIR_BLOCK
+    uint8_t* busy;        // [stream][n_blocks]  a frame seems to be on the air at the block's end (zb_chain_key), or null
 };
+
+// Scheduling hint only -- it never touches a result.  The discriminator output of an O-QPSK burst moves by +-pi/4 per sample
+// (sum of f^2 over 64 samples: 37..51 at 25..9 dB Es/N0, p99 66), noise on an empty channel gives 172 (p1 125), a GFSK burst
+// in a shared bin of a mixed capture about 10 (measured on the oracle's channel streams).
+constexpr float kZbBusyLo = 24.0f, kZbBusyHi = 92.0f;
+constexpr int kZbBusyWindow = 64;
+constexpr int kZbKeys = 10;           // zb_chain_key() values 0 .. kZbKeys - 1
 
 // A (stream, block) unit is one thread's SNRX_IIR_BLOCK-sample serial recurrence from 0.  Its samples are contiguous and
 // 128-byte aligned, so the thread streams them as float4 with the next 32 samples (8 loads) already in
@@ -576,6 +584,17 @@ __global__ void __launch_bounds__(64) k_zb_iir_sum(ZbIirArgs a) {
     }
     for (int i = n4 << 2; i < len; i++) l = zb_iir_step(l, f[i]);
     a.block_end[(size_t)s * a.n_blocks + b] = l;
+    if (a.busy) {
+        float e = 0.0f;
+        if (len == SNRX_IIR_BLOCK) {
+#pragma unroll
+            for (int k = 0; k < kZbBusyWindow / 4; k++) {
+                const float4 v = __ldg(f4 + (SNRX_IIR_BLOCK - kZbBusyWindow) / 4 + k);      // just read: L1
+                e += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            }
+        }
+        a.busy[(size_t)s * a.n_blocks + b] = (uint8_t)(e > kZbBusyLo && e < kZbBusyHi);
+    }
 }
 
 // carried state entering block b: folded from the SNRX_IIR_MEMORY_BLOCKS preceding blocks (all full
@@ -709,6 +728,7 @@ struct ZbRxArgs {
     const int32_t* channel_numbers;
     snrx_frame_t* slots; uint32_t* counts; int64_t* good_end;
     uint32_t* queue;             // next chain to hand out (zeroed before the launch)
+    const uint32_t* order;       // [n_chains] queue position -> chain in natural order (k_zb_order), or null = natural order
     uint32_t* overflow;          // set to 1 when a chain found more frames than it has slots
     float* z_dbg;                // [stream][f_stride] or null
     float* chips_dbg; int64_t chips_cap; int64_t* nchips_dbg;
@@ -748,10 +768,11 @@ __global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxMinCtas) k_zb_rx(const _
     for (;;) {
         if (!have && more) {
             // consecutive chains belong to different streams, so that a warp touches many DRAM pages at once
-            const uint32_t idx = atomicAdd(a.queue, 1u);
-            if (idx >= total) {
+            const uint32_t pos = atomicAdd(a.queue, 1u);
+            if (pos >= total) {
                 more = false;
             } else {
+                const uint32_t idx = a.order ? __ldg(a.order + pos) : pos;
                 const uint32_t seg = idx / n_streams, sc = idx % n_streams;
                 const uint32_t cap = sc / p.n_channels, ch = sc % p.n_channels;
                 chain = sc * (uint32_t)p.n_segments + seg;                 // output order
@@ -788,8 +809,9 @@ __global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxMinCtas) k_zb_rx(const _
 #else
     for (;;) {
         // consecutive chains belong to different streams, so that a warp touches many DRAM pages at once
-        const uint32_t idx = atomicAdd(a.queue, 1u);
-        if (idx >= total) break;
+        const uint32_t pos = atomicAdd(a.queue, 1u);
+        if (pos >= total) break;
+        const uint32_t idx = a.order ? __ldg(a.order + pos) : pos;
         const uint32_t seg = idx / n_streams, sc = idx % n_streams;
         const uint32_t cap = sc / p.n_channels, ch = sc % p.n_channels;
         const uint32_t chain = sc * (uint32_t)p.n_segments + seg;      // output order
@@ -820,6 +842,64 @@ __global__ void __launch_bounds__(kZbRxWarps * 32, kZbRxMinCtas) k_zb_rx(const _
         if (DEBUG && a.nchips_dbg) a.nchips_dbg[chain] = c.nchips;
     }
 #endif
+}
+
+// ---- the order in which k_zb_rx hands out its chains ------------------------------------------------------------------------
+// A chain that finds a frame in its body follows it through the post halo and runs up to 3.6 times as long as an empty one
+// (2048 + 4096 + 16448 samples against 6144); a lane that takes such a chain late keeps its warp -- and its CTA's 74 KB of
+// shared memory -- alive long after the queue has run dry.  ncu of round 2's k_zb_rx: 15.9 of 32 lanes active per instruction on
+// a 4.9-s capture; a model of the queue (a lane takes the next chain when it is done, a warp lives as long as its longest
+// lane) gives the same factor 2.0 for the natural order and 1.05 when the long chains go first.  So the chains are handed out
+// longest (expected) first.  The key of a chain: 0 when nothing seems to be on the air at the end of its body -- or when the
+// air has been busy without a break since two blocks before the body (a frame that is not this chain's to decode) --, else the
+// number of consecutive busy block ends from the end of its body onwards (1 .. 9: how far the chain will have to run on).
+// A wrong guess costs time, never a result: which lane runs which chain has no influence on any record (tested with one CTA
+// running 733 chains).
+SNRX_HD int zb_chain_key(const uint8_t* busy /* this stream's blocks */, int n_blocks, const ZbChainParams& p, int seg) {
+    const int32_t lo = p.origin + seg * p.segment;
+    int32_t hi = lo + p.segment;
+    if (hi > p.origin + p.body) hi = p.origin + p.body;
+    if (hi <= lo || (hi & (SNRX_IIR_BLOCK - 1)) || (lo & (SNRX_IIR_BLOCK - 1))) return 0;
+    const int kb = hi / SNRX_IIR_BLOCK - 1;                  // the block that ends where the body ends
+    if (kb < 0 || kb >= n_blocks || !busy[kb]) return 0;
+    const int kl = lo / SNRX_IIR_BLOCK - 1;                  // the block that ends where the body starts
+    if (kl >= 1) {
+        bool spans = true;
+        for (int j = kl - 1; j < kb; j++) spans = spans && busy[j] != 0;
+        if (spans) return 0;
+    }
+    int key = 0;
+    for (int j = kb; j < n_blocks && busy[j] && key < kZbKeys - 1; j++) key++;
+    return key;
+}
+
+struct ZbOrderArgs {
+    const uint8_t* busy; ZbChainParams p;
+    uint32_t* hist;       // [kZbKeys] chains per key | [kZbKeys] fill cursors (zeroed before the count pass)
+    uint32_t* order;      // [n_chains] position in the queue -> index in natural order (idx = seg * n_streams + stream)
+};
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_zb_order(ZbOrderArgs a) {
+    const uint32_t n_streams = a.p.n_captures * a.p.n_channels;
+    const uint32_t total = n_streams * (uint32_t)a.p.n_segments;
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int key = -1;
+    if (idx < total) key = zb_chain_key(a.busy + (size_t)(idx % n_streams) * a.p.n_blocks, a.p.n_blocks, a.p, (int)(idx / n_streams));
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);          // one atomic per key and warp
+    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+    const uint32_t rank = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    if (!FILL) {
+        if (key >= 0 && lane == leader) atomicAdd(a.hist + key, (uint32_t)__popc(peers));
+        return;
+    }
+    uint32_t start = 0;
+    if (key >= 0 && lane == leader) start = atomicAdd(a.hist + kZbKeys + key, (uint32_t)__popc(peers));
+    start = __shfl_sync(peers, start, (int)leader);
+    if (key < 0) return;
+    uint32_t base = 0;                                                   // longest first
+    for (int k = kZbKeys - 1; k > key; k--) base += a.hist[k];
+    a.order[base + start + rank] = idx;
 }
 
 // one thread per chain: drop the CRC-failed records that lie inside a CRC-ok frame of this or a preceding chain
@@ -870,6 +950,8 @@ struct ZbState {
     int32_t* d_channels = nullptr;
     snrx_frame_t* d_slots = nullptr; size_t slots_bytes = 0;
     uint32_t *d_counts = nullptr, *d_offsets = nullptr, *d_scratch = nullptr, *d_queue = nullptr;
+    uint32_t *d_order = nullptr, *d_hist = nullptr; uint8_t* d_busy = nullptr;      // k_zb_order
+    bool natural_order = false;   // SNRX_ZB_ORDER=0: chains handed out in natural order (A/B runs)
     int64_t* d_good_end = nullptr;
     uint32_t max_chains = 0, slots_per_chain = 0;
     float* d_chips = nullptr; int64_t* d_nchips = nullptr; int64_t chips_cap = 0;
@@ -882,7 +964,7 @@ struct ZbState {
 
 inline void zb_free(ZbState& s) {
     void* bufs[] = {s.d_f, s.d_z, s.d_block_end, s.d_carry, s.d_atan, s.d_mmse, s.d_channels, s.d_slots,
-                    s.d_counts, s.d_offsets, s.d_scratch, s.d_queue, s.d_good_end, s.d_chips, s.d_nchips, s.d_atan_pairs, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
+                    s.d_counts, s.d_offsets, s.d_scratch, s.d_queue, s.d_good_end, s.d_chips, s.d_nchips, s.d_atan_pairs, s.d_order, s.d_hist, s.d_busy, s.d_wb_taps_rho, s.d_wb_taps_flat, s.d_wb_taps_pass, s.d_wb_cf};
     for (void* b : bufs) if (b) cudaFree(b);
     s = ZbState();
 }
@@ -919,6 +1001,9 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     const size_t nblk = (max_out + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK;
     ZCK(cudaMalloc((void**)&s.d_block_end, streams * nblk * sizeof(double)));
     ZCK(cudaMalloc((void**)&s.d_carry, streams * nblk * sizeof(double)));
+    ZCK(cudaMalloc((void**)&s.d_busy, streams * nblk));
+    ZCK(cudaMalloc((void**)&s.d_hist, sizeof(uint32_t) * 2 * kZbKeys));
+    { const char* e = getenv("SNRX_ZB_ORDER"); s.natural_order = e && atoi(e) == 0; }
     s.decay = zb_iir_block_decay();
     ZCK(cudaMalloc((void**)&s.d_atan, sizeof(SNRX_ATAN_TAB)));
     ZCK(cudaMemcpy(s.d_atan, SNRX_ATAN_TAB, sizeof(SNRX_ATAN_TAB), cudaMemcpyHostToDevice));
@@ -944,6 +1029,7 @@ inline int zb_create(ZbState& s, const snrx_config_t& cfg, bool wideband, uint32
     ZCK(cudaMalloc((void**)&s.d_scratch, sizeof(uint32_t) * scan_scratch_items(s.max_chains)));
     ZCK(cudaMalloc((void**)&s.d_good_end, sizeof(int64_t) * ((size_t)s.max_chains + 1)));
     ZCK(cudaMalloc((void**)&s.d_queue, sizeof(uint32_t)));
+    ZCK(cudaMalloc((void**)&s.d_order, sizeof(uint32_t) * ((size_t)s.max_chains + 1)));
     ZCK(cudaFuncSetAttribute(k_zb_rx<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kZbRxSmem));
     ZCK(cudaFuncSetAttribute(k_zb_rx<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kZbRxSmem));
     if (keep) {
@@ -984,7 +1070,7 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     ZbIirArgs ia;
     ia.f = s.d_f; ia.stride = s.stride; ia.n = (int32_t)n_out;
     ia.n_blocks = (int32_t)((n_out + SNRX_IIR_BLOCK - 1) / SNRX_IIR_BLOCK); ia.n_streams = streams;
-    ia.block_end = s.d_block_end; ia.carry_in = s.d_carry; ia.decay = s.decay;
+    ia.block_end = s.d_block_end; ia.carry_in = s.d_carry; ia.decay = s.decay; ia.busy = s.natural_order ? nullptr : s.d_busy;
     const uint32_t nb_total = streams * (uint32_t)ia.n_blocks;
     k_zb_iir_sum<<<(nb_total + 63) / 64, 64, 0, st>>>(ia);
     k_zb_iir_carry<<<std::min<uint32_t>((nb_total + 127) / 128, (uint32_t)sm_count * 8), 128, 0, st>>>(ia);
@@ -1006,6 +1092,16 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     a.z_dbg = s.d_z; a.chips_dbg = s.d_chips; a.chips_cap = s.chips_cap; a.nchips_dbg = s.d_nchips; a.map = s.map;
     a.queue = s.d_queue;
     ZCK(cudaMemsetAsync(s.d_queue, 0, sizeof(uint32_t), st));
+    a.order = nullptr;
+    if (!s.natural_order && n_chains > 0) {                                 // longest chains first (zb_chain_key)
+        ZbOrderArgs oa;
+        oa.busy = s.d_busy; oa.p = p; oa.hist = s.d_hist; oa.order = s.d_order;
+        ZCK(cudaMemsetAsync(s.d_hist, 0, sizeof(uint32_t) * 2 * kZbKeys, st));
+        k_zb_order<false><<<(n_chains + 255) / 256, 256, 0, st>>>(oa);
+        k_zb_order<true><<<(n_chains + 255) / 256, 256, 0, st>>>(oa);
+        launches += 2;
+        a.order = s.d_order;
+    }
     const uint32_t per_cta = kZbRxWarps * 32;
     uint32_t grid = std::min<uint32_t>((n_chains + per_cta - 1) / per_cta, (uint32_t)sm_count * kZbRxCtasPerSm);
     if (s.rx_cta_cap) grid = std::min(grid, s.rx_cta_cap);
