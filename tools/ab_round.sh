@@ -1,11 +1,9 @@
 #!/bin/bash
-# A/B of k_zb_rx's chain order (SNRX_ZB_ORDER=0: natural order) on zb_wb16 / mixed_wb56
-timeout 900 python -m pytest tests -m gpu -q -x -k "zb or zigbee or mixed or c5 or shard" 2>&1 | tail -4
-for sec in 4.9 9.83; do
-for o in 0 1; do
-  echo "== zb_wb16 $sec s order=$o"; SNRX_ZB_ORDER=$o python tools/ab_front.py zb_wb16 $sec 2>&1 | tail -1
+# A/B: two vs three batches in flight (library built with -DSNRX_LANES=3) on the Zigbee / mixed workloads, then the parity soak
+L=$PWD/snout_b200/lib
+for w in "zb_wb16 4.9" "zb_wb16 9.83" "mixed_wb56 4.9"; do
+  python tools/ab_depth.py $w 2 2>&1 | tail -1
+  SNRX_LIB=$L/libsnoutrx_L3.so python tools/ab_depth.py $w 2 2>&1 | tail -1
+  SNRX_LIB=$L/libsnoutrx_L3.so python tools/ab_depth.py $w 3 2>&1 | tail -1
 done
-done
-for o in 0 1; do
-  echo "== mixed_wb56 4.9 s order=$o"; SNRX_ZB_ORDER=$o python tools/ab_front.py mixed_wb56 4.9 2>&1 | tail -1
-done
+FUZZ_BLE=40 FUZZ_ZB=60 timeout 600 python tools/fuzz_parity.py 2>&1 | tail -3 | tee gpurun_out/fuzz_parity.log
