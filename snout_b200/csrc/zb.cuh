@@ -89,11 +89,13 @@ SNRX_HD float tab_atan2_g(float y, float x, Tab tab) {
 SNRX_HD float tab_atan2(float y, float x, const float* tab /*[257]*/) { return tab_atan2_g(y, x, AtanTab{tab}); }
 
 // f = arg(x * conj(p))
-SNRX_HD float quad_demod(float xr, float xi, float pr, float pi, const float* tab) {
+template <class Tab>
+SNRX_HD float quad_demod_g(float xr, float xi, float pr, float pi, Tab tab) {
     const float re = f_add(f_mul(xr, pr), f_mul(xi, pi));
     const float im = f_sub(f_mul(xi, pr), f_mul(xr, pi));
-    return tab_atan2(im, re, tab);
+    return tab_atan2_g(im, re, tab);
 }
+SNRX_HD float quad_demod(float xr, float xi, float pr, float pi, const float* tab) { return quad_demod_g(xr, xi, pr, pi, AtanTab{tab}); }
 
 // discriminator-domain chip words of the 16 data symbols (derived from the 802.15.4 PN
 // sequences; equal CHIP_MAPPING[] & 0x7FFFFFFE of packet_sink_scapy_impl.h:28-45)
@@ -513,22 +515,40 @@ SNRX_HD uint32_t zb_slots_per_chain(uint32_t segment) { return segment / kZbMinS
 struct ZbQuadArgs {
     const float2* x; uint64_t stride; int64_t n; uint32_t n_captures;
     float* f; size_t f_stride;            // [cap][1][f_stride]
-    const float* atan_tab;
+    const float2* atan_pairs;             // [256] AtanTabPairs, global (L1 resident)
 };
 
+// Narrow-band discriminator, element-wise: a thread takes four consecutive samples (two 16-byte streaming loads + the
+// sample before them, one 16-byte store); the table is read as {value, step} pairs through L1 like in k_pfb_zb_warp.
+// Round 2's first version (one sample per thread, two 8-byte loads, the 257-entry table in shared memory at random
+// indices) took 9.8 ms per 2.56 G samples with the GPU to itself, this one 6.1 ms (5.0 TB/s of reads + writes).
 __global__ void __launch_bounds__(256) k_zb_quad(ZbQuadArgs a) {
-    __shared__ float tab[257];
-    for (int i = threadIdx.x; i < 257; i += blockDim.x) tab[i] = a.atan_tab[i];
-    __syncthreads();
-    const uint64_t total = (uint64_t)a.n_captures * (uint64_t)a.n;
+    const AtanTabPairs tab{a.atan_pairs};
+    const uint64_t n4 = ((uint64_t)a.n + 3) / 4;
+    const uint64_t total = (uint64_t)a.n_captures * n4;
     for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t cap = (uint32_t)(idx / (uint64_t)a.n);
-        const int64_t n = (int64_t)(idx % (uint64_t)a.n);
+        const uint32_t cap = (uint32_t)(idx / n4);
+        const int64_t n0 = (int64_t)(idx % n4) * 4;
         const float2* xc = a.x + (size_t)cap * a.stride;
-        const float2 cur = __ldg(xc + n);
+        float* fc = a.f + (size_t)cap * a.f_stride;
         float2 prev = make_float2(0.f, 0.f);
-        if (n > 0) prev = __ldg(xc + n - 1);
-        a.f[(size_t)cap * a.f_stride + n] = quad_demod(cur.x, cur.y, prev.x, prev.y, tab);
+        if (n0 > 0) prev = __ldg(xc + n0 - 1);
+        if (n0 + 4 <= a.n && ((reinterpret_cast<uintptr_t>(xc + n0) | reinterpret_cast<uintptr_t>(fc + n0)) & 15) == 0) {
+            const float4 u = __ldcs(reinterpret_cast<const float4*>(xc + n0));
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(xc + n0) + 1);
+            float4 o;
+            o.x = quad_demod_g(u.x, u.y, prev.x, prev.y, tab);
+            o.y = quad_demod_g(u.z, u.w, u.x, u.y, tab);
+            o.z = quad_demod_g(v.x, v.y, u.z, u.w, tab);
+            o.w = quad_demod_g(v.z, v.w, v.x, v.y, tab);
+            *reinterpret_cast<float4*>(fc + n0) = o;
+        } else {
+            for (int64_t n = n0; n < n0 + 4 && n < a.n; n++) {
+                const float2 cur = __ldg(xc + n);
+                fc[n] = quad_demod_g(cur.x, cur.y, prev.x, prev.y, tab);
+                prev = cur;
+            }
+        }
     }
 }
 
@@ -1060,8 +1080,8 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
     } else {
         ZbQuadArgs q;
         q.x = x; q.stride = stride; q.n = (int64_t)n_samples; q.n_captures = n_captures;
-        q.f = s.d_f; q.f_stride = s.stride; q.atan_tab = s.d_atan;
-        const uint64_t total = (uint64_t)n_captures * n_samples;
+        q.f = s.d_f; q.f_stride = s.stride; q.atan_pairs = s.d_atan_pairs;
+        const uint64_t total = (uint64_t)n_captures * ((n_samples + 3) / 4);
         const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sm_count * 8);
         k_zb_quad<<<grid, 256, 0, st>>>(q);
         launches++;
