@@ -34,6 +34,7 @@ struct NbArgs {
     int64_t n;                // samples per capture
     int32_t n_groups;         // ceil(n / 128)
     uint32_t n_captures;
+    uint32_t blocks_per_cap;  // the grid is n_captures * blocks_per_cap blocks: a block stays inside one capture (no 64-bit division per item)
     float scale;
     uint32_t* bits;
     BitsLayout lay;           // n_channels == 1
@@ -44,20 +45,33 @@ template <bool DEBUG>
 __global__ void __launch_bounds__(256) k_ble_slice_nb(NbArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps_per_block = blockDim.x >> 5;
-    const uint64_t n_items = (uint64_t)a.n_captures * (uint64_t)a.n_groups;
-    for (uint64_t item = (uint64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < n_items;
-         item += (uint64_t)gridDim.x * warps_per_block) {
-        const uint32_t cap = (uint32_t)(item / (uint64_t)a.n_groups);
-        const int32_t grp = (int32_t)(item % (uint64_t)a.n_groups);
-        const float2* xc = a.x + (size_t)cap * a.stride;
+    // one 32-bit division per block; the item loop below has none (ncu of the first version, which split a 64-bit item index
+    // per item: 185 instructions per 128 samples, ALU pipe 58 % busy, issue slots 67 % -- not the HBM-bound kernel it should be)
+    const uint32_t cap = blockIdx.x / a.blocks_per_cap;
+    const float2* xc = a.x + (size_t)cap * a.stride;
+    for (int32_t grp = (int32_t)((blockIdx.x % a.blocks_per_cap) * warps_per_block + (threadIdx.x >> 5)); grp < a.n_groups;
+         grp += (int32_t)(a.blocks_per_cap * warps_per_block)) {
         const int64_t n0 = (int64_t)grp * 128 + lane;             // this lane's sample of word 0
-        float I[5], Q[5];                                         // [k]: sample n0 + 32 k; [4] only matters in lane 0
+        float2 t[5];                                              // [k]: sample n0 + 32 k; [4] only matters in lane 0
+        if ((int64_t)grp * 128 + 160 <= a.n) {                    // the whole item and its successor sample lie inside the capture
+            const float2* p = xc + n0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) t[k] = __ldcs(p + 32 * k);    // streaming loads: every byte is used once
+            t[4] = make_float2(0.f, 0.f);
+            if (lane == 0) t[4] = __ldcs(p + 128);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int64_t n = n0 + 32 * k;
+                t[k] = make_float2(0.f, 0.f);                     // beyond the capture: zero fill
+                if ((k < 4 || lane == 0) && n < a.n) t[k] = __ldcs(xc + n);
+            }
+        }
+        float I[5], Q[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) {
+            I[k] = quant_exact(t[k].x, a.scale); Q[k] = quant_exact(t[k].y, a.scale);
             const int64_t n = n0 + 32 * k;
-            float2 t = make_float2(0.f, 0.f);                     // beyond the capture: zero fill
-            if ((k < 4 || lane == 0) && n < a.n) t = __ldcs(xc + n);   // streaming load: every byte is used once
-            I[k] = quant_exact(t.x, a.scale); Q[k] = quant_exact(t.y, a.scale);
             if (DEBUG && a.dbg_q8 && k < 4 && n < a.n) {
                 const size_t o = ((size_t)cap * (size_t)a.n + (size_t)n) * 2;
                 a.dbg_q8[o] = (int8_t)I[k]; a.dbg_q8[o + 1] = (int8_t)Q[k];
@@ -66,9 +80,10 @@ __global__ void __launch_bounds__(256) k_ble_slice_nb(NbArgs a) {
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            float i1 = __shfl_sync(0xffffffffu, I[k], (lane + 1) & 31), q1 = __shfl_sync(0xffffffffu, Q[k], (lane + 1) & 31);
-            const float in = __shfl_sync(0xffffffffu, I[k + 1], 0), qn = __shfl_sync(0xffffffffu, Q[k + 1], 0);
-            if (lane == 31) { i1 = in; q1 = qn; }
+            // successor of sample (word k, lane): (k, lane + 1), for lane 31 (k + 1, 0) -- lane 0 offers its sample of the NEXT
+            // word, every other lane its sample of this one: one shuffle per component
+            const float i1 = __shfl_sync(0xffffffffu, lane == 0 ? I[k + 1] : I[k], (lane + 1) & 31);
+            const float q1 = __shfl_sync(0xffffffffu, lane == 0 ? Q[k + 1] : Q[k], (lane + 1) & 31);
             w[k] = __ballot_sync(0xffffffffu, slicer_bit(I[k], Q[k], i1, q1));
         }
         if (lane < 4) {

@@ -660,8 +660,9 @@ static int launch_ble_front(snrx_handle* h, Lane& ln, const float2* x, uint32_t 
         a.x = x; a.stride = stride; a.n = (int64_t)n_in;
         a.n_groups = (int32_t)div_up(n_in, 128); a.n_captures = caps; a.scale = h->cfg.quant_scale;
         a.bits = ln.d_bits; a.lay = lay; a.dbg_q8 = ln.d_q8;
-        const uint64_t items = (uint64_t)caps * a.n_groups;
-        const int grid = grid_for(h, items, 8, 8);
+        const uint32_t per_cap_max = (uint32_t)div_up((uint64_t)a.n_groups, 8);                  // 8 warps per block, one item each
+        a.blocks_per_cap = std::max<uint32_t>(1u, std::min<uint32_t>(per_cap_max, (uint32_t)div_up((uint64_t)h->sm_count * 8, caps)));
+        const unsigned grid = a.blocks_per_cap * caps;
         if (dbg) k_ble_slice_nb<true><<<grid, 256, 0, ln.stream>>>(a);
         else k_ble_slice_nb<false><<<grid, 256, 0, ln.stream>>>(a);
     }

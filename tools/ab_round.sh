@@ -1,8 +1,10 @@
 #!/bin/bash
-# A/B: 64-row z ring (4 CTAs of k_zb_rx per SM) against the 128-row ring (3 CTAs) with the same group-level pacing
-timeout 900 python -m pytest tests -m gpu -q -x -k "nb or narrow or zigbee or zb or mixed or c5 or shard" 2>&1 | tail -3
 L=$PWD/snout_b200/lib
-for w in "zb_wb16 4.9" "zb_wb16 9.83" "mixed_wb56 4.9"; do
-  python tools/ab_front.py $w 2>&1 | tail -1
-  SNRX_LIB=$L/libsnoutrx_R128.so python tools/ab_front.py $w 2>&1 | tail -1
+for v in _NB2 "" _NB2 ""; do
+  SNRX_LIB=$L/libsnoutrx$v.so timeout 300 python bench.py --workload ble_nb --steps 8 --warmup 3 --no-cpu-baseline 2>&1 | grep '^{' | tail -1 > gpurun_out/ab_ble_nb$v.json
+  python - <<P
+import json
+d=json.load(open('gpurun_out/ab_ble_nb$v.json'))
+print('ble_nb lib$v value',round(d['value']),'ms',round(d['ms_per_step'],3),'live',round(d['roofline']['kernel_ms'],3),'alone',round(d['roofline']['alone']['kernel_ms'],3),'frac alone',round(d['roofline']['alone']['frac'],3))
+P
 done
