@@ -516,6 +516,7 @@ struct ZbQuadArgs {
     const float2* x; uint64_t stride; int64_t n; uint32_t n_captures;
     float* f; size_t f_stride;            // [cap][1][f_stride]
     const float2* atan_pairs;             // [256] AtanTabPairs, global (L1 resident)
+    uint32_t blocks_per_cap;              // the grid is n_captures * blocks_per_cap blocks
 };
 
 // Narrow-band discriminator, element-wise: a thread takes four consecutive samples (two 16-byte streaming loads + the
@@ -524,13 +525,14 @@ struct ZbQuadArgs {
 // indices) took 9.8 ms per 2.56 G samples with the GPU to itself, this one 6.1 ms (5.0 TB/s of reads + writes).
 __global__ void __launch_bounds__(256) k_zb_quad(ZbQuadArgs a) {
     const AtanTabPairs tab{a.atan_pairs};
-    const uint64_t n4 = ((uint64_t)a.n + 3) / 4;
-    const uint64_t total = (uint64_t)a.n_captures * n4;
-    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t cap = (uint32_t)(idx / n4);
-        const int64_t n0 = (int64_t)(idx % n4) * 4;
-        const float2* xc = a.x + (size_t)cap * a.stride;
-        float* fc = a.f + (size_t)cap * a.f_stride;
+    // a block stays inside one capture: one 32-bit division per block, none per item (a 64-bit item index split per item cost
+    // as much as the four discriminators it fed)
+    const uint32_t cap = blockIdx.x / a.blocks_per_cap;
+    const float2* xc = a.x + (size_t)cap * a.stride;
+    float* fc = a.f + (size_t)cap * a.f_stride;
+    const int64_t n4 = (a.n + 3) / 4;
+    for (int64_t q = (int64_t)(blockIdx.x % a.blocks_per_cap) * blockDim.x + threadIdx.x; q < n4; q += (int64_t)a.blocks_per_cap * blockDim.x) {
+        const int64_t n0 = q * 4;
         float2 prev = make_float2(0.f, 0.f);
         if (n0 > 0) prev = __ldg(xc + n0 - 1);
         if (n0 + 4 <= a.n && ((reinterpret_cast<uintptr_t>(xc + n0) | reinterpret_cast<uintptr_t>(fc + n0)) & 15) == 0) {
@@ -1081,8 +1083,9 @@ inline int zb_process(ZbState& s, const snrx_config_t& cfg, const float2* x, uin
         ZbQuadArgs q;
         q.x = x; q.stride = stride; q.n = (int64_t)n_samples; q.n_captures = n_captures;
         q.f = s.d_f; q.f_stride = s.stride; q.atan_pairs = s.d_atan_pairs;
-        const uint64_t total = (uint64_t)n_captures * ((n_samples + 3) / 4);
-        const int grid = (int)std::min<uint64_t>((total + 255) / 256, (uint64_t)sm_count * 8);
+        const uint64_t per_cap_max = ((n_samples + 3) / 4 + 255) / 256;
+        q.blocks_per_cap = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(per_cap_max, ((uint64_t)sm_count * 8 + n_captures - 1) / n_captures));
+        const unsigned grid = q.blocks_per_cap * n_captures;
         k_zb_quad<<<grid, 256, 0, st>>>(q);
         launches++;
     }
