@@ -305,6 +305,40 @@ def test_zb_nb_lanes_take_several_chains(Engine, oracle_mod, monkeypatch):
         assert np.array_equal(chips[k, : len(ck)], ck), k
 
 
+def test_zb_chain_order_is_a_scheduling_hint_only(Engine, oracle_mod, monkeypatch):
+    """k_zb_order hands the chains that are expected to run long (a burst on the air at the end of their body) to the lanes
+    first.  The order must not change a single record: natural order (SNRX_ZB_ORDER=0), longest first (default) and longest
+    first on ONE CTA all give the oracle's frames -- on a busy wideband capture (many long chains), on a narrow-band capture
+    and on an empty one (no busy block at all)."""
+    cap = synth.wideband_capture(seconds=0.03, kind="zigbee", seed=3100, esn0_db=18.0, gap=(400, 6000))
+    x = cap.iq
+    runs = {}
+    for name, env in (("natural", {"SNRX_ZB_ORDER": "0"}), ("longest first", {}), ("longest first, one CTA", {"SNRX_ZB_RX_CTAS": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Engine("zb_wb16", max_samples=len(x), keep_streams=(name == "natural")) as e:
+            runs[name] = e.run(x)
+            if name == "natural":
+                y = e.debug_stage(_abi.STAGE_CHAN_CF32)[0]
+        for k in env:
+            monkeypatch.delenv(k)
+    want = np.concatenate([oracle_mod.zb_receive_z(oracle_mod.zb_dc_remove(oracle_mod.zb_quad_demod(y[c])), 11 + c) for c in range(16)])
+    assert len(want) > 60
+    for name, got in runs.items():
+        assert_frames_equal(got, want, what=f"zigbee wideband, chains handed out {name}")
+    nb = synth.zigbee_capture(n=1_200_000, channel=18, seed=2012, esn0_db=12.0)
+    want_nb = oracle_mod.zb_receive(nb.iq, 18)
+    assert len(want_nb) > 8
+    for env in ({"SNRX_ZB_ORDER": "0"}, {}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Engine("zb_nb", channel=18, max_samples=len(nb.iq)) as e:
+            assert_frames_equal(e.run(nb.iq), want_nb, what=f"zigbee narrow band {env}")
+            assert len(e.run(np.zeros(300_000, np.complex64))) == 0
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_zb_nb_batch_and_set_channel(Engine, oracle_mod):
     n = 300_000
     caps = [synth.zigbee_capture(n=n, channel=20, seed=600 + i, esn0_db=20.0, gap=(500, 6000)).iq for i in range(3)]
