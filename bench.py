@@ -178,20 +178,20 @@ def cpu_path(workload, sample, min_seconds=0.0):
     return time.perf_counter() - t0, done, frames, cores, kind
 
 
-def ncu_traffic(n_samples):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_pfb_ble launch from the committed ncu --set full
-    summary (profiles/), valid when it was captured on this same workload size; else None."""
+def ncu_traffic(n_samples, kernel="k_pfb_ble", stem="pfb_ncu"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the workload's dominant kernel from the committed
+    ncu --set full summary (profiles/rNN_<stem>[_vM].json), valid when it was captured on this same workload size; else None."""
     best = None
     import re
     def version(name):                   # r01_pfb_ncu_v10.json -> (1, 10), r02_pfb_ncu.json -> (2, 0): newest capture last
-        m = re.match(r"r(\d+)_pfb_ncu(?:_v(\d+))?\.json$", name)
+        m = re.match(r"r(\d+)_" + stem + r"(?:_v(\d+))?\.json$", name)
         return (int(m.group(1)), int(m.group(2) or 0)) if m else (-1, -1)
     for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), key=version):
         if version(name)[0] >= 0:
             try:
                 j = json.load(open(os.path.join(ROOT, "profiles", name)))
                 for l in j["launches"]:
-                    if "k_pfb_ble" in l["kernel"] and abs(l["dram_read_bytes"] / (n_samples * 8) - 1) < 0.2:
+                    if kernel in l["kernel"] and abs(l["dram_read_bytes"] / (n_samples * 8) - 1) < 0.2:
                         best = (l["traffic_bytes"], name, l.get("pipe_fma_cycles_pct"))
             except Exception:
                 pass
@@ -614,11 +614,13 @@ def main():
                     frames_per_s=c5["config"]["frames_per_step"] * args.steps / (c5["ms_per_step"] * args.steps * 1e-3))
         line["mixed_wb56_single_capture"] = single
         line["c5"] = {"note": c5["note"]}
-    tr = ncu_traffic(n) if mode == "ble_wb40" else None
+    tr = ncu_traffic(n) if mode == "ble_wb40" else ncu_traffic(n, "k_pfb_zb_warp", "zb_wb16_ncu") if mode == "zb_wb16" else None
     if tr:
         line["roofline"]["traffic"] = tr[0]
         line["roofline"]["traffic_source"] = f"profiles/{tr[1]} (ncu --set full, dram read+write of one launch)"
-        if tr[2]:
+        if mode == "zb_wb16":
+            line["roofline"]["traffic_note"] = "includes the 2.5 GB discriminator stream f the kernel writes (4 B per channel sample, 16 channels)"
+        if tr[2] and mode == "ble_wb40":
             line["roofline"]["fp32_fma_pipe_cycles_active_pct"] = tr[2]
             line["roofline"]["note"] = ("8 B per input sample (one cf32 read). The binding unit is the FP32 FMA pipe: ncu "
                                         "sm__pipe_fma_cycles_active of the same launch, committed in profiles/; see DESIGN.md 3, 6")
