@@ -447,29 +447,24 @@ __device__ __forceinline__ void pfb_ble_tile(const PfbBleArgs& a, const float2* 
 
 // One tile per one-warp CTA: any tile (interior tiles by bulk copies, tiles that touch either end of the capture through the
 // zero-filling generic path).
-// SNRX_PFB_WARPS (measurement switch, default 1): warps per CTA, every warp an independent tile with its own slice of shared memory
-// and its own barrier -- it only changes how many CTAs the block scheduler has to start.
-#ifndef SNRX_PFB_WARPS
-#define SNRX_PFB_WARPS 1
-#endif
+// Grid = (tiles of the launch, captures): the tile's input address needs no division, so the bulk copies leave a few dozen
+// instructions after the CTA starts (the sampled profile of the 1-D grid had 7 % of the warp time in the index arithmetic
+// ahead of the copy: two 32-bit divisions through the conversion unit).  Measured and rejected: two / four warps per CTA
+// (independent tiles, fewer CTAs for the block scheduler to start): 0.337 / 0.341 ms against 0.330.
 template <int NT, bool DEBUG>
-__global__ void __launch_bounds__(32 * SNRX_PFB_WARPS, PfbBleGeom<NT>::kCtasPerSm / SNRX_PFB_WARPS) k_pfb_ble(PfbBleArgs a) {
+__global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbBleArgs a) {
     using B = PfbBleGeom<NT>;
     using G = typename B::G;
-    extern __shared__ __align__(16) unsigned char smem_all[];
-    static_assert(B::kSmemBytes % 16 == 0, "per-warp slices stay 16-byte aligned");
-    unsigned char* smem_raw = smem_all + (SNRX_PFB_WARPS > 1 ? (threadIdx.x >> 5) * B::kSmemBytes : 0);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xs = reinterpret_cast<float2*>(smem_raw);
     float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [8][32], see v_pos()
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
 
-    const int lane = threadIdx.x & 31;
-    const int t = SNRX_PFB_WARPS > 1 ? (int)(blockIdx.x * SNRX_PFB_WARPS + (threadIdx.x >> 5)) : (int)blockIdx.x;
-    if (SNRX_PFB_WARPS > 1 && t >= a.n_tiles * a.n_caps) return;
+    const int lane = threadIdx.x;
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-    const int tile = a.tile0 + t % a.n_tiles;
-    const int cap = t / a.n_tiles;
+    const int tile = a.tile0 + (int)blockIdx.x;
+    const int cap = (int)blockIdx.y;
     const float2* xcap = a.x + (size_t)cap * a.stride;
     const int g_first = B::kStride * tile;                                 // first channel sample of the tile
 

@@ -227,8 +227,8 @@ __global__ void __launch_bounds__(32, PfbZbWarpGeom<NT>::kCtasPerSm) k_pfb_zb_wa
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
 
     const int lane = threadIdx.x;
-    const int tile = (int)(blockIdx.x % a.n_tiles);
-    const int cap = blockIdx.x / a.n_tiles;
+    const int tile = (int)blockIdx.x;                      // grid = (tiles, captures): no division ahead of the bulk copies
+    const int cap = (int)blockIdx.y;
     const float2* xcap = a.x + (size_t)cap * a.stride;
     const int g_first = B::kStride * tile;
     {
@@ -353,7 +353,7 @@ inline int zb_wideband_front(ZbState& s, const snrx_config_t& cfg, const float2*
         a.n_tiles = (int32_t)std::max<uint32_t>(1u, (n_out - 1 + 30) / 31);
         a.taps_pass = reinterpret_cast<const float4*>(s.d_wb_taps_pass);
         a.f = s.d_f; a.f_stride = s.stride; a.atan_pairs = s.d_atan_pairs; a.dbg_cf = s.d_wb_cf;
-        const dim3 grid((unsigned)a.n_tiles * n_captures);
+        const dim3 grid((unsigned)a.n_tiles, n_captures);
         if (s.wb_nt == 16) {
             if (dbg) k_pfb_zb_warp<16, true><<<grid, 32, PfbZbWarpGeom<16>::kSmemBytes, st>>>(a);
             else k_pfb_zb_warp<16, false><<<grid, 32, PfbZbWarpGeom<16>::kSmemBytes, st>>>(a);

@@ -257,8 +257,8 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
     using B = PfbBleGeom<NT>;
     using G = typename B::G;
     if (!a) {
-        CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes * SNRX_PFB_WARPS));
-        CK(cudaFuncSetAttribute(k_pfb_ble<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes * SNRX_PFB_WARPS));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
+        CK(cudaFuncSetAttribute(k_pfb_ble<NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
         CK(cudaFuncSetAttribute(k_pfb_ble_run<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, B::kSmemBytes));
         CK(cudaFuncSetAttribute(k_pfb_ble<NT, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaFuncSetAttribute(k_pfb_ble_run<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -273,9 +273,9 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
         if (t1 <= t0) return;
         PfbBleArgs b = args;
         b.tile0 = t0; b.n_tiles = t1 - t0;
-        const dim3 grid(((unsigned)(t1 - t0) * caps + SNRX_PFB_WARPS - 1) / SNRX_PFB_WARPS);
-        if (dbg) k_pfb_ble<NT, true><<<grid, B::kThreads * SNRX_PFB_WARPS, B::kSmemBytes * SNRX_PFB_WARPS, st>>>(b);
-        else k_pfb_ble<NT, false><<<grid, B::kThreads * SNRX_PFB_WARPS, B::kSmemBytes * SNRX_PFB_WARPS, st>>>(b);
+        const dim3 grid((unsigned)(t1 - t0), caps);             // x: tiles, y: captures (snrx_create bounds max_captures by 65535)
+        if (dbg) k_pfb_ble<NT, true><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
+        else k_pfb_ble<NT, false><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
         h->launches++;
     };
     const int t0 = a->tile0, t1 = a->tile0 + a->n_tiles, per = pfb_tiles_per_cta();
@@ -496,6 +496,7 @@ int snrx_create(snrx_t** out, const snrx_config_t* cfg) {
         if (c.zb_threshold <= 0) c.zb_threshold = 10;
         if (c.quant_scale <= 0.0f) c.quant_scale = h->wideband ? 100.0f : 128.0f;
         if (c.max_captures == 0) c.max_captures = 1;
+        if (h->wideband && c.max_captures > 65535u) return fail(h, SNRX_ERANGE, "wideband engines take at most 65535 captures per batch (the captures are the y dimension of the channelizer grids)");
         if (c.max_samples == 0) c.max_samples = h->wideband ? 96000000ull : 10000000ull;
         if (c.max_frames == 0) c.max_frames = 1u << 17;
         if (c.zb_segment == 0) c.zb_segment = SNRX_ZB_SEGMENT_DEFAULT;
