@@ -213,6 +213,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ bool elect_one() {              // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -234,13 +239,19 @@ template <class G, int TT>
 __device__ __forceinline__ void pfb_stage_tile_bulk(float2* xs, const float2* xtile /* sample i' = 0 */, uint64_t* bar, int lane) {
     constexpr int kPer = 24 * TT;
     static_assert(G::kPieces <= 32 && G::kTileIn % 2 == 0, "one lane per piece");
-    // the barrier was initialised once per warp (count 1); every tile is one phase of it
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(G::kTileIn * sizeof(float2)));
-    __syncwarp();
-    if (lane < G::kPieces) {
-        const int lo = lane == 0 ? 0 : kPer * lane - 12;
-        const int hi = min(kPer * (lane + 1) - 12, G::kTileIn);
-        bulk_g2s(xs + lo + 8 * lane, xtile + lo, (uint32_t)((hi - lo) * sizeof(float2)), bar);
+    // the barrier was initialised once per warp (count 1); every tile is one phase of it.  ONE elected lane issues all the
+    // copies (compile-time offsets and sizes, warp-uniform addresses): with one lane per piece the compiler serialises them
+    // anyway -- a bulk copy takes its operands from uniform registers, so it elects a lane, broadcasts that lane's operands,
+    // issues, and loops (ELECT / R2UR / UBLKCP / BRA.U.ANY six times in the sampled profile).
+    (void)lane;
+    if (elect_one()) {
+        mbar_expect_tx(bar, (uint32_t)(G::kTileIn * sizeof(float2)));
+#pragma unroll
+        for (int p = 0; p < G::kPieces; p++) {
+            const int lo = p == 0 ? 0 : kPer * p - 12;
+            const int hi = kPer * (p + 1) - 12 < G::kTileIn ? kPer * (p + 1) - 12 : G::kTileIn;
+            bulk_g2s(xs + lo + 8 * p, xtile + lo, (uint32_t)((hi - lo) * sizeof(float2)), bar);
+        }
     }
 }
 
