@@ -156,6 +156,16 @@ SNRX_HD void pfb_combine_quant(const cf (&f0)[16], const cf (&f1)[16], const cf 
 // The 40 used bins in the order the slicer packs them: slot L of word A (L = 0..23) and of word B (L = 0..15)
 SNRX_HD constexpr int ble_q_of_slot_a(int L) { return L < 21 ? L : L + 8; }     // q = 0..20, 29..31
 SNRX_HD constexpr int ble_q_of_slot_b(int L) { return 32 + L; }                 // q = 32..47
+// ble_channel_of_q(ble_q_of_slot_x(L)) as a handful of selects (the lanes of a tile need it at run time, where the general
+// function costs four branches); checked against it below for every slot
+SNRX_HD constexpr int ble_channel_of_slot_a(int L) { return L <= 19 ? 17 + L : L == 20 ? 39 : L == 21 ? 37 : L - 22; }
+SNRX_HD constexpr int ble_channel_of_slot_b(int L) { return L <= 8 ? 2 + L : L == 9 ? 38 : 1 + L; }
+constexpr bool ble_slot_channels_agree() {
+    for (int L = 0; L < 24; L++) if (ble_channel_of_slot_a(L) != ble_channel_of_q(ble_q_of_slot_a(L))) return false;
+    for (int L = 0; L < 16; L++) if (ble_channel_of_slot_b(L) != ble_channel_of_q(ble_q_of_slot_b(L))) return false;
+    return true;
+}
+static_assert(ble_slot_channels_agree(), "slot -> BLE channel shortcut");
 
 // Slicer decision b[m] = I[m] Q[m+1] - I[m+1] Q[m] > 0 (btle_rx.c:1357-1361) as the sign bit of
 // 0.5 - cross: the operands are integers of magnitude <= 128, so 0.5 - cross is exact and never zero.
@@ -178,7 +188,16 @@ SNRX_HD uint32_t shift_in_sign(uint32_t acc, uint32_t sign_word) {   // (acc << 
 // One step of the 32x32 bit-matrix transpose across a warp (rows = lanes, columns = bits): exchange with
 // lane ^ j the off-diagonal j x j blocks.  m = columns whose bit j is clear.
 SNRX_HD uint32_t transpose_step(uint32_t x, uint32_t y /* value of lane ^ j */, int lane, int j, uint32_t m) {
+#ifdef __CUDA_ARCH__
+    // the same value with one rotate and one bitwise select: under m no bit of y >> j wraps, under ~m none of y << j does, so
+    // both are rotations of y; keep = the bits this lane keeps.  (The two-sided form compiled to six predicated operations.)
+    const bool hi = (lane & j) != 0;
+    const uint32_t keep = hi ? ~m : m;
+    const uint32_t r = __funnelshift_r(y, y, hi ? j : 32 - j);
+    return (x & keep) | (r & ~keep);
+#else
     return (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+#endif
 }
 
 #if defined(__CUDACC__)
@@ -315,7 +334,6 @@ struct PfbBleArgs {
     int32_t n_caps;           // captures in this launch
     int32_t tiles_per_cta;    // k_pfb_ble_run only
     int32_t tile_step;        // k_pfb_ble_run: 1 = a CTA's tiles are consecutive; gridDim.x = CTA b takes tiles b, b + grid, ...
-    int32_t l2_ahead;         // k_pfb_ble: tiles ahead whose NEW input bytes this CTA asks L2 to fetch (0 = off)
     const float4* taps_pass;  // [3][NT/4][8] float4: element (gi, d4, rl) = h[rho + 24 (4 d4 + 0..3)], rho = gi + 3 rl --
                               // the 8 FIR rows of a pass read 128 contiguous bytes per load
     float scale;              // quantiser scale
@@ -434,12 +452,16 @@ __device__ __forceinline__ void pfb_ble_tile(const PfbBleArgs& a, const float2* 
             wb = (wb & 0xFFFFu) | (o << 16);                 // lanes 0..15: times 0..15 | times 16..31 of slots 0..15
         }
         wa = transpose_step(wa, __shfl_xor_sync(0xffffffffu, wa, 16), lane, 16, 0x0000FFFFu);
-#pragma unroll
-        for (int j = 8; j >= 1; j >>= 1) {
-            const uint32_t m = j == 8 ? 0x00FF00FFu : j == 4 ? 0x0F0F0F0Fu : j == 2 ? 0x33333333u : 0x55555555u;
-            wa = transpose_step(wa, __shfl_xor_sync(0xffffffffu, wa, j), lane, j, m);
-            wb = transpose_step(wb, __shfl_xor_sync(0xffffffffu, wb, j), lane, j, m);
-        }
+        // written out: as a `for (j = 8; j >= 1; j >>= 1)` loop ptxas kept it rolled (shift counts and masks in registers, a
+        // branch per step: the sampled profile had the four steps at 4 % of the warp time)
+#define SNRX_TRANSPOSE_STEP(J, M)                                                       \
+        wa = transpose_step(wa, __shfl_xor_sync(0xffffffffu, wa, J), lane, J, M);       \
+        wb = transpose_step(wb, __shfl_xor_sync(0xffffffffu, wb, J), lane, J, M);
+        SNRX_TRANSPOSE_STEP(8, 0x00FF00FFu)
+        SNRX_TRANSPOSE_STEP(4, 0x0F0F0F0Fu)
+        SNRX_TRANSPOSE_STEP(2, 0x33333333u)
+        SNRX_TRANSPOSE_STEP(1, 0x55555555u)
+#undef SNRX_TRANSPOSE_STEP
         // lane L now holds the 32 decisions (bit = time) of slot L; the tile's last sample has no successor in it
         const uint32_t wi = (uint32_t)kBitsLeadWords + ((uint32_t)g_first >> 5);
         const int off = g_first & 31;
@@ -447,7 +469,7 @@ __device__ __forceinline__ void pfb_ble_tile(const PfbBleArgs& a, const float2* 
         for (int half = 0; half < 2; half++) {
             const uint32_t mk = (half ? wb : wa) & 0x7FFFFFFFu;
             if (lane < (half ? 16 : 24) && mk) {
-                const int ch = ble_channel_of_q(half ? ble_q_of_slot_b(lane) : ble_q_of_slot_a(lane));
+                const int ch = half ? ble_channel_of_slot_b(lane) : ble_channel_of_slot_a(lane);
                 uint32_t* dst = a.bits + a.lay.index(cap, ch, wi);
                 atomicOr(dst, mk << off);
                 if (off > 1 && (mk >> (32 - off))) atomicOr(dst + 1, mk >> (32 - off));
@@ -481,15 +503,8 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
 
     // ---- phase 0: stage the input tile (bulk copies for interior tiles, zero-filling cp.async at the capture ends)
     const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
-    if (a.l2_ahead > 0 && lane == 0) {
-        // the tile that a CTA `l2_ahead` launches behind this one will stage: ask L2 for the 744 samples it adds to the stream now,
-        // so that its bulk copy finds them there instead of waiting for HBM.  MEASURED (SNRX_PFB_L2_AHEAD = 0 / 1184 / 2368 /
-        // 4736 / 9472 tiles): 0.333 / 0.334 / 0.336 / 0.336 / 0.338 ms -- no gain, off by default: what a fresh CTA waits for is
-        // not HBM-vs-L2 latency
-        const int64_t xp = x0 + (int64_t)a.l2_ahead * kPfbD * B::kStride + G::kTileIn - kPfbD * B::kStride;
-        if (xp >= 0 && xp + kPfbD * B::kStride <= a.n_in)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(xcap + xp), "r"((uint32_t)(kPfbD * B::kStride * sizeof(float2))) : "memory");
-    }
+    // (an L2 prefetch of the input a CTA `n` launches behind this one will stage -- cp.async.bulk.prefetch.L2, 1184 ... 9472 tiles
+    // ahead -- was measured: 0.333 / 0.334 / 0.336 / 0.336 / 0.338 ms, no gain: what a fresh CTA waits for is not HBM-vs-L2 latency)
 #ifdef SNRX_PROBE_NO_STAGE                                   // measurement builds only: the tile is whatever shared memory holds
     if (pfb_tile_interior<G>(x0, a.n_in)) {
     } else

@@ -13,9 +13,6 @@
 #include <string>
 #include <vector>
 
-#ifndef SNRX_PFB_L2_AHEAD_DEFAULT
-#define SNRX_PFB_L2_AHEAD_DEFAULT 0
-#endif
 #ifndef SNRX_LANES
 #define SNRX_LANES 2
 #endif
@@ -267,7 +264,6 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
     PfbBleArgs args = *a;
     args.n_caps = (int32_t)caps;
     args.tiles_per_cta = 1;
-    { static const int ahead = getenv("SNRX_PFB_L2_AHEAD") ? atoi(getenv("SNRX_PFB_L2_AHEAD")) : SNRX_PFB_L2_AHEAD_DEFAULT; args.l2_ahead = ahead; }
     const bool dbg = (h->cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
     auto one_tile = [&](int t0, int t1) {                       // tiles [t0, t1) of every capture, one per CTA, any position
         if (t1 <= t0) return;
