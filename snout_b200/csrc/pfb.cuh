@@ -333,7 +333,6 @@ struct PfbBleArgs {
     int32_t tile0;            // first tile of this launch
     int32_t n_caps;           // captures in this launch
     int32_t tiles_per_cta;    // k_pfb_ble_run only
-    int32_t tile_step;        // k_pfb_ble_run: 1 = a CTA's tiles are consecutive; gridDim.x = CTA b takes tiles b, b + grid, ...
     const float4* taps_pass;  // [3][NT/4][8] float4: element (gi, d4, rl) = h[rho + 24 (4 d4 + 0..3)], rho = gi + 3 rl --
                               // the 8 FIR rows of a pass read 128 contiguous bytes per load
     float scale;              // quantiser scale
@@ -520,20 +519,20 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     pfb_ble_tile<NT, DEBUG>(a, xs, V, lane, cap, g_first, [] {});
 }
 
-// INTERIOR tiles only (a.tile0 .. a.tile0 + a.n_tiles - 1 of every capture lie entirely inside it), several tiles per one-warp
-// CTA: the bulk copy of the NEXT tile is issued as soon as the last FIR pass has read the current one (no second tile
-// buffer), so only a CTA's first tile waits for memory with nothing else to do.  The staging inside the loop is predicated,
-// not branched around (pfb_stage_tile_bulk_pred); ptxas still emits a second copy of the body behind a BRA.DIV for the
-// not-converged case (1240 FFMA2 in the listing), which is never executed.
-// MEASURED and REJECTED (round 2, B200, 94.4 M samples, profiles/r02_pfb_run_ncu.json): it stays off (SNRX_PFB_TILES=0).
-//   channelizer alone, one batch at a time:  one tile per CTA 0.328 ms | 2 tiles 0.388 | 8 tiles 0.390
-//   inside the two-lane pipeline (bench):    one tile per CTA 0.391 ms | 2 tiles 0.452 | 4 tiles 0.495-0.52 | 8 tiles 0.555
-//   consecutive tiles per CTA or grid-strided tiles (SNRX_PFB_ORDER=1) make no difference, so DRAM locality is not it.
-// ncu of the 8-tile launch vs the one-tile launch: same DRAM traffic (800 MB), L2 hit 47 % vs 33 %, long-scoreboard stall
-// 0.93 vs 0.60 per issue, FMA pipe 57 % vs 64 %: the tile's own copy (9 KB, issued ~40 % into the previous tile) is NOT
-// what a warp waits for any more, yet the loop-carried state costs 108 bytes of spills at the 128-register cap and the
-// long-lived CTAs interleave worse with the other lane's high-priority kernels than 126 844 seven-microsecond CTAs do.
-// The block scheduler starting a fresh one-warp CTA per tile IS the cheapest software pipeline here.
+// INTERIOR tiles only (a.tile0 .. a.tile0 + a.n_tiles - 1 of every capture lie entirely inside it), several consecutive tiles per
+// one-warp CTA: the bulk copy of the NEXT tile is issued as soon as the last FIR pass has read the current one (no second tile
+// buffer), so only a CTA's first tile waits for memory with nothing else to do, and there is no CTA start per tile.
+// MEASURED and REJECTED twice (round 2, B200, 94.4 M samples); it stays off (SNRX_PFB_TILES=0):
+//   first version (tile index split by divisions, one lane per bulk-copy piece, predicated staging; 108 B of spills):
+//     alone 0.388-0.390 ms against 0.328 for one tile per CTA; in the two-lane pipeline 0.452 / 0.495 / 0.555 ms for 2 / 4 / 8 tiles;
+//     ncu (profiles/r02_pfb_run_ncu.json): same DRAM traffic, L2 hit 47 % vs 33 %, long-scoreboard 0.93 vs 0.60 per issue;
+//   this version (no division, one elected lane issues the copies, 20 B of spills, parity suite green with SNRX_PFB_TILES=4):
+//     alone 0.333 / 0.333 / 0.337 / 0.349 ms for 2 / 4 / 8 / 16 tiles per CTA against 0.313; steps of 0.395 / 0.405 / 0.509 ms
+//     against 0.383.
+// The wait for the tile (10 % of a one-tile CTA's life) and the CTA start are gone, and it is still slower: 16 persistent warps
+// per SM start together and stay in step -- all in the FIR at once, all in the shuffle / atomic tail at once -- while
+// one-tile CTAs, started by the block scheduler whenever a slot frees up, spread their phases over the tile.  A fresh
+// 7-microsecond CTA per tile IS the cheapest software pipeline here.
 template <int NT>
 __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble_run(PfbBleArgs a) {
     using B = PfbBleGeom<NT>;
@@ -543,32 +542,33 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble_run(
     float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
 
+    // grid = (CTAs per capture, captures); a CTA takes tiles_per_cta CONSECUTIVE tiles of its capture: no division anywhere,
+    // the source pointer advances by a constant
     const int lane = threadIdx.x;
-    const int total = a.n_tiles * a.n_caps;
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
-    const int step = a.tile_step;
-    const int t_begin = step == 1 ? blockIdx.x * a.tiles_per_cta : (int)blockIdx.x;
-    const int t_end = step == 1 ? min(total, t_begin + a.tiles_per_cta) : total;
-    auto tile_src = [&](int t) {
-        const int tile = a.tile0 + t % a.n_tiles;
-        return a.x + (size_t)(t / a.n_tiles) * a.stride + ((int64_t)kPfbD * (B::kStride * tile) - G::kHist);
-    };
-    pfb_stage_tile_bulk_pred<G, kChunkT>(xs, tile_src(t_begin), bar, lane, true);
+    const int cap = (int)blockIdx.y;
+    const int t0 = a.tile0 + (int)blockIdx.x * a.tiles_per_cta;
+    const int t1 = min(a.tile0 + a.n_tiles, t0 + a.tiles_per_cta);
+    const float2* src = a.x + (size_t)cap * a.stride + ((int64_t)kPfbD * B::kStride * t0 - G::kHist);
+    pfb_stage_tile_bulk<G, kChunkT>(xs, src, bar, lane);
     uint32_t parity = 0;
 #pragma unroll 1
-    for (int t = t_begin; t < t_end; t += step) {
+    for (int tile = t0; tile < t1; tile++) {
         mbar_wait(bar, parity);
         parity ^= 1u;
-        const int tile = a.tile0 + t % a.n_tiles;
-        pfb_ble_tile<NT, false>(a, xs, V, lane, t / a.n_tiles, B::kStride * tile, [&] {
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");      // generic reads before the async-proxy writes
-            const int tn = min(t + step, total - 1);
-            pfb_stage_tile_bulk_pred<G, kChunkT>(xs, tile_src(tn), bar, lane, t + step < t_end);
+        src += kPfbD * B::kStride;
+        const bool more = tile + 1 < t1;
+        pfb_ble_tile<NT, false>(a, xs, V, lane, cap, B::kStride * tile, [&] {
+            if (more) {
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic reads before the async-proxy writes
+                pfb_stage_tile_bulk<G, kChunkT>(xs, src, bar, lane);
+            }
         });
         __syncwarp();                                            // V and the quantised values of this tile are done with
     }
 }
+
 #endif  // __CUDACC__
 
 }  // namespace snrx

@@ -285,10 +285,7 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
     {
         PfbBleArgs b = args;
         b.tile0 = lo; b.n_tiles = hi - lo; b.tiles_per_cta = per;
-        const unsigned total = (unsigned)(hi - lo) * caps;
-        static const int order = getenv("SNRX_PFB_ORDER") ? atoi(getenv("SNRX_PFB_ORDER")) : 0;
-        const unsigned grid = (total + per - 1) / per;
-        b.tile_step = order ? (int)grid : 1;
+        const dim3 grid((unsigned)((hi - lo + per - 1) / per), caps);
         k_pfb_ble_run<NT><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
         h->launches++;
     }
