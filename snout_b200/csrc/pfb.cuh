@@ -254,7 +254,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Interior tile (entirely inside the capture): lane p < kPieces copies piece p -- tile samples
 // i' in [24 TT p - 12, 24 TT (p+1) - 12) clipped to [0, kTileIn), stored at i' + 8 p.  All sizes and
 // addresses are multiples of 16 bytes (kTileIn, 24 TT and the tile origin are even).
-template <class G, int TT>
+template <class G, int TT, bool INIT = false>
 __device__ __forceinline__ void pfb_stage_tile_bulk(float2* xs, const float2* xtile /* sample i' = 0 */, uint64_t* bar, int lane) {
     constexpr int kPer = 24 * TT;
     static_assert(G::kPieces <= 32 && G::kTileIn % 2 == 0, "one lane per piece");
@@ -264,6 +264,8 @@ __device__ __forceinline__ void pfb_stage_tile_bulk(float2* xs, const float2* xt
     // issues, and loops (ELECT / R2UR / UBLKCP / BRA.U.ANY six times in the sampled profile).
     (void)lane;
     if (elect_one()) {
+        if (INIT) mbar_init(bar, 1);                      // a one-tile CTA: the elected lane also initialises the barrier (the
+                                                          // caller's __syncwarp() before the wait publishes it to the other lanes)
         mbar_expect_tx(bar, (uint32_t)(G::kTileIn * sizeof(float2)));
 #pragma unroll
         for (int p = 0; p < G::kPieces; p++) {
@@ -492,9 +494,8 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     float4* V = reinterpret_cast<float4*>(smem_raw + B::kXsBytes);         // [8][32], see v_pos()
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + B::kXsBytes + B::kVBytes);
 
-    const int lane = threadIdx.x;
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
+    int lane = threadIdx.x;
+    asm volatile("" : "+r"(lane));                         // opaque: ptxas re-read SR_TID.X (S2R + a dependent shift chain) in mid-tile
     const int tile = a.tile0 + (int)blockIdx.x;
     const int cap = (int)blockIdx.y;
     const float2* xcap = a.x + (size_t)cap * a.stride;
@@ -509,7 +510,8 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
     } else
 #endif
     if (pfb_tile_interior<G>(x0, a.n_in)) {
-        pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
+        pfb_stage_tile_bulk<G, kChunkT, true>(xs, xcap + x0, bar, lane);
+        __syncwarp();
         mbar_wait(bar, 0);
     } else {
         pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, x0, a.n_in, lane);

@@ -234,9 +234,8 @@ __global__ void __launch_bounds__(32, PfbZbWarpGeom<NT>::kCtasPerSm) k_pfb_zb_wa
     {
         const int64_t x0 = (int64_t)kPfbD * g_first - G::kHist;
         if (x0 >= 0 && x0 + G::kTileIn <= a.n_in) {
-            if (lane == 0) mbar_init(bar, 1);
+            pfb_stage_tile_bulk<G, kChunkT, true>(xs, xcap + x0, bar, lane);     // the elected lane initialises the barrier too
             __syncwarp();
-            pfb_stage_tile_bulk<G, kChunkT>(xs, xcap + x0, bar, lane);
             mbar_wait(bar, 0);
         } else {
             pfb_stage_tile<G, kChunkT, B::kThreads>(xs, xcap, x0, a.n_in, lane);

@@ -1,6 +1,10 @@
 #!/bin/bash
-# persistent multi-tile channelizer (k_pfb_ble_run, rewritten without divisions / ELECT loops): parity, then timing per tiles-per-CTA
-SNRX_PFB_TILES=4 timeout 900 python -m pytest tests -m gpu -q -x -k "ble_wb or wideband or mixed or c5" 2>&1 | tail -2
-for t in 0 2 4 8 16; do
-  echo "== tiles $t"; SNRX_PFB_TILES=$t python tools/ab_serial.py 2>&1 | tail -1 | cut -c1-150
+# A/B against the previous commit's library (snout_b200/lib/libsnoutrx_PREV.so)
+timeout 900 python -m pytest tests -m gpu -q -x -k "wb or wideband or mixed or pfb or chan" 2>&1 | tail -2
+L=$PWD/snout_b200/lib
+for v in _PREV "" _PREV ""; do
+  echo "== ble_wb40 lib$v"; SNRX_LIB=$L/libsnoutrx$v.so python tools/ab_serial.py 2>&1 | tail -1 | cut -c1-150
+done
+for v in _PREV ""; do
+  SNRX_LIB=$L/libsnoutrx$v.so python tools/ab_front.py zb_wb16 4.9 2>&1 | tail -1
 done
