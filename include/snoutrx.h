@@ -131,7 +131,7 @@ typedef struct snrx_config {
     int32_t  zb_threshold;   /* packet sink threshold (10, top_block.py:67)                */
     float    quant_scale;    /* BLE: q = clamp(rint(x*quant_scale), -128, 127)             */
     uint64_t max_samples;    /* capacity: input samples per capture                        */
-    uint32_t max_captures;   /* capacity: captures per snrx_process batch                  */
+    uint32_t max_captures;   /* capacity: captures per snrx_process batch (wideband modes: <= 65535) */
     uint32_t max_frames;     /* capacity: frames per snrx_process batch                    */
     uint32_t zb_segment;     /* Zigbee: chain segment body, channel-rate samples (0 = SNRX_ZB_SEGMENT_DEFAULT) */
     uint32_t zb_prehalo;     /* Zigbee: chain warm-up, channel-rate samples (0 = SNRX_ZB_PREHALO_DEFAULT)   */
