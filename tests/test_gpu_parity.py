@@ -496,6 +496,30 @@ def test_ble_wb40_batch_of_captures(Engine):
     assert np.array_equal(got["capture_id"], want["capture_id"])
 
 
+@pytest.mark.parametrize("mode,kind", [("zb_wb16", "zigbee"), ("mixed_wb56", "mixed")])
+def test_wideband_zigbee_and_mixed_batches_of_captures(Engine, mode, kind):
+    """The captures of a wideband batch are the y dimension of the channelizer grids (k_pfb_ble, k_pfb_zb_warp) and the outer
+    index of the Zigbee chains: a batch of captures gives each capture's own records, and more than 65535 captures per batch
+    are refused when the engine is created."""
+    caps = [synth.wideband_capture(seconds=0.012, kind=kind, seed=4700 + 31 * i, esn0_db=22.0, gap=(300, 4000)).iq for i in range(2)]
+    with Engine(mode, max_samples=len(caps[0]), max_captures=2) as e:
+        single = []
+        for i, c in enumerate(caps):
+            f = e.run(c)
+            f["capture_id"] = i
+            single.append(f)
+        got = e.run(np.stack(caps))
+    want = np.concatenate(single)
+    assert len(want) > 40 and (want["proto"] == _abi.PROTO_ZIGBEE).sum() > 2     # mixed: most 802.15.4 frames collide with BLE
+    assert_frames_equal(_canon_cap(got), _canon_cap(want), what=f"batch of {mode} captures")
+    with pytest.raises(_abi.SnrxError):
+        Engine(mode, max_samples=24 * 8192, max_captures=65536)
+
+
+def _canon_cap(fr):
+    return fr[np.lexsort((fr["sample_index"], fr["window"], fr["channel"], fr["proto"], fr["capture_id"]))]
+
+
 # ------------------------------------------------------------------------------------ BASELINE full sizes (configs[2], [3])
 def _tile_frames(fr, k, tile_ch, lo_guard=0, hi_guard=0):
     """Frames anchored in tile k (channel-rate tile length tile_ch), positions made tile relative."""
