@@ -335,6 +335,8 @@ struct PfbBleArgs {
     int32_t tile0;            // first tile of this launch
     int32_t n_caps;           // captures in this launch
     int32_t tiles_per_cta;    // k_pfb_ble_run only
+    int32_t stagger_ns;       // k_pfb_ble_run only: start delay per CTA slot of an SM (SNRX_PFB_STAGGER_NS; 0 = none)
+    int32_t sm_count;         // k_pfb_ble_run only
     const float4* taps_pass;  // [3][NT/4][8] float4: element (gi, d4, rl) = h[rho + 24 (4 d4 + 0..3)], rho = gi + 3 rl --
                               // the 8 FIR rows of a pass read 128 contiguous bytes per load
     float scale;              // quantiser scale
@@ -531,10 +533,14 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble(PfbB
 //   this version (no division, one elected lane issues the copies, 20 B of spills, parity suite green with SNRX_PFB_TILES=4):
 //     alone 0.333 / 0.333 / 0.337 / 0.349 ms for 2 / 4 / 8 / 16 tiles per CTA against 0.313; steps of 0.395 / 0.405 / 0.509 ms
 //     against 0.383.
-// The wait for the tile (10 % of a one-tile CTA's life) and the CTA start are gone, and it is still slower: 16 persistent warps
-// per SM start together and stay in step -- all in the FIR at once, all in the shuffle / atomic tail at once -- while
-// one-tile CTAs, started by the block scheduler whenever a slot frees up, spread their phases over the tile.  A fresh
-// 7-microsecond CTA per tile IS the cheapest software pipeline here.
+//     One wave (54 tiles per CTA): 0.360 ms; with the CTAs of an SM started 400 / 800 ns apart (SNRX_PFB_STAGGER_NS): 0.357 / 0.359.
+// The wait for the tile (10 % of a one-tile CTA's life) and the CTA start are gone, and it is still slower -- the more tiles per
+// CTA, the slower -- and staggering the warps' phases changes nothing, so phase lock-step is not it.  What grows with the tiles
+// per CTA is the number of separate input regions read at once (2368 CTAs each walking its own stretch of the capture, where
+// the one-tile kernel's resident CTAs form ONE compact window moving through it): the first version's ncu capture already
+// showed the long-scoreboard stall at 0.93 per issue against 0.60.  Not measured with this version: grid-strided tiles (CTA b
+// takes tiles b, b + grid, ...), which keep the window compact.  Until then a fresh 7-microsecond CTA per tile IS the cheapest
+// software pipeline here.
 template <int NT>
 __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble_run(PfbBleArgs a) {
     using B = PfbBleGeom<NT>;
@@ -550,6 +556,9 @@ __global__ void __launch_bounds__(32, PfbBleGeom<NT>::kCtasPerSm) k_pfb_ble_run(
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
     const int cap = (int)blockIdx.y;
+    // measurement switch: the CTAs of one SM (block b lands on SM b % sm_count in the first wave) start a fraction of a tile
+    // apart, so that persistent warps do not run through their phases in step
+    if (a.stagger_ns > 0) __nanosleep((unsigned)(((blockIdx.x / (unsigned)a.sm_count) & 15u) * (unsigned)a.stagger_ns));
     const int t0 = a.tile0 + (int)blockIdx.x * a.tiles_per_cta;
     const int t1 = min(a.tile0 + a.n_tiles, t0 + a.tiles_per_cta);
     const float2* src = a.x + (size_t)cap * a.stride + ((int64_t)kPfbD * B::kStride * t0 - G::kHist);

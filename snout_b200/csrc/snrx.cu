@@ -263,7 +263,7 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
     }
     PfbBleArgs args = *a;
     args.n_caps = (int32_t)caps;
-    args.tiles_per_cta = 1;
+    args.tiles_per_cta = 1; args.stagger_ns = 0; args.sm_count = h->sm_count;
     const bool dbg = (h->cfg.flags & SNRX_F_KEEP_STREAMS) != 0;
     auto one_tile = [&](int t0, int t1) {                       // tiles [t0, t1) of every capture, one per CTA, any position
         if (t1 <= t0) return;
@@ -285,6 +285,7 @@ static int pfb_ble_go(snrx_handle* h, const PfbBleArgs* a, cudaStream_t st, uint
     {
         PfbBleArgs b = args;
         b.tile0 = lo; b.n_tiles = hi - lo; b.tiles_per_cta = per;
+        { static const int ns = getenv("SNRX_PFB_STAGGER_NS") ? atoi(getenv("SNRX_PFB_STAGGER_NS")) : 0; b.stagger_ns = ns; b.sm_count = h->sm_count; }
         const dim3 grid((unsigned)((hi - lo + per - 1) / per), caps);
         k_pfb_ble_run<NT><<<grid, B::kThreads, B::kSmemBytes, st>>>(b);
         h->launches++;

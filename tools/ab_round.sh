@@ -1,10 +1,6 @@
 #!/bin/bash
-# A/B against the previous commit's library (snout_b200/lib/libsnoutrx_PREV.so)
-timeout 900 python -m pytest tests -m gpu -q -x -k "wb or wideband or mixed or pfb or chan" 2>&1 | tail -2
-L=$PWD/snout_b200/lib
-for v in _PREV "" _PREV ""; do
-  echo "== ble_wb40 lib$v"; SNRX_LIB=$L/libsnoutrx$v.so python tools/ab_serial.py 2>&1 | tail -1 | cut -c1-150
-done
-for v in _PREV ""; do
-  SNRX_LIB=$L/libsnoutrx$v.so python tools/ab_front.py zb_wb16 4.9 2>&1 | tail -1
+# persistent multi-tile channelizer with staggered CTA starts (SNRX_PFB_STAGGER_NS per CTA slot of an SM)
+for cfg in "0 0" "54 0" "54 400" "54 800" "27 400"; do
+  set -- $cfg
+  echo "== tiles $1 stagger $2 ns"; SNRX_PFB_TILES=$1 SNRX_PFB_STAGGER_NS=$2 python tools/ab_serial.py 2>&1 | tail -1 | cut -c1-150
 done
