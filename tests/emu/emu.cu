@@ -41,6 +41,20 @@ void emu_idft96(const float* in, float* out) {
 
 int emu_ble_channel_of_q(int q) { return ble_channel_of_q(q); }
 
+// k_zb_order's per-chain key (a scheduling hint: which chains k_zb_rx hands out first) and the busy flag k_zb_iir_sum derives
+// from the last 64 discriminator samples of a block
+int emu_zb_chain_key(const uint8_t* busy, int n_blocks, int origin, int body, int segment, int seg) {
+    ZbChainParams p{};
+    p.origin = origin; p.body = body; p.segment = segment; p.n_blocks = n_blocks;
+    return zb_chain_key(busy, n_blocks, p, seg);
+}
+int emu_zb_block_busy(const float* f_last64) {
+    float e = 0.0f;
+    for (int i = 0; i < kZbBusyWindow; i++) e += f_last64[i] * f_last64[i];
+    return (e > kZbBusyLo && e < kZbBusyHi) ? 1 : 0;
+}
+int emu_zb_keys() { return kZbKeys; }
+
 }  // extern "C"
 
 // ---- one tile of k_pfb_ble<NT, *>, phases 0..3 --------------------------------------------------

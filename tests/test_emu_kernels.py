@@ -215,3 +215,58 @@ def test_pfb_zb_tile_kernel(emu, oracle_mod, nt, name):
         ok += len(truth & {bytes(q["bytes"][:q["len"]]) for q in fr if q["crc_ok"]})
         tot += len(truth)
     assert tot >= 8 and ok >= 0.9 * tot, (ok, tot)
+
+
+def test_zb_chain_order_key(emu, oracle_mod):
+    """k_zb_order's key (csrc/zb.cuh zb_chain_key): which chains k_zb_rx hands out first.  It is a scheduling hint -- no record
+    depends on it (GPU test test_zb_chain_order_is_a_scheduling_hint_only) -- but it indexes the counting sort, so its range and
+    its meaning are pinned here: 0 when the air is idle at the end of the chain's body or has been busy without a break since
+    two blocks before the body, else the number of consecutive busy block ends from the end of the body on (at most 9)."""
+    import ctypes
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    K = emu.emu_zb_keys()
+    assert K == 10
+
+    def key(busy, origin, body, segment, seg):
+        return emu.emu_zb_chain_key(P(busy), len(busy), origin, body, segment, seg)
+
+    def want(busy, origin, body, segment, seg):
+        lo = origin + seg * segment
+        hi = min(lo + segment, origin + body)
+        if hi <= lo or hi % 2048 or lo % 2048:
+            return 0
+        kb, kl = hi // 2048 - 1, lo // 2048 - 1
+        if kb < 0 or kb >= len(busy) or not busy[kb]:
+            return 0
+        if kl >= 1 and all(busy[j] for j in range(kl - 1, kb)):
+            return 0
+        k, j = 0, kb
+        while j < len(busy) and busy[j] and k < K - 1:
+            k, j = k + 1, j + 1
+        return k
+
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        nb = int(rng.integers(4, 80))
+        busy = (rng.random(nb) < rng.choice([0.1, 0.5, 0.9])).astype(np.uint8)
+        segment = int(rng.choice([2048, 4096, 8192, 16384]))
+        origin = int(rng.choice([0, 2048 * 3, 2048 * 49]))
+        body = nb * 2048 - origin - int(rng.choice([0, 0, 700]))
+        if body <= 0:
+            continue
+        for seg in range(-(-body // segment)):
+            k = key(busy, origin, body, segment, seg)
+            assert 0 <= k < K and k == want(busy, origin, body, segment, seg), (trial, seg, k)
+    # a frame that starts inside the body and runs on for three blocks past it; the same frame seen by the NEXT chain (on the air
+    # since before its body) is not that chain's to decode
+    busy = np.zeros(20, np.uint8); busy[5:9] = 1            # busy at the ends of blocks 5..8 = samples 12288 .. 18432
+    assert key(busy, 0, 20 * 2048, 4096, 2) == 4            # body [8192, 12288): ends busy, then 3 more busy block ends
+    assert key(busy, 0, 20 * 2048, 4096, 3) == 2            # body [12288, 16384): idle at 10240, so it may be this chain's: 2 more
+    busy[3:9] = 1                                           # ... on the air since 8192: not the chain's to decode
+    assert key(busy, 0, 20 * 2048, 4096, 3) == 0
+    # the discriminator statistics the busy flag rests on: O-QPSK moves by +-pi/4 per sample, noise is uniform in (-pi, pi)
+    msk = np.full(64, np.pi / 4, np.float32) * rng.choice([-1.0, 1.0], 64).astype(np.float32)
+    noise = rng.uniform(-np.pi, np.pi, 64).astype(np.float32)
+    gfsk = np.full(64, 0.39, np.float32)
+    assert emu.emu_zb_block_busy(P(msk)) == 1 and emu.emu_zb_block_busy(P(noise)) == 0 and emu.emu_zb_block_busy(P(gfsk)) == 0
+    assert emu.emu_zb_block_busy(P(np.zeros(64, np.float32))) == 0
