@@ -270,3 +270,19 @@ def test_zb_chain_order_key(emu, oracle_mod):
     gfsk = np.full(64, 0.39, np.float32)
     assert emu.emu_zb_block_busy(P(msk)) == 1 and emu.emu_zb_block_busy(P(noise)) == 0 and emu.emu_zb_block_busy(P(gfsk)) == 0
     assert emu.emu_zb_block_busy(P(np.zeros(64, np.float32))) == 0
+
+
+def test_transpose_step_rotate_select_identity():
+    """csrc/pfb.cuh transpose_step on the device is one rotate + one bitwise select; on the host (and in the harness) it is the
+    two-sided shift form it replaced.  They are the same function: under m no bit of y >> j wraps, under ~m none of y << j does."""
+    rng = np.random.default_rng(5)
+    ror = lambda v, r: ((v >> np.uint32(r)) | (v << np.uint32(32 - r))) & np.uint32(0xFFFFFFFF) if r % 32 else v   # noqa: E731
+    for j, m in ((8, 0x00FF00FF), (4, 0x0F0F0F0F), (2, 0x33333333), (1, 0x55555555), (16, 0x0000FFFF)):
+        m = np.uint32(m)
+        x = rng.integers(0, 1 << 32, 2000, dtype=np.uint64).astype(np.uint32)
+        y = rng.integers(0, 1 << 32, 2000, dtype=np.uint64).astype(np.uint32)
+        for hi in (False, True):
+            two_sided = ((x & ~m) | ((y >> np.uint32(j)) & m)) if hi else ((x & m) | ((y << np.uint32(j)) & ~m))
+            keep = ~m if hi else m
+            rot = ror(y, j if hi else 32 - j)
+            assert np.array_equal(two_sided, (x & keep) | (rot & ~keep)), (j, hi)
